@@ -1,0 +1,71 @@
+#!/usr/bin/env python
+"""Generate the golden outputs under tests/golden/ by running the UNMODIFIED reference binary
+(oracle/_ref/bin/Gap2Seq-core-stats, built from /root/reference by oracle/build_ref.sh) on the seeded
+cases of tests/cases.py:  `-nb-cores 1 -randseed 1` is the only deterministic mode.
+
+Runs only in the build container (the reference is not present on the GPU box); the outputs are
+committed so that the tests can run anywhere.
+
+    python tests/golden/make_golden.py [case ...]
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import time
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+import cases  # noqa: E402
+
+REF = os.path.join(cases.ROOT, "oracle", "_ref", "bin", "Gap2Seq-core-stats")
+REF_PLAIN = os.path.join(cases.ROOT, "oracle", "_ref", "bin", "Gap2Seq-core")
+
+
+def run_case(case: cases.Case) -> None:
+    w = cases.build(case)
+    tmp = tempfile.mkdtemp(prefix="g2s_golden_")
+    try:
+        paths = w.write(tmp)
+        t0 = time.time()
+        cmd = [REF] + cases.ref_cmd_flags(case) + ["-reads", paths["reads"], "-scaffolds", paths["gaps"], "-filled",
+                                                   os.path.join(tmp, "filled.fa")]
+        # one working directory per invocation: the reference writes ./.h5
+        p = subprocess.run("ulimit -s unlimited; " + " ".join(cmd), shell=True, cwd=tmp, capture_output=True, text=True,
+                           timeout=3600)
+        if p.returncode != 0:
+            raise RuntimeError(f"{case.name}: reference failed rc={p.returncode}\n{p.stdout[-2000:]}\n{p.stderr[-2000:]}")
+        # the -DSTATS build and the plain build must agree on the FASTA (sanity check of the golden itself)
+        os.remove(os.path.join(tmp, ".h5")) if os.path.exists(os.path.join(tmp, ".h5")) else None
+        cmd2 = [REF_PLAIN] + cases.ref_cmd_flags(case) + ["-reads", paths["reads"], "-scaffolds", paths["gaps"],
+                                                         "-filled", os.path.join(tmp, "filled2.fa")]
+        p2 = subprocess.run("ulimit -s unlimited; " + " ".join(cmd2), shell=True, cwd=tmp, capture_output=True,
+                            text=True, timeout=3600)
+        assert p2.returncode == 0
+        a = open(os.path.join(tmp, "filled.fa")).read()
+        b = open(os.path.join(tmp, "filled2.fa")).read()
+        assert a == b, f"{case.name}: reference is not deterministic?"
+        fa, log = cases.golden_paths(case.name)
+        with open(fa, "w") as f:
+            f.write(a)
+        with open(log, "w") as f:
+            f.write(cases.filter_log(p.stdout))
+        print(f"{case.name}: {len(w.gaps)} records, {time.time() - t0:.1f} s, "
+              f"{cases.filter_log(p.stdout).strip().splitlines()[-1]}")
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
+def main() -> None:
+    if not os.path.exists(REF):
+        sys.exit("oracle/_ref is not built: run oracle/build_ref.sh in the container that has /root/reference")
+    names = sys.argv[1:] or [c.name for c in cases.CASES]
+    for n in names:
+        run_case(cases.CASE_BY_NAME[n])
+
+
+if __name__ == "__main__":
+    main()
