@@ -43,6 +43,6 @@ def test_known_answer_cell_counts(case_inputs):
         left, right = rec.seq[i - 41:i], rec.seq[i + gl:i + gl + 41]
         res, fill = g.fill_gap(left, right, gl, 500, 10, 10)
         assert res.cells_right == 10 + -(-(gl + 500) // 2) + 1
-        assert res.cells_left == min(gl // 2 + 250 + 10, 10 + gl + 31 + 10 + 1)
+        assert res.cells_left == max(gl // 2 + 250 + 10, 10 + gl + 31 + 10 + 1)
         assert res.count == 1 and fill[:-31] == rec.truth and fill.isupper()
         assert res.substats[0] == gl + 43 and res.substats[1] == gl + 42
