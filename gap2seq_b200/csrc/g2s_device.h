@@ -1,0 +1,35 @@
+// g2s_device.h - host-callable entry points of the CUDA translation units (internal to libg2s_gpu.so).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "g2s_common.cuh"
+
+namespace g2s {
+
+struct DeviceTable {
+  Slot *slots = nullptr;
+  uint64_t cap = 0;   // slots (power of two)
+  uint64_t n = 0;     // k-mers stored
+  int k = 0;
+};
+
+Table table_view(const DeviceTable &dt);
+cudaError_t table_alloc(DeviceTable *dt, int k, uint64_t n_keys, int sms, cudaStream_t st);
+cudaError_t table_fill(DeviceTable *dt, const uint64_t *keys_dev, const uint32_t *counts_dev, uint32_t solid, uint64_t n,
+                       int sms, cudaStream_t st);
+cudaError_t table_from_reads(DeviceTable *dt, int k, const char *bases_host, const uint64_t *offsets_host,
+                             uint64_t n_reads, int solid, int sms, cudaStream_t st);
+cudaError_t table_export(const DeviceTable &dt, uint64_t *keys_host, uint8_t *adj_host, int sms, cudaStream_t st);
+cudaError_t table_contains(const DeviceTable &dt, const char *ascii_host, uint64_t n, uint8_t *out_host, cudaStream_t st);
+
+struct FillParams;
+// thin tier: one warp per gap, persistent over a device work queue.  groups = number of scratch slices.
+cudaError_t launch_fill_warp(const FillParams &p, int groups, cudaStream_t st);
+// wide tier: one CTA (512 threads) per gap
+cudaError_t launch_fill_cta(const FillParams &p, int groups, cudaStream_t st);
+int fill_warps_per_cta();
+int fill_max_resident_warp_groups(int sms);   // occupancy-derived number of warp groups that fit the device
+int fill_max_resident_cta_groups(int sms);
+
+}  // namespace g2s

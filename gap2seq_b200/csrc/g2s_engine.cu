@@ -1,0 +1,516 @@
+// g2s_engine.cu - host side of libg2s_gpu.so: the C ABI of include/g2s.h, batching of gaps into device passes
+// (thin warp-per-gap tier, then wide CTA-per-gap tiers for gaps that outgrow their scratch slice), and the two
+// stages of Gap2Seq::fill_gap that are inherently sequential on the host:
+//   * the SCC contraction / branch counter of src/Gap2Seq.cpp:1314-1434 for the (rare) gaps whose path subgraph
+//     is not a plain level DAG (the device classifies the DAG case itself),
+//   * the random traceback of src/Gap2Seq.cpp:1437-1517, which must consume libc rand() in input order
+//      and therefore walks the device-built predecessor trellis gap after gap.
+// There is no CPU implementation of the DP here: without a CUDA device every call fails with G2S_E_CUDA.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/g2s.h"
+#include "g2s_device.h"
+#include "g2s_fill.cuh"
+#include "g2s_finish.h"
+#include "g2s_scaffold.h"
+
+using namespace g2s;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string &msg) { g_err = msg; return code; }
+#define CUDA_TRY(x)                                                                                         \
+  do {                                                                                                      \
+    cudaError_t e_ = (x);                                                                                   \
+    if (e_ != cudaSuccess)                                                                                  \
+      return fail(e_ == cudaErrorMemoryAllocation ? G2S_E_NOMEM : G2S_E_CUDA,                               \
+                  std::string(#x) + ": " + cudaGetErrorString(e_));                                         \
+  } while (0)
+
+namespace {
+
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e == cudaSuccess) cap = bytes;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+struct PinBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr; cap = 0;
+    cudaError_t e = cudaMallocHost(&p, bytes);
+    if (e == cudaSuccess) cap = bytes;
+    return e;
+  }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+struct Pass {                   // one device pass over a subset of the batch
+  int tier = 0;
+  std::vector<uint32_t> order;  // gap ids, longest first
+  SliceLayout lay{};
+  int groups = 0;
+  unsigned long long pack_cap = 0;
+  std::vector<PackRec> pack;    // host copy of the pack arena (filled by finish)
+  unsigned long long pack_used = 0;
+  DevBuf d_pack;
+};
+
+}  // namespace
+
+struct g2s_engine {
+  g2s_config cfg{};
+  int sms = 0;
+  size_t budget = 0;
+  cudaStream_t st = nullptr;
+  cudaEvent_t ev[4]{};
+  DeviceTable table;
+  // batch state
+  std::vector<g2s_gap> gaps;           // pointers rewired into flank_store
+  std::vector<char> flank_store;
+  std::vector<GapDev> gapdev;
+  std::vector<GapOut> outs;
+  std::vector<int> out_pass;           // pass that produced outs[i]
+  std::vector<Pass> passes;
+  bool uploaded = false, ran = false;
+  DevBuf d_flanks, d_gaps, d_order, d_outs, d_scratch, d_counters;
+  PinBuf h_outs, h_stage;
+  g2s_timing tm{};
+  int max_dmax = 0, max_rmf = 0;
+};
+
+// ------------------------------------------------------------------------------------------------ C ABI: basics
+extern "C" const char *g2s_last_error(void) { return g_err.c_str(); }
+extern "C" int g2s_abi_version(void) { return G2S_ABI_VERSION; }
+
+extern "C" int g2s_create(const g2s_config *cfg, g2s_engine **out) {
+  if (!cfg || !out) return fail(G2S_E_ARG, "g2s_create: null argument");
+  if (cfg->abi_version != G2S_ABI_VERSION) return fail(G2S_E_ARG, "g2s_create: ABI version mismatch");
+  if (cfg->k < 3 || cfg->k > 31) return fail(G2S_E_ARG, "g2s_create: k must be in [3, 31]");
+  if (cfg->max_fuz < 0 || cfg->max_fuz > MAX_FUZ) return fail(G2S_E_ARG, "g2s_create: max_fuz must be in [0, 31]");
+  int ndev = 0;
+  CUDA_TRY(cudaGetDeviceCount(&ndev));
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(G2S_E_CUDA, "g2s_create: no such CUDA device");
+  CUDA_TRY(cudaSetDevice(cfg->device));
+  g2s_engine *e = new g2s_engine();
+  e->cfg = *cfg;
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, cfg->device));
+  e->sms = prop.multiProcessorCount;
+  CUDA_TRY(cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking));
+  for (auto &v : e->ev) CUDA_TRY(cudaEventCreate(&v));
+  size_t fr = 0, tot = 0;
+  CUDA_TRY(cudaMemGetInfo(&fr, &tot));
+  e->budget = cfg->max_mem_bytes > 0 ? (size_t)cfg->max_mem_bytes : (size_t)(fr * 0.6);
+  CUDA_TRY(e->d_counters.reserve(64));
+  *out = e;
+  return G2S_OK;
+}
+
+extern "C" void g2s_destroy(g2s_engine *e) {
+  if (!e) return;
+  cudaSetDevice(e->cfg.device);
+  for (auto &p : e->passes) p.d_pack.release();
+  e->d_flanks.release(); e->d_gaps.release(); e->d_order.release(); e->d_outs.release();
+  e->d_scratch.release(); e->d_counters.release(); e->h_outs.release(); e->h_stage.release();
+  if (e->table.slots) cudaFree(e->table.slots);
+  for (auto &v : e->ev) if (v) cudaEventDestroy(v);
+  if (e->st) cudaStreamDestroy(e->st);
+  delete e;
+}
+
+extern "C" int g2s_import_kmers(g2s_engine *e, const uint64_t *canon, size_t n) {
+  if (!e || (!canon && n)) return fail(G2S_E_ARG, "g2s_import_kmers: null argument");
+  CUDA_TRY(cudaSetDevice(e->cfg.device));
+  uint64_t *d_keys = nullptr;
+  CUDA_TRY(table_alloc(&e->table, e->cfg.k, n, e->sms, e->st));
+  if (n) {
+    CUDA_TRY(cudaMalloc(&d_keys, n * 8));
+    cudaError_t er = cudaMemcpyAsync(d_keys, canon, n * 8, cudaMemcpyHostToDevice, e->st);
+    if (er == cudaSuccess) er = table_fill(&e->table, d_keys, nullptr, 0, n, e->sms, e->st);
+    cudaFree(d_keys);
+    CUDA_TRY(er);
+  } else {
+    CUDA_TRY(cudaStreamSynchronize(e->st));
+  }
+  return G2S_OK;
+}
+
+extern "C" int g2s_build_from_reads(g2s_engine *e, const char *bases, const uint64_t *offsets, size_t n_reads, int solid) {
+  if (!e || !bases || !offsets) return fail(G2S_E_ARG, "g2s_build_from_reads: null argument");
+  CUDA_TRY(cudaSetDevice(e->cfg.device));
+  CUDA_TRY(table_from_reads(&e->table, e->cfg.k, bases, offsets, n_reads, solid, e->sms, e->st));
+  return G2S_OK;
+}
+
+extern "C" int64_t g2s_num_kmers(const g2s_engine *e) { return e ? (int64_t)e->table.n : -1; }
+
+extern "C" int g2s_export_kmers(g2s_engine *e, uint64_t *canon_sorted, uint8_t *adjacency) {
+  if (!e || !canon_sorted) return fail(G2S_E_ARG, "g2s_export_kmers: null argument");
+  if (!e->table.slots) return fail(G2S_E_STATE, "g2s_export_kmers: no graph imported");
+  CUDA_TRY(cudaSetDevice(e->cfg.device));
+  CUDA_TRY(table_export(e->table, canon_sorted, adjacency, e->sms, e->st));
+  return G2S_OK;
+}
+
+extern "C" int g2s_contains(g2s_engine *e, const char *kmers_ascii, size_t n, uint8_t *out) {
+  if (!e || !kmers_ascii || !out) return fail(G2S_E_ARG, "g2s_contains: null argument");
+  if (!e->table.slots) return fail(G2S_E_STATE, "g2s_contains: no graph imported");
+  CUDA_TRY(cudaSetDevice(e->cfg.device));
+  CUDA_TRY(table_contains(e->table, kmers_ascii, n, out, e->st));
+  return G2S_OK;
+}
+
+extern "C" int g2s_get_timing(const g2s_engine *e, g2s_timing *out) {
+  if (!e || !out) return fail(G2S_E_ARG, "g2s_get_timing: null argument");
+  *out = e->tm;
+  return G2S_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ device passes
+static int dmax_of(const g2s_gap &g) { return g.gap_len + g.gap_err + g.left_max_fuz + g.right_max_fuz; }
+
+static int plan_pass(g2s_engine *e, Pass &p) {
+  // scratch geometry of this tier
+  uint64_t cap0 = (uint64_t)4 * ((uint64_t)e->max_dmax + 2) + 1024;
+  if (cap0 < 4096) cap0 = 4096;
+  uint64_t cap = cap0;
+  for (int t = 0; t < p.tier; t++) cap *= 16;
+  uint32_t hlog = p.tier == 0 ? ceil_log2(2 * cap) : std::max<uint32_t>(16, ceil_log2(cap / 4));
+  p.lay = make_layout(cap, hlog, (uint32_t)e->max_dmax + 1, (uint32_t)e->max_rmf + 1);
+  if (cap >= (1ULL << 31) || p.lay.bytes > e->budget) return -1;   // largest tier exceeded
+  size_t fit = e->budget / p.lay.bytes;
+  int resident = p.tier == 0 ? fill_max_resident_warp_groups(e->sms) : fill_max_resident_cta_groups(e->sms);
+  size_t groups = std::min<size_t>({p.order.size(), (size_t)resident, fit});
+  p.groups = (int)std::max<size_t>(groups, 1);
+  // output arena
+  unsigned long long want = 0;
+  if (p.tier == 0) {
+    for (uint32_t gi : p.order) want += 2ULL * ((unsigned long long)dmax_of(e->gaps[gi]) + 256);
+  } else {
+    want = (unsigned long long)p.order.size() * cap;
+  }
+  unsigned long long lim = (unsigned long long)(e->budget / 4 / sizeof(PackRec));
+  p.pack_cap = std::max<unsigned long long>(std::min(want, lim), 1 << 16);
+  return 0;
+}
+
+static int run_pass(g2s_engine *e, Pass &p) {
+  CUDA_TRY(e->d_scratch.reserve((size_t)p.groups * p.lay.bytes));
+  CUDA_TRY(p.d_pack.reserve(p.pack_cap * sizeof(PackRec)));
+  CUDA_TRY(e->d_order.reserve(p.order.size() * 4));
+  CUDA_TRY(cudaMemcpyAsync(e->d_order.p, p.order.data(), p.order.size() * 4, cudaMemcpyHostToDevice, e->st));
+  CUDA_TRY(cudaMemsetAsync(e->d_counters.p, 0, 64, e->st));
+  FillParams P{};
+  P.table = table_view(e->table);
+  P.flanks = (const char *)e->d_flanks.p;
+  P.gaps = (const GapDev *)e->d_gaps.p;
+  P.order = (const uint32_t *)e->d_order.p;
+  P.n_gaps = (uint32_t)p.order.size();
+  P.outs = (GapOut *)e->d_outs.p;
+  P.scratch = (unsigned char *)e->d_scratch.p;
+  P.lay = p.lay;
+  P.pack = (PackRec *)p.d_pack.p;
+  P.pack_cap = p.pack_cap;
+  P.pack_cursor = (unsigned long long *)((char *)e->d_counters.p + 8);
+  P.queue_head = (uint32_t *)e->d_counters.p;
+  CUDA_TRY(cudaEventRecord(e->ev[0], e->st));
+  if (p.tier == 0) CUDA_TRY(launch_fill_warp(P, p.groups, e->st));
+  else CUDA_TRY(launch_fill_cta(P, p.groups, e->st));
+  CUDA_TRY(cudaEventRecord(e->ev[1], e->st));
+  e->tm.launches++;
+  // the per-gap summaries decide whether another tier is needed
+  CUDA_TRY(cudaMemcpyAsync(e->h_outs.p, e->d_outs.p, e->gaps.size() * sizeof(GapOut), cudaMemcpyDeviceToHost, e->st));
+  unsigned long long used = 0;
+  CUDA_TRY(cudaMemcpyAsync(&used, (char *)e->d_counters.p + 8, 8, cudaMemcpyDeviceToHost, e->st));
+  CUDA_TRY(cudaStreamSynchronize(e->st));
+  float ms = 0;
+  CUDA_TRY(cudaEventElapsedTime(&ms, e->ev[0], e->ev[1]));
+  e->tm.kernel_ms += ms;
+  e->tm.d2h_bytes += e->gaps.size() * sizeof(GapOut) + 8;
+  p.pack_used = std::min(used, p.pack_cap);
+  return G2S_OK;
+}
+
+static int do_upload(g2s_engine *e, const g2s_gap *gaps, size_t n) {
+  if (!e) return fail(G2S_E_ARG, "null engine");
+  if (!e->table.slots) return fail(G2S_E_STATE, "no graph imported (g2s_import_kmers / g2s_build_from_reads)");
+  if (!gaps && n) return fail(G2S_E_ARG, "null gaps");
+  CUDA_TRY(cudaSetDevice(e->cfg.device));
+  const int k = e->cfg.k;
+  e->tm = g2s_timing{};
+  for (auto &p : e->passes) p.d_pack.release();
+  e->passes.clear();
+  e->gaps.assign(gaps, gaps + n);
+  e->gapdev.resize(n);
+  e->outs.assign(n, GapOut{});
+  e->out_pass.assign(n, -1);
+  e->max_dmax = 0; e->max_rmf = 0;
+  size_t fbytes = 0;
+  for (size_t i = 0; i < n; i++) {
+    const g2s_gap &g = gaps[i];
+    if (!g.kmer_left || !g.kmer_right) return fail(G2S_E_ARG, "gap with null flank");
+    if (g.gap_len < 0 || g.gap_err < 0 || g.left_max_fuz < 0 || g.right_max_fuz < 0 || g.left_max_fuz > e->cfg.max_fuz ||
+        g.right_max_fuz > e->cfg.max_fuz)
+      return fail(G2S_E_ARG, "gap parameters out of range (fuz must be <= g2s_config.max_fuz)");
+    if ((long long)g.gap_len + g.gap_err > (1 << 24)) return fail(G2S_E_ARG, "gap_len + gap_err too large");
+    fbytes += (size_t)2 * k + g.left_max_fuz + g.right_max_fuz;
+    e->max_dmax = std::max(e->max_dmax, dmax_of(g));
+    e->max_rmf = std::max(e->max_rmf, std::max(g.right_max_fuz, g.left_max_fuz));
+  }
+  e->flank_store.resize(fbytes + 1);
+  size_t off = 0;
+  for (size_t i = 0; i < n; i++) {
+    g2s_gap &g = e->gaps[i];
+    GapDev &d = e->gapdev[i];
+    d.flank_off = (uint32_t)off;
+    memcpy(&e->flank_store[off], g.kmer_left, (size_t)k + g.left_max_fuz);
+    g.kmer_left = nullptr;
+    off += (size_t)k + g.left_max_fuz;
+    memcpy(&e->flank_store[off], g.kmer_right, (size_t)k + g.right_max_fuz);
+    g.kmer_right = nullptr;
+    off += (size_t)k + g.right_max_fuz;
+    d.gap_len = g.gap_len; d.gap_err = g.gap_err; d.lmf = g.left_max_fuz; d.rmf = g.right_max_fuz;
+    d.flags = (uint32_t)g.flags; d.id = (uint32_t)i; d.pad = 0;
+  }
+  if (fbytes >= (1ULL << 32)) return fail(G2S_E_ARG, "batch too large");
+  CUDA_TRY(e->d_flanks.reserve(fbytes + 16));
+  CUDA_TRY(e->d_gaps.reserve(std::max<size_t>(n, 1) * sizeof(GapDev)));
+  CUDA_TRY(e->d_outs.reserve(std::max<size_t>(n, 1) * sizeof(GapOut)));
+  CUDA_TRY(e->h_outs.reserve(std::max<size_t>(n, 1) * sizeof(GapOut)));
+  CUDA_TRY(cudaEventRecord(e->ev[2], e->st));
+  if (n) {
+    CUDA_TRY(cudaMemcpyAsync(e->d_flanks.p, e->flank_store.data(), fbytes, cudaMemcpyHostToDevice, e->st));
+    CUDA_TRY(cudaMemcpyAsync(e->d_gaps.p, e->gapdev.data(), n * sizeof(GapDev), cudaMemcpyHostToDevice, e->st));
+  }
+  CUDA_TRY(cudaEventRecord(e->ev[3], e->st));
+  CUDA_TRY(cudaStreamSynchronize(e->st));
+  float ms = 0;
+  CUDA_TRY(cudaEventElapsedTime(&ms, e->ev[2], e->ev[3]));
+  e->tm.h2d_ms = ms;
+  e->tm.h2d_bytes = fbytes + n * sizeof(GapDev);
+  e->uploaded = true; e->ran = false;
+  return G2S_OK;
+}
+
+static int do_run(g2s_engine *e) {
+  if (!e || !e->uploaded) return fail(G2S_E_STATE, "g2s_run_resident: nothing uploaded");
+  CUDA_TRY(cudaSetDevice(e->cfg.device));
+  const size_t n = e->gaps.size();
+  for (auto &p : e->passes) p.d_pack.release();
+  e->passes.clear();
+  e->tm.kernel_ms = 0; e->tm.launches = 0; e->tm.gaps_big_tier = 0; e->tm.d2h_bytes = 0; e->tm.d2h_ms = 0; e->tm.host_ms = 0;
+  e->out_pass.assign(n, -1);
+  if (n == 0) { e->ran = true; return G2S_OK; }
+  CUDA_TRY(cudaMemsetAsync(e->d_outs.p, 0, n * sizeof(GapOut), e->st));
+  std::vector<uint32_t> todo(n);
+  for (size_t i = 0; i < n; i++) todo[i] = (uint32_t)i;
+  for (int tier = 0; !todo.empty(); tier++) {
+    e->passes.emplace_back();
+    Pass &p = e->passes.back();
+    p.tier = tier;
+    p.order = todo;
+    std::stable_sort(p.order.begin(), p.order.end(),
+                     [&](uint32_t a, uint32_t b) { return dmax_of(e->gaps[a]) > dmax_of(e->gaps[b]); });
+    if (plan_pass(e, p) != 0) {   // no larger tier fits the memory budget: the gaps are reported, not filled
+      for (uint32_t gi : todo) { e->outs[gi] = GapOut{}; e->outs[gi].status = GS_OVERFLOW | GS_DONE; e->out_pass[gi] = -2; }
+      e->passes.pop_back();
+      break;
+    }
+    int rc = run_pass(e, p);
+    if (rc != G2S_OK) return rc;
+    const GapOut *ho = (const GapOut *)e->h_outs.p;
+    std::vector<uint32_t> next;
+    for (uint32_t gi : todo) {
+      if (!(ho[gi].status & GS_DONE)) return fail(G2S_E_CUDA, "device pass did not finish a gap");
+      if (ho[gi].status & GS_INTERNAL) return fail(G2S_E_CUDA, "device table inconsistent with its adjacency bytes");
+      if (ho[gi].status & (GS_OVERFLOW | GS_OUT_FULL)) next.push_back(gi);
+      else { e->outs[gi] = ho[gi]; e->out_pass[gi] = (int)e->passes.size() - 1; }
+    }
+    if (tier > 0) e->tm.gaps_big_tier += (uint32_t)(todo.size() - next.size());
+    todo.swap(next);
+  }
+  e->ran = true;
+  return G2S_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ host stages
+// D2H of the pack arenas + SCC analysis: everything of the batch that the host needs, detached from the engine
+static int do_collect(g2s_engine *e, HostBatch &hb) {
+  if (!e || !e->ran) return fail(G2S_E_STATE, "no device pass has run");
+  CUDA_TRY(cudaSetDevice(e->cfg.device));
+  const size_t n = e->gaps.size();
+  hb.k = e->cfg.k;
+  hb.gaps = e->gaps;
+  hb.outs = e->outs;
+  hb.tier.assign(n, -2);
+  hb.pack_of.assign(n, 0);
+  hb.packs.resize(e->passes.size());
+  CUDA_TRY(cudaEventRecord(e->ev[2], e->st));
+  for (size_t pi = 0; pi < e->passes.size(); pi++) {
+    Pass &p = e->passes[pi];
+    hb.packs[pi].resize(p.pack_used);
+    if (p.pack_used) {
+      CUDA_TRY(cudaMemcpyAsync(hb.packs[pi].data(), p.d_pack.p, p.pack_used * sizeof(PackRec), cudaMemcpyDeviceToHost, e->st));
+      e->tm.d2h_bytes += p.pack_used * sizeof(PackRec);
+    }
+  }
+  CUDA_TRY(cudaEventRecord(e->ev[3], e->st));
+  CUDA_TRY(cudaStreamSynchronize(e->st));
+  float ms = 0;
+  CUDA_TRY(cudaEventElapsedTime(&ms, e->ev[2], e->ev[3]));
+  e->tm.d2h_ms = ms;
+  for (size_t i = 0; i < n; i++)
+    if (e->out_pass[i] >= 0) { hb.tier[i] = e->passes[e->out_pass[i]].tier; hb.pack_of[i] = e->out_pass[i]; }
+  auto t0 = std::chrono::steady_clock::now();
+  hb.analyze(e->cfg.host_threads);
+  e->tm.host_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  return G2S_OK;
+}
+
+static int do_finish(g2s_engine *e, g2s_result *results, char *const *fill_out) {
+  if (!e || !e->ran) return fail(G2S_E_STATE, "g2s_finish_resident: no device pass has run");
+  if (!results && !e->gaps.empty()) return fail(G2S_E_ARG, "null results");
+  HostBatch hb;
+  int rc = do_collect(e, hb);
+  if (rc != G2S_OK) return rc;
+  auto t0 = std::chrono::steady_clock::now();
+  // traceback in input order: the only consumer of libc rand() (src/Gap2Seq.cpp:1440, 1513)
+  for (size_t i = 0; i < hb.gaps.size(); i++) hb.trace(i, results[i], fill_out ? fill_out[i] : nullptr);
+  e->tm.host_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  return G2S_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ C ABI: fill
+extern "C" int g2s_upload_gaps(g2s_engine *e, const g2s_gap *gaps, size_t n) { return do_upload(e, gaps, n); }
+extern "C" int g2s_run_resident(g2s_engine *e) { return do_run(e); }
+extern "C" int g2s_finish_resident(g2s_engine *e, g2s_result *results, char *const *fill_out) { return do_finish(e, results, fill_out); }
+
+extern "C" int g2s_fill_batch(g2s_engine *e, const g2s_gap *gaps, size_t n, g2s_result *results, char *const *fill_out) {
+  int rc = do_upload(e, gaps, n);
+  if (rc == G2S_OK) rc = do_run(e);
+  if (rc == G2S_OK) rc = do_finish(e, results, fill_out);
+  return rc;
+}
+
+struct g2s_batch { HostBatch hb; };
+
+extern "C" int g2s_submit(g2s_engine *e, const g2s_gap *gaps, size_t n, g2s_batch **out) {
+  if (!out) return fail(G2S_E_ARG, "g2s_submit: null output");
+  int rc = do_upload(e, gaps, n);
+  if (rc == G2S_OK) rc = do_run(e);
+  if (rc != G2S_OK) return rc;
+  g2s_batch *b = new g2s_batch();
+  rc = do_collect(e, b->hb);
+  if (rc != G2S_OK) { delete b; return rc; }
+  *out = b;
+  return G2S_OK;
+}
+
+extern "C" int g2s_batch_peek(const g2s_batch *b, size_t i, int32_t *count, int32_t *right_fuz) {
+  if (!b || i >= b->hb.gaps.size()) return fail(G2S_E_ARG, "g2s_batch_peek: bad index");
+  if (count) *count = b->hb.peek_count(i);
+  if (right_fuz) *right_fuz = b->hb.peek_right_fuz(i);
+  return G2S_OK;
+}
+
+extern "C" int g2s_batch_trace(g2s_batch *b, size_t i, g2s_result *result, char *fill_out) {
+  if (!b || !result || i >= b->hb.gaps.size()) return fail(G2S_E_ARG, "g2s_batch_trace: bad argument");
+  b->hb.trace(i, *result, fill_out);
+  return G2S_OK;
+}
+
+extern "C" void g2s_batch_free(g2s_batch *b) { delete b; }
+extern "C" void g2s_free(void *p) { free(p); }
+
+extern "C" int g2s_fill_records(g2s_engine *e, const char *const *seqs, const char *const *comments, size_t n_records,
+                                const g2s_run_options *opt, char **filled_out, char **log_out, int32_t *gapcount,
+                                int32_t *filledcount, g2s_result **gap_results, size_t *n_gap_results) {
+  if (!e || !opt || (n_records && (!seqs || !comments || !filled_out))) return fail(G2S_E_ARG, "g2s_fill_records: null argument");
+  if (opt->k != e->cfg.k) return fail(G2S_E_ARG, "g2s_fill_records: k differs from the engine's k");
+  if (opt->fuz < 0 || opt->fuz > e->cfg.max_fuz) return fail(G2S_E_ARG, "g2s_fill_records: fuz exceeds g2s_config.max_fuz");
+  std::vector<std::string> s(n_records), c(n_records);
+  for (size_t i = 0; i < n_records; i++) { s[i] = seqs[i]; c[i] = comments[i] ? comments[i] : ""; }
+  RunOptions ro;
+  ro.k = opt->k; ro.d_err = opt->dist_error; ro.max_fuz = opt->fuz;
+  ro.skip_confident = opt->skip_confident != 0; ro.unique_paths = opt->unique_paths != 0; ro.all_paths = opt->all_paths != 0;
+  ScaffoldRun run(s, c, ro);
+  g2s_timing total{};
+  int err = G2S_OK;
+  SubmitFn submit = [&](const std::vector<g2s_gap> &gaps, HostBatch &hb) -> int {
+    int rc = do_upload(e, gaps.data(), gaps.size());
+    if (rc == G2S_OK) rc = do_run(e);
+    if (rc == G2S_OK) rc = do_collect(e, hb);
+    err = rc;
+    total.h2d_ms += e->tm.h2d_ms; total.kernel_ms += e->tm.kernel_ms; total.d2h_ms += e->tm.d2h_ms; total.host_ms += e->tm.host_ms;
+    total.h2d_bytes += e->tm.h2d_bytes; total.d2h_bytes += e->tm.d2h_bytes; total.launches += e->tm.launches;
+    total.gaps_big_tier += e->tm.gaps_big_tier;
+    return rc;
+  };
+  std::vector<std::string> filled;
+  std::string log;
+  int gc = 0, fc = 0;
+  std::vector<g2s_result> details;
+  auto t0 = std::chrono::steady_clock::now();
+  int rc = run.run(submit, filled, log, gc, fc, gap_results ? &details : nullptr);
+  if (rc != 0) return err != G2S_OK ? err : fail(G2S_E_STATE, "g2s_fill_records: scanner inconsistency " + std::to_string(rc));
+  const double wall = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  total.host_ms = std::max(0.0, wall - total.h2d_ms - total.kernel_ms - total.d2h_ms);
+  e->tm = total;
+  for (size_t i = 0; i < n_records; i++) filled_out[i] = strdup(filled[i].c_str());
+  if (log_out) *log_out = strdup(log.c_str());
+  if (gapcount) *gapcount = gc;
+  if (filledcount) *filledcount = fc;
+  if (gap_results && n_gap_results) {
+    *n_gap_results = details.size();
+    *gap_results = (g2s_result *)malloc(std::max<size_t>(details.size(), 1) * sizeof(g2s_result));
+    memcpy(*gap_results, details.data(), details.size() * sizeof(g2s_result));
+  }
+  return G2S_OK;
+}
+
+extern "C" int g2s_fill_gap(g2s_engine *e, const char *kmer_left, const char *kmer_right, int gap_len, int k, int gap_err,
+                            int left_max_fuz, int right_max_fuz, int *left_fuz, int *right_fuz, long long max_mem, char *fill,
+                            int skip_confident, int all_paths, g2s_subgraph_stats *substats) {
+  (void)max_mem;   // the device tiers are bounded by g2s_config.max_mem_bytes
+  if (!e) return fail(G2S_E_ARG, "null engine");
+  if (k != e->cfg.k) return fail(G2S_E_ARG, "g2s_fill_gap: k differs from the engine's k");
+  if (!left_fuz || !right_fuz || !fill) return fail(G2S_E_ARG, "g2s_fill_gap: null output");
+  g2s_gap g{};
+  g.kmer_left = kmer_left; g.kmer_right = kmer_right;
+  g.gap_len = gap_len; g.gap_err = gap_err; g.left_max_fuz = left_max_fuz; g.right_max_fuz = right_max_fuz;
+  g.flags = (skip_confident ? G2S_GAP_SKIP_CONFIDENT : 0) | (all_paths ? G2S_GAP_ALL_PATHS : 0);
+  g2s_result r;
+  std::vector<char> tmp((size_t)gap_len + k + gap_err + left_max_fuz + right_max_fuz + 3);
+  char *fo = tmp.data();
+  int rc = g2s_fill_batch(e, &g, 1, &r, &fo);
+  if (rc != G2S_OK) return rc;
+  if (r.fill_len > 0 || r.count > 0) {
+    *left_fuz = r.left_fuz; *right_fuz = r.right_fuz;
+    memcpy(fill + (left_max_fuz - r.left_fuz), tmp.data(), (size_t)r.fill_len + 1);   // same offsets as the reference
+  } else if (r.forward_count > 0) {
+    *right_fuz = r.right_fuz;
+  }
+  if (substats && r.substats_valid) *substats = r.substats;
+  return r.count;
+}

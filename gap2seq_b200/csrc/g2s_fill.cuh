@@ -1,0 +1,759 @@
+// g2s_fill.cuh - one gap of Gap2Seq::fill_gap (reference src/Gap2Seq.cpp:858-1556) as a level-synchronous
+// frontier expansion executed cooperatively by one thread group (a warp for thin gaps, a whole CTA for
+// wide ones).  Everything the reference keeps in unordered_map<Node, map_element> rows lives in a per-group
+// scratch slice in HBM:
+//
+//   node table   open addressing, 32 B entries keyed by canonical k-mer (Node identity ignores the strand,
+//                Graph.hpp:154-160): right-set membership, per-level stamps that de-duplicate a frontier,
+//                the index of the node's cell on the current level (one per strand, like map_element's
+//                forward / reverse vectors, Gap2Seq.cpp:492-493).
+//   cells        structure of arrays, appended level by level; cells [lstart[c], lstart[c+1]) ARE the border of
+//                level c, so the expansion reads its frontier coalesced.  A cell stores its oriented k-mer, the
+//                walk count (uint32, clamped to MAX_PATHS when read, Gap2Seq.cpp:1058-1060), its node entry and
+//                FOUR PREDECESSOR LINKS (slot nt = the predecessor that prepends base nt, the order of
+//                Graph::predecessors, Graph.cpp:1316-1344).  The links are recorded while expanding forward,
+//                so the backward subgraph pass (Gap2Seq.cpp:1173-1312) and the traceback (Gap2Seq.cpp:1437-1517)
+//                never query the graph or the table again - they chase indices.
+//   thit         for each right-flank target j and level d: the cell of (rnode(j), d), used by the found
+//                check (Gap2Seq.cpp:1107-1159) and as the seeds of the backward pass.
+//
+// The group ends a gap by appending its marked cells (the union of all accepted walks and the traceback
+// trellis, with safe bits when the subgraph is a plain level DAG) to a global output arena; the host then
+// replays libc rand() in input order over those records (g2s_host.cpp).
+#pragma once
+#include "g2s_common.cuh"
+
+namespace g2s {
+
+// ------------------------------------------------------------------------------------------------ portability
+#ifndef __CUDACC__
+struct uint4 { uint32_t x, y, z, w; };
+#endif
+// shared-memory words written by other threads of the group are re-read through a volatile load
+template <class T> G2S_D T ld_sh(const T *p) { return *(const volatile T *)p; }
+#ifdef G2S_DEVICE_BUILD
+template <class T> G2S_D T ld_cg(const T *p) { return __ldcg(p); }
+G2S_D uint32_t a_add(uint32_t *p, uint32_t v) { return atomicAdd(p, v); }
+G2S_D unsigned long long a_add64(unsigned long long *p, unsigned long long v) { return atomicAdd(p, v); }
+G2S_D uint32_t a_max(uint32_t *p, uint32_t v) { return atomicMax(p, v); }
+G2S_D uint32_t a_or(uint32_t *p, uint32_t v) { return atomicOr(p, v); }
+G2S_D uint32_t a_cas(uint32_t *p, uint32_t cmp, uint32_t v) { return atomicCAS(p, cmp, v); }
+G2S_D int32_t a_maxi(int32_t *p, int32_t v) { return atomicMax(p, v); }
+G2S_D int32_t a_mini(int32_t *p, int32_t v) { return atomicMin(p, v); }
+G2S_D uint64_t a_cas64(uint64_t *p, uint64_t cmp, uint64_t v) {
+  return atomicCAS((unsigned long long *)p, (unsigned long long)cmp, (unsigned long long)v);
+}
+#else
+template <class T> inline T ld_cg(const T *p) { return *p; }
+inline uint32_t a_add(uint32_t *p, uint32_t v) { uint32_t o = *p; *p = o + v; return o; }
+inline unsigned long long a_add64(unsigned long long *p, unsigned long long v) { unsigned long long o = *p; *p = o + v; return o; }
+inline uint32_t a_max(uint32_t *p, uint32_t v) { uint32_t o = *p; if (v > o) *p = v; return o; }
+inline uint32_t a_or(uint32_t *p, uint32_t v) { uint32_t o = *p; *p = o | v; return o; }
+inline uint32_t a_cas(uint32_t *p, uint32_t c, uint32_t v) { uint32_t o = *p; if (o == c) *p = v; return o; }
+inline int32_t a_maxi(int32_t *p, int32_t v) { int32_t o = *p; if (v > o) *p = v; return o; }
+inline int32_t a_mini(int32_t *p, int32_t v) { int32_t o = *p; if (v < o) *p = v; return o; }
+inline uint64_t a_cas64(uint64_t *p, uint64_t c, uint64_t v) { uint64_t o = *p; if (o == c) *p = v; return o; }
+#endif
+
+// ------------------------------------------------------------------------------------------------ data layout
+struct __attribute__((aligned(16))) NodeEnt {
+  uint64_t key;        // canonical k-mer, KEY_EMPTY when free
+  uint32_t rstamp;     // (level+1)*2 + strand of the node's last insertion into the right border
+  uint32_t flags;      // NF_* bits; bits 8..31 = level+1 of the node's marked (Phase B) cell, 0 = none
+  uint32_t fstamp[2];  // level+1 of the strand's most recent forward cell
+  uint32_t fcell[2];   // that cell
+};
+enum { NF_IN_RS = 1, NF_HAS_F = 2, NF_TARGET = 4 };
+
+enum {  // cell flag word
+  CF_B = 1,        // on an accepted walk (vertex of the Phase B subgraph)
+  CF_T = 2,        // on the traceback trellis
+  CF_SEED = 4,     // has the edge to the sink
+  CF_OMASK_SHIFT = 8
+};
+
+enum {  // PackRec.meta
+  PM_B = 1, PM_T = 2, PM_SEED = 4, PM_START = 8, PM_SAFE = 16, PM_BASE_SHIFT = 8
+};
+
+struct PackRec {       // 32 B, one marked cell
+  uint32_t pred[4];    // pack indices of the predecessors in A,C,T,G order of the prepended base (NONE32 = absent)
+  uint32_t node;       // per-gap node id (index into the node table) - vertex identity of the subgraph
+  uint32_t level;
+  uint32_t meta;       // PM_* | last base << PM_BASE_SHIFT
+  uint32_t count;      // clamped walk count of the cell
+};
+
+struct GapDev {        // 32 B input descriptor
+  uint32_t flank_off;  // left flank (k+lmf chars) at flanks[flank_off], right flank (k+rmf chars) directly after it
+  int32_t gap_len, gap_err, lmf, rmf;
+  uint32_t flags;      // G2S_GAP_* of include/g2s.h
+  uint32_t id;         // position in the caller's batch
+  uint32_t pad;
+};
+
+enum {  // GapOut.status (device side)
+  GS_ORDER_DEPENDENT = 1, GS_OVERFLOW = 2, GS_GENERAL = 4, GS_OUT_FULL = 8, GS_INTERNAL = 16, GS_DONE = 0x100
+};
+
+struct GapOut {        // 128 B
+  uint32_t status;
+  uint32_t count_fwd, count_all;
+  uint32_t n_plen;
+  int32_t plen[2];
+  int32_t reached_fuz;
+  uint32_t cells_right, cells_left, nodes;
+  uint32_t npack;
+  uint32_t start_pack[2];
+  uint32_t nB, n_edges, n_src, n_sink;
+  int32_t max_src_level, min_sink_level;
+  uint32_t top_level;
+  unsigned long long pack_off;
+  uint32_t levels_r, levels_f;
+  uint32_t pad[6];
+};
+
+struct SliceLayout {   // byte offsets inside one scratch slice; identical for every slice of a launch
+  unsigned long long bytes;
+  uint32_t cap_cells, hash_log2, max_levels, max_fuz1;
+  unsigned long long off_hash, off_ck, off_cc, off_cn, off_cp, off_cflags, off_packidx, off_packlist, off_packlevel,
+      off_lstart, off_nB, off_thit, off_lk, off_rk;
+};
+
+struct FillParams {
+  Table table;
+  const char *flanks;
+  const GapDev *gaps;
+  const uint32_t *order;       // gap indices, longest first
+  uint32_t n_gaps;
+  GapOut *outs;
+  unsigned char *scratch;
+  SliceLayout lay;
+  PackRec *pack;
+  unsigned long long pack_cap;
+  unsigned long long *pack_cursor;
+  uint32_t *queue_head;
+};
+
+struct GShared {       // per group, in shared memory
+  uint32_t ncells, nnodes, nnext, status;
+  uint32_t npack, nB, n_edges, n_src, n_sink;
+  int32_t max_src_level, min_sink_level;
+  uint32_t cells_right;
+  uint32_t n_plen;
+  int32_t plen[2];
+  int32_t reached_fuz;
+  uint32_t count_fwd;
+  int32_t found_level;
+  unsigned long long count_all;
+  unsigned long long pack_off;
+  uint32_t fc1[MAX_FUZ + 1], fc2[MAX_FUZ + 1];
+  uint32_t queue_item;
+};
+
+struct Slice {         // typed view of one scratch slice
+  NodeEnt *ent;
+  uint32_t hmask, hcap;
+  uint64_t *ck;
+  uint32_t *cc, *cn;
+  uint32_t *cp;        // 4 per cell
+  uint32_t *cflags, *packidx, *packlist, *packlevel, *lstart, *nB, *thit;
+  uint64_t *lk, *rk;   // oriented flank k-mers; bit 63 set = present in the graph; bits 62..: unused
+  uint32_t cap_cells, max_levels;
+  // right-border ping-pong buffers alias the (not yet used) cell arrays during Phase R
+  uint64_t *fk[2];
+  unsigned char *fm[2];
+};
+
+G2S_HD Slice make_slice(unsigned char *base, const SliceLayout &L) {
+  Slice s;
+  s.ent = (NodeEnt *)(base + L.off_hash);
+  s.hcap = 1u << L.hash_log2;
+  s.hmask = s.hcap - 1;
+  s.ck = (uint64_t *)(base + L.off_ck);
+  s.cc = (uint32_t *)(base + L.off_cc);
+  s.cn = (uint32_t *)(base + L.off_cn);
+  s.cp = (uint32_t *)(base + L.off_cp);
+  s.cflags = (uint32_t *)(base + L.off_cflags);
+  s.packidx = (uint32_t *)(base + L.off_packidx);
+  s.packlist = (uint32_t *)(base + L.off_packlist);
+  s.packlevel = (uint32_t *)(base + L.off_packlevel);
+  s.lstart = (uint32_t *)(base + L.off_lstart);
+  s.nB = (uint32_t *)(base + L.off_nB);
+  s.thit = (uint32_t *)(base + L.off_thit);
+  s.lk = (uint64_t *)(base + L.off_lk);
+  s.rk = (uint64_t *)(base + L.off_rk);
+  s.cap_cells = L.cap_cells;
+  s.max_levels = L.max_levels;
+  s.fk[0] = s.ck;
+  s.fk[1] = (uint64_t *)s.cp;                  // 16 B per cell: room for cap_cells 8-byte entries twice over
+  s.fm[0] = (unsigned char *)s.cc;
+  s.fm[1] = (unsigned char *)s.cn;
+  return s;
+}
+
+// ---- host-side geometry of a scratch slice (used by the engine when planning a pass)
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+inline SliceLayout make_layout(uint64_t cap_cells, uint32_t hash_log2, uint32_t max_levels, uint32_t max_fuz1) {
+  SliceLayout L{};
+  L.cap_cells = (uint32_t)cap_cells; L.hash_log2 = hash_log2; L.max_levels = max_levels; L.max_fuz1 = max_fuz1;
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 256); return (unsigned long long)r; };
+  L.off_hash = take(((size_t)1 << hash_log2) * sizeof(NodeEnt));
+  L.off_ck = take(cap_cells * 8);
+  L.off_cc = take(cap_cells * 4);
+  L.off_cn = take(cap_cells * 4);
+  L.off_cp = take(cap_cells * 16);
+  L.off_cflags = take(cap_cells * 4);
+  L.off_packidx = take(cap_cells * 4);
+  L.off_packlist = take(cap_cells * 4);
+  L.off_packlevel = take(cap_cells * 4);
+  L.off_lstart = take(((size_t)max_levels + 3) * 4);
+  L.off_nB = take(((size_t)max_levels + 3) * 4);
+  L.off_thit = take((size_t)max_fuz1 * ((size_t)max_levels + 1) * 4);
+  L.off_lk = take((size_t)max_fuz1 * 8);
+  L.off_rk = take((size_t)max_fuz1 * 8);
+  L.bytes = o;
+  return L;
+}
+
+inline uint32_t ceil_log2(uint64_t x) { uint32_t l = 0; while (((uint64_t)1 << l) < x) l++; return l; }
+
+
+static const uint64_t FLANK_PRESENT = 1ULL << 63;
+static const uint64_t FLANK_KMER = (1ULL << 62) - 1;
+
+// ------------------------------------------------------------------------------------------------ node table
+G2S_D uint32_t node_hash(uint64_t key, uint32_t hmask) { return (uint32_t)((key * 0x9E3779B97F4A7C15ULL) >> 40) & hmask; }
+
+G2S_D uint32_t node_find(const Slice &S, uint64_t key) {
+  uint32_t h = node_hash(key, S.hmask);
+  for (;;) {
+    uint64_t k0 = ld_cg(&S.ent[h].key);
+    if (k0 == key) return h;
+    if (k0 == KEY_EMPTY) return NONE32;
+    h = (h + 1) & S.hmask;
+  }
+}
+
+G2S_D uint32_t node_insert(const Slice &S, GShared &sh, uint64_t key) {
+  uint32_t h = node_hash(key, S.hmask);
+  for (;;) {
+    uint64_t k0 = ld_cg(&S.ent[h].key);
+    if (k0 == key) return h;
+    if (k0 == KEY_EMPTY) {
+      if (ld_sh(&sh.nnodes) >= S.hcap - (S.hcap >> 2)) { a_or(&sh.status, GS_OVERFLOW); return NONE32; }
+      uint64_t old = a_cas64(&S.ent[h].key, KEY_EMPTY, key);
+      if (old == KEY_EMPTY) { a_add(&sh.nnodes, 1); return h; }
+      if (old == key) return h;
+    }
+    h = (h + 1) & S.hmask;
+  }
+}
+
+G2S_D uint32_t clamp_paths(uint32_t c) { return c > MAX_PATHS ? MAX_PATHS : c; }
+
+// create the forward cell (state s of node e) on level c; the caller owns the (e,strand,level) stamp
+template <class G>
+G2S_D uint32_t new_cell(const Slice &S, GShared &sh, const GapDev &gd, uint64_t s, uint32_t e, uint32_t strand,
+                        uint32_t adj, uint32_t c, uint32_t count) {
+  uint32_t idx = a_add(&sh.ncells, 1);
+  if (idx >= S.cap_cells) { a_or(&sh.status, GS_OVERFLOW); return NONE32; }
+  S.ck[idx] = s;
+  S.cc[idx] = count;
+  S.cn[idx] = e;
+  S.cp[4 * idx + 0] = NONE32; S.cp[4 * idx + 1] = NONE32; S.cp[4 * idx + 2] = NONE32; S.cp[4 * idx + 3] = NONE32;
+  S.cflags[idx] = out_mask(adj, strand) << CF_OMASK_SHIFT;
+  S.ent[e].fcell[strand] = idx;
+  uint32_t fl = a_or(&S.ent[e].flags, NF_HAS_F);
+  if (fl & NF_TARGET) {
+    for (int j = 0; j <= gd.rmf; j++)
+      if ((S.rk[j] & FLANK_KMER) == s) S.thit[(size_t)j * (S.max_levels + 1) + c] = idx + 1;
+  }
+  return idx;
+}
+
+G2S_D uint32_t thit_count(const Slice &S, int j, int level) {
+  if (level < 0 || (uint32_t)level > S.max_levels) return 0;
+  uint32_t t = ld_cg(&S.thit[(size_t)j * (S.max_levels + 1) + level]);
+  return t ? clamp_paths(ld_cg(&S.cc[t - 1])) : 0;
+}
+
+// The first-found check of level c (Gap2Seq.cpp:1108-1154), evaluated by ONE thread.  Returns true when found.
+G2S_D bool found_at_level(const Slice &S, const GapDev &gd, int c, int *J, uint32_t *c1, uint32_t *c2, int *l1, int *l2) {
+  const int err = c - gd.gap_len - gd.lmf - gd.rmf;
+  for (int j = 0; j <= gd.rmf; j++) {
+    int len1 = gd.gap_len + gd.lmf + j + err, len2 = gd.gap_len + gd.lmf + j - err;
+    uint32_t a = thit_count(S, j, len1);
+    uint32_t b = (len2 != len1 && len2 >= 0) ? thit_count(S, j, len2) : 0;
+    if (a | b) { *J = j; *c1 = a; *c2 = b; *l1 = len1; *l2 = len2; return true; }
+  }
+  return false;
+}
+
+// ------------------------------------------------------------------------------------------------ one gap
+template <class G>
+G2S_D void process_gap(const FillParams &P, const GapDev &gd, const Slice &S, GShared &sh, GapOut *out) {
+  const Table &T = P.table;
+  const int k = T.k;
+  const int rank = G::rank(), gsz = G::size();
+  const int g = gd.gap_len, e = gd.gap_err, lmf = gd.lmf, rmf = gd.rmf;
+  const bool all_paths = (gd.flags & 2) != 0, skip_confident = (gd.flags & 1) != 0;
+  const int right_half = rmf + (g + e + 1) / 2;           // rmf + ceil((g+e)/2), Gap2Seq.cpp:862
+  const int Dmax = g + e + lmf + rmf;                      // right_half + left_half, Gap2Seq.cpp:863
+  const int prune_from = g / 2 + e / 2 + lmf;              // two integer divisions, Gap2Seq.cpp:1050
+  const char *lstr = P.flanks + gd.flank_off, *rstr = lstr + k + lmf;
+  const size_t trow = (size_t)S.max_levels + 1;
+
+  // ---- init: clear the node table, thit and the per-level counters; parse the flanks
+  {
+    uint4 *hz = (uint4 *)S.ent;
+    const uint4 z0 = {0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u}, z1 = {0u, 0u, 0u, 0u};
+    for (uint32_t i = rank; i < S.hcap; i += gsz) { hz[2 * i] = z0; hz[2 * i + 1] = z1; }
+    const size_t nth = trow * (size_t)(rmf + 1);
+    for (size_t i = rank; i < nth; i += gsz) S.thit[i] = 0;
+    for (int i = rank; i <= Dmax + 1; i += gsz) { S.nB[i] = 0; S.lstart[i] = 0; }
+    for (int d = rank; d <= lmf; d += gsz) {
+      uint64_t x = kmer_from_ascii(lstr + d, k);
+      uint32_t adj;
+      Canon c = canonical(x, k);
+      S.lk[d] = x | (table_find(T, c.key, &adj) >= 0 ? FLANK_PRESENT : 0);
+    }
+    for (int j = rank; j <= rmf; j += gsz) {
+      uint64_t x = kmer_from_ascii(rstr + j, k);
+      uint32_t adj;
+      Canon c = canonical(x, k);
+      S.rk[j] = x | (table_find(T, c.key, &adj) >= 0 ? FLANK_PRESENT : 0);
+    }
+    if (rank == 0) {
+      sh.ncells = 0; sh.nnodes = 0; sh.nnext = 0; sh.status = 0;
+      sh.npack = 0; sh.nB = 0; sh.n_edges = 0; sh.n_src = 0; sh.n_sink = 0;
+      sh.max_src_level = -1; sh.min_sink_level = 0x7fffffff;
+      sh.cells_right = 0; sh.n_plen = 0; sh.plen[0] = sh.plen[1] = -1; sh.reached_fuz = 0; sh.count_fwd = 0;
+      sh.found_level = 0x7fffffff; sh.count_all = 0; sh.pack_off = 0;
+    }
+  }
+  G::sync();
+
+  // ---- Phase R: level-synchronous backward walk from the staggered right starts (Gap2Seq.cpp:871-982).
+  // Only node membership in the right set is read later (Gap2Seq.cpp:1050): nodes get NF_IN_RS, cells are counted.
+  int levels_r = 0;
+  {
+    uint32_t n = 0;
+    int cur = 0;
+    if (rank == 0) {
+      uint64_t x = S.rk[rmf];
+      if (x & FLANK_PRESENT) {
+        x &= FLANK_KMER;
+        Canon c = canonical(x, k);
+        uint32_t adj = 0;
+        table_find(T, c.key, &adj);
+        uint32_t en = node_insert(S, sh, c.key);
+        if (en != NONE32) {
+          S.ent[en].rstamp = 2 + c.strand;
+          a_or(&S.ent[en].flags, NF_IN_RS);
+          S.fk[0][0] = x; S.fm[0][0] = (unsigned char)in_mask(adj, c.strand);
+          sh.nnext = 1; sh.cells_right = 1;
+        }
+      }
+    }
+    G::sync();
+    n = ld_sh(&sh.nnext);
+    for (int c = 1; c <= right_half; c++) {
+      if (n == 0 && c > rmf) break;
+      levels_r = c;
+      G::sync();
+      if (rank == 0) sh.nnext = 0;
+      G::sync();
+      const uint64_t *fk = S.fk[cur]; const unsigned char *fm = S.fm[cur];
+      uint64_t *nk = S.fk[cur ^ 1]; unsigned char *nm = S.fm[cur ^ 1];
+      for (uint32_t i = rank; i < n; i += gsz) {
+        const uint64_t x = fk[i];
+        uint32_t im = fm[i];
+        for (uint32_t nt = 0; nt < 4; nt++) {
+          if (!((im >> nt) & 1)) continue;
+          uint64_t p = pred_kmer(x, nt, T);
+          Canon cp = canonical(p, k);
+          uint32_t adj = 0;
+          if (table_find(T, cp.key, &adj) < 0) { a_or(&sh.status, GS_INTERNAL); continue; }
+          uint32_t en = node_insert(S, sh, cp.key);
+          if (en == NONE32) continue;
+          a_or(&S.ent[en].flags, NF_IN_RS);
+          uint32_t stamp = (uint32_t)(c + 1) * 2 + cp.strand;
+          uint32_t prev = a_max(&S.ent[en].rstamp, stamp);
+          if ((prev >> 1) < (uint32_t)(c + 1)) {
+            uint32_t idx = a_add(&sh.nnext, 1);
+            if (idx >= S.cap_cells) { a_or(&sh.status, GS_OVERFLOW); continue; }
+            nk[idx] = p; nm[idx] = (unsigned char)in_mask(adj, cp.strand);
+          } else if ((prev & 1) != cp.strand) {
+            a_or(&sh.status, GS_ORDER_DEPENDENT);   // both strands on one level
+          }
+        }
+      }
+      G::sync();
+      if (rank == 0 && c <= rmf) {   // next staggered right start (Gap2Seq.cpp:953-968)
+        uint64_t x = S.rk[rmf - c];
+        if (x & FLANK_PRESENT) {
+          x &= FLANK_KMER;
+          Canon cs = canonical(x, k);
+          uint32_t adj = 0;
+          table_find(T, cs.key, &adj);
+          uint32_t en = node_insert(S, sh, cs.key);
+          if (en != NONE32) {
+            a_or(&S.ent[en].flags, NF_IN_RS);
+            uint32_t stamp = (uint32_t)(c + 1) * 2 + cs.strand;
+            uint32_t prev = a_max(&S.ent[en].rstamp, stamp);
+            if ((prev >> 1) < (uint32_t)(c + 1)) {
+              uint32_t idx = a_add(&sh.nnext, 1);
+              if (idx >= S.cap_cells) a_or(&sh.status, GS_OVERFLOW);
+              else { nk[idx] = x; nm[idx] = (unsigned char)in_mask(adj, cs.strand); }
+            } else if ((prev & 1) != cs.strand) {
+              a_or(&sh.status, GS_ORDER_DEPENDENT);
+            }
+          }
+        }
+      }
+      G::sync();
+      n = ld_sh(&sh.nnext);
+      if (ld_sh(&sh.status) & GS_OVERFLOW) break;
+      if (rank == 0) sh.cells_right += n;
+      cur ^= 1;
+    }
+  }
+  G::sync();
+
+  // mark the right-flank targets (their node entries may not exist yet: insert them, flag TARGET)
+  if (!(ld_sh(&sh.status) & GS_OVERFLOW)) {
+    for (int j = rank; j <= rmf; j += gsz) {
+      uint64_t x = S.rk[j];
+      if (x & FLANK_PRESENT) {
+        Canon c = canonical(x & FLANK_KMER, k);
+        uint32_t en = node_insert(S, sh, c.key);
+        if (en != NONE32) a_or(&S.ent[en].flags, NF_TARGET);
+      }
+    }
+  }
+  G::sync();
+
+  // ---- Phase F: forward walk counts by exact length (Gap2Seq.cpp:984-1167)
+  int top_level = 0;       // last level that was expanded into
+  int levels_f = 0;
+  bool overflow = (ld_sh(&sh.status) & GS_OVERFLOW) != 0;
+  if (!overflow) {
+    if (rank == 0) {
+      uint64_t x = S.lk[0];
+      if (x & FLANK_PRESENT) {
+        x &= FLANK_KMER;
+        Canon c = canonical(x, k);
+        uint32_t adj = 0;
+        table_find(T, c.key, &adj);
+        uint32_t en = node_insert(S, sh, c.key);
+        if (en != NONE32) {
+          S.ent[en].fstamp[c.strand] = 1;
+          new_cell<G>(S, sh, gd, x, en, c.strand, adj, 0, 1);
+        }
+      }
+      S.lstart[0] = 0;
+    }
+    G::sync();
+    if (rank == 0) S.lstart[1] = sh.ncells;
+    G::sync();
+
+    bool found = false;
+    for (int c = 1; c <= Dmax; c++) {
+      const uint32_t lo = ld_cg(&S.lstart[c - 1]), hi = ld_cg(&S.lstart[c]);
+      const bool dead = (lo == hi) && c > lmf;   // empty border and no start left to inject
+      if (!dead) {
+        top_level = c;
+        levels_f = c;
+        for (uint32_t base = lo; base < hi; base += gsz) {
+          const uint32_t i = base + rank;
+          uint32_t cand_e[4];
+          uint32_t cand_valid = 0, cand_strand = 0, np = 0, u0 = 0;
+          if (i < hi) {
+            const uint64_t x = ld_cg(&S.ck[i]);
+            const uint32_t om = (ld_cg(&S.cflags[i]) >> CF_OMASK_SHIFT) & 15u;
+            np = clamp_paths(ld_cg(&S.cc[i]));
+            u0 = (uint32_t)(x >> (2 * (k - 1))) & 3u;
+#pragma unroll
+            for (uint32_t nt = 0; nt < 4; nt++) {
+              cand_e[nt] = NONE32;
+              if (!((om >> nt) & 1)) continue;
+              const uint64_t s = succ_kmer(x, nt, T);
+              const Canon cs = canonical(s, k);
+              uint32_t adj = 0;
+              if (table_find(T, cs.key, &adj) < 0) { a_or(&sh.status, GS_INTERNAL); continue; }
+              uint32_t en;
+              if (c < prune_from) {
+                en = node_insert(S, sh, cs.key);
+                if (en == NONE32) continue;
+              } else {   // meet in the middle: only nodes of the right set survive (Gap2Seq.cpp:1050)
+                en = node_find(S, cs.key);
+                if (en == NONE32 || !(ld_cg(&S.ent[en].flags) & NF_IN_RS)) continue;
+              }
+              const uint32_t prev = a_max(&S.ent[en].fstamp[cs.strand], (uint32_t)c + 1);
+              if (prev < (uint32_t)c + 1) {
+                if (new_cell<G>(S, sh, gd, s, en, cs.strand, adj, (uint32_t)c, 0) == NONE32) continue;
+              }
+              cand_e[nt] = en;
+              cand_valid |= 1u << nt;
+              cand_strand |= cs.strand << nt;
+            }
+          }
+          G::sync();
+          if (cand_valid && !(ld_sh(&sh.status) & GS_OVERFLOW)) {
+#pragma unroll
+            for (uint32_t nt = 0; nt < 4; nt++) {
+              if (!((cand_valid >> nt) & 1)) continue;
+              const uint32_t st = (cand_strand >> nt) & 1;
+              const NodeEnt *en = &S.ent[cand_e[nt]];
+              const uint32_t idx = ld_cg(&en->fcell[st]);
+              a_add(&S.cc[idx], np);
+              S.cp[4 * idx + u0] = i;
+              if (ld_cg(&en->fstamp[st ^ 1]) == (uint32_t)c + 1) a_or(&sh.status, GS_ORDER_DEPENDENT);
+            }
+          }
+        }
+        G::sync();
+        if (rank == 0 && c <= lmf) {   // staggered left start: count OVERWRITTEN with 1 (Gap2Seq.cpp:1082-1105)
+          uint64_t x = S.lk[c];
+          if (x & FLANK_PRESENT) {
+            x &= FLANK_KMER;
+            Canon cs = canonical(x, k);
+            uint32_t adj = 0;
+            table_find(T, cs.key, &adj);
+            uint32_t en = node_insert(S, sh, cs.key);
+            if (en != NONE32) {
+              if (S.ent[en].fstamp[cs.strand] == (uint32_t)c + 1) {
+                S.cc[S.ent[en].fcell[cs.strand]] = 1;
+              } else {
+                S.ent[en].fstamp[cs.strand] = (uint32_t)c + 1;
+                new_cell<G>(S, sh, gd, x, en, cs.strand, adj, (uint32_t)c, 1);
+              }
+              if (S.ent[en].fstamp[cs.strand ^ 1] == (uint32_t)c + 1) sh.status |= GS_ORDER_DEPENDENT;
+            }
+          }
+        }
+        G::sync();
+        if (rank == 0) S.lstart[c + 1] = sh.ncells < S.cap_cells ? sh.ncells : S.cap_cells;
+        if (ld_sh(&sh.status) & GS_OVERFLOW) { overflow = true; break; }
+      } else {
+        // the border died: no cell can appear any more; finish the found check for the remaining levels in
+        // parallel (one level per thread) and leave the level loop
+        if (!found) {
+          for (int cc2 = c + rank; cc2 <= Dmax; cc2 += gsz) {
+            if (cc2 < g + lmf + rmf) continue;
+            int J = 0, l1 = 0, l2 = 0; uint32_t c1 = 0, c2 = 0;
+            if (found_at_level(S, gd, cc2, &J, &c1, &c2, &l1, &l2)) { a_mini(&sh.found_level, cc2); break; }
+          }
+          G::sync();
+          const int fl = ld_sh(&sh.found_level);
+          if (fl <= Dmax) {
+            if (rank == 0) {
+              int J = 0, l1 = 0, l2 = 0; uint32_t c1 = 0, c2 = 0;
+              found_at_level(S, gd, fl, &J, &c1, &c2, &l1, &l2);
+              sh.reached_fuz = J;
+              uint64_t tot = 0; uint32_t n = 0;
+              if (c1) { tot += c1; sh.plen[n++] = l1; }
+              if (c2) { tot += c2; sh.plen[n++] = l2; }
+              sh.n_plen = n;
+              sh.count_fwd = tot > MAX_PATHS ? MAX_PATHS : (uint32_t)tot;
+            }
+            found = true;
+          }
+          G::sync();
+        }
+        break;
+      }
+      // found check (Gap2Seq.cpp:1108-1154): one target per thread, then thread 0 takes the first in j order
+      if (!found && c >= g + lmf + rmf) {
+        G::sync();
+        const int err = c - g - lmf - rmf;
+        for (int j = rank; j <= rmf; j += gsz) {
+          int len1 = g + lmf + j + err, len2 = g + lmf + j - err;
+          sh.fc1[j] = thit_count(S, j, len1);
+          sh.fc2[j] = (len2 != len1 && len2 >= 0) ? thit_count(S, j, len2) : 0;
+        }
+        G::sync();
+        if (rank == 0) {
+          for (int j = 0; j <= rmf; j++) {
+            if (sh.fc1[j] | sh.fc2[j]) {
+              uint64_t tot = 0; uint32_t n = 0;
+              if (sh.fc1[j]) { tot += sh.fc1[j]; sh.plen[n++] = g + lmf + j + err; }
+              if (sh.fc2[j]) { tot += sh.fc2[j]; sh.plen[n++] = g + lmf + j - err; }
+              sh.n_plen = n; sh.reached_fuz = j;
+              sh.count_fwd = tot > MAX_PATHS ? MAX_PATHS : (uint32_t)tot;
+              sh.found_level = c;
+              break;
+            }
+          }
+        }
+        G::sync();
+        found = ld_sh(&sh.n_plen) != 0;
+        if (found && !all_paths) break;   // -best-only stops at the first hit (Gap2Seq.cpp:1156-1158)
+      } else {
+        G::sync();
+      }
+    }
+  }
+  G::sync();
+
+  // ---- Phase B + traceback trellis: backward marking through the predecessor links (Gap2Seq.cpp:1173-1312)
+  const uint32_t n_plen = ld_sh(&sh.n_plen);
+  const uint32_t count_fwd = ld_sh(&sh.count_fwd);
+  const uint32_t ncells = ld_sh(&sh.ncells) < S.cap_cells ? ld_sh(&sh.ncells) : S.cap_cells;
+  bool general = false;
+  if (!overflow && count_fwd > 0 && n_plen > 0) {
+    const int J = ld_sh(&sh.reached_fuz);
+    const int p0 = ld_sh(&sh.plen[0]), p1 = n_plen > 1 ? ld_sh(&sh.plen[1]) : -1;
+    // seeds
+    if (!skip_confident) {
+      if (all_paths) {
+        if (rmf >= 1) {
+          const int jt = rmf - 1;   // Gap2Seq.cpp:1197-1206: effectively only target rmf-1
+          int dlo = lmf + g - e; if (dlo < 0) dlo = 0;
+          for (int d = dlo + rank; d <= top_level; d += gsz) {
+            uint32_t t = ld_cg(&S.thit[(size_t)jt * trow + d]);
+            if (!t) continue;
+            a_or(&S.cflags[t - 1], CF_B | CF_SEED);
+            a_add64(&sh.count_all, clamp_paths(ld_cg(&S.cc[t - 1])));
+            a_add(&sh.n_sink, 1);
+            a_mini(&sh.min_sink_level, d);
+          }
+        }
+      } else if (rank == 0) {
+        for (uint32_t q = 0; q < n_plen; q++) {
+          int d = q ? p1 : p0;
+          uint32_t t = S.thit[(size_t)J * trow + d];
+          if (t) { a_or(&S.cflags[t - 1], CF_B | CF_SEED); sh.n_sink++; if (d < sh.min_sink_level) sh.min_sink_level = d; }
+        }
+      }
+    }
+    if (rank == 0) {
+      for (uint32_t q = 0; q < n_plen; q++) {
+        uint32_t t = S.thit[(size_t)J * trow + (q ? p1 : p0)];
+        if (t) a_or(&S.cflags[t - 1], CF_T);
+      }
+    }
+    G::sync();
+
+    for (int d = top_level; d >= 0; d--) {
+      const uint32_t lo = ld_cg(&S.lstart[d]), hi = ld_cg(&S.lstart[d + 1]);
+      const uint64_t lcanon = (d <= lmf) ? canonical(S.lk[d] & FLANK_KMER, k).key : KEY_EMPTY;
+      for (uint32_t i = lo + rank; i < hi; i += gsz) {
+        const uint32_t f = ld_cg(&S.cflags[i]);
+        if (!(f & (CF_B | CF_T))) continue;
+        const uint32_t pi = a_add(&sh.npack, 1);
+        S.packidx[i] = pi; S.packlist[pi] = i; S.packlevel[pi] = (uint32_t)d;
+        const uint32_t en = S.cn[i];
+        const bool start = d <= lmf && ld_cg(&S.ent[en].key) == lcanon;
+        uint32_t p[4];
+        p[0] = ld_cg(&S.cp[4 * i]); p[1] = ld_cg(&S.cp[4 * i + 1]); p[2] = ld_cg(&S.cp[4 * i + 2]); p[3] = ld_cg(&S.cp[4 * i + 3]);
+        if (f & CF_B) {
+          a_add(&S.nB[d], 1);
+          a_add(&sh.nB, 1);
+          // vertex identity is the node: a node marked on two levels collapses levels -> general subgraph
+          uint32_t fl = ld_cg(&S.ent[en].flags);
+          for (;;) {
+            uint32_t lv = fl >> 8;
+            if (lv == 0) {
+              uint32_t old = a_cas(&S.ent[en].flags, fl, fl | ((uint32_t)(d + 1) << 8));
+              if (old == fl) break;
+              fl = old;
+            } else {
+              if (lv != (uint32_t)d + 1) a_or(&sh.status, GS_GENERAL);
+              else a_or(&sh.status, GS_ORDER_DEPENDENT);   // two marked cells of one node on one level
+              break;
+            }
+          }
+          if (start) { a_add(&sh.n_src, 1); a_maxi(&sh.max_src_level, d); }
+          else {
+            uint32_t np = 0;
+#pragma unroll
+            for (int q = 0; q < 4; q++) if (p[q] != NONE32) { a_or(&S.cflags[p[q]], CF_B); np++; }
+            a_add(&sh.n_edges, np);
+          }
+        }
+        if ((f & CF_T) && !start) {
+#pragma unroll
+          for (int q = 0; q < 4; q++) if (p[q] != NONE32) a_or(&S.cflags[p[q]], CF_T);
+        }
+      }
+      G::sync();
+    }
+    general = (ld_sh(&sh.status) & GS_GENERAL) != 0;
+
+    // ---- pack: append the marked cells to the output arena
+    const uint32_t npack = ld_sh(&sh.npack);
+    if (rank == 0) {
+      unsigned long long off = a_add64(P.pack_cursor, (unsigned long long)npack);
+      sh.pack_off = off;
+      if (off + npack > P.pack_cap) sh.status |= GS_OUT_FULL;
+    }
+    G::sync();
+    if (!(ld_sh(&sh.status) & GS_OUT_FULL)) {
+      PackRec *outp = P.pack + ld_sh(&sh.pack_off);
+      const int max_src = ld_sh(&sh.max_src_level), min_sink = ld_sh(&sh.min_sink_level);
+      const bool sink_safe = ld_sh(&sh.n_sink) > 0;   // the sink lies on every source->sink path unless isolated (Q6)
+      for (uint32_t pi = rank; pi < npack; pi += gsz) {
+        const uint32_t i = S.packlist[pi];
+        const uint32_t d = S.packlevel[pi];
+        const uint32_t f = ld_cg(&S.cflags[i]);
+        const uint32_t en = S.cn[i];
+        const uint64_t x = S.ck[i];
+        const bool start = (int)d <= lmf && S.ent[en].key == canonical(S.lk[d] & FLANK_KMER, k).key;
+        PackRec r;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          uint32_t p = S.cp[4 * i + q];
+          r.pred[q] = (p == NONE32 || start) ? NONE32 : S.packidx[p];
+        }
+        r.node = en;
+        r.level = d;
+        uint32_t meta = (f & 7u) | (start ? PM_START : 0) | ((uint32_t)(x & 3) << PM_BASE_SHIFT);
+        if (!skip_confident && !general) {
+          // level-DAG case: a vertex is on every source->sink path iff it is alone on its level and no source
+          // or sink edge jumps over that level
+          uint32_t lv = S.ent[en].flags >> 8;
+          bool safe;
+          if (lv == 0) safe = sink_safe;   // node2boost default-inserts the sink
+          else { int bl = (int)lv - 1; safe = S.nB[bl] == 1 && bl >= max_src && bl <= min_sink; }
+          if (safe) meta |= PM_SAFE;
+        }
+        r.meta = meta;
+        r.count = clamp_paths(S.cc[i]);
+        outp[pi] = r;
+      }
+    }
+  }
+  G::sync();
+
+  if (rank == 0) {
+    GapOut o;
+    o.status = sh.status | GS_DONE;
+    o.count_fwd = sh.count_fwd;
+    o.count_all = sh.count_all > MAX_PATHS ? MAX_PATHS : (uint32_t)sh.count_all;
+    o.n_plen = sh.n_plen; o.plen[0] = sh.plen[0]; o.plen[1] = sh.plen[1];
+    o.reached_fuz = sh.reached_fuz;
+    o.cells_right = sh.cells_right; o.cells_left = ncells; o.nodes = sh.nnodes;
+    o.npack = sh.npack;
+    o.start_pack[0] = o.start_pack[1] = NONE32;
+    if (sh.count_fwd > 0 && !overflow) {
+      for (uint32_t q = 0; q < sh.n_plen; q++) {
+        uint32_t t = S.thit[(size_t)sh.reached_fuz * trow + sh.plen[q]];
+        if (t) o.start_pack[q] = S.packidx[t - 1];
+      }
+    }
+    o.nB = sh.nB; o.n_edges = sh.n_edges; o.n_src = sh.n_src; o.n_sink = sh.n_sink;
+    o.max_src_level = sh.max_src_level; o.min_sink_level = sh.min_sink_level;
+    o.top_level = (uint32_t)top_level;
+    o.pack_off = sh.pack_off;
+    o.levels_r = (uint32_t)levels_r; o.levels_f = (uint32_t)levels_f;
+    for (int q = 0; q < 6; q++) o.pad[q] = 0;
+    *out = o;
+  }
+  G::sync();
+}
+
+}  // namespace g2s

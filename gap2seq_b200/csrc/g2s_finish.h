@@ -1,0 +1,244 @@
+// g2s_finish.h - the host stages that follow the device pass of one gap (host-only code, part of the product):
+//   analyze_general  SCC contraction + branch counter of src/Gap2Seq.cpp:1314-1434 for path subgraphs that are
+//                    not a plain level DAG (the device classifies the DAG case itself, g2s_fill.cuh)
+//   finish_one       result assembly + the random traceback of src/Gap2Seq.cpp:1437-1517 over the device-built
+//                    predecessor trellis; the only consumer of libc rand()
+#pragma once
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <atomic>
+#include <thread>
+#include <vector>
+
+#include "../../include/g2s.h"
+#include "g2s_fill.cuh"
+
+namespace g2s {
+
+struct GeneralResult {
+  g2s_subgraph_stats st{};
+  std::vector<uint8_t> safe;   // per pack record
+};
+
+// SCC contraction + branch counter for a subgraph that is not a level DAG (src/Gap2Seq.cpp:1314-1434).
+// Vertices are the distinct nodes of the B records plus sink (0) and source (1); edges are de-duplicated
+// exactly like the reference's `if (!edge(u,v).second) add_edge` (Gap2Seq.cpp:1222-1297).
+inline void analyze_general(const PackRec *pk, uint32_t npack, GeneralResult &R) {
+  std::vector<uint32_t> nodes;
+  for (uint32_t i = 0; i < npack; i++) if (pk[i].meta & PM_B) nodes.push_back(pk[i].node);
+  std::sort(nodes.begin(), nodes.end());
+  nodes.erase(std::unique(nodes.begin(), nodes.end()), nodes.end());
+  auto vid = [&](uint32_t node) { return (uint32_t)(std::lower_bound(nodes.begin(), nodes.end(), node) - nodes.begin()) + 2; };
+  const uint32_t V = (uint32_t)nodes.size() + 2;
+  std::vector<uint64_t> edges;
+  for (uint32_t i = 0; i < npack; i++) {
+    if (!(pk[i].meta & PM_B)) continue;
+    const uint32_t v = vid(pk[i].node);
+    if (pk[i].meta & PM_START) edges.push_back(((uint64_t)1 << 32) | v);
+    else for (int q = 0; q < 4; q++) if (pk[i].pred[q] != NONE32) edges.push_back(((uint64_t)vid(pk[pk[i].pred[q]].node) << 32) | v);
+    if (pk[i].meta & PM_SEED) edges.push_back(((uint64_t)v << 32) | 0u);
+  }
+  std::sort(edges.begin(), edges.end());
+  edges.erase(std::unique(edges.begin(), edges.end()), edges.end());
+  const size_t E = edges.size();
+  std::vector<uint32_t> ostart(V + 1, 0), otgt(E);
+  for (uint64_t ed : edges) ostart[(ed >> 32) + 1]++;
+  for (uint32_t v = 0; v < V; v++) ostart[v + 1] += ostart[v];
+  for (size_t i = 0; i < E; i++) otgt[i] = (uint32_t)edges[i];   // edges are sorted by source already
+
+  // iterative Tarjan
+  std::vector<uint32_t> index(V, NONE32), low(V, 0), comp(V, NONE32), pos(V, 0), stack, call;
+  std::vector<uint8_t> on(V, 0);
+  uint32_t counter = 0, ncomp = 0;
+  for (uint32_t r = 0; r < V; r++) {
+    if (index[r] != NONE32) continue;
+    call.push_back(r); index[r] = low[r] = counter++; stack.push_back(r); on[r] = 1; pos[r] = ostart[r];
+    while (!call.empty()) {
+      uint32_t v = call.back();
+      if (pos[v] < ostart[v + 1]) {
+        uint32_t w = otgt[pos[v]++];
+        if (index[w] == NONE32) { index[w] = low[w] = counter++; stack.push_back(w); on[w] = 1; pos[w] = ostart[w]; call.push_back(w); }
+        else if (on[w]) low[v] = std::min(low[v], index[w]);
+      } else {
+        call.pop_back();
+        if (!call.empty()) low[call.back()] = std::min(low[call.back()], low[v]);
+        if (low[v] == index[v]) {
+          for (;;) { uint32_t w = stack.back(); stack.pop_back(); on[w] = 0; comp[w] = ncomp; if (w == v) break; }
+          ncomp++;
+        }
+      }
+    }
+  }
+  std::vector<uint32_t> csize(ncomp, 0);
+  for (uint32_t v = 0; v < V; v++) csize[comp[v]]++;
+  uint64_t nontriv = 0, size_nontriv = 0, self_loops_trivial = 0, cross = 0;
+  for (uint32_t c = 0; c < ncomp; c++) if (csize[c] > 1) { nontriv++; size_nontriv += csize[c]; }
+  // condensed multigraph: every cross-component edge exactly once (Gap2Seq.cpp:1346-1370)
+  std::vector<uint32_t> indeg(ncomp, 0), outdeg(ncomp, 0);
+  for (uint64_t ed : edges) {
+    uint32_t u = (uint32_t)(ed >> 32), v = (uint32_t)ed;
+    if (comp[u] == comp[v]) { if (u == v && csize[comp[u]] == 1) self_loops_trivial++; continue; }
+    cross++; outdeg[comp[u]]++; indeg[comp[v]]++;
+  }
+  R.st.vertices = V;
+  R.st.edges = E - self_loops_trivial;
+  R.st.nontrivial_components = nontriv;
+  R.st.size_nontrivial_components = size_nontriv;
+  R.st.vertices_final = V + nontriv - size_nontriv;
+  R.st.edges_final = cross;
+  // branch counter in a topological order of the condensation (order invariant).  Tarjan numbers
+  // components in reverse topological order, so descending component id is a valid order.
+  std::vector<int> branch(ncomp, 0);
+  long long bc = 1;
+  for (uint32_t c = ncomp; c-- > 0;) {
+    if (indeg[c] == 0 && outdeg[c] == 0) continue;
+    if (indeg[c] > 1) bc -= (long long)indeg[c] - 1;
+    branch[c] = (int)bc;
+    if (outdeg[c] > 1) bc += (long long)outdeg[c] - 1;
+  }
+  auto vertex_safe = [&](uint32_t v) { return csize[comp[v]] == 1 && branch[comp[v]] == 1; };
+  const bool sink_safe = vertex_safe(0);
+  R.safe.assign(npack, 0);
+  for (uint32_t i = 0; i < npack; i++) {
+    auto it = std::lower_bound(nodes.begin(), nodes.end(), pk[i].node);
+    if (it != nodes.end() && *it == pk[i].node) R.safe[i] = vertex_safe((uint32_t)(it - nodes.begin()) + 2);
+    else R.safe[i] = sink_safe;   // node2boost[] default-inserts the sink
+  }
+}
+
+
+// Assemble the g2s_result of one gap and run its traceback.  `fill_out` (may be null) receives what the
+// reference leaves at &fill[left_max_fuz - left_fuz].
+inline void finish_one(const g2s_gap &g, const GapOut &o, const PackRec *pk, int k, int tier, const GeneralResult &gen,
+                       g2s_result &r, char *fill_out, std::vector<char> &buf) {
+  static const char NT[4] = {'A', 'C', 'T', 'G'};
+  memset(&r, 0, sizeof(r));
+  const bool skip_confident = (g.flags & G2S_GAP_SKIP_CONFIDENT) != 0, all_paths = (g.flags & G2S_GAP_ALL_PATHS) != 0;
+  r.cells_right = o.cells_right; r.cells_left = o.cells_left; r.nodes = o.nodes;
+  r.forward_count = (int32_t)o.count_fwd;
+  r.n_path_lengths = (int32_t)o.n_plen; r.path_lengths[0] = o.plen[0]; r.path_lengths[1] = o.plen[1];
+  r.reached_fuz = o.reached_fuz;
+  if (o.status & GS_ORDER_DEPENDENT) r.status |= G2S_ST_ORDER_DEPENDENT;
+  if (tier > 0) r.status |= G2S_ST_BIG_TIER;
+  if (o.count_fwd == 0 || o.n_plen == 0) return;
+  const bool general = (o.status & GS_GENERAL) != 0 && !skip_confident;
+  int count = (int)o.count_fwd;
+  r.right_fuz = o.reached_fuz;
+  if (!skip_confident) {
+    if (general) {
+      r.substats = gen.st;
+      r.status |= G2S_ST_GENERAL_SUBGRAPH;
+    } else {   // level DAG: no contraction happens, the device counted vertices and edges
+      r.substats.vertices = (uint64_t)o.nB + 2;
+      r.substats.edges = (uint64_t)o.n_edges + o.n_src + o.n_sink;
+      r.substats.vertices_final = r.substats.vertices;
+      r.substats.edges_final = r.substats.edges;
+    }
+    r.substats_valid = 1;
+    if (all_paths) count = (int)o.count_all;   // the Phase B recount replaces the first-found count (Gap2Seq.cpp:1192)
+  }
+  r.rand_calls = 1;
+  const uint32_t q = (uint32_t)(rand() % (int)o.n_plen);   // Gap2Seq.cpp:1440
+  int d = o.plen[q];
+  const int d0 = d;
+  int last_solid = d;
+  uint32_t cur = o.start_pack[q];
+  buf.assign((size_t)d0 + 1, 0);
+  int left_fuz = 0;
+  bool broken = (cur == NONE32);
+  while (d >= 0 && !broken) {
+    const PackRec &rec = pk[cur];
+    if (d <= g.left_max_fuz && (rec.meta & PM_START)) { left_fuz = g.left_max_fuz - d; break; }
+    if (d > 0) {
+      const bool safe = skip_confident || (general ? gen.safe[cur] != 0 : (rec.meta & PM_SAFE) != 0);
+      if (safe) last_solid = d;
+      const char c = NT[(rec.meta >> PM_BASE_SHIFT) & 3];
+      buf[d - 1] = (d > last_solid - k) ? c : (char)(c | 0x20);
+      uint32_t back[4]; int nb = 0;
+      for (int t = 0; t < 4; t++) if (rec.pred[t] != NONE32) back[nb++] = rec.pred[t];
+      if (nb == 0) { broken = true; break; }
+      r.rand_calls++;
+      cur = back[rand() % nb];   // one rand() per step even when nb == 1 (Gap2Seq.cpp:1513)
+    }
+    d--;
+  }
+  if (broken) {   // "Unable to backtrace!" (Gap2Seq.cpp:1493-1510): the reference returns 0
+    r.status |= G2S_ST_UNABLE_TO_BACKTRACE;
+    r.count = 0;
+    return;
+  }
+  r.left_fuz = left_fuz;
+  const int from = g.left_max_fuz - left_fuz;
+  r.fill_len = d0 - from;
+  if (fill_out) { memcpy(fill_out, &buf[from], (size_t)r.fill_len); fill_out[r.fill_len] = 0; }
+  r.count = count;
+}
+
+// Everything the host keeps of one device batch: per-gap summaries and the pack records, detached from the
+// engine so that several batches can be traced later in any chosen order (the scaffold scanner needs that).
+struct HostBatch {
+  int k = 0;
+  std::vector<g2s_gap> gaps;                  // flank pointers are not kept
+  std::vector<GapOut> outs;
+  std::vector<int> tier;                      // tier that produced the gap; -2 = outgrew the largest tier
+  std::vector<int> pack_of;                   // index into packs
+  std::vector<std::vector<PackRec>> packs;    // one arena per device pass
+  std::vector<GeneralResult> gen;
+  std::vector<char> buf;
+
+  const PackRec *pack_ptr(size_t i) const { return packs[pack_of[i]].data() + outs[i].pack_off; }
+
+  // SCC analysis of the general-subgraph gaps, independent per gap -> host threads
+  void analyze(int threads) {
+    const size_t n = gaps.size();
+    gen.assign(n, GeneralResult());
+    std::vector<uint32_t> ids;
+    for (size_t i = 0; i < n; i++)
+      if (tier[i] >= 0 && (outs[i].status & GS_GENERAL) && outs[i].count_fwd > 0 && !(gaps[i].flags & G2S_GAP_SKIP_CONFIDENT))
+        ids.push_back((uint32_t)i);
+    if (ids.empty()) return;
+    int nt = threads > 0 ? threads : (int)std::thread::hardware_concurrency();
+    nt = std::max(1, std::min<int>(nt, (int)ids.size()));
+    std::atomic<size_t> next{0};
+    auto work = [&]() {
+      for (;;) {
+        size_t j = next.fetch_add(1);
+        if (j >= ids.size()) break;
+        analyze_general(pack_ptr(ids[j]), outs[ids[j]].npack, gen[ids[j]]);
+      }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt; t++) th.emplace_back(work);
+    work();
+    for (auto &t : th) t.join();
+  }
+
+  // what fill_gap will return / write to *right_fuz, known before the traceback (needed by the scanner to decide
+  // where the next gap of the same record starts, src/Gap2Seq.cpp:392-402)
+  int peek_count(size_t i) const {
+    if (tier[i] == -2) return -1;
+    const GapOut &o = outs[i];
+    if (o.count_fwd == 0 || o.n_plen == 0) return 0;
+    const bool skip = (gaps[i].flags & G2S_GAP_SKIP_CONFIDENT) != 0, all = (gaps[i].flags & G2S_GAP_ALL_PATHS) != 0;
+    return (!skip && all) ? (int)o.count_all : (int)o.count_fwd;
+  }
+  int peek_right_fuz(size_t i) const {
+    if (tier[i] == -2) return 0;
+    const GapOut &o = outs[i];
+    return (o.count_fwd == 0 || o.n_plen == 0) ? 0 : o.reached_fuz;
+  }
+
+  // consumes libc rand(): call in the order the reference would call fill_gap
+  void trace(size_t i, g2s_result &r, char *fill_out) {
+    if (fill_out) fill_out[0] = 0;
+    if (tier[i] == -2) {
+      memset(&r, 0, sizeof(r));
+      r.count = -1; r.status = G2S_ST_MEM_LIMIT;
+      return;
+    }
+    finish_one(gaps[i], outs[i], pack_ptr(i), k, tier[i], gen[i], r, fill_out, buf);
+  }
+};
+
+}  // namespace g2s

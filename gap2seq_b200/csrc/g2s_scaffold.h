@@ -1,0 +1,246 @@
+// g2s_scaffold.h - the gap driver around the engine: the scaffold scanner / splicer of Gap2Seq::execute()
+// (reference src/Gap2Seq.cpp:329-432) and print_statistics (src/Gap2Seq.cpp:100-156), restructured so that
+// all gaps of all records go to the device in a few large batches instead of one fill_gap call at a time.
+//
+// The reference scans a record left to right and a gap's flanks can depend on the PREVIOUS gap's result
+// (prevGapEnd moves by right_fuz when that gap was filled).  Phase 1 therefore submits gaps in waves: a gap is
+// submitted as soon as its parameters are decided, which is immediately unless the previous attempted gap of the
+// same record ends less than k + 2*fuz bases before it.  Phase 2 then replays the exact reference control flow in
+// record order, tracing each attempted gap (that is where libc rand() is consumed, so the rand() stream is the
+// one of `Gap2Seq-core -nb-cores 1`), printing the statistics lines and splicing - including the reference's
+// prefix-dropping `filledSeq = ...` assignment for multi-gap records (src/Gap2Seq.cpp:396).
+#pragma once
+#include <cctype>
+#include <cstdio>
+#include <functional>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "g2s_finish.h"
+
+namespace g2s {
+
+struct RunOptions {
+  int k = 31, d_err = 500, max_fuz = 10;
+  bool skip_confident = false, unique_paths = false, all_paths = true;
+};
+
+// device pass for a list of gaps -> detached host batch (no rand() consumed)
+typedef std::function<int(const std::vector<g2s_gap> &, HostBatch &)> SubmitFn;
+
+struct GapReq {
+  int kmer_start, lmf, rmf, gap;
+  size_t i_after;          // index just after the N run
+  int batch = -1, idx = -1;
+};
+
+struct RecScan {
+  size_t i = 0;
+  long long prev = 0;          // prevGapEnd when known
+  int last_attempt = -1;       // request whose result decides prev, -1 when prev is exact
+  std::vector<GapReq> reqs;
+  bool done = false;
+};
+
+inline bool is_gap_char(char c) { return c == 'N' || c == 'n'; }
+
+// src/Gap2Seq.cpp:100-156
+inline void format_statistics(std::string &log, int filledStart, int gapStart, int gapEnd, int paths, const char *fill,
+                              int fill_len, int k, int lmf, int rmf, int lf, int rf, bool skip_confident, bool unique_paths,
+                              const g2s_subgraph_stats &ss, int gap, const std::string &comment) {
+  char buf[1024];
+  if (paths > 0 && (!unique_paths || paths == 1)) {
+    const int filledLen = fill_len - k;
+    if (!skip_confident) {
+      int upper = 0, lower = 0;
+      for (int j = 0; j < filledLen; j++) { if (isupper((unsigned char)fill[j])) upper++; else lower++; }
+      snprintf(buf, sizeof buf,
+               " GapStart: %d GapEnd: %d GapLength: %d PathsFound: %d FilledStart: %d FilledEnd: %d FilledGapLength: %d"
+               " LeftMaxFuz: %d LeftFuz: %d RightMaxFuz: %d RightFuz: %d ConfidentBases: %d TotalBases: %d\n",
+               gapStart, gapEnd, gap, paths, filledStart, filledStart + filledLen, filledLen, lmf, lf, rmf, rf, upper,
+               upper + lower);
+      log += "Scaffold: " + comment + buf;
+      snprintf(buf, sizeof buf,
+               "SubgraphStats: Vertices: %llu Edges: %llu NontrivialStrongComponents: %llu"
+               " SizeNontrivialStrongComponents: %llu VerticesFinal: %llu EdgesFinal: %llu\n",
+               (unsigned long long)ss.vertices, (unsigned long long)ss.edges, (unsigned long long)ss.nontrivial_components,
+               (unsigned long long)ss.size_nontrivial_components, (unsigned long long)ss.vertices_final,
+               (unsigned long long)ss.edges_final);
+      log += buf;
+    } else {
+      snprintf(buf, sizeof buf,
+               " GapStart: %d GapEnd: %d GapLength: %d PathsFound: %d FilledStart: %d FilledEnd: %d FilledGapLength: %d"
+               " LeftFuz: %d RightFuz: %d\n",
+               gapStart, gapEnd, gap, paths, filledStart, filledStart + filledLen, filledLen, lf, rf);
+      log += "Scaffold: " + comment + buf;
+    }
+  } else {
+    snprintf(buf, sizeof buf,
+             " GapStart: %d GapEnd: %d GapLength: %d PathsFound: 0 FilledStart: 0 FilledEnd: 0 FilledGapLength: 0"
+             " LeftMaxFuz: %d LeftFuz: %d RightMaxFuz: %d RightFuz: %d%s\n",
+             gapStart, gapEnd, gap, lmf, lf, rmf, rf, paths == -1 ? " Memory limit exceeded" : "");
+    log += "Scaffold: " + comment + buf;
+  }
+}
+
+struct ScaffoldRun {
+  const std::vector<std::string> &seqs;
+  const std::vector<std::string> &comments;
+  RunOptions opt;
+  std::vector<RecScan> recs;
+  std::vector<std::unique_ptr<HostBatch>> batches;
+  std::vector<std::vector<std::string>> flank_keep;   // flank strings of each batch (the gap structs point into them)
+
+  ScaffoldRun(const std::vector<std::string> &s, const std::vector<std::string> &c, const RunOptions &o)
+      : seqs(s), comments(c), opt(o), recs(s.size()) {}
+
+  bool filled_status(int count) const { return count > 0 && (!opt.unique_paths || count == 1); }
+
+  // Phase 1 helper: scan record r as far as its gaps are decided, appending requests to `out`.
+  void scan(size_t r, std::vector<std::pair<size_t, int>> &out) {
+    const std::string &seq = seqs[r];
+    RecScan &rs = recs[r];
+    const int k = opt.k, fuz = opt.max_fuz;
+    while (rs.i < seq.size()) {
+      if (!is_gap_char(seq[rs.i])) { rs.i++; continue; }
+      const size_t gs = rs.i;
+      bool independent = false;
+      if (rs.last_attempt >= 0) {
+        const GapReq &pr = rs.reqs[rs.last_attempt];
+        if (pr.batch >= 0 && batches[pr.batch]) {
+          const HostBatch &hb = *batches[pr.batch];
+          const int cnt = hb.peek_count(pr.idx);
+          rs.prev = (long long)pr.i_after + (filled_status(cnt) ? hb.peek_right_fuz(pr.idx) : 0);
+          rs.last_attempt = -1;
+        } else if ((long long)gs - (long long)pr.i_after >= (long long)k + 2 * fuz) {
+          independent = true;   // left flank cannot reach back to wherever the previous gap ends
+        } else {
+          return;               // suspended until the previous gap's batch has run
+        }
+      }
+      GapReq q;
+      q.lmf = independent ? fuz : (int)std::min<long long>((long long)gs + k - rs.prev, fuz);
+      q.kmer_start = (int)gs - k - q.lmf;
+      size_t i = gs;
+      int gap = 0;
+      while (i < seq.size() && is_gap_char(seq[i])) { i++; gap++; }
+      q.gap = gap;
+      q.i_after = i;
+      q.rmf = (int)std::min<long long>((long long)seq.size() - ((long long)i + k), fuz);
+      // a right flank shorter than k is undefined behaviour in the reference (negative right_max_fuz): skipped here
+      bool ok = q.rmf >= 0 && i + k + q.rmf <= seq.size();
+      for (int j = 0; j < k + q.rmf && ok; j++) if (is_gap_char(seq[i + j])) ok = false;
+      const bool left_ok = independent || (long long)q.kmer_start >= rs.prev;
+      if (left_ok && ok) {
+        rs.reqs.push_back(q);
+        rs.last_attempt = (int)rs.reqs.size() - 1;
+        out.push_back(std::make_pair(r, rs.last_attempt));
+      } else if (!independent) {
+        rs.prev = (long long)i;
+        rs.last_attempt = -1;
+      } else {
+        // independent but right flank invalid: the gap is skipped whatever the previous result is
+        rs.prev = (long long)i;
+        rs.last_attempt = -1;
+      }
+      rs.i = i;
+    }
+    rs.done = true;
+  }
+
+  int run(const SubmitFn &submit, std::vector<std::string> &filled, std::string &log, int &gapcount, int &filledcount,
+          std::vector<g2s_result> *details) {
+    const int k = opt.k;
+    // ---- phase 1: device waves
+    for (;;) {
+      std::vector<std::pair<size_t, int>> wave;
+      bool any_open = false;
+      for (size_t r = 0; r < recs.size(); r++) {
+        if (recs[r].done) continue;
+        scan(r, wave);
+        if (!recs[r].done) any_open = true;
+      }
+      if (wave.empty()) { if (any_open) return -1; break; }
+      const int b = (int)batches.size();
+      batches.emplace_back(new HostBatch());
+      flank_keep.emplace_back();
+      std::vector<std::string> &keep = flank_keep.back();
+      keep.reserve(wave.size() * 2);
+      std::vector<g2s_gap> gaps(wave.size());
+      for (size_t j = 0; j < wave.size(); j++) {
+        GapReq &q = recs[wave[j].first].reqs[wave[j].second];
+        const std::string &seq = seqs[wave[j].first];
+        q.batch = b; q.idx = (int)j;
+        keep.push_back(seq.substr(q.kmer_start, (size_t)k + q.lmf));
+        keep.push_back(seq.substr(q.i_after, (size_t)k + q.rmf));
+        g2s_gap &g = gaps[j];
+        g.kmer_left = keep[2 * j].data(); g.kmer_right = keep[2 * j + 1].data();
+        g.gap_len = q.gap; g.gap_err = opt.d_err; g.left_max_fuz = q.lmf; g.right_max_fuz = q.rmf;
+        g.flags = (opt.skip_confident ? G2S_GAP_SKIP_CONFIDENT : 0) | (opt.all_paths ? G2S_GAP_ALL_PATHS : 0);
+        g.reserved = 0;
+      }
+      int rc = submit(gaps, *batches.back());
+      if (rc != 0) return rc;
+      if (!any_open) {
+        bool all_done = true;
+        for (auto &rs : recs) if (!rs.done) all_done = false;
+        if (all_done) break;
+      }
+    }
+    // ---- phase 2: the reference's control flow, record by record (src/Gap2Seq.cpp:329-432)
+    filled.assign(seqs.size(), std::string());
+    std::vector<char> fillbuf;
+    for (size_t r = 0; r < seqs.size(); r++) {
+      const std::string &seq = seqs[r];
+      const std::string &comment = comments[r];
+      std::string filledSeq;
+      long long prev = 0;
+      size_t i = 0, next_req = 0;
+      while (i < seq.size()) {
+        if (!is_gap_char(seq[i])) { i++; continue; }
+        gapcount++;
+        const int lmf = (int)std::min<long long>((long long)i + k - prev, opt.max_fuz);
+        const int kmer_start = (int)i - k - lmf;
+        int gap = 0;
+        while (i < seq.size() && is_gap_char(seq[i])) { i++; gap++; }
+        const int rmf = (int)std::min<long long>((long long)seq.size() - ((long long)i + k), opt.max_fuz);
+        bool ok = rmf >= 0 && i + k + rmf <= seq.size();
+        for (int j = 0; j < k + rmf && ok; j++) if (is_gap_char(seq[i + j])) ok = false;
+        if ((long long)kmer_start >= prev && ok) {
+          if (next_req >= recs[r].reqs.size()) return -2;
+          const GapReq &q = recs[r].reqs[next_req++];
+          if (q.kmer_start != kmer_start || q.lmf != lmf || q.rmf != rmf || q.gap != gap || q.i_after != i) return -3;
+          g2s_result res;
+          fillbuf.assign((size_t)gap + k + opt.d_err + lmf + rmf + 3, 0);
+          batches[q.batch]->trace((size_t)q.idx, res, fillbuf.data());
+          if (details) details->push_back(res);
+          const int s = res.count;
+          const int filledStart = (int)filledSeq.length() + kmer_start + k + lmf - res.left_fuz - (int)prev;
+          const int gapStart = kmer_start + k + lmf;
+          format_statistics(log, filledStart, gapStart, (int)i, s, fillbuf.data(), res.fill_len, k, lmf, rmf, res.left_fuz,
+                            res.right_fuz, opt.skip_confident, opt.unique_paths, res.substats, gap, comment);
+          if (filled_status(s)) {
+            filledcount++;
+            // '=' not '+=': the prefix of a multi-gap record is dropped, as in the reference
+            filledSeq = seq.substr((size_t)prev, (size_t)(kmer_start + k + lmf - res.left_fuz - prev)) +
+                        std::string(fillbuf.data(), (size_t)res.fill_len);
+            filledSeq.resize(filledSeq.size() - k);   // drop the right k-mer
+            i += res.right_fuz;
+          } else {
+            filledSeq += seq.substr((size_t)prev, (size_t)(kmer_start + k + lmf + gap - prev));
+          }
+        } else {
+          filledSeq += seq.substr((size_t)prev, (size_t)(kmer_start + k + lmf + gap - prev));
+        }
+        prev = (long long)i;
+      }
+      if (next_req != recs[r].reqs.size()) return -4;
+      filledSeq += seq.substr((size_t)prev);
+      filled[r].swap(filledSeq);
+    }
+    return 0;
+  }
+};
+
+}  // namespace g2s

@@ -1,0 +1,281 @@
+// g2s_table.cu - the device-resident de Bruijn graph: an open-addressing table of canonical k-mers with one
+// adjacency byte per node.  Replaces the query side of GATB's Graph (Bloom filter + cFP set + MPHF,
+// gatb-core/src/gatb/debruijn/impl/Graph.hpp:1249-1272; neighbours by shift/insert + 4 membership tests,
+// Graph.cpp:1284-1345) and, for stand-alone use, its construction (DSK solid k-mer counting invoked from
+// src/Gap2Seq.cpp:213-214) by sort + run-length counting on the device.
+#include <cub/cub.cuh>
+#include <cuda_runtime.h>
+
+#include "g2s_common.cuh"
+#include "g2s_device.h"
+
+namespace g2s {
+
+// ---------------------------------------------------------------------------------------------- table build
+__global__ void k_clear_slots(Slot *slots, uint64_t cap) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (; i < cap; i += stride) { slots[i].key = KEY_EMPTY; slots[i].val = 0; }
+}
+
+// insert keys[i] when its abundance passes; counts == nullptr means "insert all"
+__global__ void k_insert(Slot *slots, uint64_t cap_mask, const uint64_t *keys, const uint32_t *counts, uint32_t solid,
+                         uint64_t n, unsigned long long *n_inserted) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  unsigned long long mine = 0;
+  for (; i < n; i += stride) {
+    const uint64_t key = keys[i];
+    if (key == KEY_EMPTY) continue;
+    if (counts && counts[i] < solid) continue;
+    uint64_t h = mix64(key) & cap_mask;
+    for (;;) {
+      unsigned long long old = atomicCAS((unsigned long long *)&slots[h].key, (unsigned long long)KEY_EMPTY,
+                                         (unsigned long long)key);
+      if (old == KEY_EMPTY) { mine++; break; }
+      if (old == key) break;
+      h = (h + 1) & cap_mask;
+    }
+  }
+  // one atomic per warp
+  for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+  if ((threadIdx.x & 31) == 0 && mine) atomicAdd(n_inserted, mine);
+}
+
+// adjacency byte of every node: 8 probes (4 successors, 4 predecessors of the canonical orientation),
+// the same byte Graph::precomputeAdjacency computes (Graph.cpp:3486-3530)
+__global__ void k_adjacency(Slot *slots, Table t) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  const uint64_t cap = t.cap_mask + 1;
+  for (; i < cap; i += stride) {
+    const uint64_t key = slots[i].key;
+    if (key == KEY_EMPTY) continue;
+    uint32_t adj = 0, dummy;
+#pragma unroll
+    for (uint32_t nt = 0; nt < 4; nt++) {
+      if (table_find(t, canonical(succ_kmer(key, nt, t), t.k).key, &dummy) >= 0) adj |= 1u << nt;
+      if (table_find(t, canonical(pred_kmer(key, nt, t), t.k).key, &dummy) >= 0) adj |= 1u << (4 + nt);
+    }
+    slots[i].val = adj;
+  }
+}
+
+__global__ void k_count_solid(const uint32_t *counts, const int *n_runs, const uint64_t *keys, uint32_t solid,
+                              unsigned long long *n_solid) {
+  const uint64_t n = (uint64_t)*n_runs;
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  unsigned long long mine = 0;
+  for (; i < n; i += stride) mine += (counts[i] >= solid && keys[i] != KEY_EMPTY) ? 1 : 0;
+  for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+  if ((threadIdx.x & 31) == 0 && mine) atomicAdd(n_solid, mine);
+}
+
+// one thread per (read, position): canonical k-mer or KEY_EMPTY when the window holds an invalid character
+// ((c >> 3) & 1, tools/misc/api/Data.hpp:176; such k-mers are not counted, kmer/impl/Sequence2SuperKmer.hpp:93)
+__global__ void k_extract(const char *bases, const uint64_t *offsets, const uint64_t *kmer_offsets, uint64_t n_reads,
+                          int k, uint64_t *out, uint64_t total) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (; i < total; i += stride) {
+    // binary search the read that owns output index i
+    uint64_t lo = 0, hi = n_reads;
+    while (hi - lo > 1) { uint64_t mid = (lo + hi) >> 1; if (kmer_offsets[mid] <= i) lo = mid; else hi = mid; }
+    const char *s = bases + offsets[lo] + (i - kmer_offsets[lo]);
+    uint64_t v = 0; uint32_t bad = 0;
+    for (int j = 0; j < k; j++) {
+      const unsigned char c = (unsigned char)s[j];
+      bad |= (c >> 3) & 1;
+      v = (v << 2) | ((c >> 1) & 3);
+    }
+    out[i] = bad ? KEY_EMPTY : canonical(v, k).key;
+  }
+}
+
+__global__ void k_compact(const Slot *slots, uint64_t cap, uint64_t *keys_out, unsigned long long *cursor) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (; i < cap; i += stride) {
+    const uint64_t key = slots[i].key;
+    if (key != KEY_EMPTY) keys_out[atomicAdd(cursor, 1ULL)] = key;
+  }
+}
+
+__global__ void k_lookup_adj(Table t, const uint64_t *keys, uint64_t n, uint8_t *adj_out) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t adj = 0;
+  adj_out[i] = table_find(t, keys[i], &adj) >= 0 ? (uint8_t)adj : 0;
+}
+
+__global__ void k_contains(Table t, const char *ascii, uint64_t n, uint8_t *out) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t adj;
+  out[i] = table_find(t, canonical(kmer_from_ascii(ascii + i * t.k, t.k), t.k).key, &adj) >= 0;
+}
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return e_; } while (0)
+
+static int grid_for(uint64_t n, int block, int sms) {
+  uint64_t b = (n + block - 1) / block;
+  uint64_t cap = (uint64_t)sms * 32;
+  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+cudaError_t table_alloc(DeviceTable *dt, int k, uint64_t n_keys, int sms, cudaStream_t st) {
+  uint64_t cap = 1024;
+  while (cap < 2 * n_keys + 2) cap <<= 1;
+  if (dt->slots) { cudaFree(dt->slots); dt->slots = nullptr; }
+  CK(cudaMalloc(&dt->slots, cap * sizeof(Slot)));
+  dt->cap = cap;
+  dt->k = k;
+  dt->n = 0;
+  k_clear_slots<<<grid_for(cap, 256, sms), 256, 0, st>>>(dt->slots, cap);
+  return cudaGetLastError();
+}
+
+Table table_view(const DeviceTable &dt) {
+  Table t;
+  t.slots = dt.slots;
+  t.cap_mask = dt.cap - 1;
+  t.k = dt.k;
+  t.kmask = dt.k >= 32 ? ~0ULL : ((1ULL << (2 * dt.k)) - 1);
+  return t;
+}
+
+// keys_dev: device array of canonical k-mers (counts_dev optional)
+cudaError_t table_fill(DeviceTable *dt, const uint64_t *keys_dev, const uint32_t *counts_dev, uint32_t solid, uint64_t n,
+                       int sms, cudaStream_t st) {
+  unsigned long long *d_n;
+  CK(cudaMalloc(&d_n, sizeof(unsigned long long)));
+  CK(cudaMemsetAsync(d_n, 0, sizeof(unsigned long long), st));
+  k_insert<<<grid_for(n, 256, sms), 256, 0, st>>>(dt->slots, dt->cap - 1, keys_dev, counts_dev, solid, n, d_n);
+  CK(cudaGetLastError());
+  k_adjacency<<<grid_for(dt->cap, 256, sms), 256, 0, st>>>(dt->slots, table_view(*dt));
+  CK(cudaGetLastError());
+  unsigned long long h_n = 0;
+  CK(cudaMemcpyAsync(&h_n, d_n, sizeof(h_n), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  cudaFree(d_n);
+  dt->n = h_n;
+  return cudaSuccess;
+}
+
+cudaError_t table_from_reads(DeviceTable *dt, int k, const char *bases_host, const uint64_t *offsets_host, uint64_t n_reads,
+                             int solid, int sms, cudaStream_t st) {
+  // per-read k-mer counts -> exclusive offsets (host; linear in the number of reads)
+  uint64_t *koff = (uint64_t *)malloc((n_reads + 1) * sizeof(uint64_t));
+  if (!koff) return cudaErrorMemoryAllocation;
+  uint64_t total = 0;
+  for (uint64_t i = 0; i < n_reads; i++) {
+    koff[i] = total;
+    uint64_t len = offsets_host[i + 1] - offsets_host[i];
+    total += len >= (uint64_t)k ? len - k + 1 : 0;
+  }
+  koff[n_reads] = total;
+  const uint64_t nbytes = offsets_host[n_reads];
+  char *d_bases = nullptr; uint64_t *d_off = nullptr, *d_koff = nullptr, *d_keys = nullptr, *d_sorted = nullptr;
+  uint64_t *d_unique = nullptr; uint32_t *d_counts = nullptr; int *d_nruns = nullptr; void *d_tmp = nullptr;
+  unsigned long long *d_nsolid = nullptr;
+  cudaError_t err = cudaSuccess;
+#define CKG(x) do { err = (x); if (err != cudaSuccess) goto done; } while (0)
+  {
+    if (total == 0) { CKG(table_alloc(dt, k, 0, sms, st)); CKG(cudaStreamSynchronize(st)); goto done; }
+    if (total >= (1ULL << 31)) { err = cudaErrorInvalidValue; goto done; }   // cub run-length API counts in int
+    CKG(cudaMalloc(&d_bases, nbytes + 1));
+    CKG(cudaMalloc(&d_off, (n_reads + 1) * 8));
+    CKG(cudaMalloc(&d_koff, (n_reads + 1) * 8));
+    CKG(cudaMalloc(&d_keys, total * 8));
+    CKG(cudaMalloc(&d_sorted, total * 8));
+    CKG(cudaMemcpyAsync(d_bases, bases_host, nbytes, cudaMemcpyHostToDevice, st));
+    CKG(cudaMemcpyAsync(d_off, offsets_host, (n_reads + 1) * 8, cudaMemcpyHostToDevice, st));
+    CKG(cudaMemcpyAsync(d_koff, koff, (n_reads + 1) * 8, cudaMemcpyHostToDevice, st));
+    k_extract<<<grid_for(total, 256, sms), 256, 0, st>>>(d_bases, d_off, d_koff, n_reads, k, d_keys, total);
+    CKG(cudaGetLastError());
+    size_t tmp_bytes = 0;
+    CKG(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, d_keys, d_sorted, (int)total, 0, 64, st));
+    CKG(cudaMalloc(&d_tmp, tmp_bytes));
+    CKG(cub::DeviceRadixSort::SortKeys(d_tmp, tmp_bytes, d_keys, d_sorted, (int)total, 0, 64, st));
+    cudaFree(d_tmp); d_tmp = nullptr;
+    // d_keys is free again: reuse it for the unique keys
+    d_unique = d_keys;
+    CKG(cudaMalloc(&d_counts, total * 4));
+    CKG(cudaMalloc(&d_nruns, sizeof(int)));
+    tmp_bytes = 0;
+    CKG(cub::DeviceRunLengthEncode::Encode(nullptr, tmp_bytes, d_sorted, d_unique, d_counts, d_nruns, (int)total, st));
+    CKG(cudaMalloc(&d_tmp, tmp_bytes));
+    CKG(cub::DeviceRunLengthEncode::Encode(d_tmp, tmp_bytes, d_sorted, d_unique, d_counts, d_nruns, (int)total, st));
+    CKG(cudaMalloc(&d_nsolid, 8));
+    CKG(cudaMemsetAsync(d_nsolid, 0, 8, st));
+    k_count_solid<<<grid_for(total, 256, sms), 256, 0, st>>>(d_counts, d_nruns, d_unique, (uint32_t)solid, d_nsolid);
+    CKG(cudaGetLastError());
+    unsigned long long n_solid = 0; int n_runs = 0;
+    CKG(cudaMemcpyAsync(&n_solid, d_nsolid, 8, cudaMemcpyDeviceToHost, st));
+    CKG(cudaMemcpyAsync(&n_runs, d_nruns, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CKG(cudaStreamSynchronize(st));
+    CKG(table_alloc(dt, k, n_solid, sms, st));
+    CKG(table_fill(dt, d_unique, d_counts, (uint32_t)solid, (uint64_t)n_runs, sms, st));
+  }
+done:
+#undef CKG
+  free(koff);
+  cudaFree(d_bases); cudaFree(d_off); cudaFree(d_koff); cudaFree(d_keys); cudaFree(d_sorted);
+  cudaFree(d_counts); cudaFree(d_nruns); cudaFree(d_tmp); cudaFree(d_nsolid);
+  return err;
+}
+
+cudaError_t table_export(const DeviceTable &dt, uint64_t *keys_host, uint8_t *adj_host, int sms, cudaStream_t st) {
+  if (dt.n == 0) return cudaSuccess;
+  uint64_t *d_keys = nullptr, *d_sorted = nullptr; unsigned long long *d_cur = nullptr; void *d_tmp = nullptr;
+  uint8_t *d_adj = nullptr;
+  cudaError_t err = cudaSuccess;
+#define CKG(x) do { err = (x); if (err != cudaSuccess) goto done; } while (0)
+  {
+    CKG(cudaMalloc(&d_keys, dt.n * 8));
+    CKG(cudaMalloc(&d_sorted, dt.n * 8));
+    CKG(cudaMalloc(&d_cur, 8));
+    CKG(cudaMemsetAsync(d_cur, 0, 8, st));
+    k_compact<<<grid_for(dt.cap, 256, sms), 256, 0, st>>>(dt.slots, dt.cap, d_keys, d_cur);
+    CKG(cudaGetLastError());
+    size_t tmp_bytes = 0;
+    CKG(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, d_keys, d_sorted, (int)dt.n, 0, 64, st));
+    CKG(cudaMalloc(&d_tmp, tmp_bytes));
+    CKG(cub::DeviceRadixSort::SortKeys(d_tmp, tmp_bytes, d_keys, d_sorted, (int)dt.n, 0, 64, st));
+    CKG(cudaMemcpyAsync(keys_host, d_sorted, dt.n * 8, cudaMemcpyDeviceToHost, st));
+    if (adj_host) {
+      CKG(cudaMalloc(&d_adj, dt.n));
+      k_lookup_adj<<<(unsigned)((dt.n + 255) / 256), 256, 0, st>>>(table_view(dt), d_sorted, dt.n, d_adj);
+      CKG(cudaGetLastError());
+      CKG(cudaMemcpyAsync(adj_host, d_adj, dt.n, cudaMemcpyDeviceToHost, st));
+    }
+    CKG(cudaStreamSynchronize(st));
+  }
+done:
+#undef CKG
+  cudaFree(d_keys); cudaFree(d_sorted); cudaFree(d_cur); cudaFree(d_tmp); cudaFree(d_adj);
+  return err;
+}
+
+cudaError_t table_contains(const DeviceTable &dt, const char *ascii_host, uint64_t n, uint8_t *out_host, cudaStream_t st) {
+  if (n == 0) return cudaSuccess;
+  char *d_a = nullptr; uint8_t *d_o = nullptr;
+  cudaError_t err = cudaSuccess;
+#define CKG(x) do { err = (x); if (err != cudaSuccess) goto done; } while (0)
+  {
+    CKG(cudaMalloc(&d_a, n * dt.k));
+    CKG(cudaMalloc(&d_o, n));
+    CKG(cudaMemcpyAsync(d_a, ascii_host, n * dt.k, cudaMemcpyHostToDevice, st));
+    k_contains<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(table_view(dt), d_a, n, d_o);
+    CKG(cudaGetLastError());
+    CKG(cudaMemcpyAsync(out_host, d_o, n, cudaMemcpyDeviceToHost, st));
+    CKG(cudaStreamSynchronize(st));
+  }
+done:
+#undef CKG
+  cudaFree(d_a); cudaFree(d_o);
+  return err;
+}
+
+}  // namespace g2s

@@ -1,0 +1,171 @@
+/* g2s.h - C ABI of the B200 gap-filling engine (libg2s_gpu.so).
+ *
+ * The reference (rikuu/Gap2Seq) has no plugin/FFI layer: its hot path is the member function
+ *     int Gap2Seq::fill_gap(const Graph&, const std::string &kmer_left, const std::string &kmer_right,
+ *                           int gap_len, int k, int gap_err, int left_max_fuz, int right_max_fuz,
+ *                           int *left_fuz, int *right_fuz, long long max_mem, char *fill,
+ *                           bool skip_confident, bool all_paths, struct subgraph_stats *substats)
+ * declared at src/Gap2Seq.hpp:74-76, defined at src/Gap2Seq.cpp:858-1556 and called from exactly two
+ * places, src/Gap2Seq.cpp:252 (single-gap mode) and src/Gap2Seq.cpp:380 (scaffold mode).  The entry
+ * points below are what a cgo/JNI/ctypes/C++ binding for that path binds; INTEGRATION.md shows the
+ * reference-side change.  Plain pointers and sizes only; all buffers are caller owned.
+ *
+ * Every function returns 0 (or a non-negative count where stated) on success and a negative
+ * G2S_E_* code on failure; g2s_last_error() then describes the failure.  There is no CPU fallback:
+ * without a CUDA device every compute call fails with G2S_E_CUDA.
+ */
+#ifndef G2S_H
+#define G2S_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define G2S_ABI_VERSION 1
+
+enum {
+  G2S_OK = 0,
+  G2S_E_CUDA = -1,      /* CUDA runtime error or no device */
+  G2S_E_ARG = -2,       /* invalid argument */
+  G2S_E_STATE = -3,     /* call out of order (e.g. fill before a graph was imported) */
+  G2S_E_NOMEM = -4      /* host or device allocation failed */
+};
+
+/* per-gap status bits (g2s_result.status) */
+enum {
+  G2S_ST_ORDER_DEPENDENT = 1,  /* a border set received both strands of one k-mer: the reference's result depends on
+                                  libstdc++ hashtable iteration order; reported, not reproduced */
+  G2S_ST_MEM_LIMIT = 2,        /* the DP outgrew the largest device tier (the analogue of the reference's
+                                  "Memory limit exceeded", src/Gap2Seq.cpp:147); count is -1 */
+  G2S_ST_GENERAL_SUBGRAPH = 4, /* informational: the path subgraph had a k-mer at several levels, SCC analysis ran */
+  G2S_ST_UNABLE_TO_BACKTRACE = 8,
+  G2S_ST_BIG_TIER = 16         /* informational: the gap was re-run in the wide (one CTA per gap) tier */
+};
+
+/* gap flags */
+enum {
+  G2S_GAP_SKIP_CONFIDENT = 1,  /* -all-upper: skip the safe/unsafe classification (fill_gap's skip_confident) */
+  G2S_GAP_ALL_PATHS = 2        /* default mode; cleared by -best-only (fill_gap's all_paths) */
+};
+
+typedef struct g2s_engine g2s_engine;
+
+typedef struct g2s_config {
+  int32_t abi_version;   /* G2S_ABI_VERSION */
+  int32_t device;        /* CUDA device ordinal */
+  int32_t k;             /* k-mer size, 3 <= k <= 31 (the -k flag, src/Gap2Seq.cpp:164) */
+  int32_t max_fuz;       /* upper bound of left/right_max_fuz over all gaps, <= 31 (the -fuz flag) */
+  int64_t max_mem_bytes; /* device memory budget for DP scratch; 0 = 60 % of the free memory (the -max-mem flag) */
+  int32_t host_threads;  /* threads for the host-side subgraph analysis; 0 = hardware concurrency (-nb-cores) */
+  int32_t reserved;
+} g2s_config;
+
+/* mirror of struct subgraph_stats, src/Gap2Seq.hpp:51-59 */
+typedef struct g2s_subgraph_stats {
+  uint64_t vertices, edges, nontrivial_components, size_nontrivial_components, vertices_final, edges_final;
+} g2s_subgraph_stats;
+
+/* one call of fill_gap: the arguments of src/Gap2Seq.hpp:74-76 that vary per gap */
+typedef struct g2s_gap {
+  const char *kmer_left;    /* k + left_max_fuz characters (need not be NUL terminated) */
+  const char *kmer_right;   /* k + right_max_fuz characters */
+  int32_t gap_len, gap_err, left_max_fuz, right_max_fuz;
+  int32_t flags;            /* G2S_GAP_* */
+  int32_t reserved;
+} g2s_gap;
+
+typedef struct g2s_result {
+  int32_t count;            /* fill_gap's return value: paths found, 0, or -1 (G2S_ST_MEM_LIMIT) */
+  int32_t left_fuz, right_fuz;
+  int32_t status;           /* G2S_ST_* bits */
+  int32_t fill_len;         /* strlen(&fill[left_max_fuz - left_fuz]); ends with the right k-mer; 0 if not traced */
+  int32_t substats_valid;   /* substats were written (Phase B ran) */
+  int32_t forward_count;    /* count after the first-found check (before the all-paths recount) */
+  int32_t n_path_lengths, path_lengths[2], reached_fuz;
+  int32_t rand_calls;       /* libc rand() calls consumed by this gap's traceback */
+  g2s_subgraph_stats substats;
+  uint64_t cells_right, cells_left;   /* DP cells materialised (== the reference's -DSTATS "Nonzeros") */
+  uint64_t nodes;                     /* distinct canonical k-mers touched by the gap */
+} g2s_result;
+
+typedef struct g2s_timing {
+  double h2d_ms, kernel_ms, d2h_ms, host_ms;   /* of the last g2s_fill_batch / g2s_run_resident call */
+  uint64_t h2d_bytes, d2h_bytes;
+  uint32_t launches;                            /* kernels launched by that call */
+  uint32_t gaps_big_tier;
+} g2s_timing;
+
+const char *g2s_last_error(void);
+int g2s_abi_version(void);
+
+int g2s_create(const g2s_config *cfg, g2s_engine **out);
+void g2s_destroy(g2s_engine *e);
+
+/* Graph import: replaces the GATB neighbour queries (Graph::successors/predecessors/contains,
+ * gatb-core/src/gatb/debruijn/impl/Graph.cpp:1284-1345, 2193-2213) by an open-addressing table of 2-bit
+ * packed canonical k-mers (GATB code A=0,C=1,T=2,G=3) with an 8-bit in/out edge mask per node
+ * (the byte Graph::precomputeAdjacency defines, Graph.cpp:3486-3530).  `canon` is a HOST array of the
+ * solid canonical k-mers, e.g. the values of graph.iterator() (Graph.cpp:2243-2362). */
+int g2s_import_kmers(g2s_engine *e, const uint64_t *canon, size_t n);
+
+/* Graph construction on the device, the stand-in for Graph::create(... -abundance-min solid ...)
+ * (src/Gap2Seq.cpp:213-214): counts canonical k-mers of `n_reads` reads (ASCII, read i is
+ * bases[offsets[i] .. offsets[i+1]) ) and keeps those seen >= solid times.  Timed separately from the fill. */
+int g2s_build_from_reads(g2s_engine *e, const char *bases, const uint64_t *offsets, size_t n_reads, int solid);
+
+int64_t g2s_num_kmers(const g2s_engine *e);
+/* copies the table contents (sorted canonical k-mers and their adjacency bytes) to host arrays of g2s_num_kmers() */
+int g2s_export_kmers(g2s_engine *e, uint64_t *canon_sorted, uint8_t *adjacency);
+/* Graph::contains for n canonical-or-not k-mers given as ASCII strings of length k, one per k bytes */
+int g2s_contains(g2s_engine *e, const char *kmers_ascii, size_t n, uint8_t *out);
+
+/* The drop-in for Gap2Seq::fill_gap (src/Gap2Seq.hpp:74-76): same arguments minus the Graph (owned by the
+ * engine), same return value, same `fill` buffer contract (caller allocates gap_len+k+gap_err+lmf+rmf+3 bytes,
+ * the valid string starts at &fill[left_max_fuz - *left_fuz]), consumes libc rand() exactly like the reference. */
+int g2s_fill_gap(g2s_engine *e, const char *kmer_left, const char *kmer_right, int gap_len, int k, int gap_err,
+                 int left_max_fuz, int right_max_fuz, int *left_fuz, int *right_fuz, long long max_mem, char *fill,
+                 int skip_confident, int all_paths, g2s_subgraph_stats *substats);
+
+/* Batched form: n independent gaps in one device pass; the host-side random traceback then replays libc
+ * rand() in array order, so the results equal n successive g2s_fill_gap calls.  fill_out[i] (may be NULL)
+ * receives the NUL-terminated fill string, i.e. what the reference leaves at &fill[left_max_fuz - left_fuz];
+ * it must hold gap_len+k+gap_err+lmf+rmf+3 bytes. */
+int g2s_fill_batch(g2s_engine *e, const g2s_gap *gaps, size_t n, g2s_result *results, char *const *fill_out);
+
+/* Split form used by bench.py to time the device pass with inputs already resident in HBM:
+ * upload once, run the device pass any number of times, then finish (D2H + host traceback) once. */
+int g2s_upload_gaps(g2s_engine *e, const g2s_gap *gaps, size_t n);
+int g2s_run_resident(g2s_engine *e);          /* device pass only; synchronous */
+int g2s_finish_resident(g2s_engine *e, g2s_result *results, char *const *fill_out);
+
+/* Detached batches: the device pass of n gaps without the traceback, so that several batches can be traced
+ * later in a caller-chosen order (the scaffold driver needs this: a gap's flanks may depend on the previous
+ * gap's count / right_fuz, which are known before the traceback, src/Gap2Seq.cpp:392-402). */
+typedef struct g2s_batch g2s_batch;
+int g2s_submit(g2s_engine *e, const g2s_gap *gaps, size_t n, g2s_batch **out);   /* consumes no rand() */
+int g2s_batch_peek(const g2s_batch *b, size_t i, int32_t *count, int32_t *right_fuz);
+int g2s_batch_trace(g2s_batch *b, size_t i, g2s_result *result, char *fill_out);  /* consumes rand() */
+void g2s_batch_free(g2s_batch *b);
+
+/* The gap driver of Gap2Seq::execute() (src/Gap2Seq.cpp:285-434): scans n_records scaffold records for N/n runs,
+ * fills them through the engine in large batches, and returns for every record the filled sequence
+ * (filled_out[i], malloc'ed, release with g2s_free) plus the stdout lines the reference prints per gap
+ * (*log_out, malloc'ed).  Byte-identical to `Gap2Seq-core -nb-cores 1` for the same libc rand() state. */
+typedef struct g2s_run_options {
+  int32_t k, dist_error, fuz;
+  int32_t skip_confident, unique_paths, all_paths;
+} g2s_run_options;
+int g2s_fill_records(g2s_engine *e, const char *const *seqs, const char *const *comments, size_t n_records,
+                     const g2s_run_options *opt, char **filled_out, char **log_out, int32_t *gapcount,
+                     int32_t *filledcount, g2s_result **gap_results, size_t *n_gap_results);
+void g2s_free(void *p);
+
+int g2s_get_timing(const g2s_engine *e, g2s_timing *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* G2S_H */

@@ -1,0 +1,156 @@
+// g2s_emul.cpp - TEST INFRASTRUCTURE ONLY.  Compiles the per-gap device algorithm (gap2seq_b200/csrc/g2s_fill.cuh)
+// as plain host C++ with a thread group of size 1 (-DG2S_HOST_EMUL) so its sequential logic can be checked
+// against the oracle in the CPU test suite (no GPU in the build container).  It shares the algorithm source and
+// the host finish stage with libg2s_gpu.so but is never loaded by the product; races and warp-level behaviour
+// are only exercised by the `-m gpu` tests on the real kernels.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../../include/g2s.h"
+#include "../../gap2seq_b200/csrc/g2s_fill.cuh"
+#include "../../gap2seq_b200/csrc/g2s_finish.h"
+#include "../../gap2seq_b200/csrc/g2s_scaffold.h"
+
+using namespace g2s;
+
+struct EmulGroup {
+  static int rank() { return 0; }
+  static int size() { return 1; }
+  static void sync() {}
+};
+
+struct EmulGraph {
+  std::vector<Slot> slots;
+  Table t;
+};
+
+static uint32_t host_adj(const Table &t, uint64_t key) {
+  uint32_t adj = 0, dummy;
+  for (uint32_t nt = 0; nt < 4; nt++) {
+    if (table_find(t, canonical(succ_kmer(key, nt, t), t.k).key, &dummy) >= 0) adj |= 1u << nt;
+    if (table_find(t, canonical(pred_kmer(key, nt, t), t.k).key, &dummy) >= 0) adj |= 1u << (4 + nt);
+  }
+  return adj;
+}
+
+extern "C" {
+
+void *emul_graph_from_kmers(int k, const uint64_t *kmers, size_t n) {
+  EmulGraph *g = new EmulGraph();
+  uint64_t cap = 1024;
+  while (cap < 2 * n + 2) cap <<= 1;
+  g->slots.assign(cap, Slot{KEY_EMPTY, 0});
+  g->t.slots = g->slots.data();
+  g->t.cap_mask = cap - 1;
+  g->t.k = k;
+  g->t.kmask = (1ULL << (2 * k)) - 1;
+  for (size_t i = 0; i < n; i++) {
+    uint64_t h = mix64(kmers[i]) & g->t.cap_mask;
+    while (g->slots[h].key != KEY_EMPTY && g->slots[h].key != kmers[i]) h = (h + 1) & g->t.cap_mask;
+    g->slots[h].key = kmers[i];
+  }
+  for (uint64_t h = 0; h < cap; h++)
+    if (g->slots[h].key != KEY_EMPTY) g->slots[h].val = host_adj(g->t, g->slots[h].key);
+  return g;
+}
+
+void emul_graph_free(void *g) { delete (EmulGraph *)g; }
+
+void emul_adjacency(void *gp, const uint64_t *kmers, size_t n, uint8_t *out) {
+  EmulGraph *g = (EmulGraph *)gp;
+  for (size_t i = 0; i < n; i++) { uint32_t a = 0; table_find(g->t, kmers[i], &a); out[i] = (uint8_t)a; }
+}
+
+// device pass of a list of gaps, emulated: fills a detached HostBatch exactly like the engine's do_collect
+static int emul_submit(EmulGraph *g, int k, const g2s_gap *gaps, size_t n, HostBatch &hb, int cap0) {
+  hb.k = k;
+  hb.gaps.assign(gaps, gaps + n);
+  hb.outs.assign(n, GapOut{});
+  hb.tier.assign(n, 0);
+  hb.pack_of.assign(n, 0);
+  hb.packs.assign(n, std::vector<PackRec>());
+  for (size_t i = 0; i < n; i++) {
+    const g2s_gap &gg = gaps[i];
+    std::vector<char> flanks((size_t)2 * k + gg.left_max_fuz + gg.right_max_fuz + 1);
+    memcpy(flanks.data(), gg.kmer_left, (size_t)k + gg.left_max_fuz);
+    memcpy(flanks.data() + k + gg.left_max_fuz, gg.kmer_right, (size_t)k + gg.right_max_fuz);
+    GapDev gd{};
+    gd.flank_off = 0; gd.gap_len = gg.gap_len; gd.gap_err = gg.gap_err; gd.lmf = gg.left_max_fuz; gd.rmf = gg.right_max_fuz;
+    gd.flags = (uint32_t)gg.flags; gd.id = (uint32_t)i;
+    const int dmax = gg.gap_len + gg.gap_err + gg.left_max_fuz + gg.right_max_fuz;
+    uint64_t cap = cap0 > 0 ? (uint64_t)cap0 : (uint64_t)4 * (dmax + 2) + 1024;
+    GapOut out{};
+    std::vector<PackRec> pack;
+    int tier = 0;
+    for (;; tier++, cap *= 16) {
+      uint32_t hlog = tier == 0 ? ceil_log2(2 * cap) : (ceil_log2(cap / 4) > 16 ? ceil_log2(cap / 4) : 16);
+      SliceLayout L = make_layout(cap, hlog, (uint32_t)dmax + 1, (uint32_t)std::max(gg.left_max_fuz, gg.right_max_fuz) + 1);
+      std::vector<unsigned char> scratch(L.bytes);
+      pack.assign(cap, PackRec{});
+      unsigned long long cursor = 0;
+      uint32_t order = 0, qh = 0;
+      FillParams P{};
+      P.table = g->t; P.flanks = flanks.data(); P.gaps = &gd; P.order = &order; P.n_gaps = 1; P.outs = &out;
+      P.scratch = scratch.data(); P.lay = L; P.pack = pack.data(); P.pack_cap = cap; P.pack_cursor = &cursor; P.queue_head = &qh;
+      GShared sh{};
+      Slice S = make_slice(scratch.data(), L);
+      process_gap<EmulGroup>(P, gd, S, sh, &out);
+      if (out.status & GS_INTERNAL) return -100;
+      if (!(out.status & (GS_OVERFLOW | GS_OUT_FULL))) break;
+      if (cap > (1ULL << 28)) return -101;
+    }
+    pack.resize(out.npack + out.pack_off);
+    hb.outs[i] = out;
+    hb.tier[i] = tier;
+    hb.pack_of[i] = (int)i;
+    hb.packs[i].swap(pack);
+    hb.gaps[i].kmer_left = hb.gaps[i].kmer_right = nullptr;
+  }
+  hb.analyze(1);
+  return 0;
+}
+
+// same contract as g2s_fill_batch; cap0 > 0 forces the first tier's cell capacity (to exercise tier escalation)
+int emul_fill_batch(void *gp, int k, const g2s_gap *gaps, size_t n, g2s_result *results, char *const *fill_out, int cap0) {
+  HostBatch hb;
+  int rc = emul_submit((EmulGraph *)gp, k, gaps, n, hb, cap0);
+  if (rc) return rc;
+  for (size_t i = 0; i < n; i++) hb.trace(i, results[i], fill_out ? fill_out[i] : nullptr);
+  return 0;
+}
+
+// same contract as g2s_fill_records
+int emul_fill_records(void *gp, const char *const *seqs, const char *const *comments, size_t n_records,
+                      const g2s_run_options *opt, char **filled_out, char **log_out, int32_t *gapcount, int32_t *filledcount,
+                      g2s_result **gap_results, size_t *n_gap_results) {
+  std::vector<std::string> s(n_records), c(n_records);
+  for (size_t i = 0; i < n_records; i++) { s[i] = seqs[i]; c[i] = comments[i]; }
+  RunOptions ro;
+  ro.k = opt->k; ro.d_err = opt->dist_error; ro.max_fuz = opt->fuz;
+  ro.skip_confident = opt->skip_confident != 0; ro.unique_paths = opt->unique_paths != 0; ro.all_paths = opt->all_paths != 0;
+  ScaffoldRun run(s, c, ro);
+  SubmitFn submit = [&](const std::vector<g2s_gap> &gaps, HostBatch &hb) -> int {
+    return emul_submit((EmulGraph *)gp, opt->k, gaps.data(), gaps.size(), hb, 0);
+  };
+  std::vector<std::string> filled;
+  std::string log;
+  int gc = 0, fc = 0;
+  std::vector<g2s_result> details;
+  int rc = run.run(submit, filled, log, gc, fc, &details);
+  if (rc) return rc;
+  for (size_t i = 0; i < n_records; i++) filled_out[i] = strdup(filled[i].c_str());
+  *log_out = strdup(log.c_str());
+  *gapcount = gc; *filledcount = fc;
+  if (gap_results) {
+    *n_gap_results = details.size();
+    *gap_results = (g2s_result *)malloc((details.size() + 1) * sizeof(g2s_result));
+    memcpy(*gap_results, details.data(), details.size() * sizeof(g2s_result));
+  }
+  return 0;
+}
+
+void emul_free(void *p) { free(p); }
+
+}  // extern "C"
