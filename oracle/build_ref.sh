@@ -46,4 +46,6 @@ g++ $CXXF $INC "$REF/src/Gap2Seq.cpp" "$REF/src/main.cpp" $LIB -o "$OUT/bin/Gap2
 g++ $CXXF -DSTATS $INC "$REF/src/Gap2Seq.cpp" "$REF/src/main.cpp" $LIB -o "$OUT/bin/Gap2Seq-core-stats"
 g++ $CXXF $INC "$REF/src/GapCutter.cpp" $LIB -o "$OUT/bin/GapCutter"
 g++ $CXXF $INC "$REF/src/GapMerger.cpp" $LIB -o "$OUT/bin/GapMerger"
+# the GATB build tree (200 MB of objects) is scratch: only the binaries stay
+rm -rf "$BLD"
 echo "build_ref: done -> $OUT/bin" >&2
