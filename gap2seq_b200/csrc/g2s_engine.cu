@@ -274,7 +274,7 @@ static int do_upload(g2s_engine *e, const g2s_gap *gaps, size_t n) {
         g.right_max_fuz > e->cfg.max_fuz)
       return fail(G2S_E_ARG, "gap parameters out of range (fuz must be <= g2s_config.max_fuz)");
     if ((long long)g.gap_len + g.gap_err > (1 << 24)) return fail(G2S_E_ARG, "gap_len + gap_err too large");
-    fbytes += (size_t)2 * k + g.left_max_fuz + g.right_max_fuz;
+    fbytes += (size_t)2 * k + g.left_max_fuz + g.right_max_fuz + (g.kmer_right_starts ? (size_t)k + g.right_max_fuz : 0);
     e->max_dmax = std::max(e->max_dmax, dmax_of(g));
     e->max_rmf = std::max(e->max_rmf, std::max(g.right_max_fuz, g.left_max_fuz));
   }
@@ -287,11 +287,18 @@ static int do_upload(g2s_engine *e, const g2s_gap *gaps, size_t n) {
     memcpy(&e->flank_store[off], g.kmer_left, (size_t)k + g.left_max_fuz);
     g.kmer_left = nullptr;
     off += (size_t)k + g.left_max_fuz;
+    d.rstart_off = (uint32_t)off;
     memcpy(&e->flank_store[off], g.kmer_right, (size_t)k + g.right_max_fuz);
     g.kmer_right = nullptr;
     off += (size_t)k + g.right_max_fuz;
+    if (g.kmer_right_starts) {
+      d.rstart_off = (uint32_t)off;
+      memcpy(&e->flank_store[off], g.kmer_right_starts, (size_t)k + g.right_max_fuz);
+      g.kmer_right_starts = nullptr;
+      off += (size_t)k + g.right_max_fuz;
+    }
     d.gap_len = g.gap_len; d.gap_err = g.gap_err; d.lmf = g.left_max_fuz; d.rmf = g.right_max_fuz;
-    d.flags = (uint32_t)g.flags; d.id = (uint32_t)i; d.pad = 0;
+    d.flags = (uint32_t)g.flags; d.id = (uint32_t)i;
   }
   if (fbytes >= (1ULL << 32)) return fail(G2S_E_ARG, "batch too large");
   CUDA_TRY(e->d_flanks.reserve(fbytes + 16));
@@ -498,6 +505,10 @@ extern "C" int g2s_fill_gap(g2s_engine *e, const char *kmer_left, const char *km
   if (!left_fuz || !right_fuz || !fill) return fail(G2S_E_ARG, "g2s_fill_gap: null output");
   g2s_gap g{};
   g.kmer_left = kmer_left; g.kmer_right = kmer_right;
+  const size_t rlen = strlen(kmer_right);
+  if (strlen(kmer_left) < (size_t)k + left_max_fuz || rlen < (size_t)k + right_max_fuz)
+    return fail(G2S_E_ARG, "g2s_fill_gap: flank shorter than k + max_fuz");
+  if (rlen > (size_t)k + right_max_fuz) g.kmer_right_starts = kmer_right + (rlen - k - right_max_fuz);
   g.gap_len = gap_len; g.gap_err = gap_err; g.left_max_fuz = left_max_fuz; g.right_max_fuz = right_max_fuz;
   g.flags = (skip_confident ? G2S_GAP_SKIP_CONFIDENT : 0) | (all_paths ? G2S_GAP_ALL_PATHS : 0);
   g2s_result r;

@@ -89,7 +89,9 @@ struct GapDev {        // 32 B input descriptor
   int32_t gap_len, gap_err, lmf, rmf;
   uint32_t flags;      // G2S_GAP_* of include/g2s.h
   uint32_t id;         // position in the caller's batch
-  uint32_t pad;
+  uint32_t rstart_off; // k+rmf chars whose k-mers START the right pass: fill_gap takes them from the END of kmer_right
+                       // (Gap2Seq.cpp:871-885, 953-957) but the targets from its beginning (Gap2Seq.cpp:1119); the two
+                       // differ only when kmer_right is longer than k+right_max_fuz (single-gap mode, Gap2Seq.cpp:239-252)
 };
 
 enum {  // GapOut.status (device side)
@@ -303,7 +305,7 @@ G2S_D void process_gap(const FillParams &P, const GapDev &gd, const Slice &S, GS
   const int right_half = rmf + (g + e + 1) / 2;           // rmf + ceil((g+e)/2), Gap2Seq.cpp:862
   const int Dmax = g + e + lmf + rmf;                      // right_half + left_half, Gap2Seq.cpp:863
   const int prune_from = g / 2 + e / 2 + lmf;              // two integer divisions, Gap2Seq.cpp:1050
-  const char *lstr = P.flanks + gd.flank_off, *rstr = lstr + k + lmf;
+  const char *lstr = P.flanks + gd.flank_off, *rstr = lstr + k + lmf, *rsstr = P.flanks + gd.rstart_off;
   const size_t trow = (size_t)S.max_levels + 1;
 
   // ---- init: clear the node table, thit and the per-level counters; parse the flanks
@@ -343,12 +345,10 @@ G2S_D void process_gap(const FillParams &P, const GapDev &gd, const Slice &S, GS
     uint32_t n = 0;
     int cur = 0;
     if (rank == 0) {
-      uint64_t x = S.rk[rmf];
-      if (x & FLANK_PRESENT) {
-        x &= FLANK_KMER;
-        Canon c = canonical(x, k);
-        uint32_t adj = 0;
-        table_find(T, c.key, &adj);
+      uint64_t x = kmer_from_ascii(rsstr + rmf, k);
+      Canon c = canonical(x, k);
+      uint32_t adj = 0;
+      if (table_find(T, c.key, &adj) >= 0) {
         uint32_t en = node_insert(S, sh, c.key);
         if (en != NONE32) {
           S.ent[en].rstamp = 2 + c.strand;
@@ -393,12 +393,10 @@ G2S_D void process_gap(const FillParams &P, const GapDev &gd, const Slice &S, GS
       }
       G::sync();
       if (rank == 0 && c <= rmf) {   // next staggered right start (Gap2Seq.cpp:953-968)
-        uint64_t x = S.rk[rmf - c];
-        if (x & FLANK_PRESENT) {
-          x &= FLANK_KMER;
-          Canon cs = canonical(x, k);
-          uint32_t adj = 0;
-          table_find(T, cs.key, &adj);
+        uint64_t x = kmer_from_ascii(rsstr + (rmf - c), k);
+        Canon cs = canonical(x, k);
+        uint32_t adj = 0;
+        if (table_find(T, cs.key, &adj) >= 0) {
           uint32_t en = node_insert(S, sh, cs.key);
           if (en != NONE32) {
             a_or(&S.ent[en].flags, NF_IN_RS);

@@ -40,7 +40,8 @@ class G2SSubgraphStats(C.Structure):
 
 class G2SGap(C.Structure):
     _fields_ = [("kmer_left", C.c_char_p), ("kmer_right", C.c_char_p), ("gap_len", C.c_int32), ("gap_err", C.c_int32),
-                ("left_max_fuz", C.c_int32), ("right_max_fuz", C.c_int32), ("flags", C.c_int32), ("reserved", C.c_int32)]
+                ("left_max_fuz", C.c_int32), ("right_max_fuz", C.c_int32), ("flags", C.c_int32), ("reserved", C.c_int32),
+                ("kmer_right_starts", C.c_char_p)]
 
 
 class G2SResult(C.Structure):
@@ -119,6 +120,7 @@ class GapSpec:
     right_max_fuz: int = 10
     skip_confident: bool = False
     all_paths: bool = True
+    right_starts: str | None = None   # see g2s_gap.kmer_right_starts (right flank longer than k + right_max_fuz)
 
     def fill_capacity(self, k: int) -> int:
         return self.gap_len + k + self.gap_err + self.left_max_fuz + self.right_max_fuz + 3
@@ -135,6 +137,10 @@ def pack_gaps(gaps: list[GapSpec]):
         arr[i].gap_len, arr[i].gap_err = g.gap_len, g.gap_err
         arr[i].left_max_fuz, arr[i].right_max_fuz = g.left_max_fuz, g.right_max_fuz
         arr[i].flags = (GAP_SKIP_CONFIDENT if g.skip_confident else 0) | (GAP_ALL_PATHS if g.all_paths else 0)
+        if g.right_starts is not None:
+            rs = g.right_starts.encode()
+            keep.append(rs)
+            arr[i].kmer_right_starts = rs
     return arr, keep
 
 

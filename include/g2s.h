@@ -75,6 +75,10 @@ typedef struct g2s_gap {
   int32_t gap_len, gap_err, left_max_fuz, right_max_fuz;
   int32_t flags;            /* G2S_GAP_* */
   int32_t reserved;
+  const char *kmer_right_starts; /* NULL (= kmer_right) or k + right_max_fuz characters whose k-mers start the right
+                               pass.  fill_gap takes those from the END of its kmer_right string but the targets from its
+                               beginning (src/Gap2Seq.cpp:871-885 vs :1119); they differ only when the caller's right flank
+                               is longer than k + right_max_fuz, which single-gap mode allows (src/Gap2Seq.cpp:239-252) */
 } g2s_gap;
 
 typedef struct g2s_result {

@@ -73,10 +73,15 @@ static int emul_submit(EmulGraph *g, int k, const g2s_gap *gaps, size_t n, HostB
   hb.packs.assign(n, std::vector<PackRec>());
   for (size_t i = 0; i < n; i++) {
     const g2s_gap &gg = gaps[i];
-    std::vector<char> flanks((size_t)2 * k + gg.left_max_fuz + gg.right_max_fuz + 1);
+    std::vector<char> flanks((size_t)3 * k + gg.left_max_fuz + 2 * gg.right_max_fuz + 1);
     memcpy(flanks.data(), gg.kmer_left, (size_t)k + gg.left_max_fuz);
     memcpy(flanks.data() + k + gg.left_max_fuz, gg.kmer_right, (size_t)k + gg.right_max_fuz);
     GapDev gd{};
+    gd.rstart_off = (uint32_t)(k + gg.left_max_fuz);
+    if (gg.kmer_right_starts) {
+      gd.rstart_off = (uint32_t)(2 * k + gg.left_max_fuz + gg.right_max_fuz);
+      memcpy(flanks.data() + gd.rstart_off, gg.kmer_right_starts, (size_t)k + gg.right_max_fuz);
+    }
     gd.flank_off = 0; gd.gap_len = gg.gap_len; gd.gap_err = gg.gap_err; gd.lmf = gg.left_max_fuz; gd.rmf = gg.right_max_fuz;
     gd.flags = (uint32_t)gg.flags; gd.id = (uint32_t)i;
     const int dmax = gg.gap_len + gg.gap_err + gg.left_max_fuz + gg.right_max_fuz;

@@ -59,12 +59,42 @@ def run_case(case: cases.Case) -> None:
         shutil.rmtree(tmp, ignore_errors=True)
 
 
+def run_single_gap() -> None:
+    """Single-gap mode (-left/-right/-length, src/Gap2Seq.cpp:227-283) with flanks LONGER than k+fuz: the right pass then
+    starts from the end of the right flank while the targets sit at its beginning."""
+    case = cases.CASE_BY_NAME["cfg1_small"]
+    w = cases.build(case)
+    tmp = tempfile.mkdtemp(prefix="g2s_golden_")
+    try:
+        paths = w.write(tmp)
+        out_fa, out_log = [], []
+        for gi, (fl, fr) in enumerate([(41, 41), (60, 55), (35, 48)]):
+            rec = w.gaps[gi]
+            i = rec.seq.index("N")
+            left, right = rec.seq[i - fl:i], rec.seq[i + rec.gap_len:i + rec.gap_len + fr]
+            cmd = [REF_PLAIN] + cases.ref_cmd_flags(case) + ["-reads", paths["reads"], "-filled", os.path.join(tmp, "f.fa"),
+                                                           "-left", left, "-right", right, "-length", str(rec.gap_len)]
+            p = subprocess.run(" ".join(cmd), shell=True, cwd=tmp, capture_output=True, text=True, timeout=600)
+            assert p.returncode == 0, p.stdout[-2000:]
+            out_fa.append(open(os.path.join(tmp, "f.fa")).read())
+            out_log.append(cases.filter_log(p.stdout))
+        fa, log = cases.golden_paths("single_gap")
+        open(fa, "w").write("".join(out_fa))
+        open(log, "w").write("".join(out_log))
+        print("single_gap:", [len(x) for x in out_fa], out_log[1].strip()[:120])
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
 def main() -> None:
     if not os.path.exists(REF):
         sys.exit("oracle/_ref is not built: run oracle/build_ref.sh in the container that has /root/reference")
-    names = sys.argv[1:] or [c.name for c in cases.CASES]
+    names = sys.argv[1:] or [c.name for c in cases.CASES] + ["single_gap"]
     for n in names:
-        run_case(cases.CASE_BY_NAME[n])
+        if n == "single_gap":
+            run_single_gap()
+        else:
+            run_case(cases.CASE_BY_NAME[n])
 
 
 if __name__ == "__main__":

@@ -35,7 +35,7 @@ def test_no_cpu_fallback_without_device():
 
 
 def test_struct_sizes_match_header():
-    assert C.sizeof(engine.G2SGap) == 40
+    assert C.sizeof(engine.G2SGap) == 48
     assert C.sizeof(engine.G2SResult) == 48 + 48 + 24
     assert C.sizeof(engine.G2SConfig) == 32
 

@@ -34,3 +34,30 @@ def test_emulated_adjacency_matches_oracle(case_inputs, emul_engine):
     case, w, g = case_inputs("cfg2_small")
     keys, adj = g.kmers(with_adjacency=True)
     assert (emul_engine("cfg2_small").adjacency(keys) == adj).all()
+
+
+def single_gap_inputs(w):
+    out = []
+    for gi, (fl, fr) in enumerate([(41, 41), (60, 55), (35, 48)]):
+        rec = w.gaps[gi]
+        i = rec.seq.index("N")
+        out.append((rec.seq[i - fl:i], rec.seq[i + rec.gap_len:i + rec.gap_len + fr], rec.gap_len))
+    return out
+
+
+def test_single_gap_mode_with_long_flanks(case_inputs, emul_engine):
+    """-left/-right/-length (src/Gap2Seq.cpp:227-283): flanks longer than k+fuz; the right pass starts from the END of the
+    right flank (kmer_right_starts), the targets sit at its beginning."""
+    from gap2seq_b200.engine import GapSpec
+    import oracle_lib
+    case, w, g = case_inputs("cfg1_small")
+    eng = emul_engine("cfg1_small")
+    k, fuz = w.k, w.fuz
+    want = open(cases.golden_paths("single_gap")[0]).read().split(">\n")[1:]
+    for (left, right, length), gold in zip(single_gap_inputs(w), want):
+        lmf, rmf = min(len(left) - k, fuz), min(len(right) - k, fuz)
+        spec = GapSpec(left[:k + lmf], right[:k + rmf], length, 500, lmf, rmf, right_starts=right[len(right) - k - rmf:])
+        oracle_lib.srand(1)
+        (r,), (fill,) = eng.fill_batch([spec])
+        assert r.count == 1
+        assert left[:len(left) - r.left_fuz] + fill == gold.strip()
