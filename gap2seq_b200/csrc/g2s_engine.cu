@@ -196,7 +196,7 @@ static int plan_pass(g2s_engine *e, Pass &p) {
   if (cap0 < 4096) cap0 = 4096;
   uint64_t cap = cap0;
   for (int t = 0; t < p.tier; t++) cap *= 16;
-  uint32_t hlog = p.tier == 0 ? ceil_log2(2 * cap) : std::max<uint32_t>(16, ceil_log2(cap / 4));
+  uint32_t hlog = p.tier == 0 ? ceil_log2(3 * ((uint64_t)e->max_dmax + 64)) : std::max<uint32_t>(16, ceil_log2(cap / 4));
   p.lay = make_layout(cap, hlog, (uint32_t)e->max_dmax + 1, (uint32_t)e->max_rmf + 1);
   if (cap >= (1ULL << 31) || p.lay.bytes > e->budget) return -1;   // largest tier exceeded
   size_t fit = e->budget / p.lay.bytes;

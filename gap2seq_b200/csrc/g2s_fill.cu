@@ -8,7 +8,7 @@
 
 namespace g2s {
 
-static const int WARPS_PER_CTA = 4;
+static const int WARPS_PER_CTA = 1;   // one warp group per CTA: few long gaps spread over all SMs
 static const int CTA_THREADS = 512;
 
 struct WarpGroup {

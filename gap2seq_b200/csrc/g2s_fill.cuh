@@ -119,7 +119,7 @@ struct SliceLayout {   // byte offsets inside one scratch slice; identical for e
   unsigned long long bytes;
   uint32_t cap_cells, hash_log2, max_levels, max_fuz1;
   unsigned long long off_hash, off_ck, off_cc, off_cn, off_cp, off_cflags, off_packidx, off_packlist, off_packlevel,
-      off_lstart, off_nB, off_thit, off_lk, off_rk;
+      off_lstart, off_nB, off_lrun, off_thit, off_lk, off_rk;
 };
 
 struct FillParams {
@@ -137,6 +137,8 @@ struct FillParams {
   uint32_t *queue_head;
 };
 
+static const int CHAIN_LEN = 32;   // levels a chain batch looks ahead
+
 struct GShared {       // per group, in shared memory
   uint32_t ncells, nnodes, nnext, status;
   uint32_t npack, nB, n_edges, n_src, n_sink;
@@ -151,6 +153,12 @@ struct GShared {       // per group, in shared memory
   unsigned long long pack_off;
   uint32_t fc1[MAX_FUZ + 1], fc2[MAX_FUZ + 1];
   uint32_t queue_item;
+  // chain mode (a border of exactly one cell): the scout's look-ahead and the bulk backward marking
+  uint32_t ch_len, ch_valid, ch_base, ch_cnt;
+  int32_t tlo;          // first level that has thit entries: max(0, g + lmf - e)
+  uint32_t trow;        // entries per target row: Dmax - tlo + 1
+  uint64_t ch_s[CHAIN_LEN];
+  uint32_t ch_a[CHAIN_LEN], ch_e[CHAIN_LEN];
 };
 
 struct Slice {         // typed view of one scratch slice
@@ -159,7 +167,7 @@ struct Slice {         // typed view of one scratch slice
   uint64_t *ck;
   uint32_t *cc, *cn;
   uint32_t *cp;        // 4 per cell
-  uint32_t *cflags, *packidx, *packlist, *packlevel, *lstart, *nB, *thit;
+  uint32_t *cflags, *packidx, *packlist, *packlevel, *lstart, *nB, *lrun, *thit;
   uint64_t *lk, *rk;   // oriented flank k-mers; bit 63 set = present in the graph; bits 62..: unused
   uint32_t cap_cells, max_levels;
   // right-border ping-pong buffers alias the (not yet used) cell arrays during Phase R
@@ -182,6 +190,7 @@ G2S_HD Slice make_slice(unsigned char *base, const SliceLayout &L) {
   s.packlevel = (uint32_t *)(base + L.off_packlevel);
   s.lstart = (uint32_t *)(base + L.off_lstart);
   s.nB = (uint32_t *)(base + L.off_nB);
+  s.lrun = (uint32_t *)(base + L.off_lrun);
   s.thit = (uint32_t *)(base + L.off_thit);
   s.lk = (uint64_t *)(base + L.off_lk);
   s.rk = (uint64_t *)(base + L.off_rk);
@@ -213,6 +222,7 @@ inline SliceLayout make_layout(uint64_t cap_cells, uint32_t hash_log2, uint32_t 
   L.off_packlevel = take(cap_cells * 4);
   L.off_lstart = take(((size_t)max_levels + 3) * 4);
   L.off_nB = take(((size_t)max_levels + 3) * 4);
+  L.off_lrun = take(((size_t)max_levels + 3) * 4);
   L.off_thit = take((size_t)max_fuz1 * ((size_t)max_levels + 1) * 4);
   L.off_lk = take((size_t)max_fuz1 * 8);
   L.off_rk = take((size_t)max_fuz1 * 8);
@@ -269,29 +279,228 @@ G2S_D uint32_t new_cell(const Slice &S, GShared &sh, const GapDev &gd, uint64_t 
   S.cflags[idx] = out_mask(adj, strand) << CF_OMASK_SHIFT;
   S.ent[e].fcell[strand] = idx;
   uint32_t fl = a_or(&S.ent[e].flags, NF_HAS_F);
-  if (fl & NF_TARGET) {
+  if ((fl & NF_TARGET) && (int)c >= sh.tlo) {
     for (int j = 0; j <= gd.rmf; j++)
-      if ((S.rk[j] & FLANK_KMER) == s) S.thit[(size_t)j * (S.max_levels + 1) + c] = idx + 1;
+      if ((S.rk[j] & FLANK_KMER) == s) S.thit[(size_t)j * sh.trow + (c - (uint32_t)sh.tlo)] = idx + 1;
   }
   return idx;
 }
 
-G2S_D uint32_t thit_count(const Slice &S, int j, int level) {
-  if (level < 0 || (uint32_t)level > S.max_levels) return 0;
-  uint32_t t = ld_cg(&S.thit[(size_t)j * (S.max_levels + 1) + level]);
+// thit holds, for target j and level d >= tlo, the cell of (rnode(j), d) + 1.  Levels below tlo = g + lmf - e are
+// never looked up: the found check reads lengths >= g + lmf - err, the seeds levels >= lmf + g - e.
+G2S_D uint32_t thit_get(const Slice &S, const GShared &sh, int j, int level) {
+  if (level < sh.tlo || (uint32_t)(level - sh.tlo) >= sh.trow) return 0;
+  return ld_cg(&S.thit[(size_t)j * sh.trow + (uint32_t)(level - sh.tlo)]);
+}
+G2S_D uint32_t thit_count(const Slice &S, const GShared &sh, int j, int level) {
+  const uint32_t t = thit_get(S, sh, j, level);
   return t ? clamp_paths(ld_cg(&S.cc[t - 1])) : 0;
 }
 
 // The first-found check of level c (Gap2Seq.cpp:1108-1154), evaluated by ONE thread.  Returns true when found.
-G2S_D bool found_at_level(const Slice &S, const GapDev &gd, int c, int *J, uint32_t *c1, uint32_t *c2, int *l1, int *l2) {
+G2S_D bool found_at_level(const Slice &S, const GShared &sh, const GapDev &gd, int c, int *J, uint32_t *c1, uint32_t *c2, int *l1, int *l2) {
   const int err = c - gd.gap_len - gd.lmf - gd.rmf;
   for (int j = 0; j <= gd.rmf; j++) {
     int len1 = gd.gap_len + gd.lmf + j + err, len2 = gd.gap_len + gd.lmf + j - err;
-    uint32_t a = thit_count(S, j, len1);
-    uint32_t b = (len2 != len1 && len2 >= 0) ? thit_count(S, j, len2) : 0;
+    uint32_t a = thit_count(S, sh, j, len1);
+    uint32_t b = (len2 != len1 && len2 >= 0) ? thit_count(S, sh, j, len2) : 0;
     if (a | b) { *J = j; *c1 = a; *c2 = b; *l1 = len1; *l2 = len2; return true; }
   }
   return false;
+}
+
+// Collective: first level in [lo, hi] whose found check succeeds (one level per thread); fills the shared found
+// state like the per-level check does.  Returns true when a level was found.
+template <class G>
+G2S_D bool found_scan(const Slice &S, const GapDev &gd, GShared &sh, int lo, int hi) {
+  for (int c = lo + G::rank(); c <= hi; c += G::size()) {
+    int J = 0, l1 = 0, l2 = 0; uint32_t c1 = 0, c2 = 0;
+    if (found_at_level(S, sh, gd, c, &J, &c1, &c2, &l1, &l2)) { a_mini(&sh.found_level, c); break; }
+  }
+  G::sync();
+  const int fl = ld_sh(&sh.found_level);
+  const bool found = fl <= hi;
+  if (found && G::rank() == 0) {
+    int J = 0, l1 = 0, l2 = 0; uint32_t c1 = 0, c2 = 0;
+    found_at_level(S, sh, gd, fl, &J, &c1, &c2, &l1, &l2);
+    sh.reached_fuz = J;
+    uint64_t tot = 0; uint32_t n = 0;
+    if (c1) { tot += c1; sh.plen[n++] = l1; }
+    if (c2) { tot += c2; sh.plen[n++] = l2; }
+    sh.n_plen = n;
+    sh.count_fwd = tot > MAX_PATHS ? MAX_PATHS : (uint32_t)tot;
+  }
+  G::sync();
+  return found;
+}
+
+// ---- chain mode.  While a border holds exactly ONE state with exactly one neighbour, the only true dependency
+// between levels is the adjacency byte of the next k-mer (it decides which base comes after it).  One thread (the
+// scout) therefore walks up to CHAIN_LEN levels ahead through the global table - one dependent gather per level -
+// and the whole group then does everything else for those levels (node table, prune test, cells, links, target
+// hits) in parallel, one level per thread.  Results are identical to the level-by-level path.
+
+// Right pass: advances the single-node border S.fk[cur][0] by up to CHAIN_LEN levels starting with level c.
+template <class G>
+G2S_D int chain_right(const Table &T, const Slice &S, GShared &sh, int cur, int c, int right_half) {
+  const int k = T.k;
+  if (G::rank() == 0) {
+    uint64_t x = S.fk[cur][0];
+    uint32_t im = S.fm[cur][0];
+    int len = 0;
+    const int maxlen = right_half - c + 1 < CHAIN_LEN ? right_half - c + 1 : CHAIN_LEN;
+    while (len < maxlen && (im == 1 || im == 2 || im == 4 || im == 8)) {
+      const uint32_t nt = im == 1 ? 0 : im == 2 ? 1 : im == 4 ? 2 : 3;
+      const uint64_t p = pred_kmer(x, nt, T);
+      const Canon cp = canonical(p, k);
+      uint32_t adj = 0;
+      if (table_find(T, cp.key, &adj) < 0) { a_or(&sh.status, GS_INTERNAL); break; }
+      sh.ch_s[len] = p; sh.ch_a[len] = adj | (cp.strand << 8);
+      len++;
+      x = p; im = in_mask(adj, cp.strand);
+    }
+    sh.ch_len = (uint32_t)len;
+    if (len) { S.fk[cur][0] = x; S.fm[cur][0] = (unsigned char)im; sh.cells_right += (uint32_t)len; }
+  }
+  G::sync();
+  const int len = (int)ld_sh(&sh.ch_len);
+  for (int t = G::rank(); t < len; t += G::size()) {
+    const Canon cp = canonical(sh.ch_s[t], k);
+    const uint32_t en = node_insert(S, sh, cp.key);
+    if (en == NONE32) continue;
+    a_or(&S.ent[en].flags, NF_IN_RS);
+    a_max(&S.ent[en].rstamp, (uint32_t)(c + t + 1) * 2 + cp.strand);
+  }
+  G::sync();
+  return len;
+}
+
+// Forward pass: the border of level c-1 is the single cell `lo`.  Creates the cells of levels c .. c+ret-1.
+template <class G>
+G2S_D int chain_forward(const Table &T, const Slice &S, GShared &sh, const GapDev &gd, uint32_t lo, int c, int Dmax,
+                        int prune_from) {
+  const int k = T.k;
+  if (G::rank() == 0) {
+    uint64_t x = ld_cg(&S.ck[lo]);
+    uint32_t om = (ld_cg(&S.cflags[lo]) >> CF_OMASK_SHIFT) & 15u;
+    int len = 0;
+    const int maxlen = Dmax - c + 1 < CHAIN_LEN ? Dmax - c + 1 : CHAIN_LEN;
+    while (len < maxlen && (om == 1 || om == 2 || om == 4 || om == 8)) {
+      const uint32_t nt = om == 1 ? 0 : om == 2 ? 1 : om == 4 ? 2 : 3;
+      const uint64_t s = succ_kmer(x, nt, T);
+      const Canon cs = canonical(s, k);
+      uint32_t adj = 0;
+      if (table_find(T, cs.key, &adj) < 0) { a_or(&sh.status, GS_INTERNAL); break; }
+      sh.ch_s[len] = s; sh.ch_a[len] = adj | (cs.strand << 8);
+      len++;
+      x = s; om = out_mask(adj, cs.strand);
+    }
+    sh.ch_len = (uint32_t)len;
+    sh.ch_valid = (uint32_t)len;
+    sh.ch_base = sh.ncells;
+  }
+  G::sync();
+  const int len = (int)ld_sh(&sh.ch_len);
+  if (len == 0) return 0;
+  // node table + prune test, one level per thread
+  for (int t = G::rank(); t < len; t += G::size()) {
+    const Canon cs = canonical(sh.ch_s[t], k);
+    uint32_t en;
+    bool ok;
+    if (c + t < prune_from) { en = node_insert(S, sh, cs.key); ok = en != NONE32; }
+    else { en = node_find(S, cs.key); ok = en != NONE32 && (ld_cg(&S.ent[en].flags) & NF_IN_RS); }
+    sh.ch_e[t] = en;
+    if (!ok) a_mini((int32_t *)&sh.ch_valid, t);
+  }
+  G::sync();
+  const int len2 = (int)ld_sh(&sh.ch_valid);   // levels before the first pruned one
+  const uint32_t base = ld_sh(&sh.ch_base);
+  if ((ld_sh(&sh.status) & GS_OVERFLOW) || (uint64_t)base + len2 > S.cap_cells) { a_or(&sh.status, GS_OVERFLOW); G::sync(); return 0; }
+  const uint32_t np = clamp_paths(ld_cg(&S.cc[lo]));   // the count rides along a chain unchanged
+  const uint32_t run_first = ld_cg(&S.lrun[c - 1]) ? ld_cg(&S.lrun[c - 1]) : (uint32_t)c;
+  for (int t = G::rank(); t < len2; t += G::size()) {
+    const uint32_t idx = base + t, level = (uint32_t)(c + t);
+    const uint64_t s = sh.ch_s[t];
+    const uint32_t adj = sh.ch_a[t] & 0xFF, strand = sh.ch_a[t] >> 8, en = sh.ch_e[t];
+    const uint64_t prev = t ? sh.ch_s[t - 1] : ld_cg(&S.ck[lo]);
+    const uint32_t u0 = (uint32_t)(prev >> (2 * (k - 1))) & 3u;
+    S.ck[idx] = s; S.cc[idx] = np; S.cn[idx] = en;
+    S.cp[4 * idx + 0] = NONE32; S.cp[4 * idx + 1] = NONE32; S.cp[4 * idx + 2] = NONE32; S.cp[4 * idx + 3] = NONE32;
+    S.cp[4 * idx + u0] = t ? idx - 1 : lo;
+    S.cflags[idx] = out_mask(adj, strand) << CF_OMASK_SHIFT;
+    a_max(&S.ent[en].fstamp[strand], level + 1);
+    S.ent[en].fcell[strand] = idx;
+    const uint32_t fl = a_or(&S.ent[en].flags, NF_HAS_F);
+    if ((fl & NF_TARGET) && (int)level >= sh.tlo) {
+      for (int j = 0; j <= gd.rmf; j++)
+        if ((S.rk[j] & FLANK_KMER) == s) S.thit[(size_t)j * sh.trow + (level - (uint32_t)sh.tlo)] = idx + 1;
+    }
+    S.lstart[level + 1] = idx + 1;
+    S.lrun[level] = run_first;
+  }
+  if (G::rank() == 0) {
+    sh.ncells = base + (uint32_t)len2;
+    if (len2 < len) S.lstart[c + len2 + 1] = base + (uint32_t)len2;   // the next level is empty: its only candidate was pruned
+  }
+  G::sync();
+  return len2;
+}
+
+// Backward marking of a run of chain levels [rs, d] (single cell per level, single link to the level below): the
+// marks of the upper cells flow down unconditionally, so the run is processed CHAIN_LEN levels at a time.
+template <class G>
+G2S_D void chain_mark(const Slice &S, GShared &sh, int rs, int d) {
+  const uint32_t top_cell = ld_cg(&S.lstart[d]);
+  uint32_t carry = 0;   // meaningful on rank 0 only
+  for (int hi = d; hi >= rs; hi -= CHAIN_LEN) {
+    const int n = hi - rs + 1 < CHAIN_LEN ? hi - rs + 1 : CHAIN_LEN;
+    for (int t = G::rank(); t < n; t += G::size()) sh.ch_a[t] = ld_cg(&S.cflags[top_cell - (uint32_t)(d - (hi - t))]);
+    G::sync();
+    if (G::rank() == 0) {
+      uint32_t cnt = 0, nb = 0;
+      for (int t = 0; t < n; t++) {
+        carry |= sh.ch_a[t] & (CF_B | CF_T);
+        sh.ch_a[t] = (sh.ch_a[t] & ~(uint32_t)(CF_B | CF_T)) | carry;
+        sh.ch_e[t] = carry ? cnt++ : NONE32;
+        if (carry & CF_B) nb++;
+      }
+      sh.ch_base = sh.npack;
+      sh.npack += cnt;
+      sh.nB += nb;
+      sh.n_edges += nb;   // every chain cell has exactly one predecessor and is no start cell (level > lmf)
+    }
+    G::sync();
+    const uint32_t base = ld_sh(&sh.ch_base);
+    for (int t = G::rank(); t < n; t += G::size()) {
+      if (sh.ch_e[t] == NONE32) continue;
+      const int level = hi - t;
+      const uint32_t i = top_cell - (uint32_t)(d - level), f = sh.ch_a[t], pi = base + sh.ch_e[t];
+      S.cflags[i] = f;
+      S.packidx[i] = pi; S.packlist[pi] = i; S.packlevel[pi] = (uint32_t)level;
+      if (f & CF_B) {
+        a_add(&S.nB[level], 1);
+        const uint32_t en = S.cn[i];
+        uint32_t fl = ld_cg(&S.ent[en].flags);
+        for (;;) {
+          const uint32_t lv = fl >> 8;
+          if (lv == 0) {
+            const uint32_t old = a_cas(&S.ent[en].flags, fl, fl | ((uint32_t)(level + 1) << 8));
+            if (old == fl) break;
+            fl = old;
+          } else {
+            a_or(&sh.status, lv != (uint32_t)level + 1 ? GS_GENERAL : GS_ORDER_DEPENDENT);
+            break;
+          }
+        }
+      }
+    }
+    G::sync();
+  }
+  if (G::rank() == 0 && carry) {   // hand the marks to the (general) level below the run
+    const uint32_t i = top_cell - (uint32_t)(d - rs);
+    for (int q = 0; q < 4; q++) { const uint32_t p = S.cp[4 * i + q]; if (p != NONE32) a_or(&S.cflags[p], carry); }
+  }
+  G::sync();
 }
 
 // ------------------------------------------------------------------------------------------------ one gap
@@ -306,7 +515,8 @@ G2S_D void process_gap(const FillParams &P, const GapDev &gd, const Slice &S, GS
   const int Dmax = g + e + lmf + rmf;                      // right_half + left_half, Gap2Seq.cpp:863
   const int prune_from = g / 2 + e / 2 + lmf;              // two integer divisions, Gap2Seq.cpp:1050
   const char *lstr = P.flanks + gd.flank_off, *rstr = lstr + k + lmf, *rsstr = P.flanks + gd.rstart_off;
-  const size_t trow = (size_t)S.max_levels + 1;
+  const int tlo = g + lmf - e > 0 ? g + lmf - e : 0;
+  const size_t trow = (size_t)(Dmax - tlo + 1);
 
   // ---- init: clear the node table, thit and the per-level counters; parse the flanks
   {
@@ -315,7 +525,7 @@ G2S_D void process_gap(const FillParams &P, const GapDev &gd, const Slice &S, GS
     for (uint32_t i = rank; i < S.hcap; i += gsz) { hz[2 * i] = z0; hz[2 * i + 1] = z1; }
     const size_t nth = trow * (size_t)(rmf + 1);
     for (size_t i = rank; i < nth; i += gsz) S.thit[i] = 0;
-    for (int i = rank; i <= Dmax + 1; i += gsz) { S.nB[i] = 0; S.lstart[i] = 0; }
+    for (int i = rank; i <= Dmax + 1; i += gsz) { S.nB[i] = 0; S.lstart[i] = 0; S.lrun[i] = 0; }
     for (int d = rank; d <= lmf; d += gsz) {
       uint64_t x = kmer_from_ascii(lstr + d, k);
       uint32_t adj;
@@ -329,6 +539,7 @@ G2S_D void process_gap(const FillParams &P, const GapDev &gd, const Slice &S, GS
       S.rk[j] = x | (table_find(T, c.key, &adj) >= 0 ? FLANK_PRESENT : 0);
     }
     if (rank == 0) {
+      sh.tlo = tlo; sh.trow = (uint32_t)trow;
       sh.ncells = 0; sh.nnodes = 0; sh.nnext = 0; sh.status = 0;
       sh.npack = 0; sh.nB = 0; sh.n_edges = 0; sh.n_src = 0; sh.n_sink = 0;
       sh.max_src_level = -1; sh.min_sink_level = 0x7fffffff;
@@ -363,6 +574,11 @@ G2S_D void process_gap(const FillParams &P, const GapDev &gd, const Slice &S, GS
     for (int c = 1; c <= right_half; c++) {
       if (n == 0 && c > rmf) break;
       levels_r = c;
+      if (n == 1 && c > rmf) {   // single-node border, no start left to inject: chain mode
+        const int adv = chain_right<G>(T, S, sh, cur, c, right_half);
+        if (ld_sh(&sh.status) & GS_OVERFLOW) break;
+        if (adv > 0) { levels_r = c + adv - 1; c += adv - 1; continue; }
+      }
       G::sync();
       if (rank == 0) sh.nnext = 0;
       G::sync();
@@ -462,6 +678,27 @@ G2S_D void process_gap(const FillParams &P, const GapDev &gd, const Slice &S, GS
     for (int c = 1; c <= Dmax; c++) {
       const uint32_t lo = ld_cg(&S.lstart[c - 1]), hi = ld_cg(&S.lstart[c]);
       const bool dead = (lo == hi) && c > lmf;   // empty border and no start left to inject
+      if (hi - lo == 1 && c > lmf) {   // single-cell border, no start left to inject: chain mode
+        const int adv = chain_forward<G>(T, S, sh, gd, lo, c, Dmax, prune_from);
+        if (ld_sh(&sh.status) & GS_OVERFLOW) { overflow = true; break; }
+        if (adv > 0) {
+          const int last = c + adv - 1;
+          top_level = levels_f = last;
+          if (!found && last >= g + lmf + rmf) {
+            found = found_scan<G>(S, gd, sh, c > g + lmf + rmf ? c : g + lmf + rmf, last);
+            if (found && !all_paths) {   // -best-only: the table ends at the level of the first hit
+              const int fl = ld_sh(&sh.found_level);
+              G::sync();
+              if (rank == 0) sh.ncells = S.lstart[fl + 1];
+              top_level = levels_f = fl;
+              G::sync();
+              break;
+            }
+          }
+          c = last;
+          continue;
+        }
+      }
       if (!dead) {
         top_level = c;
         levels_f = c;
@@ -539,29 +776,7 @@ G2S_D void process_gap(const FillParams &P, const GapDev &gd, const Slice &S, GS
       } else {
         // the border died: no cell can appear any more; finish the found check for the remaining levels in
         // parallel (one level per thread) and leave the level loop
-        if (!found) {
-          for (int cc2 = c + rank; cc2 <= Dmax; cc2 += gsz) {
-            if (cc2 < g + lmf + rmf) continue;
-            int J = 0, l1 = 0, l2 = 0; uint32_t c1 = 0, c2 = 0;
-            if (found_at_level(S, gd, cc2, &J, &c1, &c2, &l1, &l2)) { a_mini(&sh.found_level, cc2); break; }
-          }
-          G::sync();
-          const int fl = ld_sh(&sh.found_level);
-          if (fl <= Dmax) {
-            if (rank == 0) {
-              int J = 0, l1 = 0, l2 = 0; uint32_t c1 = 0, c2 = 0;
-              found_at_level(S, gd, fl, &J, &c1, &c2, &l1, &l2);
-              sh.reached_fuz = J;
-              uint64_t tot = 0; uint32_t n = 0;
-              if (c1) { tot += c1; sh.plen[n++] = l1; }
-              if (c2) { tot += c2; sh.plen[n++] = l2; }
-              sh.n_plen = n;
-              sh.count_fwd = tot > MAX_PATHS ? MAX_PATHS : (uint32_t)tot;
-            }
-            found = true;
-          }
-          G::sync();
-        }
+        if (!found && Dmax >= g + lmf + rmf) found = found_scan<G>(S, gd, sh, c > g + lmf + rmf ? c : g + lmf + rmf, Dmax);
         break;
       }
       // found check (Gap2Seq.cpp:1108-1154): one target per thread, then thread 0 takes the first in j order
@@ -570,8 +785,8 @@ G2S_D void process_gap(const FillParams &P, const GapDev &gd, const Slice &S, GS
         const int err = c - g - lmf - rmf;
         for (int j = rank; j <= rmf; j += gsz) {
           int len1 = g + lmf + j + err, len2 = g + lmf + j - err;
-          sh.fc1[j] = thit_count(S, j, len1);
-          sh.fc2[j] = (len2 != len1 && len2 >= 0) ? thit_count(S, j, len2) : 0;
+          sh.fc1[j] = thit_count(S, sh, j, len1);
+          sh.fc2[j] = (len2 != len1 && len2 >= 0) ? thit_count(S, sh, j, len2) : 0;
         }
         G::sync();
         if (rank == 0) {
@@ -612,7 +827,7 @@ G2S_D void process_gap(const FillParams &P, const GapDev &gd, const Slice &S, GS
           const int jt = rmf - 1;   // Gap2Seq.cpp:1197-1206: effectively only target rmf-1
           int dlo = lmf + g - e; if (dlo < 0) dlo = 0;
           for (int d = dlo + rank; d <= top_level; d += gsz) {
-            uint32_t t = ld_cg(&S.thit[(size_t)jt * trow + d]);
+            uint32_t t = thit_get(S, sh, jt, d);
             if (!t) continue;
             a_or(&S.cflags[t - 1], CF_B | CF_SEED);
             a_add64(&sh.count_all, clamp_paths(ld_cg(&S.cc[t - 1])));
@@ -623,20 +838,22 @@ G2S_D void process_gap(const FillParams &P, const GapDev &gd, const Slice &S, GS
       } else if (rank == 0) {
         for (uint32_t q = 0; q < n_plen; q++) {
           int d = q ? p1 : p0;
-          uint32_t t = S.thit[(size_t)J * trow + d];
+          uint32_t t = thit_get(S, sh, J, d);
           if (t) { a_or(&S.cflags[t - 1], CF_B | CF_SEED); sh.n_sink++; if (d < sh.min_sink_level) sh.min_sink_level = d; }
         }
       }
     }
     if (rank == 0) {
       for (uint32_t q = 0; q < n_plen; q++) {
-        uint32_t t = S.thit[(size_t)J * trow + (q ? p1 : p0)];
+        uint32_t t = thit_get(S, sh, J, q ? p1 : p0);
         if (t) a_or(&S.cflags[t - 1], CF_T);
       }
     }
     G::sync();
 
     for (int d = top_level; d >= 0; d--) {
+      const uint32_t rs = ld_cg(&S.lrun[d]);
+      if (rs != 0 && (int)rs < d) { chain_mark<G>(S, sh, (int)rs, d); d = (int)rs; continue; }
       const uint32_t lo = ld_cg(&S.lstart[d]), hi = ld_cg(&S.lstart[d + 1]);
       const uint64_t lcanon = (d <= lmf) ? canonical(S.lk[d] & FLANK_KMER, k).key : KEY_EMPTY;
       for (uint32_t i = lo + rank; i < hi; i += gsz) {
@@ -739,7 +956,7 @@ G2S_D void process_gap(const FillParams &P, const GapDev &gd, const Slice &S, GS
     o.start_pack[0] = o.start_pack[1] = NONE32;
     if (sh.count_fwd > 0 && !overflow) {
       for (uint32_t q = 0; q < sh.n_plen; q++) {
-        uint32_t t = S.thit[(size_t)sh.reached_fuz * trow + sh.plen[q]];
+        uint32_t t = thit_get(S, sh, sh.reached_fuz, sh.plen[q]);
         if (t) o.start_pack[q] = S.packidx[t - 1];
       }
     }

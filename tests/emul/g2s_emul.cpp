@@ -90,7 +90,7 @@ static int emul_submit(EmulGraph *g, int k, const g2s_gap *gaps, size_t n, HostB
     std::vector<PackRec> pack;
     int tier = 0;
     for (;; tier++, cap *= 16) {
-      uint32_t hlog = tier == 0 ? ceil_log2(2 * cap) : (ceil_log2(cap / 4) > 16 ? ceil_log2(cap / 4) : 16);
+      uint32_t hlog = tier == 0 ? ceil_log2(3 * ((uint64_t)dmax + 64)) : (ceil_log2(cap / 4) > 16 ? ceil_log2(cap / 4) : 16);
       SliceLayout L = make_layout(cap, hlog, (uint32_t)dmax + 1, (uint32_t)std::max(gg.left_max_fuz, gg.right_max_fuz) + 1);
       std::vector<unsigned char> scratch(L.bytes);
       pack.assign(cap, PackRec{});
