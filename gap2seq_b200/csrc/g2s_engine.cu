@@ -163,6 +163,27 @@ extern "C" int g2s_build_from_reads(g2s_engine *e, const char *bases, const uint
   return G2S_OK;
 }
 
+extern "C" int g2s_table_raw(g2s_engine *e, void **device_ptr, uint64_t *capacity_slots, uint64_t *n_kmers, uint64_t *bytes) {
+  if (!e || !device_ptr) return fail(G2S_E_ARG, "g2s_table_raw: null argument");
+  if (!e->table.slots) return fail(G2S_E_STATE, "g2s_table_raw: no graph imported");
+  *device_ptr = e->table.slots;
+  if (capacity_slots) *capacity_slots = e->table.cap;
+  if (n_kmers) *n_kmers = e->table.n;
+  if (bytes) *bytes = e->table.cap * sizeof(Slot);
+  return G2S_OK;
+}
+
+extern "C" int g2s_table_adopt(g2s_engine *e, uint64_t capacity_slots, uint64_t n_kmers, void **device_ptr) {
+  if (!e || !device_ptr) return fail(G2S_E_ARG, "g2s_table_adopt: null argument");
+  if (capacity_slots < 2 || (capacity_slots & (capacity_slots - 1))) return fail(G2S_E_ARG, "g2s_table_adopt: capacity must be a power of two");
+  CUDA_TRY(cudaSetDevice(e->cfg.device));
+  if (e->table.slots) { cudaFree(e->table.slots); e->table.slots = nullptr; }
+  CUDA_TRY(cudaMalloc(&e->table.slots, capacity_slots * sizeof(Slot)));
+  e->table.cap = capacity_slots; e->table.n = n_kmers; e->table.k = e->cfg.k;
+  *device_ptr = e->table.slots;
+  return G2S_OK;
+}
+
 extern "C" int64_t g2s_num_kmers(const g2s_engine *e) { return e ? (int64_t)e->table.n : -1; }
 
 extern "C" int g2s_export_kmers(g2s_engine *e, uint64_t *canon_sorted, uint8_t *adjacency) {

@@ -65,7 +65,7 @@ class G2SRunOptions(C.Structure):
 
 # every symbol include/g2s.h declares (tests check that the library exports all of them)
 ABI_SYMBOLS = ["g2s_last_error", "g2s_abi_version", "g2s_create", "g2s_destroy", "g2s_import_kmers",
-               "g2s_build_from_reads", "g2s_num_kmers", "g2s_export_kmers", "g2s_contains", "g2s_fill_gap",
+               "g2s_build_from_reads", "g2s_table_raw", "g2s_table_adopt", "g2s_num_kmers", "g2s_export_kmers", "g2s_contains", "g2s_fill_gap",
                "g2s_fill_batch", "g2s_upload_gaps", "g2s_run_resident", "g2s_finish_resident", "g2s_submit",
                "g2s_batch_peek", "g2s_batch_trace", "g2s_batch_free", "g2s_fill_records", "g2s_free",
                "g2s_get_timing"]
@@ -87,6 +87,9 @@ def load_library(path: str | None = None):
     L.g2s_destroy.argtypes = [C.c_void_p]
     L.g2s_import_kmers.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
     L.g2s_build_from_reads.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
+    L.g2s_table_raw.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
+                                C.POINTER(C.c_uint64)]
+    L.g2s_table_adopt.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(C.c_void_p)]
     L.g2s_num_kmers.restype = C.c_int64
     L.g2s_num_kmers.argtypes = [C.c_void_p]
     L.g2s_export_kmers.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
@@ -184,6 +187,18 @@ class Engine:
         n, length = reads.shape
         off = np.arange(n + 1, dtype=np.uint64) * np.uint64(length)
         self._check(self.L.g2s_build_from_reads(self.h, reads.ctypes.data, off.ctypes.data, n, solid))
+
+    def table_raw(self):
+        """(device pointer, capacity in slots, k-mers, bytes) of the built table - for replication to other GPUs."""
+        p, cap, n, nb = C.c_void_p(), C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self._check(self.L.g2s_table_raw(self.h, C.byref(p), C.byref(cap), C.byref(n), C.byref(nb)))
+        return p.value, cap.value, n.value, nb.value
+
+    def table_adopt(self, capacity_slots: int, n_kmers: int) -> int:
+        """Allocate an empty table of the given shape; returns its device pointer (fill it, e.g. by broadcast)."""
+        p = C.c_void_p()
+        self._check(self.L.g2s_table_adopt(self.h, capacity_slots, n_kmers, C.byref(p)))
+        return p.value
 
     def num_kmers(self) -> int:
         return int(self.L.g2s_num_kmers(self.h))

@@ -120,6 +120,12 @@ int g2s_import_kmers(g2s_engine *e, const uint64_t *canon, size_t n);
  * bases[offsets[i] .. offsets[i+1]) ) and keeps those seen >= solid times.  Timed separately from the fill. */
 int g2s_build_from_reads(g2s_engine *e, const char *bases, const uint64_t *offsets, size_t n_reads, int solid);
 
+/* Replication of a built table to other GPUs (one NCCL broadcast over NVLink, done by the caller - e.g.
+ * torch.distributed.broadcast in bench.py): the owner exposes its device buffer, the receivers allocate an
+ * identically shaped one, the caller copies/broadcasts the bytes device to device and then commits. */
+int g2s_table_raw(g2s_engine *e, void **device_ptr, uint64_t *capacity_slots, uint64_t *n_kmers, uint64_t *bytes);
+int g2s_table_adopt(g2s_engine *e, uint64_t capacity_slots, uint64_t n_kmers, void **device_ptr);
+
 int64_t g2s_num_kmers(const g2s_engine *e);
 /* copies the table contents (sorted canonical k-mers and their adjacency bytes) to host arrays of g2s_num_kmers() */
 int g2s_export_kmers(g2s_engine *e, uint64_t *canon_sorted, uint8_t *adjacency);

@@ -161,3 +161,26 @@ def test_property_error_free_genome_fills_equal_truth():
         o, of = og.fill_gap(s.left, s.right, s.gap_len, s.gap_err, s.left_max_fuz, s.right_max_fuz)
         assert (r.count, f) == (o.count, of)
     eng.close()
+
+
+def test_table_replication_roundtrip(case_inputs, gpu_engine):
+    """g2s_table_raw / g2s_table_adopt: the device-to-device replication path bench.py uses under torchrun."""
+    import torch
+    from gap2seq_b200.shard import DeviceBytes
+    case, w, g = case_inputs("cfg1_small")
+    src = gpu_engine("cfg1_small")
+    ptr, cap, n, nbytes = src.table_raw()
+    dst = engine.Engine(k=w.k, max_fuz=w.fuz)
+    dptr = dst.table_adopt(cap, n)
+    torch.as_tensor(DeviceBytes(dptr, nbytes), device="cuda").copy_(torch.as_tensor(DeviceBytes(ptr, nbytes), device="cuda"))
+    torch.cuda.synchronize()
+    k1, a1 = src.export_kmers()
+    k2, a2 = dst.export_kmers()
+    assert np.array_equal(k1, k2) and np.array_equal(a1, a2)
+    specs = [s for rec in w.gaps for s in record_gaps(rec.seq, w.k, w.fuz, 500)]
+    oracle_lib.srand(1)
+    r1, f1 = src.fill_batch(specs)
+    oracle_lib.srand(1)
+    r2, f2 = dst.fill_batch(specs)
+    assert f1 == f2 and all(f[:-w.k] == rec.truth for f, rec in zip(f1, w.gaps))
+    dst.close()
