@@ -266,6 +266,7 @@ def main():
         launches += t.launches
     barrier()
     t_region = time.perf_counter() - t_region
+    phase_sum, phase_slowest = eng.phase_cycles()
     res, fills = eng.finish_resident()
     cells = sum(r.cells_left + r.cells_right for r in res)
     filled = sum(1 for r in res if r.count > 0)
@@ -326,6 +327,8 @@ def main():
                          "algorithmic_bytes_per_cell": BYTES_PER_CELL,
                          "note": "thin gaps are chains of dependent gathers (1 cell per level): latency bound, see DESIGN.md"},
             "timed_region_wall_s": t_region,
+            "phase_cycles_slowest_gap": dict(zip(["init", "right", "forward", "backward", "pack", "total"], phase_slowest)),
+            "phase_cycles_sum": dict(zip(["init", "right", "forward", "backward", "pack", "total"], phase_sum)),
         }
         if world == 1:
             keys, _ = eng.export_kmers()

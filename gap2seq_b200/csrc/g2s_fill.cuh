@@ -112,7 +112,7 @@ struct GapOut {        // 128 B
   uint32_t top_level;
   unsigned long long pack_off;
   uint32_t levels_r, levels_f;
-  uint32_t pad[6];
+  uint32_t cyc[6];     // SM cycles (>> 4) spent in: init, right pass, forward pass, backward marking, pack, total
 };
 
 struct SliceLayout {   // byte offsets inside one scratch slice; identical for every slice of a launch
@@ -137,7 +137,8 @@ struct FillParams {
   uint32_t *queue_head;
 };
 
-static const int CHAIN_LEN = 32;   // levels a chain batch looks ahead
+static const int CHAIN_LEN = 32;   // levels a narrow batch looks ahead
+static const int NARROW_W = 4;     // widest border handled in narrow mode
 
 struct GShared {       // per group, in shared memory
   uint32_t ncells, nnodes, nnext, status;
@@ -154,11 +155,13 @@ struct GShared {       // per group, in shared memory
   uint32_t fc1[MAX_FUZ + 1], fc2[MAX_FUZ + 1];
   uint32_t queue_item;
   // chain mode (a border of exactly one cell): the scout's look-ahead and the bulk backward marking
-  uint32_t ch_len, ch_valid, ch_base, ch_cnt;
+  uint32_t ch_len, ch_valid, ch_base, ch_cnt, nw_stop, nw_alive;
   int32_t tlo;          // first level that has thit entries: max(0, g + lmf - e)
   uint32_t trow;        // entries per target row: Dmax - tlo + 1
-  uint64_t ch_s[CHAIN_LEN];
-  uint32_t ch_a[CHAIN_LEN], ch_e[CHAIN_LEN];
+  uint64_t nw_x[NARROW_W];
+  uint32_t nw_m[NARROW_W];
+  uint64_t ch_s[CHAIN_LEN][NARROW_W];
+  uint32_t ch_a[CHAIN_LEN][NARROW_W], ch_e[CHAIN_LEN][NARROW_W];
 };
 
 struct Slice {         // typed view of one scratch slice
@@ -264,6 +267,14 @@ G2S_D uint32_t node_insert(const Slice &S, GShared &sh, uint64_t key) {
   }
 }
 
+G2S_D unsigned long long now_cycles() {
+#ifdef __CUDA_ARCH__
+  return (unsigned long long)clock64();
+#else
+  return 0;
+#endif
+}
+
 G2S_D uint32_t clamp_paths(uint32_t c) { return c > MAX_PATHS ? MAX_PATHS : c; }
 
 // create the forward cell (state s of node e) on level c; the caller owns the (e,strand,level) stamp
@@ -334,100 +345,203 @@ G2S_D bool found_scan(const Slice &S, const GapDev &gd, GShared &sh, int lo, int
   return found;
 }
 
-// ---- chain mode.  While a border holds exactly ONE state with exactly one neighbour, the only true dependency
-// between levels is the adjacency byte of the next k-mer (it decides which base comes after it).  One thread (the
-// scout) therefore walks up to CHAIN_LEN levels ahead through the global table - one dependent gather per level -
-// and the whole group then does everything else for those levels (node table, prune test, cells, links, target
-// hits) in parallel, one level per thread.  Results are identical to the level-by-level path.
+// ---- narrow mode.  While a border holds at most NARROW_W states and each of them has at most one neighbour, the
+// only true dependency between levels is the adjacency byte of the next k-mer of each chain (it decides which base
+// comes after it).  One scout thread per border state therefore walks up to CHAIN_LEN levels ahead through the
+// global table - one dependent gather per level, the chains' gathers in flight together - and the group then does
+// everything else for those levels in bulk: node-table work and prune tests in parallel (one thread per level and
+// chain), a short serial pass over shared memory that merges chains meeting in one state (bubbles closing), adds
+// their counts and lays out the cells, and a parallel commit of stamps / target hits.  Branching levels (a state
+// with two neighbours) and the levels that inject flank starts stay on the level-by-level path.  Results are
+// identical to it.
 
-// Right pass: advances the single-node border S.fk[cur][0] by up to CHAIN_LEN levels starting with level c.
-template <class G>
-G2S_D int chain_right(const Table &T, const Slice &S, GShared &sh, int cur, int c, int right_half) {
-  const int k = T.k;
-  if (G::rank() == 0) {
-    uint64_t x = S.fk[cur][0];
-    uint32_t im = S.fm[cur][0];
-    int len = 0;
-    const int maxlen = right_half - c + 1 < CHAIN_LEN ? right_half - c + 1 : CHAIN_LEN;
-    while (len < maxlen && (im == 1 || im == 2 || im == 4 || im == 8)) {
-      const uint32_t nt = im == 1 ? 0 : im == 2 ? 1 : im == 4 ? 2 : 3;
-      const uint64_t p = pred_kmer(x, nt, T);
-      const Canon cp = canonical(p, k);
-      uint32_t adj = 0;
-      if (table_find(T, cp.key, &adj) < 0) { a_or(&sh.status, GS_INTERNAL); break; }
-      sh.ch_s[len] = p; sh.ch_a[len] = adj | (cp.strand << 8);
-      len++;
-      x = p; im = in_mask(adj, cp.strand);
-    }
-    sh.ch_len = (uint32_t)len;
-    if (len) { S.fk[cur][0] = x; S.fm[cur][0] = (unsigned char)im; sh.cells_right += (uint32_t)len; }
-  }
+// Scout phase shared by both passes.  Returns the number of levels looked ahead (0: a border state branches).
+// ch_s[l][t] / ch_a[l][t] receive chain t's state and (adj | strand << 8 | 1 << 16) on level l, ch_a == 0: no state.
+template <class G, bool FORWARD>
+G2S_D int narrow_scout(const Table &T, GShared &sh, int w, int maxlen) {
+  // per-chain state lives in shared memory (sh.nw_x / sh.nw_m, mask 0xFF = chain ended) so that any group size,
+  // including the size-1 host emulation, can play the w scouts
+  const int k = T.k, rank = G::rank(), gsz = G::size();
+  if (rank == 0) { sh.nw_stop = 0; sh.nw_alive = 0; }
   G::sync();
-  const int len = (int)ld_sh(&sh.ch_len);
-  for (int t = G::rank(); t < len; t += G::size()) {
-    const Canon cp = canonical(sh.ch_s[t], k);
-    const uint32_t en = node_insert(S, sh, cp.key);
-    if (en == NONE32) continue;
-    a_or(&S.ent[en].flags, NF_IN_RS);
-    a_max(&S.ent[en].rstamp, (uint32_t)(c + t + 1) * 2 + cp.strand);
+  int len = 0;
+  for (int l = 0; l < maxlen; l++) {
+    for (int t = rank; t < w; t += gsz) {
+      const uint32_t mask = sh.nw_m[t];
+      if (mask == 0xFF) continue;
+      if (mask == 0) sh.nw_m[t] = 0xFF;                              // dead end
+      else if (mask & (mask - 1)) sh.nw_stop = 1;                    // two neighbours: not a chain any more
+      else sh.nw_alive = (uint32_t)l + 1;
+    }
+    G::sync();
+    if (ld_sh(&sh.nw_stop) || ld_sh(&sh.nw_alive) < (uint32_t)l + 1) {
+      // a branch ends the look-ahead BEFORE this level; "all chains ended" keeps the (empty) level so that the
+      // caller records the border as dead
+      if (!ld_sh(&sh.nw_stop)) { for (int t = rank; t < w; t += gsz) sh.ch_a[l][t] = 0; len = l + 1; }
+      break;
+    }
+    for (int t = rank; t < w; t += gsz) {
+      const uint32_t mask = sh.nw_m[t];
+      if (mask == 0xFF) { sh.ch_a[l][t] = 0; continue; }
+      const uint32_t nt = mask == 1 ? 0 : mask == 2 ? 1 : mask == 4 ? 2 : 3;
+      const uint64_t s = FORWARD ? succ_kmer(sh.nw_x[t], nt, T) : pred_kmer(sh.nw_x[t], nt, T);
+      const Canon cs = canonical(s, k);
+      uint32_t adj = 0;
+      if (table_find(T, cs.key, &adj) < 0) { a_or(&sh.status, GS_INTERNAL); sh.nw_m[t] = 0xFF; sh.ch_a[l][t] = 0; continue; }
+      sh.ch_s[l][t] = s; sh.ch_a[l][t] = adj | (cs.strand << 8) | (1u << 16);
+      sh.nw_x[t] = s; sh.nw_m[t] = FORWARD ? out_mask(adj, cs.strand) : in_mask(adj, cs.strand);
+    }
+    len = l + 1;
+    G::sync();
   }
   G::sync();
   return len;
 }
 
-// Forward pass: the border of level c-1 is the single cell `lo`.  Creates the cells of levels c .. c+ret-1.
+// Right pass: advances the border S.fk[cur][0..n) (n <= NARROW_W) by up to CHAIN_LEN levels starting with level c.
+// Returns the number of levels done; *n_out receives the size of the new border.
 template <class G>
-G2S_D int chain_forward(const Table &T, const Slice &S, GShared &sh, const GapDev &gd, uint32_t lo, int c, int Dmax,
-                        int prune_from) {
-  const int k = T.k;
-  if (G::rank() == 0) {
-    uint64_t x = ld_cg(&S.ck[lo]);
-    uint32_t om = (ld_cg(&S.cflags[lo]) >> CF_OMASK_SHIFT) & 15u;
-    int len = 0;
-    const int maxlen = Dmax - c + 1 < CHAIN_LEN ? Dmax - c + 1 : CHAIN_LEN;
-    while (len < maxlen && (om == 1 || om == 2 || om == 4 || om == 8)) {
-      const uint32_t nt = om == 1 ? 0 : om == 2 ? 1 : om == 4 ? 2 : 3;
-      const uint64_t s = succ_kmer(x, nt, T);
-      const Canon cs = canonical(s, k);
-      uint32_t adj = 0;
-      if (table_find(T, cs.key, &adj) < 0) { a_or(&sh.status, GS_INTERNAL); break; }
-      sh.ch_s[len] = s; sh.ch_a[len] = adj | (cs.strand << 8);
-      len++;
-      x = s; om = out_mask(adj, cs.strand);
-    }
-    sh.ch_len = (uint32_t)len;
-    sh.ch_valid = (uint32_t)len;
-    sh.ch_base = sh.ncells;
-  }
-  G::sync();
-  const int len = (int)ld_sh(&sh.ch_len);
+G2S_D int narrow_right(const Table &T, const Slice &S, GShared &sh, int cur, int c, int right_half, int n, uint32_t *n_out) {
+  const int k = T.k, rank = G::rank();
+  for (int t = rank; t < n; t += G::size()) { sh.nw_x[t] = S.fk[cur][t]; sh.nw_m[t] = S.fm[cur][t]; }
+  const int maxlen = right_half - c + 1 < CHAIN_LEN ? right_half - c + 1 : CHAIN_LEN;
+  const int len = narrow_scout<G, false>(T, sh, n, maxlen);
   if (len == 0) return 0;
-  // node table + prune test, one level per thread
-  for (int t = G::rank(); t < len; t += G::size()) {
-    const Canon cs = canonical(sh.ch_s[t], k);
-    uint32_t en;
-    bool ok;
-    if (c + t < prune_from) { en = node_insert(S, sh, cs.key); ok = en != NONE32; }
-    else { en = node_find(S, cs.key); ok = en != NONE32 && (ld_cg(&S.ent[en].flags) & NF_IN_RS); }
-    sh.ch_e[t] = en;
-    if (!ok) a_mini((int32_t *)&sh.ch_valid, t);
+  for (int q = rank; q < len * n; q += G::size()) {
+    const int l = q / n, t = q - l * n;
+    if (!sh.ch_a[l][t]) continue;
+    const Canon cp = canonical(sh.ch_s[l][t], k);
+    const uint32_t en = node_insert(S, sh, cp.key);
+    if (en == NONE32) continue;
+    a_or(&S.ent[en].flags, NF_IN_RS);
+    a_max(&S.ent[en].rstamp, (uint32_t)(c + l + 1) * 2 + cp.strand);
+  }
+  if (rank == 0) {   // distinct states per level = cells of the right table (chains that met are counted once)
+    uint32_t cells = 0, nlast = 0;
+    for (int l = 0; l < len; l++) {
+      uint64_t st[NARROW_W]; uint32_t ns = 0;
+      for (int t = 0; t < n; t++) {
+        if (!sh.ch_a[l][t]) continue;
+        const uint64_t s = sh.ch_s[l][t];
+        bool dup = false;
+        for (uint32_t j = 0; j < ns; j++) {
+          if (st[j] == s) dup = true;
+          else if (st[j] == revcomp(s, k)) a_or(&sh.status, GS_ORDER_DEPENDENT);   // both strands on one level (Q3)
+        }
+        if (!dup) {
+          st[ns++] = s;
+          if (l == len - 1) { S.fk[cur][nlast] = s; S.fm[cur][nlast] = (unsigned char)in_mask(sh.ch_a[l][t] & 0xFF, (sh.ch_a[l][t] >> 8) & 1); nlast++; }
+        }
+      }
+      cells += ns;
+    }
+    sh.cells_right += cells;
+    sh.nnext = nlast;
   }
   G::sync();
-  const int len2 = (int)ld_sh(&sh.ch_valid);   // levels before the first pruned one
-  const uint32_t base = ld_sh(&sh.ch_base);
-  if ((ld_sh(&sh.status) & GS_OVERFLOW) || (uint64_t)base + len2 > S.cap_cells) { a_or(&sh.status, GS_OVERFLOW); G::sync(); return 0; }
-  const uint32_t np = clamp_paths(ld_cg(&S.cc[lo]));   // the count rides along a chain unchanged
-  const uint32_t run_first = ld_cg(&S.lrun[c - 1]) ? ld_cg(&S.lrun[c - 1]) : (uint32_t)c;
-  for (int t = G::rank(); t < len2; t += G::size()) {
-    const uint32_t idx = base + t, level = (uint32_t)(c + t);
-    const uint64_t s = sh.ch_s[t];
-    const uint32_t adj = sh.ch_a[t] & 0xFF, strand = sh.ch_a[t] >> 8, en = sh.ch_e[t];
-    const uint64_t prev = t ? sh.ch_s[t - 1] : ld_cg(&S.ck[lo]);
-    const uint32_t u0 = (uint32_t)(prev >> (2 * (k - 1))) & 3u;
-    S.ck[idx] = s; S.cc[idx] = np; S.cn[idx] = en;
-    S.cp[4 * idx + 0] = NONE32; S.cp[4 * idx + 1] = NONE32; S.cp[4 * idx + 2] = NONE32; S.cp[4 * idx + 3] = NONE32;
-    S.cp[4 * idx + u0] = t ? idx - 1 : lo;
-    S.cflags[idx] = out_mask(adj, strand) << CF_OMASK_SHIFT;
+  *n_out = ld_sh(&sh.nnext);
+  return len;
+}
+
+// Forward pass: the border of level c-1 is cells [lo, lo+w), w <= NARROW_W.  Creates the cells of levels
+// c .. c+ret-1 (a returned level may be empty: the border died).
+template <class G>
+G2S_D int narrow_forward(const Table &T, const Slice &S, GShared &sh, const GapDev &gd, uint32_t lo, int w, int c, int Dmax,
+                         int prune_from) {
+  const int k = T.k, rank = G::rank();
+  for (int t = rank; t < w; t += G::size()) {
+    sh.nw_x[t] = ld_cg(&S.ck[lo + t]);
+    sh.nw_m[t] = (ld_cg(&S.cflags[lo + t]) >> CF_OMASK_SHIFT) & 15u;
+  }
+  const int maxlen = Dmax - c + 1 < CHAIN_LEN ? Dmax - c + 1 : CHAIN_LEN;
+  const int len = narrow_scout<G, true>(T, sh, w, maxlen);
+  if (len == 0) return 0;
+  // node table + prune test, one (level, chain) per thread: ch_e = node entry, NONE32 = pruned / absent
+  for (int q = rank; q < len * w; q += G::size()) {
+    const int l = q / w, t = q - l * w;
+    uint32_t en = NONE32;
+    if (sh.ch_a[l][t]) {
+      const Canon cs = canonical(sh.ch_s[l][t], k);
+      if (c + l < prune_from) en = node_insert(S, sh, cs.key);
+      else { en = node_find(S, cs.key); if (en != NONE32 && !(ld_cg(&S.ent[en].flags) & NF_IN_RS)) en = NONE32; }
+    }
+    sh.ch_e[l][t] = en;
+  }
+  G::sync();
+  if (ld_sh(&sh.status) & GS_OVERFLOW) return 0;
+  // serial merge + layout (shared memory and stores only; no dependent global loads after the first few)
+  if (rank == 0) {
+    uint32_t cell[NARROW_W], cnt[NARROW_W];
+    uint64_t pst[NARROW_W];   // oriented k-mer of each chain's current cell (its first base names the link slot)
+    bool alive[NARROW_W];
+    for (int t = 0; t < w; t++) {
+      cell[t] = lo + t; cnt[t] = clamp_paths(ld_cg(&S.cc[lo + t])); pst[t] = ld_cg(&S.ck[lo + t]); alive[t] = true;
+    }
+    const uint32_t base = sh.ncells;
+    uint32_t created = 0;
+    uint32_t prev_n = (uint32_t)w, run_prev = ld_cg(&S.lrun[c - 1]);
+    int done = len;
+    for (int l = 0; l < len; l++) {
+      const uint32_t level = (uint32_t)(c + l);
+      uint64_t nstate[NARROW_W]; uint32_t nidx[NARROW_W], ncnt[NARROW_W], nnode[NARROW_W], nstrand[NARROW_W], nlinks[NARROW_W];
+      uint32_t nn = 0;
+      uint32_t next[NARROW_W];
+      for (int t = 0; t < w; t++) {
+        next[t] = NONE32;
+        if (!alive[t]) continue;
+        bool alias = false;   // a chain that merged into an earlier one just follows it
+        for (int u = 0; u < t; u++) if (alive[u] && cell[u] == cell[t]) { next[t] = next[u]; alias = true; break; }
+        if (alias) continue;
+        const uint32_t a = sh.ch_a[l][t], en = sh.ch_e[l][t];
+        if (!a || en == NONE32) continue;   // dead end or pruned: the chain ends
+        const uint64_t s = sh.ch_s[l][t];
+        const uint32_t strand = (a >> 8) & 1;
+        const uint32_t u0 = (uint32_t)(pst[t] >> (2 * (k - 1))) & 3u;
+        uint32_t j = 0;
+        for (; j < nn; j++) if (nstate[j] == s) break;
+        if (j == nn) {
+          if ((uint64_t)base + created >= S.cap_cells) { a_or(&sh.status, GS_OVERFLOW); break; }
+          for (uint32_t q = 0; q < nn; q++) if (nnode[q] == en && nstrand[q] != strand) a_or(&sh.status, GS_ORDER_DEPENDENT);
+          const uint32_t idx = base + created++;
+          nstate[nn] = s; nidx[nn] = idx; ncnt[nn] = 0; nnode[nn] = en; nstrand[nn] = strand; nlinks[nn] = 0; nn++;
+          S.ck[idx] = s; S.cn[idx] = en;
+          S.cp[4 * idx + 0] = NONE32; S.cp[4 * idx + 1] = NONE32; S.cp[4 * idx + 2] = NONE32; S.cp[4 * idx + 3] = NONE32;
+          S.cflags[idx] = out_mask(a & 0xFF, strand) << CF_OMASK_SHIFT;
+          S.packlevel[idx] = level;   // scratch: read back by the parallel commit below
+        }
+        ncnt[j] += cnt[t];            // <= 4 * MAX_PATHS < 2^32
+        nlinks[j]++;
+        S.cp[4 * nidx[j] + u0] = cell[t];
+        next[t] = nidx[j];
+      }
+      if (ld_sh(&sh.status) & GS_OVERFLOW) { done = l; break; }
+      for (uint32_t j = 0; j < nn; j++) S.cc[nidx[j]] = ncnt[j];
+      for (int t = 0; t < w; t++) {
+        alive[t] = alive[t] && next[t] != NONE32;
+        if (alive[t]) {
+          cell[t] = next[t];
+          for (uint32_t j = 0; j < nn; j++) if (nidx[j] == next[t]) { cnt[t] = clamp_paths(ncnt[j]); pst[t] = nstate[j]; }
+        }
+      }
+      S.lstart[level + 1] = base + created;
+      // a level with one cell whose single link comes from the single cell below belongs to a chain run
+      uint32_t run = 0;
+      if (nn == 1 && prev_n == 1 && nlinks[0] == 1) run = run_prev ? run_prev : level;
+      S.lrun[level] = run;
+      run_prev = run; prev_n = nn;
+      if (nn == 0) { done = l + 1; break; }   // the border died on this level
+    }
+    sh.ch_base = base;
+    sh.ch_cnt = created;
+    sh.ch_len = (uint32_t)done;
+    sh.ncells = base + created;
+  }
+  G::sync();
+  const uint32_t base = ld_sh(&sh.ch_base), created = ld_sh(&sh.ch_cnt);
+  for (uint32_t q = rank; q < created; q += G::size()) {
+    const uint32_t idx = base + q, en = S.cn[idx], level = S.packlevel[idx];
+    const uint64_t s = S.ck[idx];
+    const uint32_t strand = canonical(s, k).strand;
     a_max(&S.ent[en].fstamp[strand], level + 1);
     S.ent[en].fcell[strand] = idx;
     const uint32_t fl = a_or(&S.ent[en].flags, NF_HAS_F);
@@ -435,15 +549,9 @@ G2S_D int chain_forward(const Table &T, const Slice &S, GShared &sh, const GapDe
       for (int j = 0; j <= gd.rmf; j++)
         if ((S.rk[j] & FLANK_KMER) == s) S.thit[(size_t)j * sh.trow + (level - (uint32_t)sh.tlo)] = idx + 1;
     }
-    S.lstart[level + 1] = idx + 1;
-    S.lrun[level] = run_first;
-  }
-  if (G::rank() == 0) {
-    sh.ncells = base + (uint32_t)len2;
-    if (len2 < len) S.lstart[c + len2 + 1] = base + (uint32_t)len2;   // the next level is empty: its only candidate was pruned
   }
   G::sync();
-  return len2;
+  return (int)ld_sh(&sh.ch_len);
 }
 
 // Backward marking of a run of chain levels [rs, d] (single cell per level, single link to the level below): the
@@ -454,14 +562,14 @@ G2S_D void chain_mark(const Slice &S, GShared &sh, int rs, int d) {
   uint32_t carry = 0;   // meaningful on rank 0 only
   for (int hi = d; hi >= rs; hi -= CHAIN_LEN) {
     const int n = hi - rs + 1 < CHAIN_LEN ? hi - rs + 1 : CHAIN_LEN;
-    for (int t = G::rank(); t < n; t += G::size()) sh.ch_a[t] = ld_cg(&S.cflags[top_cell - (uint32_t)(d - (hi - t))]);
+    for (int t = G::rank(); t < n; t += G::size()) sh.ch_a[t][0] = ld_cg(&S.cflags[top_cell - (uint32_t)(d - (hi - t))]);
     G::sync();
     if (G::rank() == 0) {
       uint32_t cnt = 0, nb = 0;
       for (int t = 0; t < n; t++) {
-        carry |= sh.ch_a[t] & (CF_B | CF_T);
-        sh.ch_a[t] = (sh.ch_a[t] & ~(uint32_t)(CF_B | CF_T)) | carry;
-        sh.ch_e[t] = carry ? cnt++ : NONE32;
+        carry |= sh.ch_a[t][0] & (CF_B | CF_T);
+        sh.ch_a[t][0] = (sh.ch_a[t][0] & ~(uint32_t)(CF_B | CF_T)) | carry;
+        sh.ch_e[t][0] = carry ? cnt++ : NONE32;
         if (carry & CF_B) nb++;
       }
       sh.ch_base = sh.npack;
@@ -472,9 +580,9 @@ G2S_D void chain_mark(const Slice &S, GShared &sh, int rs, int d) {
     G::sync();
     const uint32_t base = ld_sh(&sh.ch_base);
     for (int t = G::rank(); t < n; t += G::size()) {
-      if (sh.ch_e[t] == NONE32) continue;
+      if (sh.ch_e[t][0] == NONE32) continue;
       const int level = hi - t;
-      const uint32_t i = top_cell - (uint32_t)(d - level), f = sh.ch_a[t], pi = base + sh.ch_e[t];
+      const uint32_t i = top_cell - (uint32_t)(d - level), f = sh.ch_a[t][0], pi = base + sh.ch_e[t][0];
       S.cflags[i] = f;
       S.packidx[i] = pi; S.packlist[pi] = i; S.packlevel[pi] = (uint32_t)level;
       if (f & CF_B) {
@@ -518,6 +626,7 @@ G2S_D void process_gap(const FillParams &P, const GapDev &gd, const Slice &S, GS
   const int tlo = g + lmf - e > 0 ? g + lmf - e : 0;
   const size_t trow = (size_t)(Dmax - tlo + 1);
 
+  const unsigned long long t_start = now_cycles();
   // ---- init: clear the node table, thit and the per-level counters; parse the flanks
   {
     uint4 *hz = (uint4 *)S.ent;
@@ -549,6 +658,7 @@ G2S_D void process_gap(const FillParams &P, const GapDev &gd, const Slice &S, GS
   }
   G::sync();
 
+  const unsigned long long t_init = now_cycles();
   // ---- Phase R: level-synchronous backward walk from the staggered right starts (Gap2Seq.cpp:871-982).
   // Only node membership in the right set is read later (Gap2Seq.cpp:1050): nodes get NF_IN_RS, cells are counted.
   int levels_r = 0;
@@ -574,10 +684,11 @@ G2S_D void process_gap(const FillParams &P, const GapDev &gd, const Slice &S, GS
     for (int c = 1; c <= right_half; c++) {
       if (n == 0 && c > rmf) break;
       levels_r = c;
-      if (n == 1 && c > rmf) {   // single-node border, no start left to inject: chain mode
-        const int adv = chain_right<G>(T, S, sh, cur, c, right_half);
+      if (n >= 1 && n <= (uint32_t)NARROW_W && c > rmf) {   // narrow border, no start left to inject
+        uint32_t n2 = n;
+        const int adv = narrow_right<G>(T, S, sh, cur, c, right_half, (int)n, &n2);
         if (ld_sh(&sh.status) & GS_OVERFLOW) break;
-        if (adv > 0) { levels_r = c + adv - 1; c += adv - 1; continue; }
+        if (adv > 0) { n = n2; levels_r = c + adv - 1; c += adv - 1; continue; }
       }
       G::sync();
       if (rank == 0) sh.nnext = 0;
@@ -637,6 +748,7 @@ G2S_D void process_gap(const FillParams &P, const GapDev &gd, const Slice &S, GS
   }
   G::sync();
 
+  const unsigned long long t_right = now_cycles();
   // mark the right-flank targets (their node entries may not exist yet: insert them, flag TARGET)
   if (!(ld_sh(&sh.status) & GS_OVERFLOW)) {
     for (int j = rank; j <= rmf; j += gsz) {
@@ -678,8 +790,8 @@ G2S_D void process_gap(const FillParams &P, const GapDev &gd, const Slice &S, GS
     for (int c = 1; c <= Dmax; c++) {
       const uint32_t lo = ld_cg(&S.lstart[c - 1]), hi = ld_cg(&S.lstart[c]);
       const bool dead = (lo == hi) && c > lmf;   // empty border and no start left to inject
-      if (hi - lo == 1 && c > lmf) {   // single-cell border, no start left to inject: chain mode
-        const int adv = chain_forward<G>(T, S, sh, gd, lo, c, Dmax, prune_from);
+      if (hi > lo && hi - lo <= (uint32_t)NARROW_W && c > lmf) {   // narrow border, no start left to inject
+        const int adv = narrow_forward<G>(T, S, sh, gd, lo, (int)(hi - lo), c, Dmax, prune_from);
         if (ld_sh(&sh.status) & GS_OVERFLOW) { overflow = true; break; }
         if (adv > 0) {
           const int last = c + adv - 1;
@@ -812,6 +924,8 @@ G2S_D void process_gap(const FillParams &P, const GapDev &gd, const Slice &S, GS
   }
   G::sync();
 
+  const unsigned long long t_fwd = now_cycles();
+  unsigned long long t_back = t_fwd;
   // ---- Phase B + traceback trellis: backward marking through the predecessor links (Gap2Seq.cpp:1173-1312)
   const uint32_t n_plen = ld_sh(&sh.n_plen);
   const uint32_t count_fwd = ld_sh(&sh.count_fwd);
@@ -898,6 +1012,7 @@ G2S_D void process_gap(const FillParams &P, const GapDev &gd, const Slice &S, GS
       G::sync();
     }
     general = (ld_sh(&sh.status) & GS_GENERAL) != 0;
+    t_back = now_cycles();
 
     // ---- pack: append the marked cells to the output arena
     const uint32_t npack = ld_sh(&sh.npack);
@@ -965,7 +1080,10 @@ G2S_D void process_gap(const FillParams &P, const GapDev &gd, const Slice &S, GS
     o.top_level = (uint32_t)top_level;
     o.pack_off = sh.pack_off;
     o.levels_r = (uint32_t)levels_r; o.levels_f = (uint32_t)levels_f;
-    for (int q = 0; q < 6; q++) o.pad[q] = 0;
+    const unsigned long long t_end = now_cycles();
+    o.cyc[0] = (uint32_t)((t_init - t_start) >> 4); o.cyc[1] = (uint32_t)((t_right - t_init) >> 4);
+    o.cyc[2] = (uint32_t)((t_fwd - t_right) >> 4); o.cyc[3] = (uint32_t)((t_back - t_fwd) >> 4);
+    o.cyc[4] = (uint32_t)((t_end - t_back) >> 4); o.cyc[5] = (uint32_t)((t_end - t_start) >> 4);
     *out = o;
   }
   G::sync();

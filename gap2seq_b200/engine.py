@@ -68,7 +68,7 @@ ABI_SYMBOLS = ["g2s_last_error", "g2s_abi_version", "g2s_create", "g2s_destroy",
                "g2s_build_from_reads", "g2s_table_raw", "g2s_table_adopt", "g2s_num_kmers", "g2s_export_kmers", "g2s_contains", "g2s_fill_gap",
                "g2s_fill_batch", "g2s_upload_gaps", "g2s_run_resident", "g2s_finish_resident", "g2s_submit",
                "g2s_batch_peek", "g2s_batch_trace", "g2s_batch_free", "g2s_fill_records", "g2s_free",
-               "g2s_get_timing"]
+               "g2s_get_timing", "g2s_get_phase_cycles"]
 
 _lib = None
 
@@ -107,6 +107,7 @@ def load_library(path: str | None = None):
                                    C.POINTER(C.c_size_t)]
     L.g2s_free.argtypes = [C.c_void_p]
     L.g2s_get_timing.argtypes = [C.c_void_p, C.POINTER(G2STiming)]
+    L.g2s_get_phase_cycles.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     if path is None:
         _lib = L
     return L
@@ -287,6 +288,12 @@ class Engine:
         if gr.value:
             free(gr)
         return out, logs, gc.value, fc.value, results
+
+    def phase_cycles(self):
+        """SM cycles per phase (init, right, forward, backward, pack, total) of the last device pass: (sum, slowest gap)."""
+        a, b = (C.c_double * 6)(), (C.c_double * 6)()
+        self._check(self.L.g2s_get_phase_cycles(self.h, a, b))
+        return list(a), list(b)
 
     def timing(self) -> G2STiming:
         t = G2STiming()
