@@ -158,8 +158,10 @@ struct GShared {       // per group, in shared memory
   uint32_t ch_len, ch_valid, ch_base, ch_cnt, nw_stop, nw_alive;
   int32_t tlo;          // first level that has thit entries: max(0, g + lmf - e)
   uint32_t trow;        // entries per target row: Dmax - tlo + 1
-  uint64_t nw_x[NARROW_W];
-  uint32_t nw_m[NARROW_W];
+  uint64_t nw_x[NARROW_W], nw_x0[NARROW_W];
+  uint32_t nw_m[NARROW_W], nw_cnt0[NARROW_W];
+  int32_t nw_fail[NARROW_W];
+  uint32_t nw_n[CHAIN_LEN], nw_off[CHAIN_LEN], nw_run[CHAIN_LEN];
   uint64_t ch_s[CHAIN_LEN][NARROW_W];
   uint32_t ch_a[CHAIN_LEN][NARROW_W], ch_e[CHAIN_LEN][NARROW_W];
 };
@@ -402,12 +404,14 @@ G2S_D int narrow_scout(const Table &T, GShared &sh, int w, int maxlen) {
 // Returns the number of levels done; *n_out receives the size of the new border.
 template <class G>
 G2S_D int narrow_right(const Table &T, const Slice &S, GShared &sh, int cur, int c, int right_half, int n, uint32_t *n_out) {
-  const int k = T.k, rank = G::rank();
-  for (int t = rank; t < n; t += G::size()) { sh.nw_x[t] = S.fk[cur][t]; sh.nw_m[t] = S.fm[cur][t]; }
+  const int k = T.k, rank = G::rank(), gsz = G::size();
+  for (int t = rank; t < n; t += gsz) { sh.nw_x[t] = S.fk[cur][t]; sh.nw_m[t] = S.fm[cur][t]; }
   const int maxlen = right_half - c + 1 < CHAIN_LEN ? right_half - c + 1 : CHAIN_LEN;
   const int len = narrow_scout<G, false>(T, sh, n, maxlen);
   if (len == 0) return 0;
-  for (int q = rank; q < len * n; q += G::size()) {
+  if (rank == 0) { sh.ch_cnt = 0; sh.nnext = 0; }
+  G::sync();
+  for (int q = rank; q < len * n; q += gsz) {
     const int l = q / n, t = q - l * n;
     if (!sh.ch_a[l][t]) continue;
     const Canon cp = canonical(sh.ch_s[l][t], k);
@@ -416,48 +420,64 @@ G2S_D int narrow_right(const Table &T, const Slice &S, GShared &sh, int cur, int
     a_or(&S.ent[en].flags, NF_IN_RS);
     a_max(&S.ent[en].rstamp, (uint32_t)(c + l + 1) * 2 + cp.strand);
   }
-  if (rank == 0) {   // distinct states per level = cells of the right table (chains that met are counted once)
-    uint32_t cells = 0, nlast = 0;
-    for (int l = 0; l < len; l++) {
-      uint64_t st[NARROW_W]; uint32_t ns = 0;
-      for (int t = 0; t < n; t++) {
-        if (!sh.ch_a[l][t]) continue;
-        const uint64_t s = sh.ch_s[l][t];
-        bool dup = false;
-        for (uint32_t j = 0; j < ns; j++) {
-          if (st[j] == s) dup = true;
-          else if (st[j] == revcomp(s, k)) a_or(&sh.status, GS_ORDER_DEPENDENT);   // both strands on one level (Q3)
-        }
-        if (!dup) {
-          st[ns++] = s;
-          if (l == len - 1) { S.fk[cur][nlast] = s; S.fm[cur][nlast] = (unsigned char)in_mask(sh.ch_a[l][t] & 0xFF, (sh.ch_a[l][t] >> 8) & 1); nlast++; }
-        }
+  // distinct states per level = cells of the right table (chains that met are counted once); one level per thread
+  for (int l = rank; l < len; l += gsz) {
+    uint32_t ns = 0;
+#pragma unroll
+    for (int t = 0; t < NARROW_W; t++) {
+      if (t >= n || !sh.ch_a[l][t]) continue;
+      const uint64_t s = sh.ch_s[l][t];
+      bool dup = false;
+#pragma unroll
+      for (int u = 0; u < NARROW_W; u++) {
+        if (u >= t || !sh.ch_a[l][u]) continue;
+        if (sh.ch_s[l][u] == s) dup = true;
+        else if (sh.ch_s[l][u] == revcomp(s, k)) a_or(&sh.status, GS_ORDER_DEPENDENT);   // both strands on one level (Q3)
       }
-      cells += ns;
+      if (dup) continue;
+      if (l == len - 1) {
+        S.fk[cur][ns] = s;
+        S.fm[cur][ns] = (unsigned char)in_mask(sh.ch_a[l][t] & 0xFF, (sh.ch_a[l][t] >> 8) & 1);
+      }
+      ns++;
     }
-    sh.cells_right += cells;
-    sh.nnext = nlast;
+    a_add(&sh.ch_cnt, ns);
+    if (l == len - 1) sh.nnext = ns;
   }
   G::sync();
+  if (rank == 0) sh.cells_right += sh.ch_cnt;
   *n_out = ld_sh(&sh.nnext);
+  G::sync();
   return len;
 }
 
 // Forward pass: the border of level c-1 is cells [lo, lo+w), w <= NARROW_W.  Creates the cells of levels
-// c .. c+ret-1 (a returned level may be empty: the border died).
+// c .. c+ret-1 (the last returned level may be empty: the border died there).
+//
+// Chains never split in narrow mode, they only end (dead end, pruned) or meet (equal states, bubbles closing), and
+// once met they stay equal.  So everything about level l follows from level l's candidates alone:
+//   alive(t, l)  = l < first failing level of chain t
+//   cell of t    = the lowest alive chain with the same state on level l
+//   its count    = sum of the INITIAL counts of the alive chains with that state (clamping commutes)
+//   its links    = the cells of those chains on level l-1
+// which lets one thread per level lay out and write that level's cells once a prefix sum has placed the levels.
 template <class G>
 G2S_D int narrow_forward(const Table &T, const Slice &S, GShared &sh, const GapDev &gd, uint32_t lo, int w, int c, int Dmax,
                          int prune_from) {
-  const int k = T.k, rank = G::rank();
-  for (int t = rank; t < w; t += G::size()) {
-    sh.nw_x[t] = ld_cg(&S.ck[lo + t]);
+  const int k = T.k, rank = G::rank(), gsz = G::size();
+  for (int t = rank; t < w; t += gsz) {
+    const uint64_t x = ld_cg(&S.ck[lo + t]);
+    sh.nw_x[t] = x; sh.nw_x0[t] = x;
     sh.nw_m[t] = (ld_cg(&S.cflags[lo + t]) >> CF_OMASK_SHIFT) & 15u;
+    sh.nw_cnt0[t] = clamp_paths(ld_cg(&S.cc[lo + t]));
   }
   const int maxlen = Dmax - c + 1 < CHAIN_LEN ? Dmax - c + 1 : CHAIN_LEN;
   const int len = narrow_scout<G, true>(T, sh, w, maxlen);
   if (len == 0) return 0;
-  // node table + prune test, one (level, chain) per thread: ch_e = node entry, NONE32 = pruned / absent
-  for (int q = rank; q < len * w; q += G::size()) {
+  for (int t = rank; t < w; t += gsz) sh.nw_fail[t] = len;
+  G::sync();
+  // node table + prune test, one (level, chain) per thread: ch_e = node entry; first failing level per chain
+  for (int q = rank; q < len * w; q += gsz) {
     const int l = q / w, t = q - l * w;
     uint32_t en = NONE32;
     if (sh.ch_a[l][t]) {
@@ -466,92 +486,113 @@ G2S_D int narrow_forward(const Table &T, const Slice &S, GShared &sh, const GapD
       else { en = node_find(S, cs.key); if (en != NONE32 && !(ld_cg(&S.ent[en].flags) & NF_IN_RS)) en = NONE32; }
     }
     sh.ch_e[l][t] = en;
+    if (en == NONE32) a_mini(&sh.nw_fail[t], l);
   }
   G::sync();
   if (ld_sh(&sh.status) & GS_OVERFLOW) return 0;
-  // serial merge + layout (shared memory and stores only; no dependent global loads after the first few)
-  if (rank == 0) {
-    uint32_t cell[NARROW_W], cnt[NARROW_W];
-    uint64_t pst[NARROW_W];   // oriented k-mer of each chain's current cell (its first base names the link slot)
-    bool alive[NARROW_W];
-    for (int t = 0; t < w; t++) {
-      cell[t] = lo + t; cnt[t] = clamp_paths(ld_cg(&S.cc[lo + t])); pst[t] = ld_cg(&S.ck[lo + t]); alive[t] = true;
+  // distinct cells per level
+  for (int l = rank; l < len; l += gsz) {
+    uint32_t nn = 0;
+#pragma unroll
+    for (int t = 0; t < NARROW_W; t++) {
+      if (t >= w || l >= sh.nw_fail[t]) continue;
+      bool dup = false;
+#pragma unroll
+      for (int u = 0; u < NARROW_W; u++) if (u < t && l < sh.nw_fail[u] && sh.ch_s[l][u] == sh.ch_s[l][t]) dup = true;
+      if (!dup) nn++;
     }
+    sh.nw_n[l] = nn;
+  }
+  G::sync();
+  if (rank == 0) {   // place the levels: prefix sum, end of the border, chain runs
     const uint32_t base = sh.ncells;
-    uint32_t created = 0;
-    uint32_t prev_n = (uint32_t)w, run_prev = ld_cg(&S.lrun[c - 1]);
+    uint32_t off = 0, prev_n = (uint32_t)w, run_prev = ld_cg(&S.lrun[c - 1]);
     int done = len;
     for (int l = 0; l < len; l++) {
-      const uint32_t level = (uint32_t)(c + l);
-      uint64_t nstate[NARROW_W]; uint32_t nidx[NARROW_W], ncnt[NARROW_W], nnode[NARROW_W], nstrand[NARROW_W], nlinks[NARROW_W];
-      uint32_t nn = 0;
-      uint32_t next[NARROW_W];
-      for (int t = 0; t < w; t++) {
-        next[t] = NONE32;
-        if (!alive[t]) continue;
-        bool alias = false;   // a chain that merged into an earlier one just follows it
-        for (int u = 0; u < t; u++) if (alive[u] && cell[u] == cell[t]) { next[t] = next[u]; alias = true; break; }
-        if (alias) continue;
-        const uint32_t a = sh.ch_a[l][t], en = sh.ch_e[l][t];
-        if (!a || en == NONE32) continue;   // dead end or pruned: the chain ends
-        const uint64_t s = sh.ch_s[l][t];
-        const uint32_t strand = (a >> 8) & 1;
-        const uint32_t u0 = (uint32_t)(pst[t] >> (2 * (k - 1))) & 3u;
-        uint32_t j = 0;
-        for (; j < nn; j++) if (nstate[j] == s) break;
-        if (j == nn) {
-          if ((uint64_t)base + created >= S.cap_cells) { a_or(&sh.status, GS_OVERFLOW); break; }
-          for (uint32_t q = 0; q < nn; q++) if (nnode[q] == en && nstrand[q] != strand) a_or(&sh.status, GS_ORDER_DEPENDENT);
-          const uint32_t idx = base + created++;
-          nstate[nn] = s; nidx[nn] = idx; ncnt[nn] = 0; nnode[nn] = en; nstrand[nn] = strand; nlinks[nn] = 0; nn++;
-          S.ck[idx] = s; S.cn[idx] = en;
-          S.cp[4 * idx + 0] = NONE32; S.cp[4 * idx + 1] = NONE32; S.cp[4 * idx + 2] = NONE32; S.cp[4 * idx + 3] = NONE32;
-          S.cflags[idx] = out_mask(a & 0xFF, strand) << CF_OMASK_SHIFT;
-          S.packlevel[idx] = level;   // scratch: read back by the parallel commit below
-        }
-        ncnt[j] += cnt[t];            // <= 4 * MAX_PATHS < 2^32
-        nlinks[j]++;
-        S.cp[4 * nidx[j] + u0] = cell[t];
-        next[t] = nidx[j];
-      }
-      if (ld_sh(&sh.status) & GS_OVERFLOW) { done = l; break; }
-      for (uint32_t j = 0; j < nn; j++) S.cc[nidx[j]] = ncnt[j];
-      for (int t = 0; t < w; t++) {
-        alive[t] = alive[t] && next[t] != NONE32;
-        if (alive[t]) {
-          cell[t] = next[t];
-          for (uint32_t j = 0; j < nn; j++) if (nidx[j] == next[t]) { cnt[t] = clamp_paths(ncnt[j]); pst[t] = nstate[j]; }
-        }
-      }
-      S.lstart[level + 1] = base + created;
-      // a level with one cell whose single link comes from the single cell below belongs to a chain run
-      uint32_t run = 0;
-      if (nn == 1 && prev_n == 1 && nlinks[0] == 1) run = run_prev ? run_prev : level;
-      S.lrun[level] = run;
+      const uint32_t nn = sh.nw_n[l];
+      sh.nw_off[l] = off;
+      off += nn;
+      const uint32_t run = (nn == 1 && prev_n == 1) ? (run_prev ? run_prev : (uint32_t)(c + l)) : 0;
+      sh.nw_run[l] = run;
       run_prev = run; prev_n = nn;
-      if (nn == 0) { done = l + 1; break; }   // the border died on this level
+      if (nn == 0) { done = l + 1; break; }
     }
-    sh.ch_base = base;
-    sh.ch_cnt = created;
-    sh.ch_len = (uint32_t)done;
-    sh.ncells = base + created;
+    if ((uint64_t)base + off > S.cap_cells) { a_or(&sh.status, GS_OVERFLOW); done = 0; off = 0; }
+    sh.ch_base = base; sh.ch_len = (uint32_t)done;
+    sh.ncells = base + off;
   }
   G::sync();
-  const uint32_t base = ld_sh(&sh.ch_base), created = ld_sh(&sh.ch_cnt);
-  for (uint32_t q = rank; q < created; q += G::size()) {
-    const uint32_t idx = base + q, en = S.cn[idx], level = S.packlevel[idx];
-    const uint64_t s = S.ck[idx];
-    const uint32_t strand = canonical(s, k).strand;
-    a_max(&S.ent[en].fstamp[strand], level + 1);
-    S.ent[en].fcell[strand] = idx;
-    const uint32_t fl = a_or(&S.ent[en].flags, NF_HAS_F);
-    if ((fl & NF_TARGET) && (int)level >= sh.tlo) {
-      for (int j = 0; j <= gd.rmf; j++)
-        if ((S.rk[j] & FLANK_KMER) == s) S.thit[(size_t)j * sh.trow + (level - (uint32_t)sh.tlo)] = idx + 1;
+  const int done = (int)ld_sh(&sh.ch_len);
+  const uint32_t base = ld_sh(&sh.ch_base);
+  for (int l = rank; l < done; l += gsz) {
+    const uint32_t level = (uint32_t)(c + l);
+    uint32_t ord = 0;
+#pragma unroll
+    for (int t = 0; t < NARROW_W; t++) {
+      if (t >= w || l >= sh.nw_fail[t]) continue;
+      const uint64_t s = sh.ch_s[l][t];
+      bool dup = false;
+#pragma unroll
+      for (int u = 0; u < NARROW_W; u++) if (u < t && l < sh.nw_fail[u] && sh.ch_s[l][u] == s) dup = true;
+      if (dup) continue;
+      const uint32_t idx = base + sh.nw_off[l] + ord++;
+      const uint32_t a = sh.ch_a[l][t], en = sh.ch_e[l][t], strand = (a >> 8) & 1;
+      uint32_t cnt = 0;
+      uint32_t link[4] = {NONE32, NONE32, NONE32, NONE32};
+#pragma unroll
+      for (int v = 0; v < NARROW_W; v++) {
+        if (v >= w || l >= sh.nw_fail[v] || sh.ch_s[l][v] != s) continue;
+        cnt += sh.nw_cnt0[v];   // <= 4 * MAX_PATHS < 2^32
+        // the cell of chain v on the level below: lowest alive chain with v's state there
+        const uint64_t ps = l ? sh.ch_s[l - 1][v] : sh.nw_x0[v];
+        uint32_t pord = 0, prep = (uint32_t)v;
+#pragma unroll
+        for (int u = 0; u < NARROW_W; u++) {
+          if (u >= w || u >= v) continue;
+          const bool ualive = l ? (l - 1 < sh.nw_fail[u]) : true;
+          if (!ualive) continue;
+          const uint64_t us = l ? sh.ch_s[l - 1][u] : sh.nw_x0[u];
+          if (us == ps) { if (prep == (uint32_t)v) prep = (uint32_t)u; }
+        }
+        // ordinal of the representative among the distinct alive states of the level below
+#pragma unroll
+        for (int u = 0; u < NARROW_W; u++) {
+          if (u >= w || (uint32_t)u >= prep) continue;
+          const bool ualive = l ? (l - 1 < sh.nw_fail[u]) : true;
+          if (!ualive) continue;
+          const uint64_t us = l ? sh.ch_s[l - 1][u] : sh.nw_x0[u];
+          bool udup = false;
+#pragma unroll
+          for (int z = 0; z < NARROW_W; z++) {
+            if (z >= u) continue;
+            const bool zalive = l ? (l - 1 < sh.nw_fail[z]) : true;
+            if (zalive && (l ? sh.ch_s[l - 1][z] : sh.nw_x0[z]) == us) udup = true;
+          }
+          if (!udup) pord++;
+        }
+        const uint32_t pidx = l ? base + sh.nw_off[l - 1] + pord : lo + prep;
+        link[(uint32_t)(ps >> (2 * (k - 1))) & 3u] = pidx;
+      }
+      S.ck[idx] = s; S.cc[idx] = cnt; S.cn[idx] = en;
+      S.cp[4 * idx + 0] = link[0]; S.cp[4 * idx + 1] = link[1]; S.cp[4 * idx + 2] = link[2]; S.cp[4 * idx + 3] = link[3];
+      S.cflags[idx] = out_mask(a & 0xFF, strand) << CF_OMASK_SHIFT;
+      // both strands of one node on one level (Q3)
+#pragma unroll
+      for (int u = 0; u < NARROW_W; u++)
+        if (u < w && u != t && l < sh.nw_fail[u] && sh.ch_e[l][u] == en && sh.ch_s[l][u] != s) a_or(&sh.status, GS_ORDER_DEPENDENT);
+      a_max(&S.ent[en].fstamp[strand], level + 1);
+      S.ent[en].fcell[strand] = idx;
+      const uint32_t fl = a_or(&S.ent[en].flags, NF_HAS_F);
+      if ((fl & NF_TARGET) && (int)level >= sh.tlo) {
+        for (int j = 0; j <= gd.rmf; j++)
+          if ((S.rk[j] & FLANK_KMER) == s) S.thit[(size_t)j * sh.trow + (level - (uint32_t)sh.tlo)] = idx + 1;
+      }
     }
+    S.lstart[level + 1] = base + sh.nw_off[l] + sh.nw_n[l];
+    S.lrun[level] = sh.nw_run[l];
   }
   G::sync();
-  return (int)ld_sh(&sh.ch_len);
+  return done;
 }
 
 // Backward marking of a run of chain levels [rs, d] (single cell per level, single link to the level below): the
