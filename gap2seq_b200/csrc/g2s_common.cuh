@@ -32,7 +32,16 @@ static const int MAX_FUZ = 31;
 struct __attribute__((aligned(16))) Slot {
   uint64_t key;   // canonical k-mer, KEY_EMPTY when free
   uint64_t val;   // bits 0-7: adjacency byte (low nibble out A,C,T,G, high nibble in; canonical orientation)
+                  // bits 8-35 / 36-63: skip hint of the canonical / reverse-complement orientation (see hint_of)
 };
+
+// Skip hints.  For an oriented k-mer x the hint lists the next j <= HINT_MAX bases of its UNIQUE forward extension:
+// x and the j-1 nodes after it each have exactly one successor (the listed base); nothing is claimed about the node
+// the last base leads to.  A walker that holds a hint can therefore emit j levels from ONE table gather - the
+// per-level dependent gather of a chain of unitig-interior nodes disappears - while every node still becomes its
+// own DP cell.  28 bits: bases at 2 bits each (first base lowest), length in bits 24-27.
+static const int HINT_MAX = 12;
+G2S_HD uint32_t hint_of(uint64_t val, uint32_t strand) { return (uint32_t)(val >> (8 + 28 * strand)) & 0xFFFFFFFu; }
 
 struct Table {
   const Slot *slots;
@@ -107,6 +116,39 @@ G2S_D int64_t table_find(const Table &t, uint64_t canon, uint32_t *adj) {
     if (s.key == KEY_EMPTY) return -1;
     h = (h + 1) & t.cap_mask;
   }
+}
+
+// same, returning the whole value word (adjacency byte + skip hints)
+G2S_D int64_t table_find_val(const Table &t, uint64_t canon, uint64_t *val) {
+  uint64_t h = mix64(canon) & t.cap_mask;
+  for (;;) {
+    Slot s = load_slot(t.slots + h);
+    if (s.key == canon) { *val = s.val; return (int64_t)h; }
+    if (s.key == KEY_EMPTY) return -1;
+    h = (h + 1) & t.cap_mask;
+  }
+}
+
+// Skip hints of one node, computed from the adjacency bytes by walking (used by the table build kernel and by the
+// host emulation in tests/): returns the 56 hint bits to be stored at bit 8 of Slot::val.
+G2S_D uint64_t compute_hints(const Table &t, uint64_t key, uint32_t adj) {
+  uint64_t out = 0;
+  for (uint32_t o = 0; o < 2; o++) {
+    uint64_t x = o ? revcomp(key, t.k) : key;
+    uint32_t mask = out_mask(adj, o), bits = 0, len = 0;
+    while (len < (uint32_t)HINT_MAX && mask != 0 && !(mask & (mask - 1))) {
+      const uint32_t nt = mask == 1 ? 0 : mask == 2 ? 1 : mask == 4 ? 2 : 3;
+      bits |= nt << (2 * len);
+      len++;
+      x = succ_kmer(x, nt, t);
+      const Canon c = canonical(x, t.k);
+      uint32_t a2 = 0;
+      if (table_find(t, c.key, &a2) < 0) break;   // cannot happen: the adjacency byte said the neighbour exists
+      mask = out_mask(a2, c.strand);
+    }
+    out |= (uint64_t)((bits & 0xFFFFFFu) | (len << 24)) << (28 * o);
+  }
+  return out;
 }
 
 // ASCII -> oriented k-mer value (no validity check, exactly like Graph::buildNode, Graph.cpp:1726-1744)

@@ -106,7 +106,8 @@ extern "C" int g2s_abi_version(void) { return G2S_ABI_VERSION; }
 extern "C" int g2s_create(const g2s_config *cfg, g2s_engine **out) {
   if (!cfg || !out) return fail(G2S_E_ARG, "g2s_create: null argument");
   if (cfg->abi_version != G2S_ABI_VERSION) return fail(G2S_E_ARG, "g2s_create: ABI version mismatch");
-  if (cfg->k < 3 || cfg->k > 31) return fail(G2S_E_ARG, "g2s_create: k must be in [3, 31]");
+  if (cfg->k < 3 || cfg->k > 31 || !(cfg->k & 1))
+    return fail(G2S_E_ARG, "g2s_create: k must be odd and in [3, 31] (even k has palindromic k-mers, SURVEY Q11)");
   if (cfg->max_fuz < 0 || cfg->max_fuz > MAX_FUZ) return fail(G2S_E_ARG, "g2s_create: max_fuz must be in [0, 31]");
   int ndev = 0;
   CUDA_TRY(cudaGetDeviceCount(&ndev));

@@ -159,7 +159,7 @@ struct GShared {       // per group, in shared memory
   int32_t tlo;          // first level that has thit entries: max(0, g + lmf - e)
   uint32_t trow;        // entries per target row: Dmax - tlo + 1
   uint64_t nw_x[NARROW_W], nw_x0[NARROW_W];
-  uint32_t nw_m[NARROW_W], nw_cnt0[NARROW_W];
+  uint32_t nw_m[NARROW_W], nw_cnt0[NARROW_W], nw_hb[NARROW_W], nw_hl[NARROW_W];
   int32_t nw_fail[NARROW_W];
   uint32_t nw_n[CHAIN_LEN], nw_off[CHAIN_LEN], nw_run[CHAIN_LEN];
   uint64_t ch_s[CHAIN_LEN][NARROW_W];
@@ -361,8 +361,11 @@ G2S_D bool found_scan(const Slice &S, const GapDev &gd, GShared &sh, int lo, int
 // ch_s[l][t] / ch_a[l][t] receive chain t's state and (adj | strand << 8 | 1 << 16) on level l, ch_a == 0: no state.
 template <class G, bool FORWARD>
 G2S_D int narrow_scout(const Table &T, GShared &sh, int w, int maxlen) {
-  // per-chain state lives in shared memory (sh.nw_x / sh.nw_m, mask 0xFF = chain ended) so that any group size,
-  // including the size-1 host emulation, can play the w scouts
+  // Per-chain state lives in shared memory so that any group size, including the size-1 host emulation, can play the
+  // w scouts: nw_x = the chain's tip in WALK orientation (forward pass: the state itself; right pass: its reverse
+  // complement, so that walking predecessors is walking successors), nw_m = its out-mask in that orientation
+  // (0xFF = chain ended), nw_hb / nw_hl = what is left of the tip's skip hint.  A gather happens only where a hint
+  // ends; between gathers a level costs a shift and an insert.
   const int k = T.k, rank = G::rank(), gsz = G::size();
   if (rank == 0) { sh.nw_stop = 0; sh.nw_alive = 0; }
   G::sync();
@@ -386,12 +389,24 @@ G2S_D int narrow_scout(const Table &T, GShared &sh, int w, int maxlen) {
       const uint32_t mask = sh.nw_m[t];
       if (mask == 0xFF) { sh.ch_a[l][t] = 0; continue; }
       const uint32_t nt = mask == 1 ? 0 : mask == 2 ? 1 : mask == 4 ? 2 : 3;
-      const uint64_t s = FORWARD ? succ_kmer(sh.nw_x[t], nt, T) : pred_kmer(sh.nw_x[t], nt, T);
-      const Canon cs = canonical(s, k);
-      uint32_t adj = 0;
-      if (table_find(T, cs.key, &adj) < 0) { a_or(&sh.status, GS_INTERNAL); sh.nw_m[t] = 0xFF; sh.ch_a[l][t] = 0; continue; }
-      sh.ch_s[l][t] = s; sh.ch_a[l][t] = adj | (cs.strand << 8) | (1u << 16);
-      sh.nw_x[t] = s; sh.nw_m[t] = FORWARD ? out_mask(adj, cs.strand) : in_mask(adj, cs.strand);
+      const uint64_t y = succ_kmer(sh.nw_x[t], nt, T);
+      const Canon cy = canonical(y, k);
+      uint32_t nmask;
+      if (sh.nw_hl[t] > 1) {           // y is an interior node of the hint: exactly one successor, its base is known
+        const uint32_t hb = sh.nw_hb[t] >> 2;
+        nmask = 1u << (hb & 3);
+        sh.nw_hb[t] = hb; sh.nw_hl[t]--;
+      } else {                         // the hint ends at y (or there is none yet): gather y
+        uint64_t val = 0;
+        if (table_find_val(T, cy.key, &val) < 0) { a_or(&sh.status, GS_INTERNAL); sh.nw_m[t] = 0xFF; sh.ch_a[l][t] = 0; continue; }
+        nmask = out_mask((uint32_t)(val & 0xFF), cy.strand);
+        const uint32_t h = hint_of(val, cy.strand);
+        sh.nw_hb[t] = h & 0xFFFFFFu; sh.nw_hl[t] = h >> 24;
+      }
+      // emit the state of this level in the orientation of the pass, with its mask in the direction of the pass
+      if (FORWARD) { sh.ch_s[l][t] = y; sh.ch_a[l][t] = nmask | (cy.strand << 8) | (1u << 16); }
+      else { sh.ch_s[l][t] = revcomp(y, k); sh.ch_a[l][t] = swap2(nmask) | ((cy.strand ^ 1u) << 8) | (1u << 16); }
+      sh.nw_x[t] = y; sh.nw_m[t] = nmask;
     }
     len = l + 1;
     G::sync();
@@ -405,7 +420,7 @@ G2S_D int narrow_scout(const Table &T, GShared &sh, int w, int maxlen) {
 template <class G>
 G2S_D int narrow_right(const Table &T, const Slice &S, GShared &sh, int cur, int c, int right_half, int n, uint32_t *n_out) {
   const int k = T.k, rank = G::rank(), gsz = G::size();
-  for (int t = rank; t < n; t += gsz) { sh.nw_x[t] = S.fk[cur][t]; sh.nw_m[t] = S.fm[cur][t]; }
+  for (int t = rank; t < n; t += gsz) { sh.nw_x[t] = revcomp(S.fk[cur][t], k); sh.nw_m[t] = swap2(S.fm[cur][t]); sh.nw_hl[t] = 0; sh.nw_hb[t] = 0; }
   const int maxlen = right_half - c + 1 < CHAIN_LEN ? right_half - c + 1 : CHAIN_LEN;
   const int len = narrow_scout<G, false>(T, sh, n, maxlen);
   if (len == 0) return 0;
@@ -437,7 +452,7 @@ G2S_D int narrow_right(const Table &T, const Slice &S, GShared &sh, int cur, int
       if (dup) continue;
       if (l == len - 1) {
         S.fk[cur][ns] = s;
-        S.fm[cur][ns] = (unsigned char)in_mask(sh.ch_a[l][t] & 0xFF, (sh.ch_a[l][t] >> 8) & 1);
+        S.fm[cur][ns] = (unsigned char)(sh.ch_a[l][t] & 0xFF);   // already the in-mask of the emitted state
       }
       ns++;
     }
@@ -470,6 +485,7 @@ G2S_D int narrow_forward(const Table &T, const Slice &S, GShared &sh, const GapD
     sh.nw_x[t] = x; sh.nw_x0[t] = x;
     sh.nw_m[t] = (ld_cg(&S.cflags[lo + t]) >> CF_OMASK_SHIFT) & 15u;
     sh.nw_cnt0[t] = clamp_paths(ld_cg(&S.cc[lo + t]));
+    sh.nw_hl[t] = 0; sh.nw_hb[t] = 0;
   }
   const int maxlen = Dmax - c + 1 < CHAIN_LEN ? Dmax - c + 1 : CHAIN_LEN;
   const int len = narrow_scout<G, true>(T, sh, w, maxlen);
@@ -575,7 +591,7 @@ G2S_D int narrow_forward(const Table &T, const Slice &S, GShared &sh, const GapD
       }
       S.ck[idx] = s; S.cc[idx] = cnt; S.cn[idx] = en;
       S.cp[4 * idx + 0] = link[0]; S.cp[4 * idx + 1] = link[1]; S.cp[4 * idx + 2] = link[2]; S.cp[4 * idx + 3] = link[3];
-      S.cflags[idx] = out_mask(a & 0xFF, strand) << CF_OMASK_SHIFT;
+      S.cflags[idx] = (a & 0xFF) << CF_OMASK_SHIFT;   // the scout emits the oriented out-mask
       // both strands of one node on one level (Q3)
 #pragma unroll
       for (int u = 0; u < NARROW_W; u++)

@@ -61,6 +61,24 @@ __global__ void k_adjacency(Slot *slots, Table t) {
   }
 }
 
+// skip hints of every node (g2s_common.cuh hint_of): up to 12 dependent probes per orientation, run once at import
+__global__ void k_hints(const Slot *slots, Table t, uint64_t *hints) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  const uint64_t cap = t.cap_mask + 1;
+  for (; i < cap; i += stride) {
+    const uint64_t key = slots[i].key;
+    hints[i] = key == KEY_EMPTY ? 0 : compute_hints(t, key, (uint32_t)(slots[i].val & 0xFF));
+  }
+}
+
+// second step so that k_hints reads a table nobody writes (its probes use the read-only path)
+__global__ void k_apply_hints(Slot *slots, uint64_t cap, const uint64_t *hints) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (; i < cap; i += stride) slots[i].val = (slots[i].val & 0xFF) | (hints[i] << 8);
+}
+
 __global__ void k_count_solid(const uint32_t *counts, const int *n_runs, const uint64_t *keys, uint32_t solid,
                               unsigned long long *n_solid) {
   const uint64_t n = (uint64_t)*n_runs;
@@ -155,10 +173,17 @@ cudaError_t table_fill(DeviceTable *dt, const uint64_t *keys_dev, const uint32_t
   CK(cudaGetLastError());
   k_adjacency<<<grid_for(dt->cap, 256, sms), 256, 0, st>>>(dt->slots, table_view(*dt));
   CK(cudaGetLastError());
+  uint64_t *d_hints = nullptr;
+  CK(cudaMalloc(&d_hints, dt->cap * sizeof(uint64_t)));
+  k_hints<<<grid_for(dt->cap, 256, sms), 256, 0, st>>>(dt->slots, table_view(*dt), d_hints);
+  CK(cudaGetLastError());
+  k_apply_hints<<<grid_for(dt->cap, 256, sms), 256, 0, st>>>(dt->slots, dt->cap, d_hints);
+  CK(cudaGetLastError());
   unsigned long long h_n = 0;
   CK(cudaMemcpyAsync(&h_n, d_n, sizeof(h_n), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   cudaFree(d_n);
+  cudaFree(d_hints);
   dt->n = h_n;
   return cudaSuccess;
 }

@@ -56,7 +56,7 @@ typedef struct g2s_engine g2s_engine;
 typedef struct g2s_config {
   int32_t abi_version;   /* G2S_ABI_VERSION */
   int32_t device;        /* CUDA device ordinal */
-  int32_t k;             /* k-mer size, 3 <= k <= 31 (the -k flag, src/Gap2Seq.cpp:164) */
+  int32_t k;             /* k-mer size, odd, 3 <= k <= 31 (the -k flag, src/Gap2Seq.cpp:164) */
   int32_t max_fuz;       /* upper bound of left/right_max_fuz over all gaps, <= 31 (the -fuz flag) */
   int64_t max_mem_bytes; /* device memory budget for DP scratch; 0 = 60 % of the free memory (the -max-mem flag) */
   int32_t host_threads;  /* threads for the host-side subgraph analysis; 0 = hardware concurrency (-nb-cores) */

@@ -53,6 +53,9 @@ void *emul_graph_from_kmers(int k, const uint64_t *kmers, size_t n) {
   }
   for (uint64_t h = 0; h < cap; h++)
     if (g->slots[h].key != KEY_EMPTY) g->slots[h].val = host_adj(g->t, g->slots[h].key);
+  for (uint64_t h = 0; h < cap; h++)
+    if (g->slots[h].key != KEY_EMPTY)
+      g->slots[h].val = (g->slots[h].val & 0xFF) | (compute_hints(g->t, g->slots[h].key, (uint32_t)(g->slots[h].val & 0xFF)) << 8);
   return g;
 }
 
