@@ -12,11 +12,13 @@ static const int WARPS_PER_CTA = 1;   // one warp group per CTA: few long gaps s
 static const int CTA_THREADS = 512;
 
 struct WarpGroup {
+  static constexpr bool kWarp = true;
   static __device__ __forceinline__ int rank() { return threadIdx.x & 31; }
   static __device__ __forceinline__ int size() { return 32; }
   static __device__ __forceinline__ void sync() { __syncwarp(); }
 };
 struct BlockGroup {
+  static constexpr bool kWarp = false;
   static __device__ __forceinline__ int rank() { return threadIdx.x; }
   static __device__ __forceinline__ int size() { return blockDim.x; }
   static __device__ __forceinline__ void sync() { __syncthreads(); }

@@ -359,8 +359,62 @@ G2S_D bool found_scan(const Slice &S, const GapDev &gd, GShared &sh, int lo, int
 
 // Scout phase shared by both passes.  Returns the number of levels looked ahead (0: a border state branches).
 // ch_s[l][t] / ch_a[l][t] receive chain t's state and (adj | strand << 8 | 1 << 16) on level l, ch_a == 0: no state.
+#ifdef G2S_DEVICE_BUILD
+// Warp flavour of the scout: lane t < w keeps chain t's tip, mask and hint in REGISTERS, the per-level "did a chain
+// branch / is any chain left" votes are warp votes, and shared memory only receives the emitted states.
+template <bool FORWARD>
+__device__ __forceinline__ int narrow_scout_warp(const Table &T, GShared &sh, int w, int maxlen) {
+  const int k = T.k;
+  const int lane = threadIdx.x & 31;
+  uint64_t x = 0; uint32_t mask = 0xFF, hb = 0, hl = 0;
+  if (lane < w) { x = sh.nw_x[lane]; mask = sh.nw_m[lane]; }
+  int len = 0;
+  for (int l = 0; l < maxlen; l++) {
+    if (mask == 0) mask = 0xFF;                                      // dead end
+    const bool ended = mask == 0xFF;
+    const bool branch = !ended && (mask & (mask - 1)) != 0;
+    if (__any_sync(0xffffffffu, branch)) break;                      // a branch ends the look-ahead BEFORE this level
+    if (!__any_sync(0xffffffffu, !ended)) {                          // every chain ended: keep the empty level
+      if (lane < w) sh.ch_a[l][lane] = 0;
+      len = l + 1;
+      break;
+    }
+    if (lane < w) {
+      if (ended) sh.ch_a[l][lane] = 0;
+      else {
+        const uint32_t nt = mask == 1 ? 0 : mask == 2 ? 1 : mask == 4 ? 2 : 3;
+        const uint64_t y = succ_kmer(x, nt, T);
+        const Canon cy = canonical(y, k);
+        uint32_t nmask;
+        bool ok = true;
+        if (hl > 1) { hb >>= 2; nmask = 1u << (hb & 3); hl--; }
+        else {
+          uint64_t val = 0;
+          if (table_find_val(T, cy.key, &val) < 0) { a_or(&sh.status, GS_INTERNAL); ok = false; nmask = 0xFF; }
+          else {
+            nmask = out_mask((uint32_t)(val & 0xFF), cy.strand);
+            const uint32_t h = hint_of(val, cy.strand);
+            hb = h & 0xFFFFFFu; hl = h >> 24;
+          }
+        }
+        if (!ok) sh.ch_a[l][lane] = 0;
+        else if (FORWARD) { sh.ch_s[l][lane] = y; sh.ch_a[l][lane] = nmask | (cy.strand << 8) | (1u << 16); }
+        else { sh.ch_s[l][lane] = revcomp(y, k); sh.ch_a[l][lane] = swap2(nmask) | ((cy.strand ^ 1u) << 8) | (1u << 16); }
+        x = y; mask = nmask;
+      }
+    }
+    len = l + 1;
+  }
+  __syncwarp();
+  return len;
+}
+#endif
+
 template <class G, bool FORWARD>
 G2S_D int narrow_scout(const Table &T, GShared &sh, int w, int maxlen) {
+#ifdef G2S_DEVICE_BUILD
+  if (G::kWarp) { G::sync(); return narrow_scout_warp<FORWARD>(T, sh, w, maxlen); }
+#endif
   // Per-chain state lives in shared memory so that any group size, including the size-1 host emulation, can play the
   // w scouts: nw_x = the chain's tip in WALK orientation (forward pass: the state itself; right pass: its reverse
   // complement, so that walking predecessors is walking successors), nw_m = its out-mask in that orientation
