@@ -30,6 +30,8 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+PHASES = ["init", "right", "forward", "backward", "pack", "total", "fwd_scout", "fwd_node", "fwd_layout", "fwd_found",
+          "fwd_general", "n_narrow_batches", "n_narrow_levels", "n_general_levels"]
 BYTES_PER_CELL = 52          # 8 B frontier read + 32 B sector gather + 4 B count update + 8 B cell write
 WORKLOAD_DESC = {
     "cfg1": "cfg1: 100 kbp random genome, 30x error-free 100 bp reads, 20 gaps 50-500 bp, k=31, dist-error 500",
@@ -327,8 +329,8 @@ def main():
                          "algorithmic_bytes_per_cell": BYTES_PER_CELL,
                          "note": "thin gaps are chains of dependent gathers (1 cell per level): latency bound, see DESIGN.md"},
             "timed_region_wall_s": t_region,
-            "phase_cycles_slowest_gap": dict(zip(["init", "right", "forward", "backward", "pack", "total"], phase_slowest)),
-            "phase_cycles_sum": dict(zip(["init", "right", "forward", "backward", "pack", "total"], phase_sum)),
+            "phase_cycles_slowest_gap": dict(zip(PHASES, phase_slowest)),
+            "phase_cycles_sum": dict(zip(PHASES, phase_sum)),
         }
         if world == 1:
             keys, _ = eng.export_kmers()

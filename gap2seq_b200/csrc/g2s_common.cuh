@@ -39,7 +39,8 @@ struct __attribute__((aligned(16))) Slot {
 // x and the j-1 nodes after it each have exactly one successor (the listed base); nothing is claimed about the node
 // the last base leads to.  A walker that holds a hint can therefore emit j levels from ONE table gather - the
 // per-level dependent gather of a chain of unitig-interior nodes disappears - while every node still becomes its
-// own DP cell.  28 bits: bases at 2 bits each (first base lowest), length in bits 24-27.
+// own DP cell.  28 bits: length j in bits 24-27, the bases as a 2j-bit big-endian string in the low bits (first base
+// highest, like a k-mer), so that the state i steps ahead is ((x << 2i) | (bases >> 2(j-i))) & kmask.
 static const int HINT_MAX = 12;
 G2S_HD uint32_t hint_of(uint64_t val, uint32_t strand) { return (uint32_t)(val >> (8 + 28 * strand)) & 0xFFFFFFFu; }
 
@@ -138,7 +139,7 @@ G2S_D uint64_t compute_hints(const Table &t, uint64_t key, uint32_t adj) {
     uint32_t mask = out_mask(adj, o), bits = 0, len = 0;
     while (len < (uint32_t)HINT_MAX && mask != 0 && !(mask & (mask - 1))) {
       const uint32_t nt = mask == 1 ? 0 : mask == 2 ? 1 : mask == 4 ? 2 : 3;
-      bits |= nt << (2 * len);
+      bits = (bits << 2) | nt;
       len++;
       x = succ_kmer(x, nt, t);
       const Canon c = canonical(x, t.k);

@@ -211,11 +211,16 @@ extern "C" int g2s_get_timing(const g2s_engine *e, g2s_timing *out) {
 
 extern "C" int g2s_get_phase_cycles(const g2s_engine *e, double *sum, double *slowest) {
   if (!e || !sum || !slowest) return fail(G2S_E_ARG, "g2s_get_phase_cycles: null argument");
-  for (int q = 0; q < 6; q++) sum[q] = slowest[q] = 0;
+  for (int q = 0; q < 14; q++) sum[q] = slowest[q] = 0;
   uint32_t worst = 0;
   for (const GapOut &o : e->outs) {
     for (int q = 0; q < 6; q++) sum[q] += 16.0 * o.cyc[q];
-    if (o.cyc[5] >= worst) { worst = o.cyc[5]; for (int q = 0; q < 6; q++) slowest[q] = 16.0 * o.cyc[q]; }
+    for (int q = 0; q < 8; q++) sum[6 + q] += (q < 5 ? 16.0 : 1.0) * o.prof[q];
+    if (o.cyc[5] >= worst) {
+      worst = o.cyc[5];
+      for (int q = 0; q < 6; q++) slowest[q] = 16.0 * o.cyc[q];
+      for (int q = 0; q < 8; q++) slowest[6 + q] = (q < 5 ? 16.0 : 1.0) * o.prof[q];
+    }
   }
   return G2S_OK;
 }

@@ -98,7 +98,7 @@ enum {  // GapOut.status (device side)
   GS_ORDER_DEPENDENT = 1, GS_OVERFLOW = 2, GS_GENERAL = 4, GS_OUT_FULL = 8, GS_INTERNAL = 16, GS_DONE = 0x100
 };
 
-struct GapOut {        // 128 B
+struct GapOut {        // 160 B
   uint32_t status;
   uint32_t count_fwd, count_all;
   uint32_t n_plen;
@@ -113,6 +113,8 @@ struct GapOut {        // 128 B
   unsigned long long pack_off;
   uint32_t levels_r, levels_f;
   uint32_t cyc[6];     // SM cycles (>> 4) spent in: init, right pass, forward pass, backward marking, pack, total
+  uint32_t prof[8];    // forward pass detail (>> 4): scout, node phase, layout, found scan, general levels; [5] narrow batches,
+                       // [6] narrow levels, [7] general levels
 };
 
 struct SliceLayout {   // byte offsets inside one scratch slice; identical for every slice of a launch
@@ -156,6 +158,7 @@ struct GShared {       // per group, in shared memory
   uint32_t queue_item;
   // chain mode (a border of exactly one cell): the scout's look-ahead and the bulk backward marking
   uint32_t ch_len, ch_valid, ch_base, ch_cnt, nw_stop, nw_alive;
+  unsigned long long prof[8];
   int32_t tlo;          // first level that has thit entries: max(0, g + lmf - e)
   uint32_t trow;        // entries per target row: Dmax - tlo + 1
   uint64_t nw_x[NARROW_W], nw_x0[NARROW_W];
@@ -360,50 +363,72 @@ G2S_D bool found_scan(const Slice &S, const GapDev &gd, GShared &sh, int lo, int
 // Scout phase shared by both passes.  Returns the number of levels looked ahead (0: a border state branches).
 // ch_s[l][t] / ch_a[l][t] receive chain t's state and (adj | strand << 8 | 1 << 16) on level l, ch_a == 0: no state.
 #ifdef G2S_DEVICE_BUILD
-// Warp flavour of the scout: lane t < w keeps chain t's tip, mask and hint in REGISTERS, the per-level "did a chain
-// branch / is any chain left" votes are warp votes, and shared memory only receives the emitted states.
+// Warp flavour of the scout.  Lane t < w owns chain t (tip, mask, hint in registers).  A round emits r levels at
+// once, r = the shortest remaining hint among the living chains: the state i steps past a tip is
+// ((tip << 2i) | (hint >> 2(j-i))) & kmask, so the lanes compute the w*r states of the round in parallel; a chain
+// gathers (one table probe) only when its hint is used up.  Shared memory only receives the emitted states.
 template <bool FORWARD>
 __device__ __forceinline__ int narrow_scout_warp(const Table &T, GShared &sh, int w, int maxlen) {
   const int k = T.k;
+  const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   uint64_t x = 0; uint32_t mask = 0xFF, hb = 0, hl = 0;
   if (lane < w) { x = sh.nw_x[lane]; mask = sh.nw_m[lane]; }
   int len = 0;
-  for (int l = 0; l < maxlen; l++) {
+  while (len < maxlen) {
     if (mask == 0) mask = 0xFF;                                      // dead end
     const bool ended = mask == 0xFF;
     const bool branch = !ended && (mask & (mask - 1)) != 0;
-    if (__any_sync(0xffffffffu, branch)) break;                      // a branch ends the look-ahead BEFORE this level
-    if (!__any_sync(0xffffffffu, !ended)) {                          // every chain ended: keep the empty level
-      if (lane < w) sh.ch_a[l][lane] = 0;
-      len = l + 1;
+    if (__any_sync(FULL, branch)) break;                             // a branch ends the look-ahead BEFORE this level
+    if (!__any_sync(FULL, !ended)) {                                 // every chain ended: keep the empty level
+      if (lane < w) sh.ch_a[len][lane] = 0;
+      len++;
       break;
     }
-    if (lane < w) {
-      if (ended) sh.ch_a[l][lane] = 0;
-      else {
-        const uint32_t nt = mask == 1 ? 0 : mask == 2 ? 1 : mask == 4 ? 2 : 3;
-        const uint64_t y = succ_kmer(x, nt, T);
-        const Canon cy = canonical(y, k);
-        uint32_t nmask;
-        bool ok = true;
-        if (hl > 1) { hb >>= 2; nmask = 1u << (hb & 3); hl--; }
+    if (!ended && hl == 0) { hb = mask == 1 ? 0 : mask == 2 ? 1 : mask == 4 ? 2 : 3; hl = 1; }   // no hint: one known step
+    int r = (int)__reduce_min_sync(FULL, ended ? 0xFFFFu : hl);
+    if (r > maxlen - len) r = maxlen - len;
+    // parallel emission of w * r states (<= 48): two fixed sweeps so that every lane takes part in the shuffles
+#pragma unroll
+    for (int sweep = 0; sweep < 2; sweep++) {
+      const int q = lane + 32 * sweep;
+      const int t = q / r, i = q - t * r + 1;                         // chain, steps past the tip (1..r)
+      const int src = t < w ? t : 0;
+      const uint64_t xt = __shfl_sync(FULL, x, src);
+      const uint32_t bt = __shfl_sync(FULL, hb, src), lt = __shfl_sync(FULL, hl, src), mt = __shfl_sync(FULL, mask, src);
+      if (t < w) {
+        const int lvl = len + i - 1;
+        if (mt == 0xFF) sh.ch_a[lvl][t] = 0;
         else {
-          uint64_t val = 0;
-          if (table_find_val(T, cy.key, &val) < 0) { a_or(&sh.status, GS_INTERNAL); ok = false; nmask = 0xFF; }
-          else {
-            nmask = out_mask((uint32_t)(val & 0xFF), cy.strand);
-            const uint32_t h = hint_of(val, cy.strand);
-            hb = h & 0xFFFFFFu; hl = h >> 24;
-          }
+          const uint64_t y = ((xt << (2 * i)) | (uint64_t)((bt >> (2 * (lt - i))) & ((1u << (2 * i)) - 1))) & T.kmask;
+          const Canon cy = canonical(y, k);
+          const uint32_t nmask = (uint32_t)i < lt ? 1u << ((bt >> (2 * (lt - i - 1))) & 3) : 0u;   // hint end: patched below
+          if (FORWARD) { sh.ch_s[lvl][t] = y; sh.ch_a[lvl][t] = nmask | (cy.strand << 8) | (1u << 16); }
+          else { sh.ch_s[lvl][t] = revcomp(y, k); sh.ch_a[lvl][t] = swap2(nmask) | ((cy.strand ^ 1u) << 8) | (1u << 16); }
         }
-        if (!ok) sh.ch_a[l][lane] = 0;
-        else if (FORWARD) { sh.ch_s[l][lane] = y; sh.ch_a[l][lane] = nmask | (cy.strand << 8) | (1u << 16); }
-        else { sh.ch_s[l][lane] = revcomp(y, k); sh.ch_a[l][lane] = swap2(nmask) | ((cy.strand ^ 1u) << 8) | (1u << 16); }
-        x = y; mask = nmask;
       }
     }
-    len = l + 1;
+    __syncwarp();
+    // owners advance their tips; a used-up hint costs one gather
+    if (lane < w && !ended) {
+      x = ((x << (2 * r)) | (uint64_t)((hb >> (2 * (hl - r))) & ((1u << (2 * r)) - 1))) & T.kmask;
+      hl -= r;
+      if (hl == 0) {
+        const Canon cx = canonical(x, k);
+        uint64_t val = 0;
+        if (table_find_val(T, cx.key, &val) < 0) { a_or(&sh.status, GS_INTERNAL); mask = 0xFF; }
+        else {
+          mask = out_mask((uint32_t)(val & 0xFF), cx.strand);
+          const uint32_t h = hint_of(val, cx.strand);
+          hb = h & 0xFFFFFFu; hl = h >> 24;
+          const int lvl = len + r - 1;
+          sh.ch_a[lvl][lane] = (sh.ch_a[lvl][lane] & ~0xFFu) | (FORWARD ? mask : swap2(mask));
+        }
+      } else {
+        mask = 1u << ((hb >> (2 * (hl - 1))) & 3);
+      }
+    }
+    len += r;
   }
   __syncwarp();
   return len;
@@ -447,9 +472,8 @@ G2S_D int narrow_scout(const Table &T, GShared &sh, int w, int maxlen) {
       const Canon cy = canonical(y, k);
       uint32_t nmask;
       if (sh.nw_hl[t] > 1) {           // y is an interior node of the hint: exactly one successor, its base is known
-        const uint32_t hb = sh.nw_hb[t] >> 2;
-        nmask = 1u << (hb & 3);
-        sh.nw_hb[t] = hb; sh.nw_hl[t]--;
+        sh.nw_hl[t]--;
+        nmask = 1u << ((sh.nw_hb[t] >> (2 * (sh.nw_hl[t] - 1))) & 3);
       } else {                         // the hint ends at y (or there is none yet): gather y
         uint64_t val = 0;
         if (table_find_val(T, cy.key, &val) < 0) { a_or(&sh.status, GS_INTERNAL); sh.nw_m[t] = 0xFF; sh.ch_a[l][t] = 0; continue; }
@@ -542,7 +566,10 @@ G2S_D int narrow_forward(const Table &T, const Slice &S, GShared &sh, const GapD
     sh.nw_hl[t] = 0; sh.nw_hb[t] = 0;
   }
   const int maxlen = Dmax - c + 1 < CHAIN_LEN ? Dmax - c + 1 : CHAIN_LEN;
+  const unsigned long long tp0 = now_cycles();
   const int len = narrow_scout<G, true>(T, sh, w, maxlen);
+  const unsigned long long tp1 = now_cycles();
+  if (rank == 0) sh.prof[0] += tp1 - tp0;
   if (len == 0) return 0;
   for (int t = rank; t < w; t += gsz) sh.nw_fail[t] = len;
   G::sync();
@@ -559,6 +586,8 @@ G2S_D int narrow_forward(const Table &T, const Slice &S, GShared &sh, const GapD
     if (en == NONE32) a_mini(&sh.nw_fail[t], l);
   }
   G::sync();
+  const unsigned long long tp2 = now_cycles();
+  if (rank == 0) sh.prof[1] += tp2 - tp1;
   if (ld_sh(&sh.status) & GS_OVERFLOW) return 0;
   // distinct cells per level
   for (int l = rank; l < len; l += gsz) {
@@ -662,6 +691,7 @@ G2S_D int narrow_forward(const Table &T, const Slice &S, GShared &sh, const GapD
     S.lrun[level] = sh.nw_run[l];
   }
   G::sync();
+  if (rank == 0) { sh.prof[2] += now_cycles() - tp2; sh.prof[5] += 1; sh.prof[6] += (unsigned long long)done; }
   return done;
 }
 
@@ -760,6 +790,7 @@ G2S_D void process_gap(const FillParams &P, const GapDev &gd, const Slice &S, GS
     }
     if (rank == 0) {
       sh.tlo = tlo; sh.trow = (uint32_t)trow;
+      for (int q = 0; q < 8; q++) sh.prof[q] = 0;
       sh.ncells = 0; sh.nnodes = 0; sh.nnext = 0; sh.status = 0;
       sh.npack = 0; sh.nB = 0; sh.n_edges = 0; sh.n_src = 0; sh.n_sink = 0;
       sh.max_src_level = -1; sh.min_sink_level = 0x7fffffff;
@@ -908,7 +939,9 @@ G2S_D void process_gap(const FillParams &P, const GapDev &gd, const Slice &S, GS
           const int last = c + adv - 1;
           top_level = levels_f = last;
           if (!found && last >= g + lmf + rmf) {
+            const unsigned long long tf0 = now_cycles();
             found = found_scan<G>(S, gd, sh, c > g + lmf + rmf ? c : g + lmf + rmf, last);
+            if (rank == 0) sh.prof[3] += now_cycles() - tf0;
             if (found && !all_paths) {   // -best-only: the table ends at the level of the first hit
               const int fl = ld_sh(&sh.found_level);
               G::sync();
@@ -922,6 +955,8 @@ G2S_D void process_gap(const FillParams &P, const GapDev &gd, const Slice &S, GS
           continue;
         }
       }
+      const unsigned long long tg0 = now_cycles();
+      if (rank == 0) sh.prof[7] += 1;
       if (!dead) {
         top_level = c;
         levels_f = c;
@@ -1031,6 +1066,7 @@ G2S_D void process_gap(const FillParams &P, const GapDev &gd, const Slice &S, GS
       } else {
         G::sync();
       }
+      if (rank == 0) sh.prof[4] += now_cycles() - tg0;
     }
   }
   G::sync();
@@ -1195,6 +1231,8 @@ G2S_D void process_gap(const FillParams &P, const GapDev &gd, const Slice &S, GS
     o.cyc[0] = (uint32_t)((t_init - t_start) >> 4); o.cyc[1] = (uint32_t)((t_right - t_init) >> 4);
     o.cyc[2] = (uint32_t)((t_fwd - t_right) >> 4); o.cyc[3] = (uint32_t)((t_back - t_fwd) >> 4);
     o.cyc[4] = (uint32_t)((t_end - t_back) >> 4); o.cyc[5] = (uint32_t)((t_end - t_start) >> 4);
+    for (int q = 0; q < 5; q++) o.prof[q] = (uint32_t)(sh.prof[q] >> 4);
+    for (int q = 5; q < 8; q++) o.prof[q] = (uint32_t)sh.prof[q];
     *out = o;
   }
   G::sync();

@@ -291,7 +291,7 @@ class Engine:
 
     def phase_cycles(self):
         """SM cycles per phase (init, right, forward, backward, pack, total) of the last device pass: (sum, slowest gap)."""
-        a, b = (C.c_double * 6)(), (C.c_double * 6)()
+        a, b = (C.c_double * 14)(), (C.c_double * 14)()
         self._check(self.L.g2s_get_phase_cycles(self.h, a, b))
         return list(a), list(b)
 

@@ -174,8 +174,9 @@ int g2s_fill_records(g2s_engine *e, const char *const *seqs, const char *const *
 void g2s_free(void *p);
 
 int g2s_get_timing(const g2s_engine *e, g2s_timing *out);
-/* profiling aid: SM cycles per phase of the last device pass, summed over gaps (sum[6]) and of the slowest gap
- * (slowest[6]); phases: init, right pass, forward pass, backward marking, pack, total */
+/* profiling aid: SM cycles per phase of the last device pass, summed over gaps (sum[14]) and of the slowest gap
+ * (slowest[14]); [0..5]: init, right pass, forward pass, backward marking, pack, total; [6..10] forward detail: scout,
+ * node phase, layout, found scan, level-by-level path; [11..13] counts: narrow batches, narrow levels, general levels */
 int g2s_get_phase_cycles(const g2s_engine *e, double *sum, double *slowest);
 
 #ifdef __cplusplus

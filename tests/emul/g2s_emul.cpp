@@ -162,3 +162,14 @@ int emul_fill_records(void *gp, const char *const *seqs, const char *const *comm
 void emul_free(void *p) { free(p); }
 
 }  // extern "C"
+
+// debugging aid: histogram of skip-hint lengths (13 bins per orientation) over all nodes
+extern "C" void emul_hint_hist(void *gp, uint64_t *hist26) {
+  EmulGraph *g = (EmulGraph *)gp;
+  for (int i = 0; i < 26; i++) hist26[i] = 0;
+  for (const Slot &s : g->slots) {
+    if (s.key == KEY_EMPTY) continue;
+    hist26[hint_of(s.val, 0) >> 24]++;
+    hist26[13 + (hint_of(s.val, 1) >> 24)]++;
+  }
+}
