@@ -11,6 +11,8 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <memory>
+#include <mutex>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -71,9 +73,14 @@ struct Pass {                   // one device pass over a subset of the batch
   SliceLayout lay{};
   int groups = 0;
   unsigned long long pack_cap = 0;
-  std::vector<PackRec> pack;    // host copy of the pack arena (filled by finish)
   unsigned long long pack_used = 0;
-  DevBuf d_pack;
+  int pack_slot = 0;            // index into the engine's persistent device pack buffers
+};
+
+struct PinPool {                // pinned host staging for pack arenas, shared by the engine and its detached batches
+  std::mutex mu;
+  std::vector<PinBuf> free;
+  ~PinPool() { for (auto &b : free) b.release(); }
 };
 
 }  // namespace
@@ -94,6 +101,8 @@ struct g2s_engine {
   std::vector<Pass> passes;
   bool uploaded = false, ran = false;
   DevBuf d_flanks, d_gaps, d_order, d_outs, d_scratch, d_counters;
+  std::vector<DevBuf> d_pack;          // persistent (grow-only) pack arena per pass ordinal
+  std::shared_ptr<PinPool> pin = std::make_shared<PinPool>();
   PinBuf h_outs, h_stage;
   g2s_timing tm{};
   int max_dmax = 0, max_rmf = 0;
@@ -131,7 +140,7 @@ extern "C" int g2s_create(const g2s_config *cfg, g2s_engine **out) {
 extern "C" void g2s_destroy(g2s_engine *e) {
   if (!e) return;
   cudaSetDevice(e->cfg.device);
-  for (auto &p : e->passes) p.d_pack.release();
+  for (auto &b : e->d_pack) b.release();
   e->d_flanks.release(); e->d_gaps.release(); e->d_order.release(); e->d_outs.release();
   e->d_scratch.release(); e->d_counters.release(); e->h_outs.release(); e->h_stage.release();
   if (e->table.slots) cudaFree(e->table.slots);
@@ -255,7 +264,9 @@ static int plan_pass(g2s_engine *e, Pass &p) {
 
 static int run_pass(g2s_engine *e, Pass &p) {
   CUDA_TRY(e->d_scratch.reserve((size_t)p.groups * p.lay.bytes));
-  CUDA_TRY(p.d_pack.reserve(p.pack_cap * sizeof(PackRec)));
+  if ((size_t)p.pack_slot >= e->d_pack.size()) e->d_pack.resize(p.pack_slot + 1);
+  if (e->d_pack[p.pack_slot].cap < p.pack_cap * sizeof(PackRec)) CUDA_TRY(e->d_pack[p.pack_slot].reserve(p.pack_cap * sizeof(PackRec)));
+  else p.pack_cap = e->d_pack[p.pack_slot].cap / sizeof(PackRec);   // use all of a buffer that is already there
   CUDA_TRY(e->d_order.reserve(p.order.size() * 4));
   CUDA_TRY(cudaMemcpyAsync(e->d_order.p, p.order.data(), p.order.size() * 4, cudaMemcpyHostToDevice, e->st));
   CUDA_TRY(cudaMemsetAsync(e->d_counters.p, 0, 64, e->st));
@@ -268,7 +279,7 @@ static int run_pass(g2s_engine *e, Pass &p) {
   P.outs = (GapOut *)e->d_outs.p;
   P.scratch = (unsigned char *)e->d_scratch.p;
   P.lay = p.lay;
-  P.pack = (PackRec *)p.d_pack.p;
+  P.pack = (PackRec *)e->d_pack[p.pack_slot].p;
   P.pack_cap = p.pack_cap;
   P.pack_cursor = (unsigned long long *)((char *)e->d_counters.p + 8);
   P.queue_head = (uint32_t *)e->d_counters.p;
@@ -297,7 +308,6 @@ static int do_upload(g2s_engine *e, const g2s_gap *gaps, size_t n) {
   CUDA_TRY(cudaSetDevice(e->cfg.device));
   const int k = e->cfg.k;
   e->tm = g2s_timing{};
-  for (auto &p : e->passes) p.d_pack.release();
   e->passes.clear();
   e->gaps.assign(gaps, gaps + n);
   e->gapdev.resize(n);
@@ -362,7 +372,6 @@ static int do_run(g2s_engine *e) {
   if (!e || !e->uploaded) return fail(G2S_E_STATE, "g2s_run_resident: nothing uploaded");
   CUDA_TRY(cudaSetDevice(e->cfg.device));
   const size_t n = e->gaps.size();
-  for (auto &p : e->passes) p.d_pack.release();
   e->passes.clear();
   e->tm.kernel_ms = 0; e->tm.launches = 0; e->tm.gaps_big_tier = 0; e->tm.d2h_bytes = 0; e->tm.d2h_ms = 0; e->tm.host_ms = 0;
   e->out_pass.assign(n, -1);
@@ -374,6 +383,7 @@ static int do_run(g2s_engine *e) {
     e->passes.emplace_back();
     Pass &p = e->passes.back();
     p.tier = tier;
+    p.pack_slot = (int)e->passes.size() - 1;
     p.order = todo;
     std::stable_sort(p.order.begin(), p.order.end(),
                      [&](uint32_t a, uint32_t b) { return dmax_of(e->gaps[a]) > dmax_of(e->gaps[b]); });
@@ -410,15 +420,29 @@ static int do_collect(g2s_engine *e, HostBatch &hb) {
   hb.outs = e->outs;
   hb.tier.assign(n, -2);
   hb.pack_of.assign(n, 0);
-  hb.packs.resize(e->passes.size());
+  hb.pack_base.assign(e->passes.size(), nullptr);
+  auto bufs = std::make_shared<std::vector<PinBuf>>(e->passes.size());
+  std::shared_ptr<PinPool> pool = e->pin;
+  hb.on_free = [bufs, pool]() {   // hand the pinned staging back to the pool when the batch dies
+    std::lock_guard<std::mutex> lk(pool->mu);
+    for (auto &b : *bufs) if (b.p) pool->free.push_back(b);
+    bufs->clear();
+  };
   CUDA_TRY(cudaEventRecord(e->ev[2], e->st));
   for (size_t pi = 0; pi < e->passes.size(); pi++) {
     Pass &p = e->passes[pi];
-    hb.packs[pi].resize(p.pack_used);
-    if (p.pack_used) {
-      CUDA_TRY(cudaMemcpyAsync(hb.packs[pi].data(), p.d_pack.p, p.pack_used * sizeof(PackRec), cudaMemcpyDeviceToHost, e->st));
-      e->tm.d2h_bytes += p.pack_used * sizeof(PackRec);
+    if (!p.pack_used) continue;
+    const size_t need = p.pack_used * sizeof(PackRec);
+    PinBuf &b = (*bufs)[pi];
+    {
+      std::lock_guard<std::mutex> lk(pool->mu);
+      for (size_t j = 0; j < pool->free.size(); j++)
+        if (pool->free[j].cap >= need) { b = pool->free[j]; pool->free.erase(pool->free.begin() + j); break; }
     }
+    if (!b.p) CUDA_TRY(b.reserve(need + need / 2));
+    CUDA_TRY(cudaMemcpyAsync(b.p, e->d_pack[p.pack_slot].p, need, cudaMemcpyDeviceToHost, e->st));
+    hb.pack_base[pi] = (const PackRec *)b.p;
+    e->tm.d2h_bytes += need;
   }
   CUDA_TRY(cudaEventRecord(e->ev[3], e->st));
   CUDA_TRY(cudaStreamSynchronize(e->st));

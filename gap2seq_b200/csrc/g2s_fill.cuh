@@ -145,7 +145,7 @@ static const int NARROW_W = 4;     // widest border handled in narrow mode
 struct GShared {       // per group, in shared memory
   uint32_t ncells, nnodes, nnext, status;
   uint32_t npack, nB, n_edges, n_src, n_sink;
-  int32_t max_src_level, min_sink_level;
+  int32_t max_src_level, min_sink_level, max_seed_level;
   uint32_t cells_right;
   uint32_t n_plen;
   int32_t plen[2];
@@ -793,7 +793,7 @@ G2S_D void process_gap(const FillParams &P, const GapDev &gd, const Slice &S, GS
       for (int q = 0; q < 8; q++) sh.prof[q] = 0;
       sh.ncells = 0; sh.nnodes = 0; sh.nnext = 0; sh.status = 0;
       sh.npack = 0; sh.nB = 0; sh.n_edges = 0; sh.n_src = 0; sh.n_sink = 0;
-      sh.max_src_level = -1; sh.min_sink_level = 0x7fffffff;
+      sh.max_src_level = -1; sh.min_sink_level = 0x7fffffff; sh.max_seed_level = -1;
       sh.cells_right = 0; sh.n_plen = 0; sh.plen[0] = sh.plen[1] = -1; sh.reached_fuz = 0; sh.count_fwd = 0;
       sh.found_level = 0x7fffffff; sh.count_all = 0; sh.pack_off = 0;
     }
@@ -1094,25 +1094,28 @@ G2S_D void process_gap(const FillParams &P, const GapDev &gd, const Slice &S, GS
             a_add64(&sh.count_all, clamp_paths(ld_cg(&S.cc[t - 1])));
             a_add(&sh.n_sink, 1);
             a_mini(&sh.min_sink_level, d);
+            a_maxi(&sh.max_seed_level, d);
           }
         }
       } else if (rank == 0) {
         for (uint32_t q = 0; q < n_plen; q++) {
           int d = q ? p1 : p0;
           uint32_t t = thit_get(S, sh, J, d);
-          if (t) { a_or(&S.cflags[t - 1], CF_B | CF_SEED); sh.n_sink++; if (d < sh.min_sink_level) sh.min_sink_level = d; }
+          if (t) { a_or(&S.cflags[t - 1], CF_B | CF_SEED); sh.n_sink++; if (d < sh.min_sink_level) sh.min_sink_level = d; a_maxi(&sh.max_seed_level, d); }
         }
       }
     }
     if (rank == 0) {
       for (uint32_t q = 0; q < n_plen; q++) {
         uint32_t t = thit_get(S, sh, J, q ? p1 : p0);
-        if (t) a_or(&S.cflags[t - 1], CF_T);
+        if (t) { a_or(&S.cflags[t - 1], CF_T); a_maxi(&sh.max_seed_level, q ? p1 : p0); }
       }
     }
     G::sync();
 
-    for (int d = top_level; d >= 0; d--) {
+    // nothing above the highest seed can be marked
+    const int sweep_top = ld_sh(&sh.max_seed_level) < top_level ? ld_sh(&sh.max_seed_level) : top_level;
+    for (int d = sweep_top; d >= 0; d--) {
       const uint32_t rs = ld_cg(&S.lrun[d]);
       if (rs != 0 && (int)rs < d) { chain_mark<G>(S, sh, (int)rs, d); d = (int)rs; continue; }
       const uint32_t lo = ld_cg(&S.lstart[d]), hi = ld_cg(&S.lstart[d + 1]);

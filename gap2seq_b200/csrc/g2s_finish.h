@@ -8,6 +8,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <atomic>
+#include <functional>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -108,6 +110,67 @@ inline void analyze_general(const PackRec *pk, uint32_t npack, GeneralResult &R)
 }
 
 
+// Consuming libc rand() values whose result is not needed.  The reference calls rand() once per traceback step even
+// when the step has a single predecessor (src/Gap2Seq.cpp:1513), so >99 % of the calls on typical gaps only advance the
+// generator - at ~20 ns per locked glibc call that is most of the host time.  glibc's default generator is the
+// additive feedback r[i] = r[i-3] + r[i-31] over a 31-word table that initstate()/setstate() expose: setstate()
+// stores the rear index in the word before the table and reloads it from there.  skip(n) switches libc to a dummy
+// state, advances the application's table n steps in place (one add per step, no lock), and switches back, so the
+// next rand() returns exactly what it would have returned after n discarded calls.  A self test (on a private
+// state, the application's stream is restored) decides once whether this libc behaves that way; if not, skip(n) just
+// calls rand() n times.
+class RandSkipper {
+ public:
+  static void skip(size_t n) {
+    if (n == 0) return;
+    if (n < 4 || !enabled()) { while (n--) rand(); return; }
+    if (!fast_skip(n)) while (n--) rand();
+  }
+  static bool enabled() {
+    static std::once_flag once;
+    static bool ok = false;
+    std::call_once(once, [] { ok = self_test(); });
+    return ok;
+  }
+
+ private:
+  static char *dummy() {
+    static int32_t buf[34];
+    static bool init = false;
+    if (!init) { char *app = initstate(1u, (char *)buf, 128); setstate(app); init = true; }
+    return (char *)buf;
+  }
+  static bool fast_skip(size_t n) {
+    int32_t *info = (int32_t *)setstate(dummy());   // libc writes its rear index into info[0] and lets go of the table
+    if (!info) return false;
+    const int type = info[0] % 5, rear = info[0] / 5;
+    if (type != 3 || rear < 0 || rear >= 31) { setstate((char *)info); return false; }
+    uint32_t *st = (uint32_t *)(info + 1);
+    int f = (rear + 3) % 31, r = rear;
+    for (size_t i = 0; i < n; i++) {
+      st[f] += st[r];
+      if (++f == 31) f = 0;
+      if (++r == 31) r = 0;
+    }
+    info[0] = r * 5 + 3;
+    setstate((char *)info);
+    return true;
+  }
+  static bool self_test() {
+    static int32_t bufa[34];
+    char *app = initstate(777u, (char *)bufa, 128);
+    if (!app) return false;
+    int ref[160];
+    for (int i = 0; i < 160; i++) ref[i] = rand();
+    initstate(777u, (char *)bufa, 128);
+    bool ok = fast_skip(133);
+    for (int i = 133; i < 160 && ok; i++) ok = rand() == ref[i];
+    if (ok) { ok = fast_skip(5); for (int i = 0; i < 3 && ok; i++) rand(); }
+    setstate(app);   // the application's stream continues exactly where it was
+    return ok;
+  }
+};
+
 // Assemble the g2s_result of one gap and run its traceback.  `fill_out` (may be null) receives what the
 // reference leaves at &fill[left_max_fuz - left_fuz].
 inline void finish_one(const g2s_gap &g, const GapOut &o, const PackRec *pk, int k, int tier, const GeneralResult &gen,
@@ -139,7 +202,10 @@ inline void finish_one(const g2s_gap &g, const GapOut &o, const PackRec *pk, int
     if (all_paths) count = (int)o.count_all;   // the Phase B recount replaces the first-found count (Gap2Seq.cpp:1192)
   }
   r.rand_calls = 1;
-  const uint32_t q = (uint32_t)(rand() % (int)o.n_plen);   // Gap2Seq.cpp:1440
+  size_t pending = 0;   // rand() values whose result cannot matter (a single choice): consumed in bulk
+  uint32_t q = 0;
+  if (o.n_plen > 1) q = (uint32_t)(rand() % (int)o.n_plen);   // Gap2Seq.cpp:1440
+  else pending++;
   int d = o.plen[q];
   const int d0 = d;
   int last_solid = d;
@@ -158,11 +224,13 @@ inline void finish_one(const g2s_gap &g, const GapOut &o, const PackRec *pk, int
       uint32_t back[4]; int nb = 0;
       for (int t = 0; t < 4; t++) if (rec.pred[t] != NONE32) back[nb++] = rec.pred[t];
       if (nb == 0) { broken = true; break; }
-      r.rand_calls++;
-      cur = back[rand() % nb];   // one rand() per step even when nb == 1 (Gap2Seq.cpp:1513)
+      r.rand_calls++;            // one rand() per step even when nb == 1 (Gap2Seq.cpp:1513)
+      if (nb == 1) { pending++; cur = back[0]; }
+      else { RandSkipper::skip(pending); pending = 0; cur = back[rand() % nb]; }
     }
     d--;
   }
+  RandSkipper::skip(pending);
   if (broken) {   // "Unable to backtrace!" (Gap2Seq.cpp:1493-1510): the reference returns 0
     r.status |= G2S_ST_UNABLE_TO_BACKTRACE;
     r.count = 0;
@@ -183,11 +251,17 @@ struct HostBatch {
   std::vector<GapOut> outs;
   std::vector<int> tier;                      // tier that produced the gap; -2 = outgrew the largest tier
   std::vector<int> pack_of;                   // index into packs
-  std::vector<std::vector<PackRec>> packs;    // one arena per device pass
+  std::vector<const PackRec *> pack_base;     // one arena per device pass (pinned staging owned by the engine's pool,
+  std::vector<std::vector<PackRec>> own;      //  or `own` when the producer has no pool)
+  std::function<void()> on_free;              // hands the staging buffers back
   std::vector<GeneralResult> gen;
   std::vector<char> buf;
 
-  const PackRec *pack_ptr(size_t i) const { return packs[pack_of[i]].data() + outs[i].pack_off; }
+  HostBatch() {}
+  HostBatch(const HostBatch &) = delete;
+  HostBatch &operator=(const HostBatch &) = delete;
+  ~HostBatch() { if (on_free) on_free(); }
+  const PackRec *pack_ptr(size_t i) const { return pack_base[pack_of[i]] + outs[i].pack_off; }
 
   // SCC analysis of the general-subgraph gaps, independent per gap -> host threads
   void analyze(int threads) {

@@ -73,7 +73,8 @@ static int emul_submit(EmulGraph *g, int k, const g2s_gap *gaps, size_t n, HostB
   hb.outs.assign(n, GapOut{});
   hb.tier.assign(n, 0);
   hb.pack_of.assign(n, 0);
-  hb.packs.assign(n, std::vector<PackRec>());
+  hb.own.assign(n, std::vector<PackRec>());
+  hb.pack_base.assign(n, nullptr);
   for (size_t i = 0; i < n; i++) {
     const g2s_gap &gg = gaps[i];
     std::vector<char> flanks((size_t)3 * k + gg.left_max_fuz + 2 * gg.right_max_fuz + 1);
@@ -113,7 +114,8 @@ static int emul_submit(EmulGraph *g, int k, const g2s_gap *gaps, size_t n, HostB
     hb.outs[i] = out;
     hb.tier[i] = tier;
     hb.pack_of[i] = (int)i;
-    hb.packs[i].swap(pack);
+    hb.own[i].swap(pack);
+    hb.pack_base[i] = hb.own[i].data();
     hb.gaps[i].kmer_left = hb.gaps[i].kmer_right = nullptr;
   }
   hb.analyze(1);
@@ -173,3 +175,6 @@ extern "C" void emul_hint_hist(void *gp, uint64_t *hist26) {
     hist26[13 + (hint_of(s.val, 1) >> 24)]++;
   }
 }
+
+extern "C" int emul_rand_skip_enabled() { return g2s::RandSkipper::enabled() ? 1 : 0; }
+extern "C" void emul_rand_skip(size_t n) { g2s::RandSkipper::skip(n); }

@@ -61,3 +61,21 @@ def test_single_gap_mode_with_long_flanks(case_inputs, emul_engine):
         (r,), (fill,) = eng.fill_batch([spec])
         assert r.count == 1
         assert left[:len(left) - r.left_fuz] + fill == gold.strip()
+
+
+def test_rand_skipping_is_exact_and_enabled():
+    """RandSkipper (g2s_finish.h): advancing glibc's generator in bulk must equal discarding rand() values one by one."""
+    import ctypes
+    L = emul_lib.lib()
+    L.emul_rand_skip.argtypes = [ctypes.c_size_t]
+    libc = ctypes.CDLL(None)
+    assert L.emul_rand_skip_enabled() == 1, "self test failed: this libc's rand() is not the TYPE_3 additive generator"
+    for seed, n in [(1, 4), (5, 1000), (77, 31), (123, 62), (9, 100003)]:
+        libc.srand(seed)
+        L.emul_rand_skip(n)
+        a = [libc.rand() for _ in range(40)]
+        libc.srand(seed)
+        for _ in range(n):
+            libc.rand()
+        b = [libc.rand() for _ in range(40)]
+        assert a == b, (seed, n)
