@@ -24,12 +24,11 @@ cudaError_t table_export(const DeviceTable &dt, uint64_t *keys_host, uint8_t *ad
 cudaError_t table_contains(const DeviceTable &dt, const char *ascii_host, uint64_t n, uint8_t *out_host, cudaStream_t st);
 
 struct FillParams;
-// thin tier: one warp per gap, persistent over a device work queue.  groups = number of scratch slices.
-cudaError_t launch_fill_warp(const FillParams &p, int groups, cudaStream_t st);
+// thin tier: one two-warp CTA per gap, persistent over a device work queue.  groups = number of scratch slices.
+cudaError_t launch_fill_thin(const FillParams &p, int groups, cudaStream_t st);
 // wide tier: one CTA (512 threads) per gap
 cudaError_t launch_fill_cta(const FillParams &p, int groups, cudaStream_t st);
-int fill_warps_per_cta();
-int fill_max_resident_warp_groups(int sms);   // occupancy-derived number of warp groups that fit the device
+int fill_max_resident_thin_groups(int sms);   // occupancy-derived number of thin groups that fit the device
 int fill_max_resident_cta_groups(int sms);
 
 }  // namespace g2s

@@ -1,5 +1,5 @@
 // g2s_engine.cu - host side of libg2s_gpu.so: the C ABI of include/g2s.h, batching of gaps into device passes
-// (thin warp-per-gap tier, then wide CTA-per-gap tiers for gaps that outgrow their scratch slice), and the two
+// (thin tier - a two-warp CTA per gap -, then wide CTA-per-gap tiers for gaps that outgrow their scratch slice), and the two
 // stages of Gap2Seq::fill_gap that are inherently sequential on the host:
 //   * the SCC contraction / branch counter of src/Gap2Seq.cpp:1314-1434 for the (rare) gaps whose path subgraph
 //     is not a plain level DAG (the device classifies the DAG case itself),
@@ -247,7 +247,7 @@ static int plan_pass(g2s_engine *e, Pass &p) {
   p.lay = make_layout(cap, hlog, (uint32_t)e->max_dmax + 1, (uint32_t)e->max_rmf + 1);
   if (cap >= (1ULL << 31) || p.lay.bytes > e->budget) return -1;   // largest tier exceeded
   size_t fit = e->budget / p.lay.bytes;
-  int resident = p.tier == 0 ? fill_max_resident_warp_groups(e->sms) : fill_max_resident_cta_groups(e->sms);
+  int resident = p.tier == 0 ? fill_max_resident_thin_groups(e->sms) : fill_max_resident_cta_groups(e->sms);
   size_t groups = std::min<size_t>({p.order.size(), (size_t)resident, fit});
   p.groups = (int)std::max<size_t>(groups, 1);
   // output arena
@@ -284,7 +284,7 @@ static int run_pass(g2s_engine *e, Pass &p) {
   P.pack_cursor = (unsigned long long *)((char *)e->d_counters.p + 8);
   P.queue_head = (uint32_t *)e->d_counters.p;
   CUDA_TRY(cudaEventRecord(e->ev[0], e->st));
-  if (p.tier == 0) CUDA_TRY(launch_fill_warp(P, p.groups, e->st));
+  if (p.tier == 0) CUDA_TRY(launch_fill_thin(P, p.groups, e->st));
   else CUDA_TRY(launch_fill_cta(P, p.groups, e->st));
   CUDA_TRY(cudaEventRecord(e->ev[1], e->st));
   e->tm.launches++;
@@ -526,10 +526,18 @@ extern "C" int g2s_fill_records(g2s_engine *e, const char *const *seqs, const ch
   ScaffoldRun run(s, c, ro);
   g2s_timing total{};
   int err = G2S_OK;
+  double w_upload = 0, w_run = 0, w_collect = 0;
+  auto ms_since = [](std::chrono::steady_clock::time_point t) {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count();
+  };
   SubmitFn submit = [&](const std::vector<g2s_gap> &gaps, HostBatch &hb) -> int {
+    auto t = std::chrono::steady_clock::now();
     int rc = do_upload(e, gaps.data(), gaps.size());
+    w_upload += ms_since(t); t = std::chrono::steady_clock::now();
     if (rc == G2S_OK) rc = do_run(e);
+    w_run += ms_since(t); t = std::chrono::steady_clock::now();
     if (rc == G2S_OK) rc = do_collect(e, hb);
+    w_collect += ms_since(t);
     err = rc;
     total.h2d_ms += e->tm.h2d_ms; total.kernel_ms += e->tm.kernel_ms; total.d2h_ms += e->tm.d2h_ms; total.host_ms += e->tm.host_ms;
     total.h2d_bytes += e->tm.h2d_bytes; total.d2h_bytes += e->tm.d2h_bytes; total.launches += e->tm.launches;
@@ -546,6 +554,10 @@ extern "C" int g2s_fill_records(g2s_engine *e, const char *const *seqs, const ch
   const double wall = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   total.host_ms = std::max(0.0, wall - total.h2d_ms - total.kernel_ms - total.d2h_ms);
   e->tm = total;
+  if (getenv("G2S_HOST_PROF"))   // profiling aid: where the wall time of this call went
+    fprintf(stderr, "g2s_fill_records: wall %.3f ms = scan+flanks %.3f | upload %.3f | run %.3f (kernel %.3f) | collect %.3f "
+            "(d2h %.3f) | trace+splice+log %.3f\n", wall, run.phase1_ms - w_upload - w_run - w_collect, w_upload, w_run,
+            total.kernel_ms, w_collect, total.d2h_ms, run.phase2_ms);
   for (size_t i = 0; i < n_records; i++) filled_out[i] = strdup(filled[i].c_str());
   if (log_out) *log_out = strdup(log.c_str());
   if (gapcount) *gapcount = gc;

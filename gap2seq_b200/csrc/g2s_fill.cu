@@ -1,6 +1,11 @@
-// g2s_fill.cu - the persistent fill kernels.  Each thread group (a warp in the thin tier, a 512-thread CTA in
-// the wide tier) owns one scratch slice, pulls gaps from a device work queue (longest first) and runs
-// process_gap (g2s_fill.cuh) on them, so many short gaps share one launch.
+// g2s_fill.cu - the persistent fill kernels.  Each thread group owns one scratch slice, pulls gaps from a device
+// work queue (longest first) and runs the phases of g2s_fill.cuh on them, so many short gaps share one launch.
+//   thin tier  k_fill_thin: a CTA of two warps per gap.  After a joint init the helper warp runs the right pass
+//              (Gap2Seq.cpp:871-982) while the main warp runs the forward pass (Gap2Seq.cpp:984-1167) up to the first
+//              level that consults the right set; a named barrier hands the finished set over.  The main warp then
+//              finishes the forward pass, marks backward and packs.
+//   wide tier  k_fill_cta: one 512-thread CTA per gap, phases one after the other, for gaps that outgrow the thin
+//              tier's scratch slice.
 #include <cuda_runtime.h>
 
 #include "g2s_device.h"
@@ -8,7 +13,7 @@
 
 namespace g2s {
 
-static const int WARPS_PER_CTA = 1;   // one warp group per CTA: few long gaps spread over all SMs
+static const int THIN_THREADS = 64;
 static const int CTA_THREADS = 512;
 
 struct WarpGroup {
@@ -24,42 +29,72 @@ struct BlockGroup {
   static __device__ __forceinline__ void sync() { __syncthreads(); }
 };
 
-template <class G>
+// named barrier 1 of the thin CTA: the helper warp arrives when the right set is complete, the main warp waits on it
+struct PairWait {
+  static constexpr bool kConcurrent = true;
+  static __device__ __forceinline__ void wait_right() {
+    __syncwarp();
+    asm volatile("bar.sync 1, 64;" ::: "memory");
+  }
+};
+static __device__ __forceinline__ void pair_signal_right() {
+  __threadfence_block();
+  __syncwarp();
+  asm volatile("bar.arrive 1, 64;" ::: "memory");
+}
+
+static __device__ __forceinline__ void process_gap_pair(const FillParams &P, const GapDev &gd, const Slice &S, GShared &sh,
+                                                        GapOut *out) {
+  const GapCtx cx = make_ctx(P, gd);
+  unsigned long long t[5];
+  t[0] = now_cycles();
+  gap_init<BlockGroup>(P, cx, S, sh);
+  t[1] = now_cycles();
+  if ((threadIdx.x >> 5) == 0) {
+    gap_right<WarpGroup>(P, cx, S, sh, sh.nbuf[0]);
+    pair_signal_right();
+  } else {
+    t[2] = t[1];
+    gap_forward<WarpGroup, PairWait>(P, gd, cx, S, sh, sh.nbuf[1]);
+    t[3] = now_cycles();
+    t[4] = gap_backward_pack<WarpGroup>(P, cx, S, sh, sh.nbuf[1]);
+    gap_finish<WarpGroup>(S, sh, out, t);
+  }
+}
+
+template <bool PAIR>
 __device__ __forceinline__ void group_loop(const FillParams &P, GShared &sh, uint32_t group_id) {
   const Slice S = make_slice(P.scratch + (size_t)group_id * P.lay.bytes, P.lay);
   for (;;) {
-    G::sync();
-    if (G::rank() == 0) sh.queue_item = atomicAdd(P.queue_head, 1u);
-    G::sync();
+    __syncthreads();
+    if (threadIdx.x == 0) sh.queue_item = atomicAdd(P.queue_head, 1u);
+    __syncthreads();
     const uint32_t q = ld_sh(&sh.queue_item);
     if (q >= P.n_gaps) break;
     const uint32_t gi = P.order[q];
     const GapDev gd = P.gaps[gi];
-    process_gap<G>(P, gd, S, sh, &P.outs[gi]);
+    if (PAIR) process_gap_pair(P, gd, S, sh, &P.outs[gi]);
+    else process_gap<BlockGroup>(P, gd, S, sh, &P.outs[gi]);
   }
 }
 
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_fill_warp(const __grid_constant__ FillParams P, int groups) {
-  __shared__ GShared sh[WARPS_PER_CTA];
-  const uint32_t w = threadIdx.x >> 5;
-  const uint32_t group_id = blockIdx.x * WARPS_PER_CTA + w;
-  if (group_id >= (uint32_t)groups) return;
-  group_loop<WarpGroup>(P, sh[w], group_id);
+__global__ void __launch_bounds__(THIN_THREADS) k_fill_thin(const __grid_constant__ FillParams P, int groups) {
+  __shared__ GShared sh;
+  if (blockIdx.x >= (uint32_t)groups) return;
+  group_loop<true>(P, sh, blockIdx.x);
 }
 
 __global__ void __launch_bounds__(CTA_THREADS) k_fill_cta(const __grid_constant__ FillParams P, int groups) {
   __shared__ GShared sh;
   if (blockIdx.x >= (uint32_t)groups) return;
-  group_loop<BlockGroup>(P, sh, blockIdx.x);
+  group_loop<false>(P, sh, blockIdx.x);
 }
 
-int fill_warps_per_cta() { return WARPS_PER_CTA; }
-
-int fill_max_resident_warp_groups(int sms) {
+int fill_max_resident_thin_groups(int sms) {
   int per_sm = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fill_warp, WARPS_PER_CTA * 32, 0) != cudaSuccess || per_sm < 1)
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fill_thin, THIN_THREADS, 0) != cudaSuccess || per_sm < 1)
     per_sm = 1;
-  return sms * per_sm * WARPS_PER_CTA;
+  return sms * per_sm;
 }
 
 int fill_max_resident_cta_groups(int sms) {
@@ -69,9 +104,8 @@ int fill_max_resident_cta_groups(int sms) {
   return sms * per_sm;
 }
 
-cudaError_t launch_fill_warp(const FillParams &p, int groups, cudaStream_t st) {
-  const int ctas = (groups + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
-  k_fill_warp<<<ctas, WARPS_PER_CTA * 32, 0, st>>>(p, groups);
+cudaError_t launch_fill_thin(const FillParams &p, int groups, cudaStream_t st) {
+  k_fill_thin<<<groups, THIN_THREADS, 0, st>>>(p, groups);
   return cudaGetLastError();
 }
 

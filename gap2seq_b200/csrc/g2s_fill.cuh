@@ -121,7 +121,7 @@ struct SliceLayout {   // byte offsets inside one scratch slice; identical for e
   unsigned long long bytes;
   uint32_t cap_cells, hash_log2, max_levels, max_fuz1;
   unsigned long long off_hash, off_ck, off_cc, off_cn, off_cp, off_cflags, off_packidx, off_packlist, off_packlevel,
-      off_lstart, off_nB, off_lrun, off_thit, off_lk, off_rk;
+      off_lstart, off_nB, off_thit, off_lk, off_rk, off_rbk[2], off_rbm[2];
 };
 
 struct FillParams {
@@ -142,8 +142,21 @@ struct FillParams {
 static const int CHAIN_LEN = 32;   // levels a narrow batch looks ahead
 static const int NARROW_W = 4;     // widest border handled in narrow mode
 
+struct NarrowBuf {     // look-ahead state of one pass (the right pass and the forward pass own one each, so that two warps
+                       // can run them concurrently)
+  uint32_t nnext;
+  uint32_t ch_len, ch_valid, ch_base, ch_cnt, nw_stop, nw_alive;
+  uint64_t nw_x[NARROW_W], nw_x0[NARROW_W];
+  uint32_t nw_m[NARROW_W], nw_cnt0[NARROW_W], nw_hb[NARROW_W], nw_hl[NARROW_W];
+  int32_t nw_fail[NARROW_W];
+  uint32_t nw_n[CHAIN_LEN + 1], nw_off[CHAIN_LEN + 1], nw_run[CHAIN_LEN], nw_poff[CHAIN_LEN];
+  uint32_t bk_p[NARROW_W][4];   // backward batches: predecessor cells of the batch's lowest level
+  uint64_t ch_s[CHAIN_LEN][NARROW_W];
+  uint32_t ch_a[CHAIN_LEN][NARROW_W], ch_e[CHAIN_LEN][NARROW_W];
+};
+
 struct GShared {       // per group, in shared memory
-  uint32_t ncells, nnodes, nnext, status;
+  uint32_t ncells, nnodes, status;
   uint32_t npack, nB, n_edges, n_src, n_sink;
   int32_t max_src_level, min_sink_level, max_seed_level;
   uint32_t cells_right;
@@ -156,17 +169,13 @@ struct GShared {       // per group, in shared memory
   unsigned long long pack_off;
   uint32_t fc1[MAX_FUZ + 1], fc2[MAX_FUZ + 1];
   uint32_t queue_item;
-  // chain mode (a border of exactly one cell): the scout's look-ahead and the bulk backward marking
-  uint32_t ch_len, ch_valid, ch_base, ch_cnt, nw_stop, nw_alive;
   unsigned long long prof[8];
   int32_t tlo;          // first level that has thit entries: max(0, g + lmf - e)
   uint32_t trow;        // entries per target row: Dmax - tlo + 1
-  uint64_t nw_x[NARROW_W], nw_x0[NARROW_W];
-  uint32_t nw_m[NARROW_W], nw_cnt0[NARROW_W], nw_hb[NARROW_W], nw_hl[NARROW_W];
-  int32_t nw_fail[NARROW_W];
-  uint32_t nw_n[CHAIN_LEN], nw_off[CHAIN_LEN], nw_run[CHAIN_LEN];
-  uint64_t ch_s[CHAIN_LEN][NARROW_W];
-  uint32_t ch_a[CHAIN_LEN][NARROW_W], ch_e[CHAIN_LEN][NARROW_W];
+  // handed from the right pass / the forward pass to the rest of the gap (the two may run on different warps)
+  int32_t levels_r, levels_f, top_level, fwd_overflow;
+  unsigned long long cyc_right;
+  NarrowBuf nbuf[2];    // [0] right pass, [1] forward pass and backward marking
 };
 
 struct Slice {         // typed view of one scratch slice
@@ -175,12 +184,13 @@ struct Slice {         // typed view of one scratch slice
   uint64_t *ck;
   uint32_t *cc, *cn;
   uint32_t *cp;        // 4 per cell
-  uint32_t *cflags, *packidx, *packlist, *packlevel, *lstart, *nB, *lrun, *thit;
+  uint32_t *cflags, *packidx, *packlist, *packlevel, *lstart, *nB, *thit;
   uint64_t *lk, *rk;   // oriented flank k-mers; bit 63 set = present in the graph; bits 62..: unused
   uint32_t cap_cells, max_levels;
-  // right-border ping-pong buffers alias the (not yet used) cell arrays during Phase R
-  uint64_t *fk[2];
-  unsigned char *fm[2];
+  // right-border ping-pong buffers (oriented k-mer, in-mask); their own arrays: the right pass may run concurrently
+  // with the forward pass
+  uint64_t *rbk[2];
+  unsigned char *rbm[2];
 };
 
 G2S_HD Slice make_slice(unsigned char *base, const SliceLayout &L) {
@@ -198,16 +208,15 @@ G2S_HD Slice make_slice(unsigned char *base, const SliceLayout &L) {
   s.packlevel = (uint32_t *)(base + L.off_packlevel);
   s.lstart = (uint32_t *)(base + L.off_lstart);
   s.nB = (uint32_t *)(base + L.off_nB);
-  s.lrun = (uint32_t *)(base + L.off_lrun);
   s.thit = (uint32_t *)(base + L.off_thit);
   s.lk = (uint64_t *)(base + L.off_lk);
   s.rk = (uint64_t *)(base + L.off_rk);
   s.cap_cells = L.cap_cells;
   s.max_levels = L.max_levels;
-  s.fk[0] = s.ck;
-  s.fk[1] = (uint64_t *)s.cp;                  // 16 B per cell: room for cap_cells 8-byte entries twice over
-  s.fm[0] = (unsigned char *)s.cc;
-  s.fm[1] = (unsigned char *)s.cn;
+  s.rbk[0] = (uint64_t *)(base + L.off_rbk[0]);
+  s.rbk[1] = (uint64_t *)(base + L.off_rbk[1]);
+  s.rbm[0] = base + L.off_rbm[0];
+  s.rbm[1] = base + L.off_rbm[1];
   return s;
 }
 
@@ -230,10 +239,10 @@ inline SliceLayout make_layout(uint64_t cap_cells, uint32_t hash_log2, uint32_t 
   L.off_packlevel = take(cap_cells * 4);
   L.off_lstart = take(((size_t)max_levels + 3) * 4);
   L.off_nB = take(((size_t)max_levels + 3) * 4);
-  L.off_lrun = take(((size_t)max_levels + 3) * 4);
   L.off_thit = take((size_t)max_fuz1 * ((size_t)max_levels + 1) * 4);
   L.off_lk = take((size_t)max_fuz1 * 8);
   L.off_rk = take((size_t)max_fuz1 * 8);
+  for (int q = 0; q < 2; q++) { L.off_rbk[q] = take(cap_cells * 8); L.off_rbm[q] = take(cap_cells); }
   L.bytes = o;
   return L;
 }
@@ -245,11 +254,21 @@ static const uint64_t FLANK_PRESENT = 1ULL << 63;
 static const uint64_t FLANK_KMER = (1ULL << 62) - 1;
 
 // ------------------------------------------------------------------------------------------------ node table
+#if defined(G2S_HOST_EMUL) && defined(G2S_EMUL_STATS)
+struct EmulStats { unsigned long long finds, find_probes, inserts, insert_probes, max_probe, width_hist[8], back_general_levels, back_chain_levels; };
+inline EmulStats &emul_stats() { static EmulStats s; return s; }
+#define G2S_STAT(x) do { x; } while (0)
+#else
+#define G2S_STAT(x) do { } while (0)
+#endif
+
 G2S_D uint32_t node_hash(uint64_t key, uint32_t hmask) { return (uint32_t)((key * 0x9E3779B97F4A7C15ULL) >> 40) & hmask; }
 
 G2S_D uint32_t node_find(const Slice &S, uint64_t key) {
   uint32_t h = node_hash(key, S.hmask);
+  G2S_STAT(emul_stats().finds++);
   for (;;) {
+    G2S_STAT(emul_stats().find_probes++);
     uint64_t k0 = ld_cg(&S.ent[h].key);
     if (k0 == key) return h;
     if (k0 == KEY_EMPTY) return NONE32;
@@ -259,7 +278,9 @@ G2S_D uint32_t node_find(const Slice &S, uint64_t key) {
 
 G2S_D uint32_t node_insert(const Slice &S, GShared &sh, uint64_t key) {
   uint32_t h = node_hash(key, S.hmask);
+  G2S_STAT(emul_stats().inserts++);
   for (;;) {
+    G2S_STAT(emul_stats().insert_probes++);
     uint64_t k0 = ld_cg(&S.ent[h].key);
     if (k0 == key) return h;
     if (k0 == KEY_EMPTY) {
@@ -368,12 +389,12 @@ G2S_D bool found_scan(const Slice &S, const GapDev &gd, GShared &sh, int lo, int
 // ((tip << 2i) | (hint >> 2(j-i))) & kmask, so the lanes compute the w*r states of the round in parallel; a chain
 // gathers (one table probe) only when its hint is used up.  Shared memory only receives the emitted states.
 template <bool FORWARD>
-__device__ __forceinline__ int narrow_scout_warp(const Table &T, GShared &sh, int w, int maxlen) {
+__device__ __forceinline__ int narrow_scout_warp(const Table &T, GShared &sh, NarrowBuf &nb, int w, int maxlen) {
   const int k = T.k;
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   uint64_t x = 0; uint32_t mask = 0xFF, hb = 0, hl = 0;
-  if (lane < w) { x = sh.nw_x[lane]; mask = sh.nw_m[lane]; }
+  if (lane < w) { x = nb.nw_x[lane]; mask = nb.nw_m[lane]; }
   int len = 0;
   while (len < maxlen) {
     if (mask == 0) mask = 0xFF;                                      // dead end
@@ -381,7 +402,7 @@ __device__ __forceinline__ int narrow_scout_warp(const Table &T, GShared &sh, in
     const bool branch = !ended && (mask & (mask - 1)) != 0;
     if (__any_sync(FULL, branch)) break;                             // a branch ends the look-ahead BEFORE this level
     if (!__any_sync(FULL, !ended)) {                                 // every chain ended: keep the empty level
-      if (lane < w) sh.ch_a[len][lane] = 0;
+      if (lane < w) nb.ch_a[len][lane] = 0;
       len++;
       break;
     }
@@ -398,13 +419,13 @@ __device__ __forceinline__ int narrow_scout_warp(const Table &T, GShared &sh, in
       const uint32_t bt = __shfl_sync(FULL, hb, src), lt = __shfl_sync(FULL, hl, src), mt = __shfl_sync(FULL, mask, src);
       if (t < w) {
         const int lvl = len + i - 1;
-        if (mt == 0xFF) sh.ch_a[lvl][t] = 0;
+        if (mt == 0xFF) nb.ch_a[lvl][t] = 0;
         else {
           const uint64_t y = ((xt << (2 * i)) | (uint64_t)((bt >> (2 * (lt - i))) & ((1u << (2 * i)) - 1))) & T.kmask;
           const Canon cy = canonical(y, k);
           const uint32_t nmask = (uint32_t)i < lt ? 1u << ((bt >> (2 * (lt - i - 1))) & 3) : 0u;   // hint end: patched below
-          if (FORWARD) { sh.ch_s[lvl][t] = y; sh.ch_a[lvl][t] = nmask | (cy.strand << 8) | (1u << 16); }
-          else { sh.ch_s[lvl][t] = revcomp(y, k); sh.ch_a[lvl][t] = swap2(nmask) | ((cy.strand ^ 1u) << 8) | (1u << 16); }
+          if (FORWARD) { nb.ch_s[lvl][t] = y; nb.ch_a[lvl][t] = nmask | (cy.strand << 8) | (1u << 16); }
+          else { nb.ch_s[lvl][t] = revcomp(y, k); nb.ch_a[lvl][t] = swap2(nmask) | ((cy.strand ^ 1u) << 8) | (1u << 16); }
         }
       }
     }
@@ -422,7 +443,7 @@ __device__ __forceinline__ int narrow_scout_warp(const Table &T, GShared &sh, in
           const uint32_t h = hint_of(val, cx.strand);
           hb = h & 0xFFFFFFu; hl = h >> 24;
           const int lvl = len + r - 1;
-          sh.ch_a[lvl][lane] = (sh.ch_a[lvl][lane] & ~0xFFu) | (FORWARD ? mask : swap2(mask));
+          nb.ch_a[lvl][lane] = (nb.ch_a[lvl][lane] & ~0xFFu) | (FORWARD ? mask : swap2(mask));
         }
       } else {
         mask = 1u << ((hb >> (2 * (hl - 1))) & 3);
@@ -436,9 +457,9 @@ __device__ __forceinline__ int narrow_scout_warp(const Table &T, GShared &sh, in
 #endif
 
 template <class G, bool FORWARD>
-G2S_D int narrow_scout(const Table &T, GShared &sh, int w, int maxlen) {
+G2S_D int narrow_scout(const Table &T, GShared &sh, NarrowBuf &nb, int w, int maxlen) {
 #ifdef G2S_DEVICE_BUILD
-  if (G::kWarp) { G::sync(); return narrow_scout_warp<FORWARD>(T, sh, w, maxlen); }
+  if (G::kWarp) { G::sync(); return narrow_scout_warp<FORWARD>(T, sh, nb, w, maxlen); }
 #endif
   // Per-chain state lives in shared memory so that any group size, including the size-1 host emulation, can play the
   // w scouts: nw_x = the chain's tip in WALK orientation (forward pass: the state itself; right pass: its reverse
@@ -446,45 +467,45 @@ G2S_D int narrow_scout(const Table &T, GShared &sh, int w, int maxlen) {
   // (0xFF = chain ended), nw_hb / nw_hl = what is left of the tip's skip hint.  A gather happens only where a hint
   // ends; between gathers a level costs a shift and an insert.
   const int k = T.k, rank = G::rank(), gsz = G::size();
-  if (rank == 0) { sh.nw_stop = 0; sh.nw_alive = 0; }
+  if (rank == 0) { nb.nw_stop = 0; nb.nw_alive = 0; }
   G::sync();
   int len = 0;
   for (int l = 0; l < maxlen; l++) {
     for (int t = rank; t < w; t += gsz) {
-      const uint32_t mask = sh.nw_m[t];
+      const uint32_t mask = nb.nw_m[t];
       if (mask == 0xFF) continue;
-      if (mask == 0) sh.nw_m[t] = 0xFF;                              // dead end
-      else if (mask & (mask - 1)) sh.nw_stop = 1;                    // two neighbours: not a chain any more
-      else sh.nw_alive = (uint32_t)l + 1;
+      if (mask == 0) nb.nw_m[t] = 0xFF;                              // dead end
+      else if (mask & (mask - 1)) nb.nw_stop = 1;                    // two neighbours: not a chain any more
+      else nb.nw_alive = (uint32_t)l + 1;
     }
     G::sync();
-    if (ld_sh(&sh.nw_stop) || ld_sh(&sh.nw_alive) < (uint32_t)l + 1) {
+    if (ld_sh(&nb.nw_stop) || ld_sh(&nb.nw_alive) < (uint32_t)l + 1) {
       // a branch ends the look-ahead BEFORE this level; "all chains ended" keeps the (empty) level so that the
       // caller records the border as dead
-      if (!ld_sh(&sh.nw_stop)) { for (int t = rank; t < w; t += gsz) sh.ch_a[l][t] = 0; len = l + 1; }
+      if (!ld_sh(&nb.nw_stop)) { for (int t = rank; t < w; t += gsz) nb.ch_a[l][t] = 0; len = l + 1; }
       break;
     }
     for (int t = rank; t < w; t += gsz) {
-      const uint32_t mask = sh.nw_m[t];
-      if (mask == 0xFF) { sh.ch_a[l][t] = 0; continue; }
+      const uint32_t mask = nb.nw_m[t];
+      if (mask == 0xFF) { nb.ch_a[l][t] = 0; continue; }
       const uint32_t nt = mask == 1 ? 0 : mask == 2 ? 1 : mask == 4 ? 2 : 3;
-      const uint64_t y = succ_kmer(sh.nw_x[t], nt, T);
+      const uint64_t y = succ_kmer(nb.nw_x[t], nt, T);
       const Canon cy = canonical(y, k);
       uint32_t nmask;
-      if (sh.nw_hl[t] > 1) {           // y is an interior node of the hint: exactly one successor, its base is known
-        sh.nw_hl[t]--;
-        nmask = 1u << ((sh.nw_hb[t] >> (2 * (sh.nw_hl[t] - 1))) & 3);
+      if (nb.nw_hl[t] > 1) {           // y is an interior node of the hint: exactly one successor, its base is known
+        nb.nw_hl[t]--;
+        nmask = 1u << ((nb.nw_hb[t] >> (2 * (nb.nw_hl[t] - 1))) & 3);
       } else {                         // the hint ends at y (or there is none yet): gather y
         uint64_t val = 0;
-        if (table_find_val(T, cy.key, &val) < 0) { a_or(&sh.status, GS_INTERNAL); sh.nw_m[t] = 0xFF; sh.ch_a[l][t] = 0; continue; }
+        if (table_find_val(T, cy.key, &val) < 0) { a_or(&sh.status, GS_INTERNAL); nb.nw_m[t] = 0xFF; nb.ch_a[l][t] = 0; continue; }
         nmask = out_mask((uint32_t)(val & 0xFF), cy.strand);
         const uint32_t h = hint_of(val, cy.strand);
-        sh.nw_hb[t] = h & 0xFFFFFFu; sh.nw_hl[t] = h >> 24;
+        nb.nw_hb[t] = h & 0xFFFFFFu; nb.nw_hl[t] = h >> 24;
       }
       // emit the state of this level in the orientation of the pass, with its mask in the direction of the pass
-      if (FORWARD) { sh.ch_s[l][t] = y; sh.ch_a[l][t] = nmask | (cy.strand << 8) | (1u << 16); }
-      else { sh.ch_s[l][t] = revcomp(y, k); sh.ch_a[l][t] = swap2(nmask) | ((cy.strand ^ 1u) << 8) | (1u << 16); }
-      sh.nw_x[t] = y; sh.nw_m[t] = nmask;
+      if (FORWARD) { nb.ch_s[l][t] = y; nb.ch_a[l][t] = nmask | (cy.strand << 8) | (1u << 16); }
+      else { nb.ch_s[l][t] = revcomp(y, k); nb.ch_a[l][t] = swap2(nmask) | ((cy.strand ^ 1u) << 8) | (1u << 16); }
+      nb.nw_x[t] = y; nb.nw_m[t] = nmask;
     }
     len = l + 1;
     G::sync();
@@ -493,21 +514,21 @@ G2S_D int narrow_scout(const Table &T, GShared &sh, int w, int maxlen) {
   return len;
 }
 
-// Right pass: advances the border S.fk[cur][0..n) (n <= NARROW_W) by up to CHAIN_LEN levels starting with level c.
+// Right pass: advances the border S.rbk[cur][0..n) (n <= NARROW_W) by up to CHAIN_LEN levels starting with level c.
 // Returns the number of levels done; *n_out receives the size of the new border.
 template <class G>
-G2S_D int narrow_right(const Table &T, const Slice &S, GShared &sh, int cur, int c, int right_half, int n, uint32_t *n_out) {
+G2S_D int narrow_right(const Table &T, const Slice &S, GShared &sh, NarrowBuf &nb, int cur, int c, int right_half, int n, uint32_t *n_out) {
   const int k = T.k, rank = G::rank(), gsz = G::size();
-  for (int t = rank; t < n; t += gsz) { sh.nw_x[t] = revcomp(S.fk[cur][t], k); sh.nw_m[t] = swap2(S.fm[cur][t]); sh.nw_hl[t] = 0; sh.nw_hb[t] = 0; }
+  for (int t = rank; t < n; t += gsz) { nb.nw_x[t] = revcomp(S.rbk[cur][t], k); nb.nw_m[t] = swap2(S.rbm[cur][t]); nb.nw_hl[t] = 0; nb.nw_hb[t] = 0; }
   const int maxlen = right_half - c + 1 < CHAIN_LEN ? right_half - c + 1 : CHAIN_LEN;
-  const int len = narrow_scout<G, false>(T, sh, n, maxlen);
+  const int len = narrow_scout<G, false>(T, sh, nb, n, maxlen);
   if (len == 0) return 0;
-  if (rank == 0) { sh.ch_cnt = 0; sh.nnext = 0; }
+  if (rank == 0) { nb.ch_cnt = 0; nb.nnext = 0; }
   G::sync();
   for (int q = rank; q < len * n; q += gsz) {
     const int l = q / n, t = q - l * n;
-    if (!sh.ch_a[l][t]) continue;
-    const Canon cp = canonical(sh.ch_s[l][t], k);
+    if (!nb.ch_a[l][t]) continue;
+    const Canon cp = canonical(nb.ch_s[l][t], k);
     const uint32_t en = node_insert(S, sh, cp.key);
     if (en == NONE32) continue;
     a_or(&S.ent[en].flags, NF_IN_RS);
@@ -518,28 +539,28 @@ G2S_D int narrow_right(const Table &T, const Slice &S, GShared &sh, int cur, int
     uint32_t ns = 0;
 #pragma unroll
     for (int t = 0; t < NARROW_W; t++) {
-      if (t >= n || !sh.ch_a[l][t]) continue;
-      const uint64_t s = sh.ch_s[l][t];
+      if (t >= n || !nb.ch_a[l][t]) continue;
+      const uint64_t s = nb.ch_s[l][t];
       bool dup = false;
 #pragma unroll
       for (int u = 0; u < NARROW_W; u++) {
-        if (u >= t || !sh.ch_a[l][u]) continue;
-        if (sh.ch_s[l][u] == s) dup = true;
-        else if (sh.ch_s[l][u] == revcomp(s, k)) a_or(&sh.status, GS_ORDER_DEPENDENT);   // both strands on one level (Q3)
+        if (u >= t || !nb.ch_a[l][u]) continue;
+        if (nb.ch_s[l][u] == s) dup = true;
+        else if (nb.ch_s[l][u] == revcomp(s, k)) a_or(&sh.status, GS_ORDER_DEPENDENT);   // both strands on one level (Q3)
       }
       if (dup) continue;
       if (l == len - 1) {
-        S.fk[cur][ns] = s;
-        S.fm[cur][ns] = (unsigned char)(sh.ch_a[l][t] & 0xFF);   // already the in-mask of the emitted state
+        S.rbk[cur][ns] = s;
+        S.rbm[cur][ns] = (unsigned char)(nb.ch_a[l][t] & 0xFF);   // already the in-mask of the emitted state
       }
       ns++;
     }
-    a_add(&sh.ch_cnt, ns);
-    if (l == len - 1) sh.nnext = ns;
+    a_add(&nb.ch_cnt, ns);
+    if (l == len - 1) nb.nnext = ns;
   }
   G::sync();
-  if (rank == 0) sh.cells_right += sh.ch_cnt;
-  *n_out = ld_sh(&sh.nnext);
+  if (rank == 0) sh.cells_right += nb.ch_cnt;
+  *n_out = ld_sh(&nb.nnext);
   G::sync();
   return len;
 }
@@ -555,35 +576,35 @@ G2S_D int narrow_right(const Table &T, const Slice &S, GShared &sh, int cur, int
 //   its links    = the cells of those chains on level l-1
 // which lets one thread per level lay out and write that level's cells once a prefix sum has placed the levels.
 template <class G>
-G2S_D int narrow_forward(const Table &T, const Slice &S, GShared &sh, const GapDev &gd, uint32_t lo, int w, int c, int Dmax,
+G2S_D int narrow_forward(const Table &T, const Slice &S, GShared &sh, NarrowBuf &nb, const GapDev &gd, uint32_t lo, int w, int c, int Dmax,
                          int prune_from) {
   const int k = T.k, rank = G::rank(), gsz = G::size();
   for (int t = rank; t < w; t += gsz) {
     const uint64_t x = ld_cg(&S.ck[lo + t]);
-    sh.nw_x[t] = x; sh.nw_x0[t] = x;
-    sh.nw_m[t] = (ld_cg(&S.cflags[lo + t]) >> CF_OMASK_SHIFT) & 15u;
-    sh.nw_cnt0[t] = clamp_paths(ld_cg(&S.cc[lo + t]));
-    sh.nw_hl[t] = 0; sh.nw_hb[t] = 0;
+    nb.nw_x[t] = x; nb.nw_x0[t] = x;
+    nb.nw_m[t] = (ld_cg(&S.cflags[lo + t]) >> CF_OMASK_SHIFT) & 15u;
+    nb.nw_cnt0[t] = clamp_paths(ld_cg(&S.cc[lo + t]));
+    nb.nw_hl[t] = 0; nb.nw_hb[t] = 0;
   }
   const int maxlen = Dmax - c + 1 < CHAIN_LEN ? Dmax - c + 1 : CHAIN_LEN;
   const unsigned long long tp0 = now_cycles();
-  const int len = narrow_scout<G, true>(T, sh, w, maxlen);
+  const int len = narrow_scout<G, true>(T, sh, nb, w, maxlen);
   const unsigned long long tp1 = now_cycles();
   if (rank == 0) sh.prof[0] += tp1 - tp0;
   if (len == 0) return 0;
-  for (int t = rank; t < w; t += gsz) sh.nw_fail[t] = len;
+  for (int t = rank; t < w; t += gsz) nb.nw_fail[t] = len;
   G::sync();
   // node table + prune test, one (level, chain) per thread: ch_e = node entry; first failing level per chain
   for (int q = rank; q < len * w; q += gsz) {
     const int l = q / w, t = q - l * w;
     uint32_t en = NONE32;
-    if (sh.ch_a[l][t]) {
-      const Canon cs = canonical(sh.ch_s[l][t], k);
+    if (nb.ch_a[l][t]) {
+      const Canon cs = canonical(nb.ch_s[l][t], k);
       if (c + l < prune_from) en = node_insert(S, sh, cs.key);
       else { en = node_find(S, cs.key); if (en != NONE32 && !(ld_cg(&S.ent[en].flags) & NF_IN_RS)) en = NONE32; }
     }
-    sh.ch_e[l][t] = en;
-    if (en == NONE32) a_mini(&sh.nw_fail[t], l);
+    nb.ch_e[l][t] = en;
+    if (en == NONE32) a_mini(&nb.nw_fail[t], l);
   }
   G::sync();
   const unsigned long long tp2 = now_cycles();
@@ -594,82 +615,79 @@ G2S_D int narrow_forward(const Table &T, const Slice &S, GShared &sh, const GapD
     uint32_t nn = 0;
 #pragma unroll
     for (int t = 0; t < NARROW_W; t++) {
-      if (t >= w || l >= sh.nw_fail[t]) continue;
+      if (t >= w || l >= nb.nw_fail[t]) continue;
       bool dup = false;
 #pragma unroll
-      for (int u = 0; u < NARROW_W; u++) if (u < t && l < sh.nw_fail[u] && sh.ch_s[l][u] == sh.ch_s[l][t]) dup = true;
+      for (int u = 0; u < NARROW_W; u++) if (u < t && l < nb.nw_fail[u] && nb.ch_s[l][u] == nb.ch_s[l][t]) dup = true;
       if (!dup) nn++;
     }
-    sh.nw_n[l] = nn;
+    nb.nw_n[l] = nn;
   }
   G::sync();
   if (rank == 0) {   // place the levels: prefix sum, end of the border, chain runs
     const uint32_t base = sh.ncells;
-    uint32_t off = 0, prev_n = (uint32_t)w, run_prev = ld_cg(&S.lrun[c - 1]);
+    uint32_t off = 0;
     int done = len;
     for (int l = 0; l < len; l++) {
-      const uint32_t nn = sh.nw_n[l];
-      sh.nw_off[l] = off;
+      const uint32_t nn = nb.nw_n[l];
+      nb.nw_off[l] = off;
       off += nn;
-      const uint32_t run = (nn == 1 && prev_n == 1) ? (run_prev ? run_prev : (uint32_t)(c + l)) : 0;
-      sh.nw_run[l] = run;
-      run_prev = run; prev_n = nn;
       if (nn == 0) { done = l + 1; break; }
     }
     if ((uint64_t)base + off > S.cap_cells) { a_or(&sh.status, GS_OVERFLOW); done = 0; off = 0; }
-    sh.ch_base = base; sh.ch_len = (uint32_t)done;
+    nb.ch_base = base; nb.ch_len = (uint32_t)done;
     sh.ncells = base + off;
   }
   G::sync();
-  const int done = (int)ld_sh(&sh.ch_len);
-  const uint32_t base = ld_sh(&sh.ch_base);
+  const int done = (int)ld_sh(&nb.ch_len);
+  const uint32_t base = ld_sh(&nb.ch_base);
   for (int l = rank; l < done; l += gsz) {
     const uint32_t level = (uint32_t)(c + l);
     uint32_t ord = 0;
 #pragma unroll
     for (int t = 0; t < NARROW_W; t++) {
-      if (t >= w || l >= sh.nw_fail[t]) continue;
-      const uint64_t s = sh.ch_s[l][t];
+      if (t >= w || l >= nb.nw_fail[t]) continue;
+      const uint64_t s = nb.ch_s[l][t];
       bool dup = false;
 #pragma unroll
-      for (int u = 0; u < NARROW_W; u++) if (u < t && l < sh.nw_fail[u] && sh.ch_s[l][u] == s) dup = true;
+      for (int u = 0; u < NARROW_W; u++) if (u < t && l < nb.nw_fail[u] && nb.ch_s[l][u] == s) dup = true;
       if (dup) continue;
-      const uint32_t idx = base + sh.nw_off[l] + ord++;
-      const uint32_t a = sh.ch_a[l][t], en = sh.ch_e[l][t], strand = (a >> 8) & 1;
+      const uint32_t idx = base + nb.nw_off[l] + ord++;
+      const uint32_t a = nb.ch_a[l][t], en = nb.ch_e[l][t], strand = (a >> 8) & 1;
       uint32_t cnt = 0;
       uint32_t link[4] = {NONE32, NONE32, NONE32, NONE32};
 #pragma unroll
       for (int v = 0; v < NARROW_W; v++) {
-        if (v >= w || l >= sh.nw_fail[v] || sh.ch_s[l][v] != s) continue;
-        cnt += sh.nw_cnt0[v];   // <= 4 * MAX_PATHS < 2^32
+        if (v >= w || l >= nb.nw_fail[v] || nb.ch_s[l][v] != s) continue;
+        cnt += nb.nw_cnt0[v];   // <= 4 * MAX_PATHS < 2^32
         // the cell of chain v on the level below: lowest alive chain with v's state there
-        const uint64_t ps = l ? sh.ch_s[l - 1][v] : sh.nw_x0[v];
+        const uint64_t ps = l ? nb.ch_s[l - 1][v] : nb.nw_x0[v];
         uint32_t pord = 0, prep = (uint32_t)v;
 #pragma unroll
         for (int u = 0; u < NARROW_W; u++) {
           if (u >= w || u >= v) continue;
-          const bool ualive = l ? (l - 1 < sh.nw_fail[u]) : true;
+          const bool ualive = l ? (l - 1 < nb.nw_fail[u]) : true;
           if (!ualive) continue;
-          const uint64_t us = l ? sh.ch_s[l - 1][u] : sh.nw_x0[u];
+          const uint64_t us = l ? nb.ch_s[l - 1][u] : nb.nw_x0[u];
           if (us == ps) { if (prep == (uint32_t)v) prep = (uint32_t)u; }
         }
         // ordinal of the representative among the distinct alive states of the level below
 #pragma unroll
         for (int u = 0; u < NARROW_W; u++) {
           if (u >= w || (uint32_t)u >= prep) continue;
-          const bool ualive = l ? (l - 1 < sh.nw_fail[u]) : true;
+          const bool ualive = l ? (l - 1 < nb.nw_fail[u]) : true;
           if (!ualive) continue;
-          const uint64_t us = l ? sh.ch_s[l - 1][u] : sh.nw_x0[u];
+          const uint64_t us = l ? nb.ch_s[l - 1][u] : nb.nw_x0[u];
           bool udup = false;
 #pragma unroll
           for (int z = 0; z < NARROW_W; z++) {
             if (z >= u) continue;
-            const bool zalive = l ? (l - 1 < sh.nw_fail[z]) : true;
-            if (zalive && (l ? sh.ch_s[l - 1][z] : sh.nw_x0[z]) == us) udup = true;
+            const bool zalive = l ? (l - 1 < nb.nw_fail[z]) : true;
+            if (zalive && (l ? nb.ch_s[l - 1][z] : nb.nw_x0[z]) == us) udup = true;
           }
           if (!udup) pord++;
         }
-        const uint32_t pidx = l ? base + sh.nw_off[l - 1] + pord : lo + prep;
+        const uint32_t pidx = l ? base + nb.nw_off[l - 1] + pord : lo + prep;
         link[(uint32_t)(ps >> (2 * (k - 1))) & 3u] = pidx;
       }
       S.ck[idx] = s; S.cc[idx] = cnt; S.cn[idx] = en;
@@ -678,7 +696,7 @@ G2S_D int narrow_forward(const Table &T, const Slice &S, GShared &sh, const GapD
       // both strands of one node on one level (Q3)
 #pragma unroll
       for (int u = 0; u < NARROW_W; u++)
-        if (u < w && u != t && l < sh.nw_fail[u] && sh.ch_e[l][u] == en && sh.ch_s[l][u] != s) a_or(&sh.status, GS_ORDER_DEPENDENT);
+        if (u < w && u != t && l < nb.nw_fail[u] && nb.ch_e[l][u] == en && nb.ch_s[l][u] != s) a_or(&sh.status, GS_ORDER_DEPENDENT);
       a_max(&S.ent[en].fstamp[strand], level + 1);
       S.ent[en].fcell[strand] = idx;
       const uint32_t fl = a_or(&S.ent[en].flags, NF_HAS_F);
@@ -687,226 +705,319 @@ G2S_D int narrow_forward(const Table &T, const Slice &S, GShared &sh, const GapD
           if ((S.rk[j] & FLANK_KMER) == s) S.thit[(size_t)j * sh.trow + (level - (uint32_t)sh.tlo)] = idx + 1;
       }
     }
-    S.lstart[level + 1] = base + sh.nw_off[l] + sh.nw_n[l];
-    S.lrun[level] = sh.nw_run[l];
+    S.lstart[level + 1] = base + nb.nw_off[l] + nb.nw_n[l];
   }
   G::sync();
   if (rank == 0) { sh.prof[2] += now_cycles() - tp2; sh.prof[5] += 1; sh.prof[6] += (unsigned long long)done; }
   return done;
 }
 
-// Backward marking of a run of chain levels [rs, d] (single cell per level, single link to the level below): the
-// marks of the upper cells flow down unconditionally, so the run is processed CHAIN_LEN levels at a time.
+// The node of a marked (Phase B) cell remembers the highest level it is marked on (bits 8.. of its flag word; the low
+// bits are not read any more once the backward sweep runs).  A node marked on two levels makes the path subgraph a
+// general graph (vertex identity is the node, Gap2Seq.cpp:1222-1297); the pack phase sees that as a marked cell whose
+// level differs from its node's.  No value is returned, so the sweep never waits for the atomic.
+G2S_D void mark_node_level(const Slice &S, uint32_t en, int level) {
+  a_max(&S.ent[en].flags, ((uint32_t)(level + 1) << 8) | 0xFFu);
+}
+
+// Backward marking of up to CHAIN_LEN consecutive narrow levels d, d-1, ... (1..NARROW_W cells each, all above lmf,
+// so none of their cells is a start cell).  The levels' flags and predecessor links are gathered in parallel, one
+// thread then pushes the marks down the batch in shared memory (a level costs a few bit operations), and the marks,
+// pack indices and per-level counts are written back in parallel.  Marks reach the level below the batch through
+// the cell flags, exactly like on the level-by-level path.  Returns the number of levels done (0: level d is wide
+// or empty).
 template <class G>
-G2S_D void chain_mark(const Slice &S, GShared &sh, int rs, int d) {
-  const uint32_t top_cell = ld_cg(&S.lstart[d]);
-  uint32_t carry = 0;   // meaningful on rank 0 only
-  for (int hi = d; hi >= rs; hi -= CHAIN_LEN) {
-    const int n = hi - rs + 1 < CHAIN_LEN ? hi - rs + 1 : CHAIN_LEN;
-    for (int t = G::rank(); t < n; t += G::size()) sh.ch_a[t][0] = ld_cg(&S.cflags[top_cell - (uint32_t)(d - (hi - t))]);
-    G::sync();
-    if (G::rank() == 0) {
-      uint32_t cnt = 0, nb = 0;
-      for (int t = 0; t < n; t++) {
-        carry |= sh.ch_a[t][0] & (CF_B | CF_T);
-        sh.ch_a[t][0] = (sh.ch_a[t][0] & ~(uint32_t)(CF_B | CF_T)) | carry;
-        sh.ch_e[t][0] = carry ? cnt++ : NONE32;
-        if (carry & CF_B) nb++;
-      }
-      sh.ch_base = sh.npack;
-      sh.npack += cnt;
-      sh.nB += nb;
-      sh.n_edges += nb;   // every chain cell has exactly one predecessor and is no start cell (level > lmf)
-    }
-    G::sync();
-    const uint32_t base = ld_sh(&sh.ch_base);
-    for (int t = G::rank(); t < n; t += G::size()) {
-      if (sh.ch_e[t][0] == NONE32) continue;
-      const int level = hi - t;
-      const uint32_t i = top_cell - (uint32_t)(d - level), f = sh.ch_a[t][0], pi = base + sh.ch_e[t][0];
-      S.cflags[i] = f;
-      S.packidx[i] = pi; S.packlist[pi] = i; S.packlevel[pi] = (uint32_t)level;
-      if (f & CF_B) {
-        a_add(&S.nB[level], 1);
-        const uint32_t en = S.cn[i];
-        uint32_t fl = ld_cg(&S.ent[en].flags);
-        for (;;) {
-          const uint32_t lv = fl >> 8;
-          if (lv == 0) {
-            const uint32_t old = a_cas(&S.ent[en].flags, fl, fl | ((uint32_t)(level + 1) << 8));
-            if (old == fl) break;
-            fl = old;
-          } else {
-            a_or(&sh.status, lv != (uint32_t)level + 1 ? GS_GENERAL : GS_ORDER_DEPENDENT);
-            break;
-          }
-        }
-      }
-    }
-    G::sync();
+G2S_D int narrow_backward(const Slice &S, GShared &sh, NarrowBuf &nb, int d, int lmf) {
+  const int rank = G::rank(), gsz = G::size();
+  const int maxlen = d - lmf < CHAIN_LEN ? d - lmf : CHAIN_LEN;   // levels d .. d-maxlen+1 are all > lmf
+  // geometry of the levels d+1-t (t = 0 is only needed for its start offset = end of level d)
+  for (int t = rank; t <= maxlen + 1; t += gsz) {
+    const uint32_t v = ld_cg(&S.lstart[d + 1 - t]);
+    if (t <= maxlen) nb.nw_off[t] = v;              // nw_off[t+1] = first cell of batch level t (level d - t)
+    else nb.nw_cnt0[0] = v;                         // first cell of the level below the deepest possible batch level
   }
-  if (G::rank() == 0 && carry) {   // hand the marks to the (general) level below the run
-    const uint32_t i = top_cell - (uint32_t)(d - rs);
-    for (int q = 0; q < 4; q++) { const uint32_t p = S.cp[4 * i + q]; if (p != NONE32) a_or(&S.cflags[p], carry); }
+  G::sync();
+  if (rank == 0) {
+    int len = 0;
+    while (len < maxlen) {
+      const uint32_t n = nb.nw_off[len] - nb.nw_off[len + 1];
+      if (n == 0 || n > (uint32_t)NARROW_W) break;
+      nb.nw_n[len] = n;
+      len++;
+    }
+    nb.ch_len = (uint32_t)len;
+  }
+  G::sync();
+  const int len = (int)ld_sh(&nb.ch_len);
+  if (len == 0) return 0;
+  // gather: own marks, node, predecessor mask relative to the level below
+  for (int q = rank; q < len * NARROW_W; q += gsz) {
+    const int t = q / NARROW_W, i = q - t * NARROW_W;
+    uint32_t a = 0;
+    if ((uint32_t)i < nb.nw_n[t]) {
+      const uint32_t idx = nb.nw_off[t + 1] + (uint32_t)i;
+      const uint32_t f = ld_cg(&S.cflags[idx]);
+      const uint32_t below = t + 1 < maxlen ? nb.nw_off[t + 2] : nb.nw_cnt0[0];
+      uint32_t pm = 0, np = 0;
+#pragma unroll
+      for (int z = 0; z < 4; z++) {
+        const uint32_t p = ld_cg(&S.cp[4 * idx + z]);
+        if (t == len - 1) nb.bk_p[i][z] = p;
+        if (p != NONE32) { np++; const uint32_t rel = p - below; if (rel < (uint32_t)NARROW_W) pm |= 1u << rel; }
+      }
+      a = (f & (CF_B | CF_T)) | (pm << 4) | (np << 8);
+      nb.ch_e[t][i] = ld_cg(&S.cn[idx]);
+    }
+    nb.ch_a[t][i] = a;
+  }
+  G::sync();
+  if (rank == 0) {   // push the marks down the batch
+    uint32_t flowB = 0, flowT = 0, npk = 0, nbt = 0, ned = 0;
+    for (int t = 0; t < len; t++) {
+      uint32_t mB = flowB, mT = flowT;
+      flowB = flowT = 0;
+#pragma unroll
+      for (int i = 0; i < NARROW_W; i++) {
+        const uint32_t a = nb.ch_a[t][i];
+        if (a & CF_B) mB |= 1u << i;
+        if (a & CF_T) mT |= 1u << i;
+      }
+#pragma unroll
+      for (int i = 0; i < NARROW_W; i++) {
+        const uint32_t a = nb.ch_a[t][i];
+        if ((mB >> i) & 1) { flowB |= (a >> 4) & 15u; ned += a >> 8; }
+        if ((mT >> i) & 1) flowT |= (a >> 4) & 15u;
+      }
+      nb.nw_run[t] = mB | (mT << 4);
+      nb.nw_poff[t] = npk;
+#ifdef __CUDA_ARCH__
+      npk += (uint32_t)__popc(mB | mT); nbt += (uint32_t)__popc(mB);
+#else
+      npk += (uint32_t)__builtin_popcount(mB | mT); nbt += (uint32_t)__builtin_popcount(mB);
+#endif
+    }
+    nb.ch_base = sh.npack;
+    sh.npack += npk; sh.nB += nbt; sh.n_edges += ned;
+  }
+  G::sync();
+  const uint32_t base = ld_sh(&nb.ch_base);
+  for (int q = rank; q < len * NARROW_W; q += gsz) {
+    const int t = q / NARROW_W, i = q - t * NARROW_W;
+    const uint32_t m = nb.nw_run[t], mB = m & 15u, mT = m >> 4, mk = mB | mT;
+    const int level = d - t;
+    if (i == 0 && mB) {
+#ifdef __CUDA_ARCH__
+      S.nB[level] = (uint32_t)__popc(mB);
+#else
+      S.nB[level] = (uint32_t)__builtin_popcount(mB);
+#endif
+    }
+    if (!((mk >> i) & 1)) continue;
+    const uint32_t idx = nb.nw_off[t + 1] + (uint32_t)i;
+    const uint32_t bits = (((mB >> i) & 1) ? (uint32_t)CF_B : 0u) | (((mT >> i) & 1) ? (uint32_t)CF_T : 0u);
+#ifdef __CUDA_ARCH__
+    const uint32_t pi = base + nb.nw_poff[t] + (uint32_t)__popc(mk & ((1u << i) - 1u));
+#else
+    const uint32_t pi = base + nb.nw_poff[t] + (uint32_t)__builtin_popcount(mk & ((1u << i) - 1u));
+#endif
+    a_or(&S.cflags[idx], bits);
+    S.packidx[idx] = pi; S.packlist[pi] = idx; S.packlevel[pi] = (uint32_t)level;
+    if (bits & CF_B) mark_node_level(S, nb.ch_e[t][i], level);
+    if (t == len - 1) {
+#pragma unroll
+      for (int z = 0; z < 4; z++) { const uint32_t p = nb.bk_p[i][z]; if (p != NONE32) a_or(&S.cflags[p], bits); }
+    }
+  }
+  G2S_STAT(emul_stats().back_chain_levels += (unsigned long long)len);
+  G::sync();
+  return len;
+}
+
+// ------------------------------------------------------------------------------------------------ one gap
+// A gap is processed in phases - init, right pass, forward pass, backward marking + pack - written as functions of
+// the executing thread group so that the kernels can map them differently: the wide tier and the host emulation
+// run them one after the other on one group; the thin tier runs the right pass on a helper warp concurrently with
+// the part of the forward pass that does not need the right set yet (levels below g/2 + e/2 + lmf).
+struct GapCtx {
+  int k, g, e, lmf, rmf, right_half, Dmax, prune_from, tlo;
+  size_t trow;
+  bool all_paths, skip_confident;
+  const char *lstr, *rstr, *rsstr;
+};
+
+G2S_D GapCtx make_ctx(const FillParams &P, const GapDev &gd) {
+  GapCtx cx;
+  cx.k = P.table.k;
+  cx.g = gd.gap_len; cx.e = gd.gap_err; cx.lmf = gd.lmf; cx.rmf = gd.rmf;
+  cx.all_paths = (gd.flags & 2) != 0; cx.skip_confident = (gd.flags & 1) != 0;
+  cx.right_half = cx.rmf + (cx.g + cx.e + 1) / 2;           // rmf + ceil((g+e)/2), Gap2Seq.cpp:862
+  cx.Dmax = cx.g + cx.e + cx.lmf + cx.rmf;                   // right_half + left_half, Gap2Seq.cpp:863
+  cx.prune_from = cx.g / 2 + cx.e / 2 + cx.lmf;              // two integer divisions, Gap2Seq.cpp:1050
+  cx.lstr = P.flanks + gd.flank_off; cx.rstr = cx.lstr + cx.k + cx.lmf; cx.rsstr = P.flanks + gd.rstart_off;
+  cx.tlo = cx.g + cx.lmf - cx.e > 0 ? cx.g + cx.lmf - cx.e : 0;
+  cx.trow = (size_t)(cx.Dmax - cx.tlo + 1);
+  return cx;
+}
+
+// the forward pass calls wait_right() exactly once, before the first level that consults the right set
+struct NoWait {
+  static constexpr bool kConcurrent = false;
+  static G2S_D void wait_right() {}
+};
+
+// ---- init: clear the node table, thit and the per-level counters; parse the flanks; flag the right-flank targets
+template <class G>
+G2S_D void gap_init(const FillParams &P, const GapCtx &cx, const Slice &S, GShared &sh) {
+  const Table &T = P.table;
+  const int k = cx.k, rank = G::rank(), gsz = G::size();
+  uint4 *hz = (uint4 *)S.ent;
+  const uint4 z0 = {0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u}, z1 = {0u, 0u, 0u, 0u};
+  for (uint32_t i = rank; i < S.hcap; i += gsz) { hz[2 * i] = z0; hz[2 * i + 1] = z1; }
+  const size_t nth = cx.trow * (size_t)(cx.rmf + 1);
+  for (size_t i = rank; i < nth; i += gsz) S.thit[i] = 0;
+  for (int i = rank; i <= cx.Dmax + 1; i += gsz) { S.nB[i] = 0; S.lstart[i] = 0; }
+  for (int d = rank; d <= cx.lmf; d += gsz) {
+    uint64_t x = kmer_from_ascii(cx.lstr + d, k);
+    uint32_t adj;
+    Canon c = canonical(x, k);
+    S.lk[d] = x | (table_find(T, c.key, &adj) >= 0 ? FLANK_PRESENT : 0);
+  }
+  for (int j = rank; j <= cx.rmf; j += gsz) {
+    uint64_t x = kmer_from_ascii(cx.rstr + j, k);
+    uint32_t adj;
+    Canon c = canonical(x, k);
+    S.rk[j] = x | (table_find(T, c.key, &adj) >= 0 ? FLANK_PRESENT : 0);
+  }
+  if (rank == 0) {
+    sh.tlo = cx.tlo; sh.trow = (uint32_t)cx.trow;
+    for (int q = 0; q < 8; q++) sh.prof[q] = 0;
+    sh.ncells = 0; sh.nnodes = 0; sh.status = 0;
+    sh.nbuf[0].nnext = 0; sh.nbuf[1].nnext = 0;
+    sh.npack = 0; sh.nB = 0; sh.n_edges = 0; sh.n_src = 0; sh.n_sink = 0;
+    sh.max_src_level = -1; sh.min_sink_level = 0x7fffffff; sh.max_seed_level = -1;
+    sh.cells_right = 0; sh.n_plen = 0; sh.plen[0] = sh.plen[1] = -1; sh.reached_fuz = 0; sh.count_fwd = 0;
+    sh.found_level = 0x7fffffff; sh.count_all = 0; sh.pack_off = 0;
+    sh.levels_r = 0; sh.levels_f = 0; sh.top_level = 0; sh.fwd_overflow = 0; sh.cyc_right = 0;
+  }
+  G::sync();
+  // the right-flank targets: their node entries exist from the start, flagged TARGET, so that the forward pass
+  // records a hit whenever it creates a cell of such a node (Gap2Seq.cpp:1119)
+  for (int j = rank; j <= cx.rmf; j += gsz) {
+    const uint64_t x = S.rk[j];
+    if (x & FLANK_PRESENT) {
+      const Canon c = canonical(x & FLANK_KMER, k);
+      const uint32_t en = node_insert(S, sh, c.key);
+      if (en != NONE32) a_or(&S.ent[en].flags, NF_TARGET);
+    }
   }
   G::sync();
 }
 
-// ------------------------------------------------------------------------------------------------ one gap
+// ---- Phase R: level-synchronous backward walk from the staggered right starts (Gap2Seq.cpp:871-982).
+// Only node membership in the right set is read later (Gap2Seq.cpp:1050): nodes get NF_IN_RS, cells are counted.
 template <class G>
-G2S_D void process_gap(const FillParams &P, const GapDev &gd, const Slice &S, GShared &sh, GapOut *out) {
+G2S_D void gap_right(const FillParams &P, const GapCtx &cx, const Slice &S, GShared &sh, NarrowBuf &nb) {
   const Table &T = P.table;
-  const int k = T.k;
-  const int rank = G::rank(), gsz = G::size();
-  const int g = gd.gap_len, e = gd.gap_err, lmf = gd.lmf, rmf = gd.rmf;
-  const bool all_paths = (gd.flags & 2) != 0, skip_confident = (gd.flags & 1) != 0;
-  const int right_half = rmf + (g + e + 1) / 2;           // rmf + ceil((g+e)/2), Gap2Seq.cpp:862
-  const int Dmax = g + e + lmf + rmf;                      // right_half + left_half, Gap2Seq.cpp:863
-  const int prune_from = g / 2 + e / 2 + lmf;              // two integer divisions, Gap2Seq.cpp:1050
-  const char *lstr = P.flanks + gd.flank_off, *rstr = lstr + k + lmf, *rsstr = P.flanks + gd.rstart_off;
-  const int tlo = g + lmf - e > 0 ? g + lmf - e : 0;
-  const size_t trow = (size_t)(Dmax - tlo + 1);
-
-  const unsigned long long t_start = now_cycles();
-  // ---- init: clear the node table, thit and the per-level counters; parse the flanks
-  {
-    uint4 *hz = (uint4 *)S.ent;
-    const uint4 z0 = {0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u}, z1 = {0u, 0u, 0u, 0u};
-    for (uint32_t i = rank; i < S.hcap; i += gsz) { hz[2 * i] = z0; hz[2 * i + 1] = z1; }
-    const size_t nth = trow * (size_t)(rmf + 1);
-    for (size_t i = rank; i < nth; i += gsz) S.thit[i] = 0;
-    for (int i = rank; i <= Dmax + 1; i += gsz) { S.nB[i] = 0; S.lstart[i] = 0; S.lrun[i] = 0; }
-    for (int d = rank; d <= lmf; d += gsz) {
-      uint64_t x = kmer_from_ascii(lstr + d, k);
-      uint32_t adj;
-      Canon c = canonical(x, k);
-      S.lk[d] = x | (table_find(T, c.key, &adj) >= 0 ? FLANK_PRESENT : 0);
-    }
-    for (int j = rank; j <= rmf; j += gsz) {
-      uint64_t x = kmer_from_ascii(rstr + j, k);
-      uint32_t adj;
-      Canon c = canonical(x, k);
-      S.rk[j] = x | (table_find(T, c.key, &adj) >= 0 ? FLANK_PRESENT : 0);
-    }
-    if (rank == 0) {
-      sh.tlo = tlo; sh.trow = (uint32_t)trow;
-      for (int q = 0; q < 8; q++) sh.prof[q] = 0;
-      sh.ncells = 0; sh.nnodes = 0; sh.nnext = 0; sh.status = 0;
-      sh.npack = 0; sh.nB = 0; sh.n_edges = 0; sh.n_src = 0; sh.n_sink = 0;
-      sh.max_src_level = -1; sh.min_sink_level = 0x7fffffff; sh.max_seed_level = -1;
-      sh.cells_right = 0; sh.n_plen = 0; sh.plen[0] = sh.plen[1] = -1; sh.reached_fuz = 0; sh.count_fwd = 0;
-      sh.found_level = 0x7fffffff; sh.count_all = 0; sh.pack_off = 0;
+  const int k = cx.k, rank = G::rank(), gsz = G::size(), rmf = cx.rmf, right_half = cx.right_half;
+  const unsigned long long t0 = now_cycles();
+  int levels_r = 0;
+  uint32_t n = 0;
+  int cur = 0;
+  if (rank == 0) {
+    uint64_t x = kmer_from_ascii(cx.rsstr + rmf, k);
+    Canon c = canonical(x, k);
+    uint32_t adj = 0;
+    if (table_find(T, c.key, &adj) >= 0) {
+      uint32_t en = node_insert(S, sh, c.key);
+      if (en != NONE32) {
+        a_max(&S.ent[en].rstamp, 2 + c.strand);
+        a_or(&S.ent[en].flags, NF_IN_RS);
+        S.rbk[0][0] = x; S.rbm[0][0] = (unsigned char)in_mask(adj, c.strand);
+        nb.nnext = 1; sh.cells_right = 1;
+      }
     }
   }
   G::sync();
-
-  const unsigned long long t_init = now_cycles();
-  // ---- Phase R: level-synchronous backward walk from the staggered right starts (Gap2Seq.cpp:871-982).
-  // Only node membership in the right set is read later (Gap2Seq.cpp:1050): nodes get NF_IN_RS, cells are counted.
-  int levels_r = 0;
-  {
-    uint32_t n = 0;
-    int cur = 0;
-    if (rank == 0) {
-      uint64_t x = kmer_from_ascii(rsstr + rmf, k);
-      Canon c = canonical(x, k);
-      uint32_t adj = 0;
-      if (table_find(T, c.key, &adj) >= 0) {
-        uint32_t en = node_insert(S, sh, c.key);
-        if (en != NONE32) {
-          S.ent[en].rstamp = 2 + c.strand;
-          a_or(&S.ent[en].flags, NF_IN_RS);
-          S.fk[0][0] = x; S.fm[0][0] = (unsigned char)in_mask(adj, c.strand);
-          sh.nnext = 1; sh.cells_right = 1;
+  n = ld_sh(&nb.nnext);
+  for (int c = 1; c <= right_half; c++) {
+    if (n == 0 && c > rmf) break;
+    levels_r = c;
+    if (n >= 1 && n <= (uint32_t)NARROW_W && c > rmf) {   // narrow border, no start left to inject
+      uint32_t n2 = n;
+      const int adv = narrow_right<G>(T, S, sh, nb, cur, c, right_half, (int)n, &n2);
+      if (ld_sh(&sh.status) & GS_OVERFLOW) break;
+      if (adv > 0) { n = n2; levels_r = c + adv - 1; c += adv - 1; continue; }
+    }
+    G::sync();
+    if (rank == 0) nb.nnext = 0;
+    G::sync();
+    const uint64_t *fk = S.rbk[cur]; const unsigned char *fm = S.rbm[cur];
+    uint64_t *nk = S.rbk[cur ^ 1]; unsigned char *nm = S.rbm[cur ^ 1];
+    for (uint32_t i = rank; i < n; i += gsz) {
+      const uint64_t x = fk[i];
+      uint32_t im = fm[i];
+      for (uint32_t nt = 0; nt < 4; nt++) {
+        if (!((im >> nt) & 1)) continue;
+        uint64_t p = pred_kmer(x, nt, T);
+        Canon cp = canonical(p, k);
+        uint32_t adj = 0;
+        if (table_find(T, cp.key, &adj) < 0) { a_or(&sh.status, GS_INTERNAL); continue; }
+        uint32_t en = node_insert(S, sh, cp.key);
+        if (en == NONE32) continue;
+        a_or(&S.ent[en].flags, NF_IN_RS);
+        uint32_t stamp = (uint32_t)(c + 1) * 2 + cp.strand;
+        uint32_t prev = a_max(&S.ent[en].rstamp, stamp);
+        if ((prev >> 1) < (uint32_t)(c + 1)) {
+          uint32_t idx = a_add(&nb.nnext, 1);
+          if (idx >= S.cap_cells) { a_or(&sh.status, GS_OVERFLOW); continue; }
+          nk[idx] = p; nm[idx] = (unsigned char)in_mask(adj, cp.strand);
+        } else if ((prev & 1) != cp.strand) {
+          a_or(&sh.status, GS_ORDER_DEPENDENT);   // both strands on one level
         }
       }
     }
     G::sync();
-    n = ld_sh(&sh.nnext);
-    for (int c = 1; c <= right_half; c++) {
-      if (n == 0 && c > rmf) break;
-      levels_r = c;
-      if (n >= 1 && n <= (uint32_t)NARROW_W && c > rmf) {   // narrow border, no start left to inject
-        uint32_t n2 = n;
-        const int adv = narrow_right<G>(T, S, sh, cur, c, right_half, (int)n, &n2);
-        if (ld_sh(&sh.status) & GS_OVERFLOW) break;
-        if (adv > 0) { n = n2; levels_r = c + adv - 1; c += adv - 1; continue; }
-      }
-      G::sync();
-      if (rank == 0) sh.nnext = 0;
-      G::sync();
-      const uint64_t *fk = S.fk[cur]; const unsigned char *fm = S.fm[cur];
-      uint64_t *nk = S.fk[cur ^ 1]; unsigned char *nm = S.fm[cur ^ 1];
-      for (uint32_t i = rank; i < n; i += gsz) {
-        const uint64_t x = fk[i];
-        uint32_t im = fm[i];
-        for (uint32_t nt = 0; nt < 4; nt++) {
-          if (!((im >> nt) & 1)) continue;
-          uint64_t p = pred_kmer(x, nt, T);
-          Canon cp = canonical(p, k);
-          uint32_t adj = 0;
-          if (table_find(T, cp.key, &adj) < 0) { a_or(&sh.status, GS_INTERNAL); continue; }
-          uint32_t en = node_insert(S, sh, cp.key);
-          if (en == NONE32) continue;
+    if (rank == 0 && c <= rmf) {   // next staggered right start (Gap2Seq.cpp:953-968)
+      uint64_t x = kmer_from_ascii(cx.rsstr + (rmf - c), k);
+      Canon cs = canonical(x, k);
+      uint32_t adj = 0;
+      if (table_find(T, cs.key, &adj) >= 0) {
+        uint32_t en = node_insert(S, sh, cs.key);
+        if (en != NONE32) {
           a_or(&S.ent[en].flags, NF_IN_RS);
-          uint32_t stamp = (uint32_t)(c + 1) * 2 + cp.strand;
+          uint32_t stamp = (uint32_t)(c + 1) * 2 + cs.strand;
           uint32_t prev = a_max(&S.ent[en].rstamp, stamp);
           if ((prev >> 1) < (uint32_t)(c + 1)) {
-            uint32_t idx = a_add(&sh.nnext, 1);
-            if (idx >= S.cap_cells) { a_or(&sh.status, GS_OVERFLOW); continue; }
-            nk[idx] = p; nm[idx] = (unsigned char)in_mask(adj, cp.strand);
-          } else if ((prev & 1) != cp.strand) {
-            a_or(&sh.status, GS_ORDER_DEPENDENT);   // both strands on one level
+            uint32_t idx = a_add(&nb.nnext, 1);
+            if (idx >= S.cap_cells) a_or(&sh.status, GS_OVERFLOW);
+            else { nk[idx] = x; nm[idx] = (unsigned char)in_mask(adj, cs.strand); }
+          } else if ((prev & 1) != cs.strand) {
+            a_or(&sh.status, GS_ORDER_DEPENDENT);
           }
         }
       }
-      G::sync();
-      if (rank == 0 && c <= rmf) {   // next staggered right start (Gap2Seq.cpp:953-968)
-        uint64_t x = kmer_from_ascii(rsstr + (rmf - c), k);
-        Canon cs = canonical(x, k);
-        uint32_t adj = 0;
-        if (table_find(T, cs.key, &adj) >= 0) {
-          uint32_t en = node_insert(S, sh, cs.key);
-          if (en != NONE32) {
-            a_or(&S.ent[en].flags, NF_IN_RS);
-            uint32_t stamp = (uint32_t)(c + 1) * 2 + cs.strand;
-            uint32_t prev = a_max(&S.ent[en].rstamp, stamp);
-            if ((prev >> 1) < (uint32_t)(c + 1)) {
-              uint32_t idx = a_add(&sh.nnext, 1);
-              if (idx >= S.cap_cells) a_or(&sh.status, GS_OVERFLOW);
-              else { nk[idx] = x; nm[idx] = (unsigned char)in_mask(adj, cs.strand); }
-            } else if ((prev & 1) != cs.strand) {
-              a_or(&sh.status, GS_ORDER_DEPENDENT);
-            }
-          }
-        }
-      }
-      G::sync();
-      n = ld_sh(&sh.nnext);
-      if (ld_sh(&sh.status) & GS_OVERFLOW) break;
-      if (rank == 0) sh.cells_right += n;
-      cur ^= 1;
     }
+    G::sync();
+    n = ld_sh(&nb.nnext);
+    if (ld_sh(&sh.status) & GS_OVERFLOW) break;
+    if (rank == 0) sh.cells_right += n;
+    cur ^= 1;
   }
   G::sync();
-
-  const unsigned long long t_right = now_cycles();
-  // mark the right-flank targets (their node entries may not exist yet: insert them, flag TARGET)
-  if (!(ld_sh(&sh.status) & GS_OVERFLOW)) {
-    for (int j = rank; j <= rmf; j += gsz) {
-      uint64_t x = S.rk[j];
-      if (x & FLANK_PRESENT) {
-        Canon c = canonical(x & FLANK_KMER, k);
-        uint32_t en = node_insert(S, sh, c.key);
-        if (en != NONE32) a_or(&S.ent[en].flags, NF_TARGET);
-      }
-    }
-  }
+  if (rank == 0) { sh.levels_r = levels_r; sh.cyc_right = now_cycles() - t0; }
   G::sync();
+}
 
-  // ---- Phase F: forward walk counts by exact length (Gap2Seq.cpp:984-1167)
+// ---- Phase F: forward walk counts by exact length (Gap2Seq.cpp:984-1167)
+template <class G, class W>
+G2S_D void gap_forward(const FillParams &P, const GapDev &gd, const GapCtx &cx, const Slice &S, GShared &sh, NarrowBuf &nb) {
+  const Table &T = P.table;
+  const int k = cx.k, rank = G::rank(), gsz = G::size();
+  const int g = cx.g, lmf = cx.lmf, rmf = cx.rmf, Dmax = cx.Dmax, prune_from = cx.prune_from;
+  const bool all_paths = cx.all_paths;
   int top_level = 0;       // last level that was expanded into
   int levels_f = 0;
+  bool waited = !W::kConcurrent;
   bool overflow = (ld_sh(&sh.status) & GS_OVERFLOW) != 0;
   if (!overflow) {
     if (rank == 0) {
@@ -930,10 +1041,13 @@ G2S_D void process_gap(const FillParams &P, const GapDev &gd, const Slice &S, GS
 
     bool found = false;
     for (int c = 1; c <= Dmax; c++) {
+      if (!waited && c >= prune_from) { W::wait_right(); waited = true; }
+      // until the right set is complete a look-ahead batch must end below the first pruned level
+      const int dlim = waited ? Dmax : (prune_from - 1 < Dmax ? prune_from - 1 : Dmax);
       const uint32_t lo = ld_cg(&S.lstart[c - 1]), hi = ld_cg(&S.lstart[c]);
       const bool dead = (lo == hi) && c > lmf;   // empty border and no start left to inject
       if (hi > lo && hi - lo <= (uint32_t)NARROW_W && c > lmf) {   // narrow border, no start left to inject
-        const int adv = narrow_forward<G>(T, S, sh, gd, lo, (int)(hi - lo), c, Dmax, prune_from);
+        const int adv = narrow_forward<G>(T, S, sh, nb, gd, lo, (int)(hi - lo), c, dlim, prune_from);
         if (ld_sh(&sh.status) & GS_OVERFLOW) { overflow = true; break; }
         if (adv > 0) {
           const int last = c + adv - 1;
@@ -1024,7 +1138,7 @@ G2S_D void process_gap(const FillParams &P, const GapDev &gd, const Slice &S, GS
                 S.ent[en].fstamp[cs.strand] = (uint32_t)c + 1;
                 new_cell<G>(S, sh, gd, x, en, cs.strand, adj, (uint32_t)c, 1);
               }
-              if (S.ent[en].fstamp[cs.strand ^ 1] == (uint32_t)c + 1) sh.status |= GS_ORDER_DEPENDENT;
+              if (S.ent[en].fstamp[cs.strand ^ 1] == (uint32_t)c + 1) a_or(&sh.status, GS_ORDER_DEPENDENT);
             }
           }
         }
@@ -1069,15 +1183,24 @@ G2S_D void process_gap(const FillParams &P, const GapDev &gd, const Slice &S, GS
       if (rank == 0) sh.prof[4] += now_cycles() - tg0;
     }
   }
+  if (!waited) W::wait_right();
   G::sync();
+  if (rank == 0) { sh.top_level = top_level; sh.levels_f = levels_f; sh.fwd_overflow = overflow ? 1 : 0; }
+  G::sync();
+}
 
-  const unsigned long long t_fwd = now_cycles();
-  unsigned long long t_back = t_fwd;
-  // ---- Phase B + traceback trellis: backward marking through the predecessor links (Gap2Seq.cpp:1173-1312)
+// ---- Phase B + traceback trellis: backward marking through the predecessor links (Gap2Seq.cpp:1173-1312), then
+// the marked cells are appended to the output arena.  Returns the cycle stamp taken between the two.
+template <class G>
+G2S_D unsigned long long gap_backward_pack(const FillParams &P, const GapCtx &cx, const Slice &S, GShared &sh, NarrowBuf &nb) {
+  const int k = cx.k, rank = G::rank(), gsz = G::size();
+  const int g = cx.g, e = cx.e, lmf = cx.lmf, rmf = cx.rmf;
+  const bool all_paths = cx.all_paths, skip_confident = cx.skip_confident;
+  const int top_level = ld_sh(&sh.top_level);
+  const bool overflow = ld_sh(&sh.fwd_overflow) != 0 || (ld_sh(&sh.status) & GS_OVERFLOW) != 0;
+  unsigned long long t_back = now_cycles();
   const uint32_t n_plen = ld_sh(&sh.n_plen);
   const uint32_t count_fwd = ld_sh(&sh.count_fwd);
-  const uint32_t ncells = ld_sh(&sh.ncells) < S.cap_cells ? ld_sh(&sh.ncells) : S.cap_cells;
-  bool general = false;
   if (!overflow && count_fwd > 0 && n_plen > 0) {
     const int J = ld_sh(&sh.reached_fuz);
     const int p0 = ld_sh(&sh.plen[0]), p1 = n_plen > 1 ? ld_sh(&sh.plen[1]) : -1;
@@ -1116,9 +1239,12 @@ G2S_D void process_gap(const FillParams &P, const GapDev &gd, const Slice &S, GS
     // nothing above the highest seed can be marked
     const int sweep_top = ld_sh(&sh.max_seed_level) < top_level ? ld_sh(&sh.max_seed_level) : top_level;
     for (int d = sweep_top; d >= 0; d--) {
-      const uint32_t rs = ld_cg(&S.lrun[d]);
-      if (rs != 0 && (int)rs < d) { chain_mark<G>(S, sh, (int)rs, d); d = (int)rs; continue; }
+      if (d > lmf) {   // batches of narrow levels (no start cells up there)
+        const int adv = narrow_backward<G>(S, sh, nb, d, lmf);
+        if (adv > 0) { d -= adv - 1; continue; }
+      }
       const uint32_t lo = ld_cg(&S.lstart[d]), hi = ld_cg(&S.lstart[d + 1]);
+      G2S_STAT(emul_stats().back_general_levels++; emul_stats().width_hist[hi - lo > 7 ? 7 : hi - lo]++);
       const uint64_t lcanon = (d <= lmf) ? canonical(S.lk[d] & FLANK_KMER, k).key : KEY_EMPTY;
       for (uint32_t i = lo + rank; i < hi; i += gsz) {
         const uint32_t f = ld_cg(&S.cflags[i]);
@@ -1132,20 +1258,7 @@ G2S_D void process_gap(const FillParams &P, const GapDev &gd, const Slice &S, GS
         if (f & CF_B) {
           a_add(&S.nB[d], 1);
           a_add(&sh.nB, 1);
-          // vertex identity is the node: a node marked on two levels collapses levels -> general subgraph
-          uint32_t fl = ld_cg(&S.ent[en].flags);
-          for (;;) {
-            uint32_t lv = fl >> 8;
-            if (lv == 0) {
-              uint32_t old = a_cas(&S.ent[en].flags, fl, fl | ((uint32_t)(d + 1) << 8));
-              if (old == fl) break;
-              fl = old;
-            } else {
-              if (lv != (uint32_t)d + 1) a_or(&sh.status, GS_GENERAL);
-              else a_or(&sh.status, GS_ORDER_DEPENDENT);   // two marked cells of one node on one level
-              break;
-            }
-          }
+          mark_node_level(S, en, d);
           if (start) { a_add(&sh.n_src, 1); a_maxi(&sh.max_src_level, d); }
           else {
             uint32_t np = 0;
@@ -1161,7 +1274,6 @@ G2S_D void process_gap(const FillParams &P, const GapDev &gd, const Slice &S, GS
       }
       G::sync();
     }
-    general = (ld_sh(&sh.status) & GS_GENERAL) != 0;
     t_back = now_cycles();
 
     // ---- pack: append the marked cells to the output arena
@@ -1169,7 +1281,7 @@ G2S_D void process_gap(const FillParams &P, const GapDev &gd, const Slice &S, GS
     if (rank == 0) {
       unsigned long long off = a_add64(P.pack_cursor, (unsigned long long)npack);
       sh.pack_off = off;
-      if (off + npack > P.pack_cap) sh.status |= GS_OUT_FULL;
+      if (off + npack > P.pack_cap) a_or(&sh.status, GS_OUT_FULL);
     }
     G::sync();
     if (!(ld_sh(&sh.status) & GS_OUT_FULL)) {
@@ -1192,10 +1304,12 @@ G2S_D void process_gap(const FillParams &P, const GapDev &gd, const Slice &S, GS
         r.node = en;
         r.level = d;
         uint32_t meta = (f & 7u) | (start ? PM_START : 0) | ((uint32_t)(x & 3) << PM_BASE_SHIFT);
-        if (!skip_confident && !general) {
+        if (!skip_confident) {
           // level-DAG case: a vertex is on every source->sink path iff it is alone on its level and no source
-          // or sink edge jumps over that level
-          uint32_t lv = S.ent[en].flags >> 8;
+          // or sink edge jumps over that level.  Vertex identity is the node: a node marked on two
+          // levels collapses them (general subgraph -> the host runs the SCC analysis and ignores these bits).
+          const uint32_t lv = ld_cg(&S.ent[en].flags) >> 8;   // highest marked level of the node + 1, 0 = none
+          if ((f & CF_B) && lv != d + 1) a_or(&sh.status, GS_GENERAL);
           bool safe;
           if (lv == 0) safe = sink_safe;   // node2boost default-inserts the sink
           else { int bl = (int)lv - 1; safe = S.nB[bl] == 1 && bl >= max_src && bl <= min_sink; }
@@ -1208,8 +1322,14 @@ G2S_D void process_gap(const FillParams &P, const GapDev &gd, const Slice &S, GS
     }
   }
   G::sync();
+  return t_back;
+}
 
-  if (rank == 0) {
+template <class G>
+G2S_D void gap_finish(const Slice &S, GShared &sh, GapOut *out, const unsigned long long *t) {
+  if (G::rank() == 0) {
+    const bool overflow = sh.fwd_overflow != 0 || (sh.status & GS_OVERFLOW) != 0;
+    const uint32_t ncells = sh.ncells < S.cap_cells ? sh.ncells : S.cap_cells;
     GapOut o;
     o.status = sh.status | GS_DONE;
     o.count_fwd = sh.count_fwd;
@@ -1221,24 +1341,41 @@ G2S_D void process_gap(const FillParams &P, const GapDev &gd, const Slice &S, GS
     o.start_pack[0] = o.start_pack[1] = NONE32;
     if (sh.count_fwd > 0 && !overflow) {
       for (uint32_t q = 0; q < sh.n_plen; q++) {
-        uint32_t t = thit_get(S, sh, sh.reached_fuz, sh.plen[q]);
-        if (t) o.start_pack[q] = S.packidx[t - 1];
+        uint32_t th = thit_get(S, sh, sh.reached_fuz, sh.plen[q]);
+        if (th) o.start_pack[q] = S.packidx[th - 1];
       }
     }
     o.nB = sh.nB; o.n_edges = sh.n_edges; o.n_src = sh.n_src; o.n_sink = sh.n_sink;
     o.max_src_level = sh.max_src_level; o.min_sink_level = sh.min_sink_level;
-    o.top_level = (uint32_t)top_level;
+    o.top_level = (uint32_t)sh.top_level;
     o.pack_off = sh.pack_off;
-    o.levels_r = (uint32_t)levels_r; o.levels_f = (uint32_t)levels_f;
+    o.levels_r = (uint32_t)sh.levels_r; o.levels_f = (uint32_t)sh.levels_f;
     const unsigned long long t_end = now_cycles();
-    o.cyc[0] = (uint32_t)((t_init - t_start) >> 4); o.cyc[1] = (uint32_t)((t_right - t_init) >> 4);
-    o.cyc[2] = (uint32_t)((t_fwd - t_right) >> 4); o.cyc[3] = (uint32_t)((t_back - t_fwd) >> 4);
-    o.cyc[4] = (uint32_t)((t_end - t_back) >> 4); o.cyc[5] = (uint32_t)((t_end - t_start) >> 4);
+    // t[0] start, t[1] after init, t[2] before the forward pass, t[3] after it, t[4] after the backward marking
+    o.cyc[0] = (uint32_t)((t[1] - t[0]) >> 4); o.cyc[1] = (uint32_t)(sh.cyc_right >> 4);
+    o.cyc[2] = (uint32_t)((t[3] - t[2]) >> 4); o.cyc[3] = (uint32_t)((t[4] - t[3]) >> 4);
+    o.cyc[4] = (uint32_t)((t_end - t[4]) >> 4); o.cyc[5] = (uint32_t)((t_end - t[0]) >> 4);
     for (int q = 0; q < 5; q++) o.prof[q] = (uint32_t)(sh.prof[q] >> 4);
     for (int q = 5; q < 8; q++) o.prof[q] = (uint32_t)sh.prof[q];
     *out = o;
   }
   G::sync();
+}
+
+// all phases on one group, one after the other (wide tier, host emulation)
+template <class G>
+G2S_D void process_gap(const FillParams &P, const GapDev &gd, const Slice &S, GShared &sh, GapOut *out) {
+  const GapCtx cx = make_ctx(P, gd);
+  unsigned long long t[5];
+  t[0] = now_cycles();
+  gap_init<G>(P, cx, S, sh);
+  t[1] = now_cycles();
+  gap_right<G>(P, cx, S, sh, sh.nbuf[0]);
+  t[2] = now_cycles();
+  gap_forward<G, NoWait>(P, gd, cx, S, sh, sh.nbuf[1]);
+  t[3] = now_cycles();
+  t[4] = gap_backward_pack<G>(P, cx, S, sh, sh.nbuf[1]);
+  gap_finish<G>(S, sh, out, t);
 }
 
 }  // namespace g2s

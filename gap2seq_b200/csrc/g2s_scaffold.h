@@ -11,6 +11,7 @@
 // prefix-dropping `filledSeq = ...` assignment for multi-gap records (src/Gap2Seq.cpp:396).
 #pragma once
 #include <cctype>
+#include <chrono>
 #include <cstdio>
 #include <functional>
 #include <memory>
@@ -91,6 +92,7 @@ struct ScaffoldRun {
   std::vector<RecScan> recs;
   std::vector<std::unique_ptr<HostBatch>> batches;
   std::vector<std::vector<std::string>> flank_keep;   // flank strings of each batch (the gap structs point into them)
+  double phase1_ms = 0, phase2_ms = 0;                // wall time of the two phases of run() (profiling aid)
 
   ScaffoldRun(const std::vector<std::string> &s, const std::vector<std::string> &c, const RunOptions &o)
       : seqs(s), comments(c), opt(o), recs(s.size()) {}
@@ -152,6 +154,7 @@ struct ScaffoldRun {
   int run(const SubmitFn &submit, std::vector<std::string> &filled, std::string &log, int &gapcount, int &filledcount,
           std::vector<g2s_result> *details) {
     const int k = opt.k;
+    const auto t_begin = std::chrono::steady_clock::now();
     // ---- phase 1: device waves
     for (;;) {
       std::vector<std::pair<size_t, int>> wave;
@@ -189,6 +192,8 @@ struct ScaffoldRun {
       }
     }
     // ---- phase 2: the reference's control flow, record by record (src/Gap2Seq.cpp:329-432)
+    const auto t_mid = std::chrono::steady_clock::now();
+    phase1_ms = std::chrono::duration<double, std::milli>(t_mid - t_begin).count();
     filled.assign(seqs.size(), std::string());
     std::vector<char> fillbuf;
     for (size_t r = 0; r < seqs.size(); r++) {
@@ -239,6 +244,7 @@ struct ScaffoldRun {
       filledSeq += seq.substr((size_t)prev);
       filled[r].swap(filledSeq);
     }
+    phase2_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_mid).count();
     return 0;
   }
 };

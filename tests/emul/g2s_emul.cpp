@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <vector>
 
 #include "../../include/g2s.h"
@@ -67,7 +68,10 @@ void emul_adjacency(void *gp, const uint64_t *kmers, size_t n, uint8_t *out) {
 }
 
 // device pass of a list of gaps, emulated: fills a detached HostBatch exactly like the engine's do_collect
+static double g_submit_s = 0, g_analyze_s = 0;
+static double now_s() { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
 static int emul_submit(EmulGraph *g, int k, const g2s_gap *gaps, size_t n, HostBatch &hb, int cap0) {
+  const double t_submit0 = now_s();
   hb.k = k;
   hb.gaps.assign(gaps, gaps + n);
   hb.outs.assign(n, GapOut{});
@@ -118,8 +122,15 @@ static int emul_submit(EmulGraph *g, int k, const g2s_gap *gaps, size_t n, HostB
     hb.pack_base[i] = hb.own[i].data();
     hb.gaps[i].kmer_left = hb.gaps[i].kmer_right = nullptr;
   }
+  const double t_an0 = now_s();
   hb.analyze(1);
+  g_analyze_s += now_s() - t_an0;
+  g_submit_s += now_s() - t_submit0;
   return 0;
+}
+extern "C" void emul_times(double *submit_s, double *analyze_s, int reset) {
+  *submit_s = g_submit_s; *analyze_s = g_analyze_s;
+  if (reset) g_submit_s = g_analyze_s = 0;
 }
 
 // same contract as g2s_fill_batch; cap0 > 0 forces the first tier's cell capacity (to exercise tier escalation)
@@ -178,3 +189,11 @@ extern "C" void emul_hint_hist(void *gp, uint64_t *hist26) {
 
 extern "C" int emul_rand_skip_enabled() { return g2s::RandSkipper::enabled() ? 1 : 0; }
 extern "C" void emul_rand_skip(size_t n) { g2s::RandSkipper::skip(n); }
+
+#ifdef G2S_EMUL_STATS
+// development aid (tools/emul_stats.py): probe / level-width counters of the emulated pass
+extern "C" void emul_stats_get(unsigned long long *out, int reset) {
+  memcpy(out, &g2s::emul_stats(), sizeof(g2s::EmulStats));
+  if (reset) memset(&g2s::emul_stats(), 0, sizeof(g2s::EmulStats));
+}
+#endif
