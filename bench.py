@@ -8,7 +8,7 @@ One "step" = one pass of the hot path over the workload's batch of gaps.
   value        gaps/s of the device pass with the gaps already resident in HBM (CUDA events on the engine's stream)
   e2e          gaps/s through the reference-facing driver call (g2s_fill_records: host strings in, filled strings
                out; H2D, kernels, D2H and the host traceback inside the timed region)
-  roofline     dominant kernel (k_fill_warp) against the HBM-gather roofline: 52 algorithmic bytes per DP cell
+  roofline     dominant kernel (k_fill_thin) against the HBM-gather roofline: 52 algorithmic bytes per DP cell
   cpu_baseline the oracle port on a bounded sample of the same gaps (1 host core)
 `--impl reference` times the unmodified reference binary (oracle/_ref/bin/Gap2Seq-core -nb-cores <all cores>) on the
 same workload on the host CPU.  Graph construction is not part of any timed region (BASELINE.json: "timed
@@ -324,7 +324,7 @@ def main():
                     "d2h_bytes_per_step": all_d2h, "ms_per_step": ms_e2e, "breakdown_ms_last_step": e2e_detail},
             "gpu_launches": int(all_launches),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "k_fill_warp", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "k_fill_thin", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                          "algorithmic_bytes_per_cell": BYTES_PER_CELL,
                          "note": "thin gaps are chains of dependent gathers (1 cell per level): latency bound, see DESIGN.md"},

@@ -151,6 +151,7 @@ struct NarrowBuf {     // look-ahead state of one pass (the right pass and the f
   int32_t nw_fail[NARROW_W];
   uint32_t nw_n[CHAIN_LEN + 1], nw_off[CHAIN_LEN + 1], nw_run[CHAIN_LEN], nw_poff[CHAIN_LEN];
   uint32_t bk_p[NARROW_W][4];   // backward batches: predecessor cells of the batch's lowest level
+  int32_t bk_len;
   uint64_t ch_s[CHAIN_LEN][NARROW_W];
   uint32_t ch_a[CHAIN_LEN][NARROW_W], ch_e[CHAIN_LEN][NARROW_W];
 };
@@ -264,34 +265,47 @@ inline EmulStats &emul_stats() { static EmulStats s; return s; }
 
 G2S_D uint32_t node_hash(uint64_t key, uint32_t hmask) { return (uint32_t)((key * 0x9E3779B97F4A7C15ULL) >> 40) & hmask; }
 
-G2S_D uint32_t node_find(const Slice &S, uint64_t key) {
+// The first 16 bytes of an entry (key, rstamp, flags) travel in one request: a lookup returns the node's flag word
+// (right-set membership, target) without a second dependent round trip.
+G2S_D void load_ent_head(const NodeEnt *p, uint64_t *key, uint32_t *flags) {
+#ifdef G2S_DEVICE_BUILD
+  const uint4 v = __ldcg((const uint4 *)p);
+  *key = (uint64_t)v.x | ((uint64_t)v.y << 32);
+  *flags = v.w;
+#else
+  *key = p->key; *flags = p->flags;
+#endif
+}
+
+G2S_D uint32_t node_find(const Slice &S, uint64_t key, uint32_t *flags) {
   uint32_t h = node_hash(key, S.hmask);
   G2S_STAT(emul_stats().finds++);
   for (;;) {
     G2S_STAT(emul_stats().find_probes++);
-    uint64_t k0 = ld_cg(&S.ent[h].key);
+    uint64_t k0;
+    load_ent_head(&S.ent[h], &k0, flags);
     if (k0 == key) return h;
     if (k0 == KEY_EMPTY) return NONE32;
     h = (h + 1) & S.hmask;
   }
 }
 
-G2S_D uint32_t node_insert(const Slice &S, GShared &sh, uint64_t key) {
+// Find or insert.  Most inserted keys are new (a walk rarely revisits a node), so the probe IS the compare-and-swap:
+// one round trip for a new node; an existing one costs a second (its flag word).  *flags receives the flag word as
+// of the lookup (0 for a new node).
+G2S_D uint32_t node_insert(const Slice &S, GShared &sh, uint64_t key, uint32_t *flags) {
   uint32_t h = node_hash(key, S.hmask);
   G2S_STAT(emul_stats().inserts++);
+  if (ld_sh(&sh.nnodes) >= S.hcap - (S.hcap >> 2)) { a_or(&sh.status, GS_OVERFLOW); return NONE32; }
   for (;;) {
     G2S_STAT(emul_stats().insert_probes++);
-    uint64_t k0 = ld_cg(&S.ent[h].key);
-    if (k0 == key) return h;
-    if (k0 == KEY_EMPTY) {
-      if (ld_sh(&sh.nnodes) >= S.hcap - (S.hcap >> 2)) { a_or(&sh.status, GS_OVERFLOW); return NONE32; }
-      uint64_t old = a_cas64(&S.ent[h].key, KEY_EMPTY, key);
-      if (old == KEY_EMPTY) { a_add(&sh.nnodes, 1); return h; }
-      if (old == key) return h;
-    }
+    const uint64_t old = a_cas64(&S.ent[h].key, KEY_EMPTY, key);
+    if (old == KEY_EMPTY) { a_add(&sh.nnodes, 1); *flags = 0; return h; }
+    if (old == key) { *flags = ld_cg(&S.ent[h].flags); return h; }
     h = (h + 1) & S.hmask;
   }
 }
+G2S_D uint32_t node_insert(const Slice &S, GShared &sh, uint64_t key) { uint32_t f; return node_insert(S, sh, key, &f); }
 
 G2S_D unsigned long long now_cycles() {
 #ifdef __CUDA_ARCH__
@@ -306,7 +320,7 @@ G2S_D uint32_t clamp_paths(uint32_t c) { return c > MAX_PATHS ? MAX_PATHS : c; }
 // create the forward cell (state s of node e) on level c; the caller owns the (e,strand,level) stamp
 template <class G>
 G2S_D uint32_t new_cell(const Slice &S, GShared &sh, const GapDev &gd, uint64_t s, uint32_t e, uint32_t strand,
-                        uint32_t adj, uint32_t c, uint32_t count) {
+                        uint32_t adj, uint32_t c, uint32_t count, uint32_t nflags) {
   uint32_t idx = a_add(&sh.ncells, 1);
   if (idx >= S.cap_cells) { a_or(&sh.status, GS_OVERFLOW); return NONE32; }
   S.ck[idx] = s;
@@ -315,8 +329,7 @@ G2S_D uint32_t new_cell(const Slice &S, GShared &sh, const GapDev &gd, uint64_t 
   S.cp[4 * idx + 0] = NONE32; S.cp[4 * idx + 1] = NONE32; S.cp[4 * idx + 2] = NONE32; S.cp[4 * idx + 3] = NONE32;
   S.cflags[idx] = out_mask(adj, strand) << CF_OMASK_SHIFT;
   S.ent[e].fcell[strand] = idx;
-  uint32_t fl = a_or(&S.ent[e].flags, NF_HAS_F);
-  if ((fl & NF_TARGET) && (int)c >= sh.tlo) {
+  if ((nflags & NF_TARGET) && (int)c >= sh.tlo) {
     for (int j = 0; j <= gd.rmf; j++)
       if ((S.rk[j] & FLANK_KMER) == s) S.thit[(size_t)j * sh.trow + (c - (uint32_t)sh.tlo)] = idx + 1;
   }
@@ -600,8 +613,10 @@ G2S_D int narrow_forward(const Table &T, const Slice &S, GShared &sh, NarrowBuf 
     uint32_t en = NONE32;
     if (nb.ch_a[l][t]) {
       const Canon cs = canonical(nb.ch_s[l][t], k);
-      if (c + l < prune_from) en = node_insert(S, sh, cs.key);
-      else { en = node_find(S, cs.key); if (en != NONE32 && !(ld_cg(&S.ent[en].flags) & NF_IN_RS)) en = NONE32; }
+      uint32_t nf = 0;
+      if (c + l < prune_from) en = node_insert(S, sh, cs.key, &nf);
+      else { en = node_find(S, cs.key, &nf); if (en != NONE32 && !(nf & NF_IN_RS)) en = NONE32; }
+      if (nf & NF_TARGET) nb.ch_a[l][t] |= 1u << 17;
     }
     nb.ch_e[l][t] = en;
     if (en == NONE32) a_mini(&nb.nw_fail[t], l);
@@ -643,69 +658,67 @@ G2S_D int narrow_forward(const Table &T, const Slice &S, GShared &sh, NarrowBuf 
   const uint32_t base = ld_sh(&nb.ch_base);
   for (int l = rank; l < done; l += gsz) {
     const uint32_t level = (uint32_t)(c + l);
+    // everything the level needs from shared memory, read once into registers
+    uint64_t st[NARROW_W], ps[NARROW_W];
+    uint32_t av[NARROW_W], ev[NARROW_W], c0[NARROW_W];
+    bool al[NARROW_W], pal[NARROW_W];
+#pragma unroll
+    for (int t = 0; t < NARROW_W; t++) {
+      const bool in = t < w;
+      const int fail = in ? nb.nw_fail[t] : 0;
+      al[t] = in && l < fail;
+      pal[t] = in && (l == 0 || l - 1 < fail);
+      st[t] = nb.ch_s[l][t];
+      ps[t] = l ? nb.ch_s[l - 1][t] : nb.nw_x0[t];
+      av[t] = nb.ch_a[l][t]; ev[t] = nb.ch_e[l][t]; c0[t] = nb.nw_cnt0[t];
+    }
+    const uint32_t off_l = nb.nw_off[l], off_p = l ? nb.nw_off[l - 1] : 0u, nn = nb.nw_n[l];
+    // a chain's cell = the lowest alive chain with the same state; cells are laid out in that order
+    uint32_t rep[NARROW_W], prep[NARROW_W];
+#pragma unroll
+    for (int t = 0; t < NARROW_W; t++) {
+      rep[t] = (uint32_t)t; prep[t] = (uint32_t)t;
+#pragma unroll
+      for (int u = NARROW_W - 1; u >= 0; u--) {
+        if (u >= t) continue;
+        if (al[u] && st[u] == st[t]) rep[t] = (uint32_t)u;
+        if (pal[u] && ps[u] == ps[t]) prep[t] = (uint32_t)u;
+      }
+    }
     uint32_t ord = 0;
 #pragma unroll
     for (int t = 0; t < NARROW_W; t++) {
-      if (t >= w || l >= nb.nw_fail[t]) continue;
-      const uint64_t s = nb.ch_s[l][t];
-      bool dup = false;
-#pragma unroll
-      for (int u = 0; u < NARROW_W; u++) if (u < t && l < nb.nw_fail[u] && nb.ch_s[l][u] == s) dup = true;
-      if (dup) continue;
-      const uint32_t idx = base + nb.nw_off[l] + ord++;
-      const uint32_t a = nb.ch_a[l][t], en = nb.ch_e[l][t], strand = (a >> 8) & 1;
-      uint32_t cnt = 0;
-      uint32_t link[4] = {NONE32, NONE32, NONE32, NONE32};
+      if (!al[t] || rep[t] != (uint32_t)t) continue;
+      const uint32_t idx = base + off_l + ord++;
+      const uint64_t sx = st[t];
+      const uint32_t a = av[t], en = ev[t], strand = (a >> 8) & 1;
+      uint32_t cnt = 0, l0 = NONE32, l1 = NONE32, l2 = NONE32, l3 = NONE32;
+      bool q3 = false;
 #pragma unroll
       for (int v = 0; v < NARROW_W; v++) {
-        if (v >= w || l >= nb.nw_fail[v] || nb.ch_s[l][v] != s) continue;
-        cnt += nb.nw_cnt0[v];   // <= 4 * MAX_PATHS < 2^32
-        // the cell of chain v on the level below: lowest alive chain with v's state there
-        const uint64_t ps = l ? nb.ch_s[l - 1][v] : nb.nw_x0[v];
-        uint32_t pord = 0, prep = (uint32_t)v;
+        if (!al[v]) continue;
+        if (st[v] != sx) { if (ev[v] == en) q3 = true; continue; }   // both strands of one node on one level (Q3)
+        cnt += c0[v];   // <= 4 * MAX_PATHS < 2^32
+        // the cell of chain v on the level below, and its position among that level's distinct states
+        uint32_t pord = 0;
 #pragma unroll
-        for (int u = 0; u < NARROW_W; u++) {
-          if (u >= w || u >= v) continue;
-          const bool ualive = l ? (l - 1 < nb.nw_fail[u]) : true;
-          if (!ualive) continue;
-          const uint64_t us = l ? nb.ch_s[l - 1][u] : nb.nw_x0[u];
-          if (us == ps) { if (prep == (uint32_t)v) prep = (uint32_t)u; }
-        }
-        // ordinal of the representative among the distinct alive states of the level below
-#pragma unroll
-        for (int u = 0; u < NARROW_W; u++) {
-          if (u >= w || (uint32_t)u >= prep) continue;
-          const bool ualive = l ? (l - 1 < nb.nw_fail[u]) : true;
-          if (!ualive) continue;
-          const uint64_t us = l ? nb.ch_s[l - 1][u] : nb.nw_x0[u];
-          bool udup = false;
-#pragma unroll
-          for (int z = 0; z < NARROW_W; z++) {
-            if (z >= u) continue;
-            const bool zalive = l ? (l - 1 < nb.nw_fail[z]) : true;
-            if (zalive && (l ? nb.ch_s[l - 1][z] : nb.nw_x0[z]) == us) udup = true;
-          }
-          if (!udup) pord++;
-        }
-        const uint32_t pidx = l ? base + nb.nw_off[l - 1] + pord : lo + prep;
-        link[(uint32_t)(ps >> (2 * (k - 1))) & 3u] = pidx;
+        for (int u = 0; u < NARROW_W; u++) if ((uint32_t)u < prep[v] && pal[u] && prep[u] == (uint32_t)u) pord++;
+        const uint32_t pidx = l ? base + off_p + pord : lo + prep[v];
+        const uint32_t pb = (uint32_t)(ps[v] >> (2 * (k - 1))) & 3u;
+        l0 = pb == 0 ? pidx : l0; l1 = pb == 1 ? pidx : l1; l2 = pb == 2 ? pidx : l2; l3 = pb == 3 ? pidx : l3;
       }
-      S.ck[idx] = s; S.cc[idx] = cnt; S.cn[idx] = en;
-      S.cp[4 * idx + 0] = link[0]; S.cp[4 * idx + 1] = link[1]; S.cp[4 * idx + 2] = link[2]; S.cp[4 * idx + 3] = link[3];
+      S.ck[idx] = sx; S.cc[idx] = cnt; S.cn[idx] = en;
+      *(uint4 *)(S.cp + 4 * (size_t)idx) = uint4{l0, l1, l2, l3};
       S.cflags[idx] = (a & 0xFF) << CF_OMASK_SHIFT;   // the scout emits the oriented out-mask
-      // both strands of one node on one level (Q3)
-#pragma unroll
-      for (int u = 0; u < NARROW_W; u++)
-        if (u < w && u != t && l < nb.nw_fail[u] && nb.ch_e[l][u] == en && nb.ch_s[l][u] != s) a_or(&sh.status, GS_ORDER_DEPENDENT);
+      if (q3) a_or(&sh.status, GS_ORDER_DEPENDENT);
       a_max(&S.ent[en].fstamp[strand], level + 1);
       S.ent[en].fcell[strand] = idx;
-      const uint32_t fl = a_or(&S.ent[en].flags, NF_HAS_F);
-      if ((fl & NF_TARGET) && (int)level >= sh.tlo) {
+      if ((a & (1u << 17)) && (int)level >= sh.tlo) {
         for (int j = 0; j <= gd.rmf; j++)
-          if ((S.rk[j] & FLANK_KMER) == s) S.thit[(size_t)j * sh.trow + (level - (uint32_t)sh.tlo)] = idx + 1;
+          if ((S.rk[j] & FLANK_KMER) == sx) S.thit[(size_t)j * sh.trow + (level - (uint32_t)sh.tlo)] = idx + 1;
       }
     }
-    S.lstart[level + 1] = base + nb.nw_off[l] + nb.nw_n[l];
+    S.lstart[level + 1] = base + off_l + nn;
   }
   G::sync();
   if (rank == 0) { sh.prof[2] += now_cycles() - tp2; sh.prof[5] += 1; sh.prof[6] += (unsigned long long)done; }
@@ -720,114 +733,131 @@ G2S_D void mark_node_level(const Slice &S, uint32_t en, int level) {
   a_max(&S.ent[en].flags, ((uint32_t)(level + 1) << 8) | 0xFFu);
 }
 
+G2S_D uint32_t popc32(uint32_t x) {
+#ifdef __CUDA_ARCH__
+  return (uint32_t)__popc(x);
+#else
+  return (uint32_t)__builtin_popcount(x);
+#endif
+}
+
+// nibble i of M = set of cells of the level below that are predecessors of cell i; returns the union over the cells in v
+G2S_D uint32_t flow_down(uint32_t M, uint32_t v) {
+  const uint32_t s = (v | (v << 3) | (v << 6) | (v << 9)) & 0x1111u;   // bit i of v -> bit 4i
+  const uint32_t sel = M & (s * 15u);
+  const uint32_t r = sel | (sel >> 8);
+  return (r | (r >> 4)) & 15u;
+}
+
 // Backward marking of up to CHAIN_LEN consecutive narrow levels d, d-1, ... (1..NARROW_W cells each, all above lmf,
-// so none of their cells is a start cell).  The levels' flags and predecessor links are gathered in parallel, one
-// thread then pushes the marks down the batch in shared memory (a level costs a few bit operations), and the marks,
-// pack indices and per-level counts are written back in parallel.  Marks reach the level below the batch through
-// the cell flags, exactly like on the level-by-level path.  Returns the number of levels done (0: level d is wide
-// or empty).
+// so none of their cells is a start cell).  One thread per level gathers the level's flags and predecessor links
+// (all loads of a batch are in flight together), one thread then pushes the marks down the batch in shared memory
+// (a level costs a few bit operations; a batch of pure chain levels only ORs), and the marks, pack indices and
+// per-level counts are written back by one thread per level without waiting for any atomic.  Marks reach the level
+// below the batch through the cell flags, exactly like on the level-by-level path.  Returns the number of levels
+// done (0: level d is wide or empty).
 template <class G>
 G2S_D int narrow_backward(const Slice &S, GShared &sh, NarrowBuf &nb, int d, int lmf) {
   const int rank = G::rank(), gsz = G::size();
   const int maxlen = d - lmf < CHAIN_LEN ? d - lmf : CHAIN_LEN;   // levels d .. d-maxlen+1 are all > lmf
-  // geometry of the levels d+1-t (t = 0 is only needed for its start offset = end of level d)
-  for (int t = rank; t <= maxlen + 1; t += gsz) {
-    const uint32_t v = ld_cg(&S.lstart[d + 1 - t]);
-    if (t <= maxlen) nb.nw_off[t] = v;              // nw_off[t+1] = first cell of batch level t (level d - t)
-    else nb.nw_cnt0[0] = v;                         // first cell of the level below the deepest possible batch level
-  }
+  if (rank == 0) { nb.bk_len = maxlen; nb.nw_stop = 0; }
   G::sync();
-  if (rank == 0) {
-    int len = 0;
-    while (len < maxlen) {
-      const uint32_t n = nb.nw_off[len] - nb.nw_off[len + 1];
-      if (n == 0 || n > (uint32_t)NARROW_W) break;
-      nb.nw_n[len] = n;
-      len++;
+  // geometry: nw_off[t] = first cell of batch level t (= level d - t), nw_n[t] = its width
+  for (int t = rank; t <= maxlen; t += gsz) {
+    const uint32_t lo = ld_cg(&S.lstart[d - t]);
+    nb.nw_off[t] = lo;
+    if (t < maxlen) {
+      const uint32_t n = ld_cg(&S.lstart[d + 1 - t]) - lo;
+      nb.nw_n[t] = n;
+      if (n == 0 || n > (uint32_t)NARROW_W) a_mini(&nb.bk_len, t);
     }
-    nb.ch_len = (uint32_t)len;
   }
   G::sync();
-  const int len = (int)ld_sh(&nb.ch_len);
+  const int len = ld_sh(&nb.bk_len);
   if (len == 0) return 0;
-  // gather: own marks, node, predecessor mask relative to the level below
-  for (int q = rank; q < len * NARROW_W; q += gsz) {
-    const int t = q / NARROW_W, i = q - t * NARROW_W;
-    uint32_t a = 0;
-    if ((uint32_t)i < nb.nw_n[t]) {
-      const uint32_t idx = nb.nw_off[t + 1] + (uint32_t)i;
-      const uint32_t f = ld_cg(&S.cflags[idx]);
-      const uint32_t below = t + 1 < maxlen ? nb.nw_off[t + 2] : nb.nw_cnt0[0];
+  // gather, one level per thread: own marks, predecessor sets relative to the level below, nodes
+  for (int t = rank; t < len; t += gsz) {
+    const uint32_t lo = nb.nw_off[t], n = nb.nw_n[t], below = nb.nw_off[t + 1];
+    uint32_t f[NARROW_W], e[NARROW_W];
+    uint4 p[NARROW_W];
+#pragma unroll
+    for (int i = 0; i < NARROW_W; i++) {
+      f[i] = 0; e[i] = 0; p[i] = uint4{NONE32, NONE32, NONE32, NONE32};
+      if ((uint32_t)i < n) {
+        f[i] = ld_cg(&S.cflags[lo + i]);
+        e[i] = ld_cg(&S.cn[lo + i]);
+        p[i] = ld_cg((const uint4 *)(S.cp + 4 * (size_t)(lo + i)));
+      }
+    }
+    uint32_t own = 0, M = 0, npw = 0;
+#pragma unroll
+    for (int i = 0; i < NARROW_W; i++) {
+      if (f[i] & CF_B) own |= 1u << i;
+      if (f[i] & CF_T) own |= 16u << i;
+      const uint32_t pp[4] = {p[i].x, p[i].y, p[i].z, p[i].w};
       uint32_t pm = 0, np = 0;
 #pragma unroll
-      for (int z = 0; z < 4; z++) {
-        const uint32_t p = ld_cg(&S.cp[4 * idx + z]);
-        if (t == len - 1) nb.bk_p[i][z] = p;
-        if (p != NONE32) { np++; const uint32_t rel = p - below; if (rel < (uint32_t)NARROW_W) pm |= 1u << rel; }
-      }
-      a = (f & (CF_B | CF_T)) | (pm << 4) | (np << 8);
-      nb.ch_e[t][i] = ld_cg(&S.cn[idx]);
+      for (int z = 0; z < 4; z++)
+        if (pp[z] != NONE32) { np++; const uint32_t rel = pp[z] - below; if (rel < (uint32_t)NARROW_W) pm |= 1u << rel; }
+      M |= pm << (4 * i);
+      npw |= np << (4 * i);
+      nb.ch_e[t][i] = e[i];
+      if (t == len - 1) { nb.bk_p[i][0] = pp[0]; nb.bk_p[i][1] = pp[1]; nb.bk_p[i][2] = pp[2]; nb.bk_p[i][3] = pp[3]; }
     }
-    nb.ch_a[t][i] = a;
+    nb.ch_a[t][0] = own | (M << 8);
+    nb.ch_a[t][1] = npw;
+    if (M != 1u || n != 1u) a_or(&nb.nw_stop, 1u);   // not a pure chain level
   }
   G::sync();
   if (rank == 0) {   // push the marks down the batch
-    uint32_t flowB = 0, flowT = 0, npk = 0, nbt = 0, ned = 0;
-    for (int t = 0; t < len; t++) {
-      uint32_t mB = flowB, mT = flowT;
-      flowB = flowT = 0;
-#pragma unroll
-      for (int i = 0; i < NARROW_W; i++) {
-        const uint32_t a = nb.ch_a[t][i];
-        if (a & CF_B) mB |= 1u << i;
-        if (a & CF_T) mT |= 1u << i;
+    uint32_t x = 0, npk = 0;
+    if (nb.nw_stop == 0) {
+      for (int t = 0; t < len; t++) {
+        x |= nb.ch_a[t][0] & 0x11u;
+        nb.nw_run[t] = x;
+        nb.nw_poff[t] = npk;
+        npk += x ? 1u : 0u;
       }
-#pragma unroll
-      for (int i = 0; i < NARROW_W; i++) {
-        const uint32_t a = nb.ch_a[t][i];
-        if ((mB >> i) & 1) { flowB |= (a >> 4) & 15u; ned += a >> 8; }
-        if ((mT >> i) & 1) flowT |= (a >> 4) & 15u;
+    } else {
+      for (int t = 0; t < len; t++) {
+        const uint32_t w0 = nb.ch_a[t][0], M = w0 >> 8;
+        const uint32_t m = (w0 & 0xFFu) | x;
+        nb.nw_run[t] = m;
+        nb.nw_poff[t] = npk;
+        npk += popc32((m | (m >> 4)) & 15u);
+        x = flow_down(M, m & 15u) | (flow_down(M, m >> 4) << 4);
       }
-      nb.nw_run[t] = mB | (mT << 4);
-      nb.nw_poff[t] = npk;
-#ifdef __CUDA_ARCH__
-      npk += (uint32_t)__popc(mB | mT); nbt += (uint32_t)__popc(mB);
-#else
-      npk += (uint32_t)__builtin_popcount(mB | mT); nbt += (uint32_t)__builtin_popcount(mB);
-#endif
     }
     nb.ch_base = sh.npack;
-    sh.npack += npk; sh.nB += nbt; sh.n_edges += ned;
+    sh.npack += npk;
   }
   G::sync();
   const uint32_t base = ld_sh(&nb.ch_base);
-  for (int q = rank; q < len * NARROW_W; q += gsz) {
-    const int t = q / NARROW_W, i = q - t * NARROW_W;
+  uint32_t nbt = 0, ned = 0;
+  for (int t = rank; t < len; t += gsz) {
     const uint32_t m = nb.nw_run[t], mB = m & 15u, mT = m >> 4, mk = mB | mT;
+    if (!mk) continue;
     const int level = d - t;
-    if (i == 0 && mB) {
-#ifdef __CUDA_ARCH__
-      S.nB[level] = (uint32_t)__popc(mB);
-#else
-      S.nB[level] = (uint32_t)__builtin_popcount(mB);
-#endif
-    }
-    if (!((mk >> i) & 1)) continue;
-    const uint32_t idx = nb.nw_off[t + 1] + (uint32_t)i;
-    const uint32_t bits = (((mB >> i) & 1) ? (uint32_t)CF_B : 0u) | (((mT >> i) & 1) ? (uint32_t)CF_T : 0u);
-#ifdef __CUDA_ARCH__
-    const uint32_t pi = base + nb.nw_poff[t] + (uint32_t)__popc(mk & ((1u << i) - 1u));
-#else
-    const uint32_t pi = base + nb.nw_poff[t] + (uint32_t)__builtin_popcount(mk & ((1u << i) - 1u));
-#endif
-    a_or(&S.cflags[idx], bits);
-    S.packidx[idx] = pi; S.packlist[pi] = idx; S.packlevel[pi] = (uint32_t)level;
-    if (bits & CF_B) mark_node_level(S, nb.ch_e[t][i], level);
-    if (t == len - 1) {
+    const uint32_t lo = nb.nw_off[t], npw = nb.ch_a[t][1];
+    if (mB) { S.nB[level] = popc32(mB); nbt += popc32(mB); }
+    uint32_t pi = base + nb.nw_poff[t];
 #pragma unroll
-      for (int z = 0; z < 4; z++) { const uint32_t p = nb.bk_p[i][z]; if (p != NONE32) a_or(&S.cflags[p], bits); }
+    for (int i = 0; i < NARROW_W; i++) {
+      if (!((mk >> i) & 1)) continue;
+      const uint32_t idx = lo + (uint32_t)i;
+      const uint32_t bits = (((mB >> i) & 1) ? (uint32_t)CF_B : 0u) | (((mT >> i) & 1) ? (uint32_t)CF_T : 0u);
+      a_or(&S.cflags[idx], bits);
+      S.packidx[idx] = pi; S.packlist[pi] = idx; S.packlevel[pi] = (uint32_t)level;
+      pi++;
+      if (bits & CF_B) { mark_node_level(S, nb.ch_e[t][i], level); ned += (npw >> (4 * i)) & 15u; }
+      if (t == len - 1) {
+#pragma unroll
+        for (int z = 0; z < 4; z++) { const uint32_t p = nb.bk_p[i][z]; if (p != NONE32) a_or(&S.cflags[p], bits); }
+      }
     }
   }
+  if (nbt) a_add(&sh.nB, nbt);
+  if (ned) a_add(&sh.n_edges, ned);
   G2S_STAT(emul_stats().back_chain_levels += (unsigned long long)len);
   G::sync();
   return len;
@@ -1027,10 +1057,11 @@ G2S_D void gap_forward(const FillParams &P, const GapDev &gd, const GapCtx &cx, 
         Canon c = canonical(x, k);
         uint32_t adj = 0;
         table_find(T, c.key, &adj);
-        uint32_t en = node_insert(S, sh, c.key);
+        uint32_t nf = 0;
+        uint32_t en = node_insert(S, sh, c.key, &nf);
         if (en != NONE32) {
           S.ent[en].fstamp[c.strand] = 1;
-          new_cell<G>(S, sh, gd, x, en, c.strand, adj, 0, 1);
+          new_cell<G>(S, sh, gd, x, en, c.strand, adj, 0, 1, nf);
         }
       }
       S.lstart[0] = 0;
@@ -1091,17 +1122,17 @@ G2S_D void gap_forward(const FillParams &P, const GapDev &gd, const GapCtx &cx, 
               const Canon cs = canonical(s, k);
               uint32_t adj = 0;
               if (table_find(T, cs.key, &adj) < 0) { a_or(&sh.status, GS_INTERNAL); continue; }
-              uint32_t en;
+              uint32_t en, nf = 0;
               if (c < prune_from) {
-                en = node_insert(S, sh, cs.key);
+                en = node_insert(S, sh, cs.key, &nf);
                 if (en == NONE32) continue;
               } else {   // meet in the middle: only nodes of the right set survive (Gap2Seq.cpp:1050)
-                en = node_find(S, cs.key);
-                if (en == NONE32 || !(ld_cg(&S.ent[en].flags) & NF_IN_RS)) continue;
+                en = node_find(S, cs.key, &nf);
+                if (en == NONE32 || !(nf & NF_IN_RS)) continue;
               }
               const uint32_t prev = a_max(&S.ent[en].fstamp[cs.strand], (uint32_t)c + 1);
               if (prev < (uint32_t)c + 1) {
-                if (new_cell<G>(S, sh, gd, s, en, cs.strand, adj, (uint32_t)c, 0) == NONE32) continue;
+                if (new_cell<G>(S, sh, gd, s, en, cs.strand, adj, (uint32_t)c, 0, nf) == NONE32) continue;
               }
               cand_e[nt] = en;
               cand_valid |= 1u << nt;
@@ -1130,13 +1161,14 @@ G2S_D void gap_forward(const FillParams &P, const GapDev &gd, const GapCtx &cx, 
             Canon cs = canonical(x, k);
             uint32_t adj = 0;
             table_find(T, cs.key, &adj);
-            uint32_t en = node_insert(S, sh, cs.key);
+            uint32_t nf = 0;
+            uint32_t en = node_insert(S, sh, cs.key, &nf);
             if (en != NONE32) {
               if (S.ent[en].fstamp[cs.strand] == (uint32_t)c + 1) {
                 S.cc[S.ent[en].fcell[cs.strand]] = 1;
               } else {
                 S.ent[en].fstamp[cs.strand] = (uint32_t)c + 1;
-                new_cell<G>(S, sh, gd, x, en, cs.strand, adj, (uint32_t)c, 1);
+                new_cell<G>(S, sh, gd, x, en, cs.strand, adj, (uint32_t)c, 1, nf);
               }
               if (S.ent[en].fstamp[cs.strand ^ 1] == (uint32_t)c + 1) a_or(&sh.status, GS_ORDER_DEPENDENT);
             }

@@ -215,6 +215,7 @@ inline void finish_one(const g2s_gap &g, const GapOut &o, const PackRec *pk, int
   bool broken = (cur == NONE32);
   while (d >= 0 && !broken) {
     const PackRec &rec = pk[cur];
+    __builtin_prefetch(&pk[cur + 24]);   // predecessors usually follow in the arena (it is filled top level first)
     if (d <= g.left_max_fuz && (rec.meta & PM_START)) { left_fuz = g.left_max_fuz - d; break; }
     if (d > 0) {
       const bool safe = skip_confident || (general ? gen.safe[cur] != 0 : (rec.meta & PM_SAFE) != 0);

@@ -161,6 +161,7 @@ int emul_fill_records(void *gp, const char *const *seqs, const char *const *comm
   std::vector<g2s_result> details;
   int rc = run.run(submit, filled, log, gc, fc, &details);
   if (rc) return rc;
+  if (getenv("G2S_HOST_PROF")) fprintf(stderr, "emul_fill_records: phase1 %.3f ms (incl. emulated device pass), trace+splice+log %.3f ms\n", run.phase1_ms, run.phase2_ms);
   for (size_t i = 0; i < n_records; i++) filled_out[i] = strdup(filled[i].c_str());
   *log_out = strdup(log.c_str());
   *gapcount = gc; *filledcount = fc;
