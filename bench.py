@@ -205,6 +205,8 @@ def cpu_baseline(w, keys, budget_s: float):
 
 def main():
     args = parse_args()
+    import faulthandler
+    faulthandler.dump_traceback_later(float(os.environ.get("G2S_BENCH_WATCHDOG_S", "240")), repeat=True, file=sys.stderr)
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -272,25 +274,34 @@ def main():
     res, fills = eng.finish_resident()
     cells = sum(r.cells_left + r.cells_right for r in res)
     filled = sum(1 for r in res if r.count > 0)
+    exact = sum(1 for f, rec in zip(fills, w.gaps) if f[:-w.k] == rec.truth) if len(fills) == len(w.gaps) else None
     big = eng.timing().gaps_big_tier
 
     # ---- end to end through the driver call, host buffers
     import ctypes
     libc = ctypes.CDLL(None)
-    for _ in range(min(args.warmup, 2)):
+    libc.srand(1)
+    ref_out = eng.fill_records(seqs, names, dist_error=w.dist_error, fuz=w.fuz, all_paths=not w.best_only)
+    prepared = eng.prepare_records(seqs, names)   # host buffers of a C caller: NUL-terminated strings
+    for _ in range(max(args.warmup, 3)):
         libc.srand(1)
-        eng.fill_records(seqs, names, dist_error=w.dist_error, fuz=w.fuz, all_paths=not w.best_only)
+        eng.fill_records_c(prepared, dist_error=w.dist_error, fuz=w.fuz, all_paths=not w.best_only)[4]()
     barrier()
     e2e_ms, h2d_b, d2h_b = [], 0, 0
+    e2e_same = True
     for _ in range(args.steps):
         flush.zero_()
         torch.cuda.synchronize()
         libc.srand(1)
         t1 = time.perf_counter()
-        out = eng.fill_records(seqs, names, dist_error=w.dist_error, fuz=w.fuz, all_paths=not w.best_only)
+        out = eng.fill_records_c(prepared, dist_error=w.dist_error, fuz=w.fuz, all_paths=not w.best_only)
         e2e_ms.append(1e3 * (time.perf_counter() - t1))
         t = eng.timing()
         h2d_b, d2h_b = t.h2d_bytes, t.d2h_bytes
+        # outside the timed region: the timed call's output equals the driver call made through the Python binding
+        e2e_same = e2e_same and out[2:4] == ref_out[2:4] and ctypes.string_at(out[1].value).decode() == ref_out[1] and \
+            all(ctypes.string_at(out[0][i]).decode() == ref_out[0][i] for i in range(len(seqs)))
+        out[4]()
     barrier()
     clocks = sampler.stop()
     e2e_detail = {"h2d_ms": t.h2d_ms, "kernel_ms": t.kernel_ms, "d2h_ms": t.d2h_ms, "host_ms": t.host_ms}
@@ -314,14 +325,16 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
             "config": {"workload": WORKLOAD_DESC.get(args.workload, args.workload), "scale": args.scale,
-                       "gaps_per_gpu": n_gaps, "filled": filled, "solid_kmers": n_kmers,
+                       "gaps_per_gpu": n_gaps, "filled": filled, "fills_equal_to_removed_bases": exact, "solid_kmers": n_kmers,
                        "l2": "256 MiB device buffer rewritten between timed iterations",
                        "graph_build_s_untimed": round(t_graph, 3), "gaps_in_wide_tier": big,
                        "parallelism": f"{world} x (one process per GPU, replicated k-mer table, disjoint gap batches)",
                        "table_broadcast_s_untimed": round(t_bcast, 4), "table_bytes": table_bytes},
             "dp_cells_per_s": all_cells / (ms_step / 1e3), "dp_cells_per_step": all_cells,
             "e2e": {"value": all_gaps / (ms_e2e / 1e3), "unit": "gaps/s", "h2d_bytes_per_step": all_h2d,
-                    "d2h_bytes_per_step": all_d2h, "ms_per_step": ms_e2e, "breakdown_ms_last_step": e2e_detail},
+                    "d2h_bytes_per_step": all_d2h, "ms_per_step": ms_e2e, "breakdown_ms_last_step": e2e_detail,
+                    "call": "g2s_fill_records (C ABI) on host strings: scan, H2D, device pass, D2H, tracebacks, splice, log",
+                    "output_identical_every_step": e2e_same},
             "gpu_launches": int(all_launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "k_fill_thin", "achieved": achieved, "peak": peak, "unit": "GB/s",

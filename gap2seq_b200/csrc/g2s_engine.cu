@@ -106,6 +106,7 @@ struct g2s_engine {
   PinBuf h_outs, h_stage;
   g2s_timing tm{};
   int max_dmax = 0, max_rmf = 0;
+  std::unique_ptr<ThreadPool> pool;    // host threads (g2s_config.host_threads) for the stages after a device pass
 };
 
 // ------------------------------------------------------------------------------------------------ C ABI: basics
@@ -133,6 +134,7 @@ extern "C" int g2s_create(const g2s_config *cfg, g2s_engine **out) {
   CUDA_TRY(cudaMemGetInfo(&fr, &tot));
   e->budget = cfg->max_mem_bytes > 0 ? (size_t)cfg->max_mem_bytes : (size_t)(fr * 0.6);
   CUDA_TRY(e->d_counters.reserve(64));
+  e->pool.reset(new ThreadPool(cfg->host_threads));
   *out = e;
   return G2S_OK;
 }
@@ -452,7 +454,7 @@ static int do_collect(g2s_engine *e, HostBatch &hb) {
   for (size_t i = 0; i < n; i++)
     if (e->out_pass[i] >= 0) { hb.tier[i] = e->passes[e->out_pass[i]].tier; hb.pack_of[i] = e->out_pass[i]; }
   auto t0 = std::chrono::steady_clock::now();
-  hb.analyze(e->cfg.host_threads);
+  hb.analyze(e->pool.get());
   e->tm.host_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   return G2S_OK;
 }
@@ -464,8 +466,17 @@ static int do_finish(g2s_engine *e, g2s_result *results, char *const *fill_out) 
   int rc = do_collect(e, hb);
   if (rc != G2S_OK) return rc;
   auto t0 = std::chrono::steady_clock::now();
-  // traceback in input order: the only consumer of libc rand() (src/Gap2Seq.cpp:1440, 1513)
-  for (size_t i = 0; i < hb.gaps.size(); i++) hb.trace(i, results[i], fill_out ? fill_out[i] : nullptr);
+  // tracebacks in input order of the libc rand() stream, its only consumer (src/Gap2Seq.cpp:1440, 1513)
+  std::vector<TraceJob> jobs(hb.gaps.size());
+  for (size_t i = 0; i < jobs.size(); i++) jobs[i] = TraceJob{&hb, i};
+  std::vector<g2s_result> res;
+  std::vector<char> arena;
+  std::vector<size_t> off;
+  trace_many(jobs, res, arena, off, e->pool.get(), nullptr);
+  for (size_t i = 0; i < jobs.size(); i++) {
+    results[i] = res[i];
+    if (fill_out && fill_out[i]) memcpy(fill_out[i], &arena[off[i]], (size_t)res[i].fill_len + 1);
+  }
   e->tm.host_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   return G2S_OK;
 }
@@ -524,6 +535,7 @@ extern "C" int g2s_fill_records(g2s_engine *e, const char *const *seqs, const ch
   ro.k = opt->k; ro.d_err = opt->dist_error; ro.max_fuz = opt->fuz;
   ro.skip_confident = opt->skip_confident != 0; ro.unique_paths = opt->unique_paths != 0; ro.all_paths = opt->all_paths != 0;
   ScaffoldRun run(s, c, ro);
+  run.pool = e->pool.get();
   g2s_timing total{};
   int err = G2S_OK;
   double w_upload = 0, w_run = 0, w_collect = 0;
@@ -556,8 +568,8 @@ extern "C" int g2s_fill_records(g2s_engine *e, const char *const *seqs, const ch
   e->tm = total;
   if (getenv("G2S_HOST_PROF"))   // profiling aid: where the wall time of this call went
     fprintf(stderr, "g2s_fill_records: wall %.3f ms = scan+flanks %.3f | upload %.3f | run %.3f (kernel %.3f) | collect %.3f "
-            "(d2h %.3f) | trace+splice+log %.3f\n", wall, run.phase1_ms - w_upload - w_run - w_collect, w_upload, w_run,
-            total.kernel_ms, w_collect, total.d2h_ms, run.phase2_ms);
+            "(d2h %.3f) | trace %.3f | splice+log %.3f\n", wall, run.phase1_ms - w_upload - w_run - w_collect, w_upload, w_run,
+            total.kernel_ms, w_collect, total.d2h_ms, run.trace_ms, run.phase2_ms - run.trace_ms);
   for (size_t i = 0; i < n_records; i++) filled_out[i] = strdup(filled[i].c_str());
   if (log_out) *log_out = strdup(log.c_str());
   if (gapcount) *gapcount = gc;

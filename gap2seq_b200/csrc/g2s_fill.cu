@@ -21,12 +21,14 @@ struct WarpGroup {
   static __device__ __forceinline__ int rank() { return threadIdx.x & 31; }
   static __device__ __forceinline__ int size() { return 32; }
   static __device__ __forceinline__ void sync() { __syncwarp(); }
+  static __device__ __forceinline__ bool any(bool p) { return __any_sync(0xffffffffu, p) != 0; }
 };
 struct BlockGroup {
   static constexpr bool kWarp = false;
   static __device__ __forceinline__ int rank() { return threadIdx.x; }
   static __device__ __forceinline__ int size() { return blockDim.x; }
   static __device__ __forceinline__ void sync() { __syncthreads(); }
+  static __device__ __forceinline__ bool any(bool p) { return __syncthreads_or(p) != 0; }
 };
 
 // named barrier 1 of the thin CTA: the helper warp arrives when the right set is complete, the main warp waits on it

@@ -307,6 +307,12 @@ G2S_D uint32_t node_insert(const Slice &S, GShared &sh, uint64_t key, uint32_t *
 }
 G2S_D uint32_t node_insert(const Slice &S, GShared &sh, uint64_t key) { uint32_t f; return node_insert(S, sh, key, &f); }
 
+// Has the gap outgrown its scratch slice?  The answer steers collective control flow (loops with group barriers), so
+// it must be the same for every thread of the group - but in the thin tier the OTHER warp of the pair may set the bit
+// at any moment, and lanes reading the word one after the other could disagree.  G::any() makes it a group decision.
+template <class G>
+G2S_D bool group_overflow(GShared &sh) { return G::any((ld_sh(&sh.status) & GS_OVERFLOW) != 0); }
+
 G2S_D unsigned long long now_cycles() {
 #ifdef __CUDA_ARCH__
   return (unsigned long long)clock64();
@@ -624,7 +630,7 @@ G2S_D int narrow_forward(const Table &T, const Slice &S, GShared &sh, NarrowBuf 
   G::sync();
   const unsigned long long tp2 = now_cycles();
   if (rank == 0) sh.prof[1] += tp2 - tp1;
-  if (ld_sh(&sh.status) & GS_OVERFLOW) return 0;
+  if (group_overflow<G>(sh)) return 0;
   // distinct cells per level
   for (int l = rank; l < len; l += gsz) {
     uint32_t nn = 0;
@@ -975,7 +981,7 @@ G2S_D void gap_right(const FillParams &P, const GapCtx &cx, const Slice &S, GSha
     if (n >= 1 && n <= (uint32_t)NARROW_W && c > rmf) {   // narrow border, no start left to inject
       uint32_t n2 = n;
       const int adv = narrow_right<G>(T, S, sh, nb, cur, c, right_half, (int)n, &n2);
-      if (ld_sh(&sh.status) & GS_OVERFLOW) break;
+      if (group_overflow<G>(sh)) break;
       if (adv > 0) { n = n2; levels_r = c + adv - 1; c += adv - 1; continue; }
     }
     G::sync();
@@ -1029,7 +1035,7 @@ G2S_D void gap_right(const FillParams &P, const GapCtx &cx, const Slice &S, GSha
     }
     G::sync();
     n = ld_sh(&nb.nnext);
-    if (ld_sh(&sh.status) & GS_OVERFLOW) break;
+    if (group_overflow<G>(sh)) break;
     if (rank == 0) sh.cells_right += n;
     cur ^= 1;
   }
@@ -1048,7 +1054,7 @@ G2S_D void gap_forward(const FillParams &P, const GapDev &gd, const GapCtx &cx, 
   int top_level = 0;       // last level that was expanded into
   int levels_f = 0;
   bool waited = !W::kConcurrent;
-  bool overflow = (ld_sh(&sh.status) & GS_OVERFLOW) != 0;
+  bool overflow = group_overflow<G>(sh);
   if (!overflow) {
     if (rank == 0) {
       uint64_t x = S.lk[0];
@@ -1079,7 +1085,7 @@ G2S_D void gap_forward(const FillParams &P, const GapDev &gd, const GapCtx &cx, 
       const bool dead = (lo == hi) && c > lmf;   // empty border and no start left to inject
       if (hi > lo && hi - lo <= (uint32_t)NARROW_W && c > lmf) {   // narrow border, no start left to inject
         const int adv = narrow_forward<G>(T, S, sh, nb, gd, lo, (int)(hi - lo), c, dlim, prune_from);
-        if (ld_sh(&sh.status) & GS_OVERFLOW) { overflow = true; break; }
+        if (group_overflow<G>(sh)) { overflow = true; break; }
         if (adv > 0) {
           const int last = c + adv - 1;
           top_level = levels_f = last;
@@ -1176,7 +1182,7 @@ G2S_D void gap_forward(const FillParams &P, const GapDev &gd, const GapCtx &cx, 
         }
         G::sync();
         if (rank == 0) S.lstart[c + 1] = sh.ncells < S.cap_cells ? sh.ncells : S.cap_cells;
-        if (ld_sh(&sh.status) & GS_OVERFLOW) { overflow = true; break; }
+        if (group_overflow<G>(sh)) { overflow = true; break; }
       } else {
         // the border died: no cell can appear any more; finish the found check for the remaining levels in
         // parallel (one level per thread) and leave the level loop
@@ -1229,7 +1235,7 @@ G2S_D unsigned long long gap_backward_pack(const FillParams &P, const GapCtx &cx
   const int g = cx.g, e = cx.e, lmf = cx.lmf, rmf = cx.rmf;
   const bool all_paths = cx.all_paths, skip_confident = cx.skip_confident;
   const int top_level = ld_sh(&sh.top_level);
-  const bool overflow = ld_sh(&sh.fwd_overflow) != 0 || (ld_sh(&sh.status) & GS_OVERFLOW) != 0;
+  const bool overflow = group_overflow<G>(sh) || ld_sh(&sh.fwd_overflow) != 0;
   unsigned long long t_back = now_cycles();
   const uint32_t n_plen = ld_sh(&sh.n_plen);
   const uint32_t count_fwd = ld_sh(&sh.count_fwd);

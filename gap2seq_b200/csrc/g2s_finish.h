@@ -15,6 +15,7 @@
 
 #include "../../include/g2s.h"
 #include "g2s_fill.cuh"
+#include "g2s_pool.h"
 
 namespace g2s {
 
@@ -119,6 +120,7 @@ inline void analyze_general(const PackRec *pk, uint32_t npack, GeneralResult &R)
 // next rand() returns exactly what it would have returned after n discarded calls.  A self test (on a private
 // state, the application's stream is restored) decides once whether this libc behaves that way; if not, skip(n) just
 // calls rand() n times.
+class RandAhead;
 class RandSkipper {
  public:
   static void skip(size_t n) {
@@ -156,6 +158,7 @@ class RandSkipper {
     setstate((char *)info);
     return true;
   }
+  friend class RandAhead;
   static bool self_test() {
     static int32_t bufa[34];
     char *app = initstate(777u, (char *)bufa, 128);
@@ -171,10 +174,122 @@ class RandSkipper {
   }
 };
 
+// The sources of random numbers a traceback can draw from.  LibcRand is the application's generator itself;
+// RandCursor reads a window of that same stream that RandAhead computed beforehand, which is what lets tracebacks of
+// different gaps run on different threads: gap j starts at the stream position where gap j-1 stopped.
+struct LibcRand {
+  int next() { return rand(); }
+  void skip(size_t n) { RandSkipper::skip(n); }
+};
+struct RandCursor {
+  const int32_t *vals;
+  size_t pos;
+  int next() { return vals[pos++]; }
+  void skip(size_t n) { pos += n; }
+};
+
+// The next values of libc rand(), computed from a private copy of the generator's table without consuming them.
+// extend(n) makes values [0, n) available (it can run on another thread while the device pass is in flight: it does
+// not touch libc); commit(used) finally advances libc by `used` values, restarting from a checkpoint of the private
+// table, so the application's stream continues exactly as after `used` rand() calls.  Only valid where RandSkipper's
+// self test recognised glibc's additive-feedback generator.
+class RandAhead {
+ public:
+  static const size_t CKPT = 4096;
+  bool begin() { return enabled() && begin_unchecked(); }
+  bool begin_unchecked() {
+    vals_.clear(); ck_.clear(); ok_ = false;
+    if (!RandSkipper::enabled()) return false;
+    int32_t *info = (int32_t *)setstate(RandSkipper::dummy());
+    if (!info) return false;
+    const int type = info[0] % 5, rear = info[0] / 5;
+    if (type == 3 && rear >= 0 && rear < 31) {
+      memcpy(st_, info + 1, sizeof st_);
+      r_ = rear; f_ = (rear + 3) % 31;
+      ok_ = true;
+    }
+    setstate((char *)info);
+    return ok_;
+  }
+  // decided once, on a private generator state (the application's stream is restored): do the values computed ahead
+  // equal what rand() returns, and does commit() leave libc where that many calls would have left it?
+  static bool enabled() {
+    static std::once_flag once;
+    static bool good = false;
+    std::call_once(once, [] {
+      if (!RandSkipper::enabled()) return;
+      static int32_t bufa[34];
+      char *app = initstate(4242u, (char *)bufa, 128);
+      if (!app) return;
+      const size_t n = 2 * CKPT + 77;
+      std::vector<int> ref(n + 8);
+      for (size_t i = 0; i < n + 8; i++) ref[i] = rand();
+      initstate(4242u, (char *)bufa, 128);
+      RandAhead a;
+      bool ok = a.begin_unchecked();
+      if (ok) { a.extend(100); a.extend(n + 8); }
+      for (size_t i = 0; i < n + 8 && ok; i++) ok = a.vals_[i] == ref[i];
+      if (ok) ok = a.commit(n);
+      for (size_t i = n; i < n + 8 && ok; i++) ok = rand() == ref[i];
+      setstate(app);
+      good = ok;
+    });
+    return good;
+  }
+  bool ok() const { return ok_; }
+  size_t size() const { return vals_.size(); }
+  const int32_t *data() const { return vals_.data(); }
+  void extend(size_t n) {
+    if (!ok_ || n <= vals_.size()) return;
+    size_t i = vals_.size();
+    vals_.resize(n);
+    int f = f_, r = r_;
+    for (; i < n; i++) {
+      if (i % CKPT == 0) { Ckpt c; memcpy(c.st, st_, sizeof st_); c.f = f; c.r = r; ck_.push_back(c); }
+      st_[f] += st_[r];
+      vals_[i] = (int32_t)(st_[f] >> 1);
+      if (++f == 31) f = 0;
+      if (++r == 31) r = 0;
+    }
+    f_ = f; r_ = r;
+  }
+  // advance libc's generator by `used` <= size() values
+  bool commit(size_t used) {
+    if (!ok_) return false;
+    if (used == 0) return true;
+    if (used > vals_.size()) return false;
+    int32_t *info = (int32_t *)setstate(RandSkipper::dummy());
+    if (!info) return false;
+    const Ckpt &c = ck_[used / CKPT < ck_.size() ? used / CKPT : ck_.size() - 1];
+    size_t at = (size_t)(&c - ck_.data()) * CKPT;
+    uint32_t *st = (uint32_t *)(info + 1);
+    memcpy(st, c.st, sizeof c.st);
+    int f = c.f, r = c.r;
+    for (; at < used; at++) {
+      st[f] += st[r];
+      if (++f == 31) f = 0;
+      if (++r == 31) r = 0;
+    }
+    info[0] = r * 5 + 3;
+    setstate((char *)info);
+    ok_ = false;
+    return true;
+  }
+
+ private:
+  struct Ckpt { uint32_t st[31]; int f, r; };
+  std::vector<int32_t> vals_;
+  std::vector<Ckpt> ck_;
+  uint32_t st_[31];
+  int f_ = 0, r_ = 0;
+  bool ok_ = false;
+};
+
 // Assemble the g2s_result of one gap and run its traceback.  `fill_out` (may be null) receives what the
 // reference leaves at &fill[left_max_fuz - left_fuz].
+template <class RS>
 inline void finish_one(const g2s_gap &g, const GapOut &o, const PackRec *pk, int k, int tier, const GeneralResult &gen,
-                       g2s_result &r, char *fill_out, std::vector<char> &buf) {
+                       g2s_result &r, char *fill_out, std::vector<char> &buf, RS &rs) {
   static const char NT[4] = {'A', 'C', 'T', 'G'};
   memset(&r, 0, sizeof(r));
   const bool skip_confident = (g.flags & G2S_GAP_SKIP_CONFIDENT) != 0, all_paths = (g.flags & G2S_GAP_ALL_PATHS) != 0;
@@ -204,7 +319,7 @@ inline void finish_one(const g2s_gap &g, const GapOut &o, const PackRec *pk, int
   r.rand_calls = 1;
   size_t pending = 0;   // rand() values whose result cannot matter (a single choice): consumed in bulk
   uint32_t q = 0;
-  if (o.n_plen > 1) q = (uint32_t)(rand() % (int)o.n_plen);   // Gap2Seq.cpp:1440
+  if (o.n_plen > 1) q = (uint32_t)(rs.next() % (int)o.n_plen);   // Gap2Seq.cpp:1440
   else pending++;
   int d = o.plen[q];
   const int d0 = d;
@@ -227,11 +342,11 @@ inline void finish_one(const g2s_gap &g, const GapOut &o, const PackRec *pk, int
       if (nb == 0) { broken = true; break; }
       r.rand_calls++;            // one rand() per step even when nb == 1 (Gap2Seq.cpp:1513)
       if (nb == 1) { pending++; cur = back[0]; }
-      else { RandSkipper::skip(pending); pending = 0; cur = back[rand() % nb]; }
+      else { rs.skip(pending); pending = 0; cur = back[rs.next() % nb]; }
     }
     d--;
   }
-  RandSkipper::skip(pending);
+  rs.skip(pending);
   if (broken) {   // "Unable to backtrace!" (Gap2Seq.cpp:1493-1510): the reference returns 0
     r.status |= G2S_ST_UNABLE_TO_BACKTRACE;
     r.count = 0;
@@ -265,7 +380,7 @@ struct HostBatch {
   const PackRec *pack_ptr(size_t i) const { return pack_base[pack_of[i]] + outs[i].pack_off; }
 
   // SCC analysis of the general-subgraph gaps, independent per gap -> host threads
-  void analyze(int threads) {
+  void analyze(ThreadPool *pool) {
     const size_t n = gaps.size();
     gen.assign(n, GeneralResult());
     std::vector<uint32_t> ids;
@@ -273,20 +388,11 @@ struct HostBatch {
       if (tier[i] >= 0 && (outs[i].status & GS_GENERAL) && outs[i].count_fwd > 0 && !(gaps[i].flags & G2S_GAP_SKIP_CONFIDENT))
         ids.push_back((uint32_t)i);
     if (ids.empty()) return;
-    int nt = threads > 0 ? threads : (int)std::thread::hardware_concurrency();
-    nt = std::max(1, std::min<int>(nt, (int)ids.size()));
-    std::atomic<size_t> next{0};
-    auto work = [&]() {
-      for (;;) {
-        size_t j = next.fetch_add(1);
-        if (j >= ids.size()) break;
-        analyze_general(pack_ptr(ids[j]), outs[ids[j]].npack, gen[ids[j]]);
-      }
-    };
-    std::vector<std::thread> th;
-    for (int t = 1; t < nt; t++) th.emplace_back(work);
-    work();
-    for (auto &t : th) t.join();
+    // largest subgraphs first: the loop ends with the small ones
+    std::sort(ids.begin(), ids.end(), [&](uint32_t a, uint32_t b) { return outs[a].npack > outs[b].npack; });
+    auto one = [&](size_t j) { analyze_general(pack_ptr(ids[j]), outs[ids[j]].npack, gen[ids[j]]); };
+    if (pool) pool->parallel_for(ids.size(), 1, one);
+    else for (size_t j = 0; j < ids.size(); j++) one(j);
   }
 
   // what fill_gap will return / write to *right_fuz, known before the traceback (needed by the scanner to decide
@@ -312,8 +418,126 @@ struct HostBatch {
       r.count = -1; r.status = G2S_ST_MEM_LIMIT;
       return;
     }
-    finish_one(gaps[i], outs[i], pack_ptr(i), k, tier[i], gen[i], r, fill_out, buf);
+    LibcRand rs;
+    finish_one(gaps[i], outs[i], pack_ptr(i), k, tier[i], gen[i], r, fill_out, buf, rs);
+  }
+
+  // the same from a precomputed window of the rand() stream; thread safe (scratch is the caller's)
+  void trace_at(size_t i, g2s_result &r, char *fill_out, RandCursor &rc, std::vector<char> &scratch) const {
+    if (fill_out) fill_out[0] = 0;
+    if (tier[i] == -2) {
+      memset(&r, 0, sizeof(r));
+      r.count = -1; r.status = G2S_ST_MEM_LIMIT;
+      return;
+    }
+    finish_one(gaps[i], outs[i], pack_ptr(i), k, tier[i], gen[i], r, fill_out, scratch, rc);
+  }
+  // upper bound of the rand() values gap i's traceback can consume (one per step plus the length choice)
+  size_t rand_bound(size_t i) const {
+    if (tier[i] == -2) return 0;
+    const GapOut &o = outs[i];
+    if (o.count_fwd == 0 || o.n_plen == 0) return 0;
+    return (size_t)std::max(o.plen[0], o.n_plen > 1 ? o.plen[1] : 0) + 2;
+  }
+  // Exact number of rand() values gap i's traceback consumes, if that does not depend on the random choices: one
+  // for the length choice plus one per step from the path's end down to the level d_end <= left_max_fuz where the
+  // walk stands on a start cell.  The device packs marked cells top level first, so the levels <= left_max_fuz are
+  // the tail of the gap's records; d_end is certain when the trellis cells (PM_T) of those levels form a chain.
+  bool rand_exact(size_t i, size_t *calls) const {
+    *calls = 0;
+    if (tier[i] == -2) return true;
+    const GapOut &o = outs[i];
+    if (o.count_fwd == 0 || o.n_plen == 0) return true;
+    *calls = (size_t)std::max(1, 1 + o.plen[0] - gaps[i].left_max_fuz);
+    if (o.n_plen != 1 || o.start_pack[0] == NONE32) return false;
+    const PackRec *pk = pack_ptr(i);
+    const int lmf = gaps[i].left_max_fuz;
+    if (o.plen[0] <= lmf) return false;
+    uint32_t n_t = 0, the_one = NONE32;   // trellis cells on level lmf
+    for (uint32_t q = o.npack; q-- > 0;) {   // tail first: levels ascend
+      const PackRec &r = pk[q];
+      if ((int)r.level > lmf) break;
+      if (!(r.meta & PM_T)) continue;
+      if ((int)r.level == lmf) { n_t++; the_one = q; }
+    }
+    // the walk stops on level lmf iff its cell there is a start; with one trellis cell on that level that is certain
+    return n_t == 1 && (pk[the_one].meta & PM_START) != 0;
+  }
+  size_t fill_bytes(size_t i) const {
+    const g2s_gap &g = gaps[i];
+    return (size_t)g.gap_len + k + g.gap_err + g.left_max_fuz + g.right_max_fuz + 3;
   }
 };
+
+// Tracebacks of many gaps, in the order the reference would call fill_gap, consuming libc rand() exactly like
+// successive calls would - but on all host threads.  Gap j's traceback starts at the stream position where gap
+// j-1's stopped, and how many values a traceback consumes is usually known without running it: one per level between
+// the path's end and the level where it meets the left start, which HostBatch::rand_exact() reads off the bottom of
+// the trellis (certain when the trellis is a single chain down there and there is one path length).  So the gaps are
+// traced in rounds: a round covers the gaps up to and including the next one whose consumption is not certain, each
+// at its position in a window of the stream computed ahead (RandAhead), on all threads; the round's last gap tells
+// the true position for the next round.  Consumption is verified after every round, so a wrong "certain" could only
+// cost a re-trace, never a wrong result.  The outcome equals tracing gap after gap from libc.
+struct TraceJob { HostBatch *hb; size_t idx; };
+struct TraceStats { std::atomic<unsigned long long> calls{0}, parallel_calls{0}, rounds{0}, retraced{0}; };
+inline TraceStats &trace_stats() { static TraceStats s; return s; }   // observability for the tests
+
+inline void trace_many(const std::vector<TraceJob> &jobs, std::vector<g2s_result> &res, std::vector<char> &arena,
+                       std::vector<size_t> &fill_off, ThreadPool *pool, RandAhead *ahead) {
+  const size_t n = jobs.size();
+  res.resize(n);
+  fill_off.resize(n + 1);
+  size_t tot = 0;
+  for (size_t j = 0; j < n; j++) { fill_off[j] = tot; tot += jobs[j].hb->fill_bytes(jobs[j].idx); }
+  fill_off[n] = tot;
+  arena.resize(tot + 1);
+  RandAhead local;
+  if (!ahead) { ahead = &local; if (pool && n >= 4) local.begin(); }
+  trace_stats().calls++;
+  if (!pool || n < 4 || !ahead->ok()) {   // sequential, straight from libc
+    if (ahead->ok()) ahead->commit(0);
+    for (size_t j = 0; j < n; j++) jobs[j].hb->trace(jobs[j].idx, res[j], &arena[fill_off[j]]);
+    return;
+  }
+  std::vector<size_t> pred(n), act(n), off(n + 1);
+  std::vector<uint8_t> certain(n);
+  std::vector<size_t> bounds(n);
+  pool->parallel_for(n, 16, [&](size_t j) {
+    const HostBatch &hb = *jobs[j].hb;
+    bounds[j] = hb.rand_bound(jobs[j].idx);
+    certain[j] = hb.rand_exact(jobs[j].idx, &pred[j]) ? 1 : 0;
+  });
+  size_t bound = 0;
+  for (size_t j = 0; j < n; j++) bound += bounds[j];
+  ahead->extend(bound + 1);
+  const int32_t *vals = ahead->data();
+  size_t final_upto = 0, base = 0;
+  trace_stats().parallel_calls++;
+  auto trace_one = [&](size_t j, std::vector<char> &scratch) {
+    RandCursor rc{vals, off[j]};
+    jobs[j].hb->trace_at(jobs[j].idx, res[j], &arena[fill_off[j]], rc, scratch);
+    act[j] = rc.pos - off[j];
+  };
+  std::vector<char> my_scratch;
+  while (final_upto < n) {
+    trace_stats().rounds++;
+    const size_t lo = final_upto;
+    size_t hi = lo;                       // last gap of the round: the first one whose consumption is uncertain
+    while (hi + 1 < n && certain[hi]) hi++;
+    off[lo] = base;
+    for (size_t j = lo; j < hi; j++) off[j + 1] = off[j] + pred[j];
+    if (hi - lo + 1 < 4) for (size_t j = lo; j <= hi; j++) trace_one(j, my_scratch);
+    else pool->parallel_for(hi - lo + 1, 2, [&](size_t q) {
+      static thread_local std::vector<char> scratch;
+      trace_one(lo + q, scratch);
+    });
+    size_t bad = hi;                      // the first gap that did not consume what was predicted ends the round
+    for (size_t j = lo; j < hi; j++) if (act[j] != pred[j]) { bad = j; trace_stats().retraced += hi - j; break; }
+    base = off[bad] + act[bad];
+    final_upto = bad + 1;
+  }
+  ahead->commit(base);
+}
+
 
 }  // namespace g2s

@@ -10,6 +10,7 @@
 // one of `Gap2Seq-core -nb-cores 1`), printing the statistics lines and splicing - including the reference's
 // prefix-dropping `filledSeq = ...` assignment for multi-gap records (src/Gap2Seq.cpp:396).
 #pragma once
+#include <atomic>
 #include <cctype>
 #include <chrono>
 #include <cstdio>
@@ -92,10 +93,13 @@ struct ScaffoldRun {
   std::vector<RecScan> recs;
   std::vector<std::unique_ptr<HostBatch>> batches;
   std::vector<std::vector<std::string>> flank_keep;   // flank strings of each batch (the gap structs point into them)
-  double phase1_ms = 0, phase2_ms = 0;                // wall time of the two phases of run() (profiling aid)
+  double phase1_ms = 0, phase2_ms = 0, trace_ms = 0;  // wall time of the two phases of run() (profiling aid)
+  ThreadPool *pool = nullptr;                         // host threads for the tracebacks and the per-record replay
+  RandAhead ahead;                                    // the libc rand() values the tracebacks will consume
 
   ScaffoldRun(const std::vector<std::string> &s, const std::vector<std::string> &c, const RunOptions &o)
       : seqs(s), comments(c), opt(o), recs(s.size()) {}
+  ~ScaffoldRun() { if (pool) pool->wait_async(); }
 
   bool filled_status(int count) const { return count > 0 && (!opt.unique_paths || count == 1); }
 
@@ -155,6 +159,8 @@ struct ScaffoldRun {
           std::vector<g2s_result> *details) {
     const int k = opt.k;
     const auto t_begin = std::chrono::steady_clock::now();
+    size_t rand_bound = 0;
+    if (pool) ahead.begin();
     // ---- phase 1: device waves
     for (;;) {
       std::vector<std::pair<size_t, int>> wave;
@@ -164,7 +170,7 @@ struct ScaffoldRun {
         scan(r, wave);
         if (!recs[r].done) any_open = true;
       }
-      if (wave.empty()) { if (any_open) return -1; break; }
+      if (wave.empty()) { if (any_open) { if (pool) pool->wait_async(); return -1; } break; }
       const int b = (int)batches.size();
       batches.emplace_back(new HostBatch());
       flank_keep.emplace_back();
@@ -183,28 +189,54 @@ struct ScaffoldRun {
         g.flags = (opt.skip_confident ? G2S_GAP_SKIP_CONFIDENT : 0) | (opt.all_paths ? G2S_GAP_ALL_PATHS : 0);
         g.reserved = 0;
       }
+      // the rand() values this wave's tracebacks can consume are computed while the device pass runs
+      for (const g2s_gap &g : gaps) rand_bound += (size_t)g.gap_len + g.gap_err + g.left_max_fuz + g.right_max_fuz + 2;
+      if (pool && ahead.ok()) {
+        pool->wait_async();
+        const size_t want = rand_bound + 1;
+        pool->run_async([this, want] { ahead.extend(want); });
+      }
       int rc = submit(gaps, *batches.back());
-      if (rc != 0) return rc;
+      if (rc != 0) { if (pool) pool->wait_async(); return rc; }
       if (!any_open) {
         bool all_done = true;
         for (auto &rs : recs) if (!rs.done) all_done = false;
         if (all_done) break;
       }
     }
-    // ---- phase 2: the reference's control flow, record by record (src/Gap2Seq.cpp:329-432)
+    // ---- phase 2: the reference's control flow, record by record (src/Gap2Seq.cpp:329-432).  The tracebacks of all
+    // attempted gaps run first, on all host threads, at their positions in the libc rand() stream (trace_many); the
+    // replay below then only formats and splices, which is independent per record.
     const auto t_mid = std::chrono::steady_clock::now();
     phase1_ms = std::chrono::duration<double, std::milli>(t_mid - t_begin).count();
-    filled.assign(seqs.size(), std::string());
-    std::vector<char> fillbuf;
+    if (pool) pool->wait_async();
+    std::vector<TraceJob> jobs;
+    std::vector<size_t> first_job(seqs.size() + 1, 0);
     for (size_t r = 0; r < seqs.size(); r++) {
+      first_job[r] = jobs.size();
+      for (const GapReq &q : recs[r].reqs) jobs.push_back(TraceJob{batches[q.batch].get(), (size_t)q.idx});
+    }
+    first_job[seqs.size()] = jobs.size();
+    std::vector<g2s_result> res;
+    std::vector<char> arena;
+    std::vector<size_t> fill_off;
+    trace_many(jobs, res, arena, fill_off, pool, ahead.ok() ? &ahead : nullptr);
+    trace_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_mid).count();
+
+    filled.assign(seqs.size(), std::string());
+    std::vector<std::string> rlog(seqs.size());
+    std::vector<int> rgc(seqs.size(), 0), rfc(seqs.size(), 0);
+    std::atomic<int> bad{0};
+    auto one_record = [&](size_t r) {
       const std::string &seq = seqs[r];
       const std::string &comment = comments[r];
       std::string filledSeq;
+      std::string &lg = rlog[r];
       long long prev = 0;
       size_t i = 0, next_req = 0;
       while (i < seq.size()) {
         if (!is_gap_char(seq[i])) { i++; continue; }
-        gapcount++;
+        rgc[r]++;
         const int lmf = (int)std::min<long long>((long long)i + k - prev, opt.max_fuz);
         const int kmer_start = (int)i - k - lmf;
         int gap = 0;
@@ -213,25 +245,24 @@ struct ScaffoldRun {
         bool ok = rmf >= 0 && i + k + rmf <= seq.size();
         for (int j = 0; j < k + rmf && ok; j++) if (is_gap_char(seq[i + j])) ok = false;
         if ((long long)kmer_start >= prev && ok) {
-          if (next_req >= recs[r].reqs.size()) return -2;
-          const GapReq &q = recs[r].reqs[next_req++];
-          if (q.kmer_start != kmer_start || q.lmf != lmf || q.rmf != rmf || q.gap != gap || q.i_after != i) return -3;
-          g2s_result res;
-          fillbuf.assign((size_t)gap + k + opt.d_err + lmf + rmf + 3, 0);
-          batches[q.batch]->trace((size_t)q.idx, res, fillbuf.data());
-          if (details) details->push_back(res);
-          const int s = res.count;
-          const int filledStart = (int)filledSeq.length() + kmer_start + k + lmf - res.left_fuz - (int)prev;
+          if (next_req >= recs[r].reqs.size()) { bad = -2; return; }
+          const GapReq &q = recs[r].reqs[next_req];
+          if (q.kmer_start != kmer_start || q.lmf != lmf || q.rmf != rmf || q.gap != gap || q.i_after != i) { bad = -3; return; }
+          const size_t jb = first_job[r] + next_req++;
+          const g2s_result &rs = res[jb];
+          const char *fill = &arena[fill_off[jb]];
+          const int s = rs.count;
+          const int filledStart = (int)filledSeq.length() + kmer_start + k + lmf - rs.left_fuz - (int)prev;
           const int gapStart = kmer_start + k + lmf;
-          format_statistics(log, filledStart, gapStart, (int)i, s, fillbuf.data(), res.fill_len, k, lmf, rmf, res.left_fuz,
-                            res.right_fuz, opt.skip_confident, opt.unique_paths, res.substats, gap, comment);
+          format_statistics(lg, filledStart, gapStart, (int)i, s, fill, rs.fill_len, k, lmf, rmf, rs.left_fuz,
+                            rs.right_fuz, opt.skip_confident, opt.unique_paths, rs.substats, gap, comment);
           if (filled_status(s)) {
-            filledcount++;
+            rfc[r]++;
             // '=' not '+=': the prefix of a multi-gap record is dropped, as in the reference
-            filledSeq = seq.substr((size_t)prev, (size_t)(kmer_start + k + lmf - res.left_fuz - prev)) +
-                        std::string(fillbuf.data(), (size_t)res.fill_len);
+            filledSeq = seq.substr((size_t)prev, (size_t)(kmer_start + k + lmf - rs.left_fuz - prev)) +
+                        std::string(fill, (size_t)rs.fill_len);
             filledSeq.resize(filledSeq.size() - k);   // drop the right k-mer
-            i += res.right_fuz;
+            i += rs.right_fuz;
           } else {
             filledSeq += seq.substr((size_t)prev, (size_t)(kmer_start + k + lmf + gap - prev));
           }
@@ -240,10 +271,18 @@ struct ScaffoldRun {
         }
         prev = (long long)i;
       }
-      if (next_req != recs[r].reqs.size()) return -4;
+      if (next_req != recs[r].reqs.size()) { bad = -4; return; }
       filledSeq += seq.substr((size_t)prev);
       filled[r].swap(filledSeq);
-    }
+    };
+    if (pool) pool->parallel_for(seqs.size(), 8, one_record);
+    else for (size_t r = 0; r < seqs.size(); r++) one_record(r);
+    if (bad.load() != 0) return bad.load();
+    size_t lbytes = 0;
+    for (const std::string &l : rlog) lbytes += l.size();
+    log.reserve(log.size() + lbytes);
+    for (size_t r = 0; r < seqs.size(); r++) { log += rlog[r]; gapcount += rgc[r]; filledcount += rfc[r]; }
+    if (details) details->insert(details->end(), res.begin(), res.end());
     phase2_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_mid).count();
     return 0;
   }

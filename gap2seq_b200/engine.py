@@ -289,6 +289,33 @@ class Engine:
             free(gr)
         return out, logs, gc.value, fc.value, results
 
+    def prepare_records(self, seqs: list[str], comments: list[str]):
+        """Host buffers (NUL-terminated C strings) for fill_records_c: what a C/C++ caller of g2s_fill_records holds."""
+        n = len(seqs)
+        return (n, (C.c_char_p * max(n, 1))(*[s.encode() for s in seqs]), (C.c_char_p * max(n, 1))(*[c.encode() for c in comments]))
+
+    def fill_records_c(self, prepared, *, dist_error=500, fuz=10, skip_confident=False, unique=False, all_paths=True,
+                       want_results=False):
+        """g2s_fill_records on prepared host buffers; returns the raw outputs (filled char**, log char*, counts) and a
+        release function, so that a caller can time exactly the C-ABI call."""
+        n, sa, ca = prepared
+        opt = G2SRunOptions(self.k, dist_error, fuz, int(skip_confident), int(unique), int(all_paths))
+        filled = (C.c_void_p * max(n, 1))()
+        log = C.c_void_p()
+        gc, fc = C.c_int32(0), C.c_int32(0)
+        gr, ngr = C.c_void_p(), C.c_size_t(0)
+        self._check(self.L.g2s_fill_records(self.h, sa, ca, n, C.byref(opt), filled, C.byref(log), C.byref(gc), C.byref(fc),
+                                            C.byref(gr) if want_results else None, C.byref(ngr) if want_results else None))
+
+        def release():
+            free = self.L.g2s_free
+            for i in range(n):
+                free(filled[i])
+            free(log)
+            if gr.value:
+                free(gr)
+        return filled, log, gc.value, fc.value, release
+
     def phase_cycles(self):
         """SM cycles per phase (init, right, forward, backward, pack, total) of the last device pass: (sum, slowest gap)."""
         a, b = (C.c_double * 14)(), (C.c_double * 14)()

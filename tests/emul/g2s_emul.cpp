@@ -20,6 +20,7 @@ struct EmulGroup {
   static int rank() { return 0; }
   static int size() { return 1; }
   static void sync() {}
+  static bool any(bool p) { return p; }
 };
 
 struct EmulGraph {
@@ -69,6 +70,12 @@ void emul_adjacency(void *gp, const uint64_t *kmers, size_t n, uint8_t *out) {
 
 // device pass of a list of gaps, emulated: fills a detached HostBatch exactly like the engine's do_collect
 static double g_submit_s = 0, g_analyze_s = 0;
+static ThreadPool *host_pool() {   // G2S_EMUL_THREADS=1 selects the sequential host stages
+  static ThreadPool *p = nullptr;
+  static bool init = false;
+  if (!init) { init = true; const char *v = getenv("G2S_EMUL_THREADS"); int n = v ? atoi(v) : 4; if (n > 1) p = new ThreadPool(n); }
+  return p;
+}
 static double now_s() { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
 static int emul_submit(EmulGraph *g, int k, const g2s_gap *gaps, size_t n, HostBatch &hb, int cap0) {
   const double t_submit0 = now_s();
@@ -123,7 +130,7 @@ static int emul_submit(EmulGraph *g, int k, const g2s_gap *gaps, size_t n, HostB
     hb.gaps[i].kmer_left = hb.gaps[i].kmer_right = nullptr;
   }
   const double t_an0 = now_s();
-  hb.analyze(1);
+  hb.analyze(host_pool());
   g_analyze_s += now_s() - t_an0;
   g_submit_s += now_s() - t_submit0;
   return 0;
@@ -138,7 +145,16 @@ int emul_fill_batch(void *gp, int k, const g2s_gap *gaps, size_t n, g2s_result *
   HostBatch hb;
   int rc = emul_submit((EmulGraph *)gp, k, gaps, n, hb, cap0);
   if (rc) return rc;
-  for (size_t i = 0; i < n; i++) hb.trace(i, results[i], fill_out ? fill_out[i] : nullptr);
+  std::vector<TraceJob> jobs(n);
+  for (size_t i = 0; i < n; i++) jobs[i] = TraceJob{&hb, i};
+  std::vector<g2s_result> res;
+  std::vector<char> arena;
+  std::vector<size_t> off;
+  trace_many(jobs, res, arena, off, host_pool(), nullptr);
+  for (size_t i = 0; i < n; i++) {
+    results[i] = res[i];
+    if (fill_out && fill_out[i]) memcpy(fill_out[i], &arena[off[i]], (size_t)res[i].fill_len + 1);
+  }
   return 0;
 }
 
@@ -152,6 +168,7 @@ int emul_fill_records(void *gp, const char *const *seqs, const char *const *comm
   ro.k = opt->k; ro.d_err = opt->dist_error; ro.max_fuz = opt->fuz;
   ro.skip_confident = opt->skip_confident != 0; ro.unique_paths = opt->unique_paths != 0; ro.all_paths = opt->all_paths != 0;
   ScaffoldRun run(s, c, ro);
+  run.pool = host_pool();
   SubmitFn submit = [&](const std::vector<g2s_gap> &gaps, HostBatch &hb) -> int {
     return emul_submit((EmulGraph *)gp, opt->k, gaps.data(), gaps.size(), hb, 0);
   };
@@ -198,3 +215,9 @@ extern "C" void emul_stats_get(unsigned long long *out, int reset) {
   if (reset) memset(&g2s::emul_stats(), 0, sizeof(g2s::EmulStats));
 }
 #endif
+
+extern "C" int emul_rand_ahead_enabled() { return g2s::RandAhead::enabled() ? 1 : 0; }
+extern "C" void emul_trace_stats(unsigned long long *out4) {
+  g2s::TraceStats &t = g2s::trace_stats();
+  out4[0] = t.calls; out4[1] = t.parallel_calls; out4[2] = t.rounds; out4[3] = t.retraced;
+}

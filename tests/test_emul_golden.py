@@ -79,3 +79,36 @@ def test_rand_skipping_is_exact_and_enabled():
             libc.rand()
         b = [libc.rand() for _ in range(40)]
         assert a == b, (seed, n)
+
+
+def test_parallel_traceback_equals_sequential_and_leaves_libc_in_place(case_inputs, emul_engine):
+    """trace_many (g2s_finish.h): tracebacks run on several host threads at predicted positions of a precomputed window of
+    the libc rand() stream (RandAhead).  The result and the state libc is left in must equal gap-after-gap tracing; cfg3
+    has gaps whose consumption is mispredicted (two path lengths, left fuz), so the re-trace rounds are exercised too."""
+    import ctypes
+    import oracle_lib
+    from gap2seq_b200.scaffold import record_gaps
+    L = emul_lib.lib()
+    libc = ctypes.CDLL(None)
+    assert L.emul_rand_ahead_enabled() == 1, "self test failed: RandAhead does not reproduce this libc's rand()"
+    st = (ctypes.c_ulonglong * 4)()
+    for name in ["cfg2_small", "cfg3_small", "cfg3_seed33"]:
+        case, w, g = case_inputs(name)
+        eng = emul_engine(name)
+        specs = [s for rec in w.gaps for s in record_gaps(rec.seq, w.k, w.fuz, 500)]
+        L.emul_trace_stats(st)
+        before = list(st)
+        oracle_lib.srand(11)
+        res, fills = eng.fill_batch(specs)
+        after_par = [libc.rand() for _ in range(8)]
+        L.emul_trace_stats(st)
+        assert st[1] > before[1], "the parallel path did not run"
+        oracle_lib.srand(11)
+        calls = 0
+        for s, r, f in zip(specs, res, fills):
+            o, of = g.fill_gap(s.left, s.right, s.gap_len, s.gap_err, s.left_max_fuz, s.right_max_fuz)
+            if o.order_dependent:
+                pytest.skip("order dependent gap")
+            assert (r.count, r.left_fuz, f, r.rand_calls) == (o.count, o.left_fuz, of, o.rand_calls)
+            calls += o.rand_calls
+        assert after_par == [libc.rand() for _ in range(8)], "libc rand() stream not where sequential tracing leaves it"
