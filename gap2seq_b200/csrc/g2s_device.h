@@ -24,11 +24,14 @@ cudaError_t table_export(const DeviceTable &dt, uint64_t *keys_host, uint8_t *ad
 cudaError_t table_contains(const DeviceTable &dt, const char *ascii_host, uint64_t n, uint8_t *out_host, cudaStream_t st);
 
 struct FillParams;
-// thin tier: one two-warp CTA per gap, persistent over a device work queue.  groups = number of scratch slices.
-cudaError_t launch_fill_thin(const FillParams &p, int groups, cudaStream_t st);
+// thin tier: one CTA per gap, persistent over a device work queue; `shape` selects how many warps a gap gets
+// (0: 1 helper + 1 main, 1: 2 + 4, 2: 4 + 8).  groups = number of scratch slices.
+cudaError_t launch_fill_thin(const FillParams &p, int groups, int shape, cudaStream_t st);
 // wide tier: one CTA (512 threads) per gap
 cudaError_t launch_fill_cta(const FillParams &p, int groups, cudaStream_t st);
-int fill_max_resident_thin_groups(int sms);   // occupancy-derived number of thin groups that fit the device
+int fill_thin_shapes();
+int fill_thin_threads(int shape);
+int fill_max_resident_thin_groups(int sms, int shape);   // occupancy-derived number of thin groups that fit the device
 int fill_max_resident_cta_groups(int sms);
 
 }  // namespace g2s

@@ -69,6 +69,7 @@ struct PinBuf {
 
 struct Pass {                   // one device pass over a subset of the batch
   int tier = 0;
+  int shape = 0;                // thin tier: warps per gap (g2s_device.h)
   std::vector<uint32_t> order;  // gap ids, longest first
   SliceLayout lay{};
   int groups = 0;
@@ -249,7 +250,23 @@ static int plan_pass(g2s_engine *e, Pass &p) {
   p.lay = make_layout(cap, hlog, (uint32_t)e->max_dmax + 1, (uint32_t)e->max_rmf + 1);
   if (cap >= (1ULL << 31) || p.lay.bytes > e->budget) return -1;   // largest tier exceeded
   size_t fit = e->budget / p.lay.bytes;
-  int resident = p.tier == 0 ? fill_max_resident_thin_groups(e->sms) : fill_max_resident_cta_groups(e->sms);
+  int resident = fill_max_resident_cta_groups(e->sms);
+  if (p.tier == 0) {
+    // Thin tier: pick the CTA shape.  A gap's latency is about levels x cycles-per-level of the shape (measured on
+    // B200, cfg4: 870 / 560 / 480 cycles for 2 / 6 / 12 warps); the pass takes the longest gap's latency or, when more
+    // gaps than resident CTAs exist, the total work spread over the resident CTAs - whichever is larger.
+    static const double cyc_per_level[3] = {870.0, 560.0, 480.0};
+    double sum_levels = 0, max_levels = 0;
+    for (uint32_t gi : p.order) { const double d = dmax_of(e->gaps[gi]) + 64.0; sum_levels += d; max_levels = std::max(max_levels, d); }
+    const char *force = getenv("G2S_THIN_SHAPE");
+    double best = 0;
+    for (int sh = 0; sh < fill_thin_shapes(); sh++) {
+      const int r = fill_max_resident_thin_groups(e->sms, sh);
+      const double slots = (double)std::max<size_t>(1, std::min<size_t>({p.order.size(), (size_t)r, fit}));
+      const double t = std::max(max_levels, sum_levels / slots) * cyc_per_level[sh];
+      if ((force && atoi(force) == sh) || (!force && (sh == 0 || t < best))) { best = t; p.shape = sh; resident = r; }
+    }
+  }
   size_t groups = std::min<size_t>({p.order.size(), (size_t)resident, fit});
   p.groups = (int)std::max<size_t>(groups, 1);
   // output arena
@@ -286,7 +303,7 @@ static int run_pass(g2s_engine *e, Pass &p) {
   P.pack_cursor = (unsigned long long *)((char *)e->d_counters.p + 8);
   P.queue_head = (uint32_t *)e->d_counters.p;
   CUDA_TRY(cudaEventRecord(e->ev[0], e->st));
-  if (p.tier == 0) CUDA_TRY(launch_fill_thin(P, p.groups, e->st));
+  if (p.tier == 0) CUDA_TRY(launch_fill_thin(P, p.groups, p.shape, e->st));
   else CUDA_TRY(launch_fill_cta(P, p.groups, e->st));
   CUDA_TRY(cudaEventRecord(e->ev[1], e->st));
   e->tm.launches++;
@@ -298,6 +315,9 @@ static int run_pass(g2s_engine *e, Pass &p) {
   float ms = 0;
   CUDA_TRY(cudaEventElapsedTime(&ms, e->ev[0], e->ev[1]));
   e->tm.kernel_ms += ms;
+  if (getenv("G2S_HOST_PROF"))
+    fprintf(stderr, "g2s: pass tier %d (shape %d): %zu gaps on %d groups, slice %.1f MB, %.3f ms\n", p.tier, p.shape,
+            p.order.size(), p.groups, p.lay.bytes / 1e6, ms);
   e->tm.d2h_bytes += e->gaps.size() * sizeof(GapOut) + 8;
   p.pack_used = std::min(used, p.pack_cap);
   return G2S_OK;
@@ -438,12 +458,21 @@ static int do_collect(g2s_engine *e, HostBatch &hb) {
     PinBuf &b = (*bufs)[pi];
     {
       std::lock_guard<std::mutex> lk(pool->mu);
+      size_t best = pool->free.size();   // best fit: a small arena must not take the buffer a large one needs
       for (size_t j = 0; j < pool->free.size(); j++)
-        if (pool->free[j].cap >= need) { b = pool->free[j]; pool->free.erase(pool->free.begin() + j); break; }
+        if (pool->free[j].cap >= need && (best == pool->free.size() || pool->free[j].cap < pool->free[best].cap)) best = j;
+      if (best < pool->free.size()) { b = pool->free[best]; pool->free.erase(pool->free.begin() + best); }
     }
-    if (!b.p) CUDA_TRY(b.reserve(need + need / 2));
+    if (!b.p) {
+      const auto ta = std::chrono::steady_clock::now();
+      CUDA_TRY(b.reserve(need + need / 2));
+      if (getenv("G2S_HOST_PROF"))
+        fprintf(stderr, "g2s: pinned staging of %.1f MB allocated in %.3f ms\n", (need + need / 2) / 1e6,
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - ta).count());
+    }
     CUDA_TRY(cudaMemcpyAsync(b.p, e->d_pack[p.pack_slot].p, need, cudaMemcpyDeviceToHost, e->st));
     hb.pack_base[pi] = (const PackRec *)b.p;
+    hb.staging.emplace_back(b.p, need);
     e->tm.d2h_bytes += need;
   }
   CUDA_TRY(cudaEventRecord(e->ev[3], e->st));
@@ -456,6 +485,7 @@ static int do_collect(g2s_engine *e, HostBatch &hb) {
   auto t0 = std::chrono::steady_clock::now();
   hb.analyze(e->pool.get());
   e->tm.host_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  if (getenv("G2S_HOST_PROF")) fprintf(stderr, "g2s: subgraph analysis %.3f ms\n", e->tm.host_ms);
   return G2S_OK;
 }
 
@@ -477,6 +507,7 @@ static int do_finish(g2s_engine *e, g2s_result *results, char *const *fill_out) 
     results[i] = res[i];
     if (fill_out && fill_out[i]) memcpy(fill_out[i], &arena[off[i]], (size_t)res[i].fill_len + 1);
   }
+  hb.flush_staging(e->pool.get());
   e->tm.host_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   return G2S_OK;
 }

@@ -13,11 +13,17 @@
 
 namespace g2s {
 
-static const int THIN_THREADS = 64;
 static const int CTA_THREADS = 512;
+// Thin-tier shapes (helper warps for the right pass, main warps for everything else).  A gap's latency falls with more
+// warps (the per-level work of a narrow batch is instruction bound on one warp) but fewer gaps are resident then; the
+// engine picks per pass: wide shapes for small batches (latency), the two-warp shape for large ones (throughput).
+static const int N_THIN_SHAPES = 3;
+static const int THIN_MAIN[N_THIN_SHAPES] = {1, 4, 8};
+static const int THIN_HELPER[N_THIN_SHAPES] = {1, 2, 4};
 
 struct WarpGroup {
   static constexpr bool kWarp = true;
+  static constexpr bool kWarpScout = false;
   static __device__ __forceinline__ int rank() { return threadIdx.x & 31; }
   static __device__ __forceinline__ int size() { return 32; }
   static __device__ __forceinline__ void sync() { __syncwarp(); }
@@ -25,46 +31,68 @@ struct WarpGroup {
 };
 struct BlockGroup {
   static constexpr bool kWarp = false;
+  static constexpr bool kWarpScout = false;
   static __device__ __forceinline__ int rank() { return threadIdx.x; }
   static __device__ __forceinline__ int size() { return blockDim.x; }
   static __device__ __forceinline__ void sync() { __syncthreads(); }
   static __device__ __forceinline__ bool any(bool p) { return __syncthreads_or(p) != 0; }
 };
-
-// named barrier 1 of the thin CTA: the helper warp arrives when the right set is complete, the main warp waits on it
+// NWARPS consecutive warps of the CTA, starting with warp FIRST, synchronised on named barrier BAR.  The per-level
+// work of a narrow batch (node table, layout, marking) is instruction bound on one warp, so the thin tier gives each
+// pass a few warps; the scout (a chain of dependent gathers) stays on the group's first warp.
+template <int BAR, int FIRST, int NWARPS>
+struct SubGroup {
+  static constexpr bool kWarp = NWARPS == 1;
+  static constexpr bool kWarpScout = NWARPS > 1;
+  static __device__ __forceinline__ int rank() { return (int)threadIdx.x - 32 * FIRST; }
+  static __device__ __forceinline__ int size() { return 32 * NWARPS; }
+  static __device__ __forceinline__ void sync() {
+    if (NWARPS == 1) __syncwarp();
+    else asm volatile("bar.sync %0, %1;" ::"n"(BAR), "n"(32 * NWARPS) : "memory");
+  }
+  static __device__ __forceinline__ bool any(bool p) {
+    if (NWARPS == 1) return __any_sync(0xffffffffu, p) != 0;
+    unsigned r;
+    asm volatile("{\n\t.reg .pred pi, po;\n\tsetp.ne.u32 pi, %1, 0;\n\tbar.red.or.pred po, %2, %3, pi;\n\tselp.u32 %0, 1, 0, po;\n\t}"
+                 : "=r"(r) : "r"((unsigned)p), "n"(BAR), "n"(32 * NWARPS) : "memory");
+    return r != 0;
+  }
+};
+// named barrier 1 of the thin CTA: the helper warps arrive when the right set is complete, the main warps wait on it
+template <int HW, int MW>
 struct PairWait {
   static constexpr bool kConcurrent = true;
   static __device__ __forceinline__ void wait_right() {
-    __syncwarp();
-    asm volatile("bar.sync 1, 64;" ::: "memory");
+    SubGroup<2, HW, MW>::sync();
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * (HW + MW)) : "memory");
   }
 };
-static __device__ __forceinline__ void pair_signal_right() {
-  __threadfence_block();
-  __syncwarp();
-  asm volatile("bar.arrive 1, 64;" ::: "memory");
-}
 
+template <int HW, int MW>
 static __device__ __forceinline__ void process_gap_pair(const FillParams &P, const GapDev &gd, const Slice &S, GShared &sh,
                                                         GapOut *out) {
+  typedef SubGroup<3, 0, HW> HelperGroup;     // right pass
+  typedef SubGroup<2, HW, MW> MainGroup;      // forward pass, backward marking, pack
   const GapCtx cx = make_ctx(P, gd);
   unsigned long long t[5];
   t[0] = now_cycles();
   gap_init<BlockGroup>(P, cx, S, sh);
   t[1] = now_cycles();
-  if ((threadIdx.x >> 5) == 0) {
-    gap_right<WarpGroup>(P, cx, S, sh, sh.nbuf[0]);
-    pair_signal_right();
+  if ((threadIdx.x >> 5) < HW) {
+    gap_right<HelperGroup>(P, cx, S, sh, sh.nbuf[0]);
+    __threadfence_block();
+    HelperGroup::sync();
+    asm volatile("bar.arrive 1, %0;" ::"n"(32 * (HW + MW)) : "memory");
   } else {
     t[2] = t[1];
-    gap_forward<WarpGroup, PairWait>(P, gd, cx, S, sh, sh.nbuf[1]);
+    gap_forward<MainGroup, PairWait<HW, MW>>(P, gd, cx, S, sh, sh.nbuf[1]);
     t[3] = now_cycles();
-    t[4] = gap_backward_pack<WarpGroup>(P, cx, S, sh, sh.nbuf[1]);
-    gap_finish<WarpGroup>(S, sh, out, t);
+    t[4] = gap_backward_pack<MainGroup>(P, cx, S, sh, sh.nbuf[1]);
+    gap_finish<MainGroup>(S, sh, out, t);
   }
 }
 
-template <bool PAIR>
+template <int HW, int MW>   // HW == 0: wide tier, the whole CTA runs the phases one after the other
 __device__ __forceinline__ void group_loop(const FillParams &P, GShared &sh, uint32_t group_id) {
   const Slice S = make_slice(P.scratch + (size_t)group_id * P.lay.bytes, P.lay);
   for (;;) {
@@ -75,27 +103,33 @@ __device__ __forceinline__ void group_loop(const FillParams &P, GShared &sh, uin
     if (q >= P.n_gaps) break;
     const uint32_t gi = P.order[q];
     const GapDev gd = P.gaps[gi];
-    if (PAIR) process_gap_pair(P, gd, S, sh, &P.outs[gi]);
+    if (HW > 0) process_gap_pair<(HW > 0 ? HW : 1), MW>(P, gd, S, sh, &P.outs[gi]);
     else process_gap<BlockGroup>(P, gd, S, sh, &P.outs[gi]);
   }
 }
 
-__global__ void __launch_bounds__(THIN_THREADS) k_fill_thin(const __grid_constant__ FillParams P, int groups) {
+template <int HW, int MW>
+__global__ void __launch_bounds__(32 * (HW + MW)) k_fill_thin(const __grid_constant__ FillParams P, int groups) {
   __shared__ GShared sh;
   if (blockIdx.x >= (uint32_t)groups) return;
-  group_loop<true>(P, sh, blockIdx.x);
+  group_loop<HW, MW>(P, sh, blockIdx.x);
 }
 
 __global__ void __launch_bounds__(CTA_THREADS) k_fill_cta(const __grid_constant__ FillParams P, int groups) {
   __shared__ GShared sh;
   if (blockIdx.x >= (uint32_t)groups) return;
-  group_loop<false>(P, sh, blockIdx.x);
+  group_loop<0, 1>(P, sh, blockIdx.x);
 }
 
-int fill_max_resident_thin_groups(int sms) {
+int fill_thin_shapes() { return N_THIN_SHAPES; }
+int fill_thin_threads(int shape) { return 32 * (THIN_MAIN[shape] + THIN_HELPER[shape]); }
+
+int fill_max_resident_thin_groups(int sms, int shape) {
   int per_sm = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fill_thin, THIN_THREADS, 0) != cudaSuccess || per_sm < 1)
-    per_sm = 1;
+  cudaError_t e = shape == 0   ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fill_thin<1, 1>, 64, 0)
+                  : shape == 1 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fill_thin<2, 4>, 192, 0)
+                               : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fill_thin<4, 8>, 384, 0);
+  if (e != cudaSuccess || per_sm < 1) per_sm = 1;
   return sms * per_sm;
 }
 
@@ -106,8 +140,10 @@ int fill_max_resident_cta_groups(int sms) {
   return sms * per_sm;
 }
 
-cudaError_t launch_fill_thin(const FillParams &p, int groups, cudaStream_t st) {
-  k_fill_thin<<<groups, THIN_THREADS, 0, st>>>(p, groups);
+cudaError_t launch_fill_thin(const FillParams &p, int groups, int shape, cudaStream_t st) {
+  if (shape == 0) k_fill_thin<1, 1><<<groups, 64, 0, st>>>(p, groups);
+  else if (shape == 1) k_fill_thin<2, 4><<<groups, 192, 0, st>>>(p, groups);
+  else k_fill_thin<4, 8><<<groups, 384, 0, st>>>(p, groups);
   return cudaGetLastError();
 }
 

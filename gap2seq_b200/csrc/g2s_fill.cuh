@@ -139,7 +139,10 @@ struct FillParams {
   uint32_t *queue_head;
 };
 
-static const int CHAIN_LEN = 32;   // levels a narrow batch looks ahead
+#ifndef G2S_CHAIN_LEN
+#define G2S_CHAIN_LEN 128
+#endif
+static const int CHAIN_LEN = G2S_CHAIN_LEN;   // levels a narrow batch looks ahead
 static const int NARROW_W = 4;     // widest border handled in narrow mode
 
 struct NarrowBuf {     // look-ahead state of one pass (the right pass and the forward pass own one each, so that two warps
@@ -151,7 +154,7 @@ struct NarrowBuf {     // look-ahead state of one pass (the right pass and the f
   int32_t nw_fail[NARROW_W];
   uint32_t nw_n[CHAIN_LEN + 1], nw_off[CHAIN_LEN + 1], nw_run[CHAIN_LEN], nw_poff[CHAIN_LEN];
   uint32_t bk_p[NARROW_W][4];   // backward batches: predecessor cells of the batch's lowest level
-  int32_t bk_len;
+  int32_t bk_len, scout_len;
   uint64_t ch_s[CHAIN_LEN][NARROW_W];
   uint32_t ch_a[CHAIN_LEN][NARROW_W], ch_e[CHAIN_LEN][NARROW_W];
 };
@@ -479,6 +482,15 @@ template <class G, bool FORWARD>
 G2S_D int narrow_scout(const Table &T, GShared &sh, NarrowBuf &nb, int w, int maxlen) {
 #ifdef G2S_DEVICE_BUILD
   if (G::kWarp) { G::sync(); return narrow_scout_warp<FORWARD>(T, sh, nb, w, maxlen); }
+  if (G::kWarpScout) {   // several warps: the first one scouts, the others wait for the emitted states
+    G::sync();
+    if (G::rank() < 32) {
+      const int l = narrow_scout_warp<FORWARD>(T, sh, nb, w, maxlen);
+      if (G::rank() == 0) nb.scout_len = l;
+    }
+    G::sync();
+    return ld_sh(&nb.scout_len);
+  }
 #endif
   // Per-chain state lives in shared memory so that any group size, including the size-1 host emulation, can play the
   // w scouts: nw_x = the chain's tip in WALK orientation (forward pass: the state itself; right pass: its reverse

@@ -19,6 +19,35 @@
 
 namespace g2s {
 
+// Evicting a byte range from the CPU caches.  The pack arenas arrive by DMA in pinned staging buffers that the engine
+// reuses; once the traceback threads have read a buffer its lines sit in several cores' caches and the next DMA into
+// it pays a snoop per line (measured on the B200 host: 5x slower D2H with 16 reader threads).  Flushing the lines
+// when a batch is done - in parallel, they are clean - keeps the next D2H at PCIe speed.
+#if defined(__x86_64__)
+__attribute__((target("clflushopt"))) inline void flush_lines_opt(const char *p, const char *e) {
+  for (; p < e; p += 64) __builtin_ia32_clflushopt((void *)p);
+  __builtin_ia32_sfence();
+}
+inline void flush_lines_plain(const char *p, const char *e) {
+  for (; p < e; p += 64) __builtin_ia32_clflush((const void *)p);
+}
+inline bool cpu_has_clflushopt() {
+  static const bool has = [] {
+    unsigned a = 7, b = 0, c = 0, d = 0;
+    __asm__ volatile("cpuid" : "+a"(a), "=b"(b), "+c"(c), "=d"(d));
+    (void)d;
+    return ((b >> 23) & 1u) != 0;
+  }();
+  return has;
+}
+inline void flush_cache_range(const void *ptr, size_t bytes) {
+  const char *p = (const char *)((uintptr_t)ptr & ~(uintptr_t)63), *e = (const char *)ptr + bytes;
+  if (cpu_has_clflushopt()) flush_lines_opt(p, e); else flush_lines_plain(p, e);
+}
+#else
+inline void flush_cache_range(const void *, size_t) {}
+#endif
+
 struct GeneralResult {
   g2s_subgraph_stats st{};
   std::vector<uint8_t> safe;   // per pack record
@@ -28,27 +57,48 @@ struct GeneralResult {
 // Vertices are the distinct nodes of the B records plus sink (0) and source (1); edges are de-duplicated
 // exactly like the reference's `if (!edge(u,v).second) add_edge` (Gap2Seq.cpp:1222-1297).
 inline void analyze_general(const PackRec *pk, uint32_t npack, GeneralResult &R) {
-  std::vector<uint32_t> nodes;
-  for (uint32_t i = 0; i < npack; i++) if (pk[i].meta & PM_B) nodes.push_back(pk[i].node);
-  std::sort(nodes.begin(), nodes.end());
-  nodes.erase(std::unique(nodes.begin(), nodes.end()), nodes.end());
-  auto vid = [&](uint32_t node) { return (uint32_t)(std::lower_bound(nodes.begin(), nodes.end(), node) - nodes.begin()) + 2; };
-  const uint32_t V = (uint32_t)nodes.size() + 2;
-  std::vector<uint64_t> edges;
+  // dense vertex numbers in first-seen order (every result below is invariant under renumbering):
+  // node-table entry -> vertex through a direct map, then once per record so that edges never search
+  uint32_t maxnode = 0;
+  for (uint32_t i = 0; i < npack; i++) if ((pk[i].meta & PM_B) && pk[i].node > maxnode) maxnode = pk[i].node;
+  std::vector<uint32_t> vmap((size_t)maxnode + 1, NONE32), vof(npack, NONE32);
+  uint32_t V = 2;   // 0 = sink, 1 = source
   for (uint32_t i = 0; i < npack; i++) {
     if (!(pk[i].meta & PM_B)) continue;
-    const uint32_t v = vid(pk[i].node);
-    if (pk[i].meta & PM_START) edges.push_back(((uint64_t)1 << 32) | v);
-    else for (int q = 0; q < 4; q++) if (pk[i].pred[q] != NONE32) edges.push_back(((uint64_t)vid(pk[pk[i].pred[q]].node) << 32) | v);
-    if (pk[i].meta & PM_SEED) edges.push_back(((uint64_t)v << 32) | 0u);
+    uint32_t &m = vmap[pk[i].node];
+    if (m == NONE32) m = V++;
+    vof[i] = m;
   }
-  std::sort(edges.begin(), edges.end());
-  edges.erase(std::unique(edges.begin(), edges.end()), edges.end());
-  const size_t E = edges.size();
-  std::vector<uint32_t> ostart(V + 1, 0), otgt(E);
-  for (uint64_t ed : edges) ostart[(ed >> 32) + 1]++;
+  // out-edges bucketed by source (counting sort), duplicates - the same node pair on several levels - removed per
+  // bucket: the reference's `if (!edge(u,v).second) add_edge`
+  std::vector<uint32_t> ostart((size_t)V + 1, 0);
+  for (uint32_t i = 0; i < npack; i++) {
+    if (!(pk[i].meta & PM_B)) continue;
+    if (pk[i].meta & PM_START) ostart[1 + 1]++;
+    else for (int q = 0; q < 4; q++) if (pk[i].pred[q] != NONE32) ostart[vof[pk[i].pred[q]] + 1]++;
+    if (pk[i].meta & PM_SEED) ostart[vof[i] + 1]++;
+  }
   for (uint32_t v = 0; v < V; v++) ostart[v + 1] += ostart[v];
-  for (size_t i = 0; i < E; i++) otgt[i] = (uint32_t)edges[i];   // edges are sorted by source already
+  std::vector<uint32_t> otgt(ostart[V]), fillp(ostart.begin(), ostart.end() - 1);
+  for (uint32_t i = 0; i < npack; i++) {
+    if (!(pk[i].meta & PM_B)) continue;
+    const uint32_t v = vof[i];
+    if (pk[i].meta & PM_START) otgt[fillp[1]++] = v;
+    else for (int q = 0; q < 4; q++) if (pk[i].pred[q] != NONE32) otgt[fillp[vof[pk[i].pred[q]]]++] = v;
+    if (pk[i].meta & PM_SEED) otgt[fillp[v]++] = 0u;
+  }
+  {
+    uint32_t w = 0;
+    for (uint32_t v = 0; v < V; v++) {
+      const uint32_t b0 = ostart[v], e0 = ostart[v + 1];
+      ostart[v] = w;
+      if (e0 - b0 > 1) std::sort(otgt.begin() + b0, otgt.begin() + e0);
+      for (uint32_t j = b0; j < e0; j++) if (j == b0 || otgt[j] != otgt[j - 1]) otgt[w++] = otgt[j];
+    }
+    ostart[V] = w;
+    otgt.resize(w);
+  }
+  const size_t E = otgt.size();
 
   // iterative Tarjan
   std::vector<uint32_t> index(V, NONE32), low(V, 0), comp(V, NONE32), pos(V, 0), stack, call;
@@ -79,10 +129,12 @@ inline void analyze_general(const PackRec *pk, uint32_t npack, GeneralResult &R)
   for (uint32_t c = 0; c < ncomp; c++) if (csize[c] > 1) { nontriv++; size_nontriv += csize[c]; }
   // condensed multigraph: every cross-component edge exactly once (Gap2Seq.cpp:1346-1370)
   std::vector<uint32_t> indeg(ncomp, 0), outdeg(ncomp, 0);
-  for (uint64_t ed : edges) {
-    uint32_t u = (uint32_t)(ed >> 32), v = (uint32_t)ed;
-    if (comp[u] == comp[v]) { if (u == v && csize[comp[u]] == 1) self_loops_trivial++; continue; }
-    cross++; outdeg[comp[u]]++; indeg[comp[v]]++;
+  for (uint32_t u = 0; u < V; u++) {
+    for (uint32_t j = ostart[u]; j < ostart[u + 1]; j++) {
+      const uint32_t v = otgt[j];
+      if (comp[u] == comp[v]) { if (u == v && csize[comp[u]] == 1) self_loops_trivial++; continue; }
+      cross++; outdeg[comp[u]]++; indeg[comp[v]]++;
+    }
   }
   R.st.vertices = V;
   R.st.edges = E - self_loops_trivial;
@@ -104,9 +156,8 @@ inline void analyze_general(const PackRec *pk, uint32_t npack, GeneralResult &R)
   const bool sink_safe = vertex_safe(0);
   R.safe.assign(npack, 0);
   for (uint32_t i = 0; i < npack; i++) {
-    auto it = std::lower_bound(nodes.begin(), nodes.end(), pk[i].node);
-    if (it != nodes.end() && *it == pk[i].node) R.safe[i] = vertex_safe((uint32_t)(it - nodes.begin()) + 2);
-    else R.safe[i] = sink_safe;   // node2boost[] default-inserts the sink
+    const uint32_t v = pk[i].node <= maxnode ? vmap[pk[i].node] : NONE32;
+    R.safe[i] = v != NONE32 ? vertex_safe(v) : sink_safe;   // node2boost[] default-inserts the sink
   }
 }
 
@@ -330,7 +381,9 @@ inline void finish_one(const g2s_gap &g, const GapOut &o, const PackRec *pk, int
   bool broken = (cur == NONE32);
   while (d >= 0 && !broken) {
     const PackRec &rec = pk[cur];
-    __builtin_prefetch(&pk[cur + 24]);   // predecessors usually follow in the arena (it is filled top level first)
+    // predecessors usually follow in the arena (it is filled top level first).  Non-temporal: the records are read
+    // once, and lines left in the cache hierarchy slow down the next DMA into the staging buffer
+    __builtin_prefetch(&pk[cur + 24], 0, 0);
     if (d <= g.left_max_fuz && (rec.meta & PM_START)) { left_fuz = g.left_max_fuz - d; break; }
     if (d > 0) {
       const bool safe = skip_confident || (general ? gen.safe[cur] != 0 : (rec.meta & PM_SAFE) != 0);
@@ -370,6 +423,7 @@ struct HostBatch {
   std::vector<const PackRec *> pack_base;     // one arena per device pass (pinned staging owned by the engine's pool,
   std::vector<std::vector<PackRec>> own;      //  or `own` when the producer has no pool)
   std::function<void()> on_free;              // hands the staging buffers back
+  std::vector<std::pair<const void *, size_t>> staging;   // DMA targets to evict from the CPU caches when done
   std::vector<GeneralResult> gen;
   std::vector<char> buf;
 
@@ -378,6 +432,22 @@ struct HostBatch {
   HostBatch &operator=(const HostBatch &) = delete;
   ~HostBatch() { if (on_free) on_free(); }
   const PackRec *pack_ptr(size_t i) const { return pack_base[pack_of[i]] + outs[i].pack_off; }
+  // call when the batch has been traced: the staging buffers leave the CPU caches before they are reused
+  void flush_staging(ThreadPool *pool) {
+    const size_t chunk = 64 << 10;
+    static const long limit = getenv("G2S_FLUSH_MB") ? atol(getenv("G2S_FLUSH_MB")) : 16;   // flushing costs more than the
+    size_t total = 0;                                                                       // snoops for large arenas
+    for (auto &st : staging) total += st.second;
+    if ((long)(total >> 20) >= limit) { staging.clear(); return; }
+    for (auto &st : staging) {
+      const char *base = (const char *)st.first;
+      const size_t bytes = st.second, nchunk = (bytes + chunk - 1) / chunk;
+      auto one = [&](size_t c) { flush_cache_range(base + c * chunk, std::min(chunk, bytes - c * chunk)); };
+      if (pool) pool->parallel_for(nchunk, 1, one);
+      else for (size_t c = 0; c < nchunk; c++) one(c);
+    }
+    staging.clear();
+  }
 
   // SCC analysis of the general-subgraph gaps, independent per gap -> host threads
   void analyze(ThreadPool *pool) {

@@ -221,6 +221,7 @@ struct ScaffoldRun {
     std::vector<char> arena;
     std::vector<size_t> fill_off;
     trace_many(jobs, res, arena, fill_off, pool, ahead.ok() ? &ahead : nullptr);
+    for (auto &b : batches) if (b) b->flush_staging(pool);
     trace_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_mid).count();
 
     filled.assign(seqs.size(), std::string());

@@ -78,7 +78,7 @@ def load_library(path: str | None = None):
     global _lib
     if _lib is not None and path is None:
         return _lib
-    p = path or LIB_PATH
+    p = path or os.environ.get("G2S_LIB") or LIB_PATH   # G2S_LIB: an experiment build of the same ABI
     if not os.path.exists(p):
         raise G2SError(f"{p} is missing: build it with `make -C gap2seq_b200/csrc` (there is no CPU fallback)")
     L = C.CDLL(p)

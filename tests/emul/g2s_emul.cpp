@@ -21,6 +21,7 @@ struct EmulGroup {
   static int size() { return 1; }
   static void sync() {}
   static bool any(bool p) { return p; }
+  static constexpr bool kWarp = false, kWarpScout = false;
 };
 
 struct EmulGraph {
