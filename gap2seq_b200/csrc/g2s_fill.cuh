@@ -152,6 +152,9 @@ struct NarrowBuf {     // look-ahead state of one pass (the right pass and the f
   uint64_t nw_x[NARROW_W], nw_x0[NARROW_W];
   uint32_t nw_m[NARROW_W], nw_cnt0[NARROW_W], nw_hb[NARROW_W], nw_hl[NARROW_W];
   int32_t nw_fail[NARROW_W];
+  int32_t nw_born[NARROW_W];   // first level (of the batch) on which the chain exists: 0, or where it split off its parent
+  uint32_t nw_w;               // chains after the scout (splits add chains)
+  uint32_t nw_par[NARROW_W];   // chain a split chain descends from
   uint32_t nw_n[CHAIN_LEN + 1], nw_off[CHAIN_LEN + 1], nw_run[CHAIN_LEN], nw_poff[CHAIN_LEN];
   uint32_t bk_p[NARROW_W][4];   // backward batches: predecessor cells of the batch's lowest level
   int32_t bk_len, scout_len;
@@ -410,7 +413,10 @@ G2S_D bool found_scan(const Slice &S, const GapDev &gd, GShared &sh, int lo, int
 // once, r = the shortest remaining hint among the living chains: the state i steps past a tip is
 // ((tip << 2i) | (hint >> 2(j-i))) & kmask, so the lanes compute the w*r states of the round in parallel; a chain
 // gathers (one table probe) only when its hint is used up.  Shared memory only receives the emitted states.
-template <bool FORWARD>
+// SPLIT (forward pass only): a tip with several neighbours does not end the look-ahead while free chain slots remain:
+// the extra neighbours become new chains, born on this level, that carry their parent's initial count and - for the
+// levels before their birth - a copy of its states, so that the layout finds their predecessor cell like any other's.
+template <bool FORWARD, bool SPLIT>
 __device__ __forceinline__ int narrow_scout_warp(const Table &T, GShared &sh, NarrowBuf &nb, int w, int maxlen) {
   const int k = T.k;
   const unsigned FULL = 0xffffffffu;
@@ -420,9 +426,35 @@ __device__ __forceinline__ int narrow_scout_warp(const Table &T, GShared &sh, Na
   int len = 0;
   while (len < maxlen) {
     if (mask == 0) mask = 0xFF;                                      // dead end
-    const bool ended = mask == 0xFF;
+    bool ended = mask == 0xFF;
     const bool branch = !ended && (mask & (mask - 1)) != 0;
-    if (__any_sync(FULL, branch)) break;                             // a branch ends the look-ahead BEFORE this level
+    if (__any_sync(FULL, branch)) {
+      if (!SPLIT) break;                                             // a branch ends the look-ahead BEFORE this level
+      const int extra = branch ? __popc(mask) - 1 : 0;
+      int total = extra;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) total += __shfl_xor_sync(FULL, total, o);
+      if (w + total > NARROW_W) break;
+      int slot = w;
+      for (int p = 0; p < w; p++) {                                  // w <= 4 parents, in chain order
+        const uint32_t mp = __shfl_sync(FULL, mask, p);
+        const uint64_t xp = __shfl_sync(FULL, x, p);
+        if (mp == 0xFF || mp == 0 || !(mp & (mp - 1))) continue;
+        uint32_t rest = mp & (mp - 1);                               // every neighbour but the first
+        if (lane == p) { mask = mp & (0u - mp); hl = 0; }            // the parent keeps the first
+        while (rest) {
+          const uint32_t bit = rest & (0u - rest);
+          rest &= rest - 1;
+          if (lane == slot) { x = xp; mask = bit; hl = 0; hb = 0; }
+          if (lane == 0) { nb.nw_x0[slot] = nb.nw_x0[p]; nb.nw_cnt0[slot] = nb.nw_cnt0[p]; nb.nw_born[slot] = len; nb.nw_par[slot] = (uint32_t)p; }
+          for (int lv = lane; lv < len; lv += 32) { nb.ch_s[lv][slot] = nb.ch_s[lv][p]; nb.ch_a[lv][slot] = 0; }
+          slot++;
+        }
+      }
+      w += total;
+      ended = mask == 0xFF;
+      __syncwarp();
+    }
     if (!__any_sync(FULL, !ended)) {                                 // every chain ended: keep the empty level
       if (lane < w) nb.ch_a[len][lane] = 0;
       len++;
@@ -473,6 +505,7 @@ __device__ __forceinline__ int narrow_scout_warp(const Table &T, GShared &sh, Na
     }
     len += r;
   }
+  if (lane == 0) nb.nw_w = (uint32_t)w;
   __syncwarp();
   return len;
 }
@@ -481,11 +514,11 @@ __device__ __forceinline__ int narrow_scout_warp(const Table &T, GShared &sh, Na
 template <class G, bool FORWARD>
 G2S_D int narrow_scout(const Table &T, GShared &sh, NarrowBuf &nb, int w, int maxlen) {
 #ifdef G2S_DEVICE_BUILD
-  if (G::kWarp) { G::sync(); return narrow_scout_warp<FORWARD>(T, sh, nb, w, maxlen); }
+  if (G::kWarp) { G::sync(); return narrow_scout_warp<FORWARD, FORWARD>(T, sh, nb, w, maxlen); }
   if (G::kWarpScout) {   // several warps: the first one scouts, the others wait for the emitted states
     G::sync();
     if (G::rank() < 32) {
-      const int l = narrow_scout_warp<FORWARD>(T, sh, nb, w, maxlen);
+      const int l = narrow_scout_warp<FORWARD, FORWARD>(T, sh, nb, w, maxlen);
       if (G::rank() == 0) nb.scout_len = l;
     }
     G::sync();
@@ -498,7 +531,7 @@ G2S_D int narrow_scout(const Table &T, GShared &sh, NarrowBuf &nb, int w, int ma
   // (0xFF = chain ended), nw_hb / nw_hl = what is left of the tip's skip hint.  A gather happens only where a hint
   // ends; between gathers a level costs a shift and an insert.
   const int k = T.k, rank = G::rank(), gsz = G::size();
-  if (rank == 0) { nb.nw_stop = 0; nb.nw_alive = 0; }
+  if (rank == 0) { nb.nw_stop = 0; nb.nw_alive = 0; nb.nw_w = (uint32_t)w; }
   G::sync();
   int len = 0;
   for (int l = 0; l < maxlen; l++) {
@@ -610,6 +643,7 @@ template <class G>
 G2S_D int narrow_forward(const Table &T, const Slice &S, GShared &sh, NarrowBuf &nb, const GapDev &gd, uint32_t lo, int w, int c, int Dmax,
                          int prune_from) {
   const int k = T.k, rank = G::rank(), gsz = G::size();
+  for (int t = rank; t < NARROW_W; t += gsz) nb.nw_born[t] = 0;
   for (int t = rank; t < w; t += gsz) {
     const uint64_t x = ld_cg(&S.ck[lo + t]);
     nb.nw_x[t] = x; nb.nw_x0[t] = x;
@@ -623,12 +657,14 @@ G2S_D int narrow_forward(const Table &T, const Slice &S, GShared &sh, NarrowBuf 
   const unsigned long long tp1 = now_cycles();
   if (rank == 0) sh.prof[0] += tp1 - tp0;
   if (len == 0) return 0;
+  w = (int)ld_sh(&nb.nw_w);   // the scout may have split chains
   for (int t = rank; t < w; t += gsz) nb.nw_fail[t] = len;
   G::sync();
   // node table + prune test, one (level, chain) per thread: ch_e = node entry; first failing level per chain
   for (int q = rank; q < len * w; q += gsz) {
     const int l = q / w, t = q - l * w;
     uint32_t en = NONE32;
+    if (l < nb.nw_born[t]) { nb.ch_e[l][t] = NONE32; continue; }   // not born yet: neither a state nor a failure
     if (nb.ch_a[l][t]) {
       const Canon cs = canonical(nb.ch_s[l][t], k);
       uint32_t nf = 0;
@@ -640,6 +676,12 @@ G2S_D int narrow_forward(const Table &T, const Slice &S, GShared &sh, NarrowBuf 
     if (en == NONE32) a_mini(&nb.nw_fail[t], l);
   }
   G::sync();
+  // the scout splits chains before it knows where chains get pruned: a chain whose parent failed before the split
+  // level descends from a state that has no cell, so it never lives (parents have lower indices than their children)
+  if (rank == 0)
+    for (int t = 1; t < w; t++)
+      if (nb.nw_born[t] > 0 && nb.nw_fail[nb.nw_par[t]] < nb.nw_born[t]) nb.nw_fail[t] = 0;
+  G::sync();
   const unsigned long long tp2 = now_cycles();
   if (rank == 0) sh.prof[1] += tp2 - tp1;
   if (group_overflow<G>(sh)) return 0;
@@ -648,10 +690,11 @@ G2S_D int narrow_forward(const Table &T, const Slice &S, GShared &sh, NarrowBuf 
     uint32_t nn = 0;
 #pragma unroll
     for (int t = 0; t < NARROW_W; t++) {
-      if (t >= w || l >= nb.nw_fail[t]) continue;
+      if (t >= w || l >= nb.nw_fail[t] || l < nb.nw_born[t]) continue;
       bool dup = false;
 #pragma unroll
-      for (int u = 0; u < NARROW_W; u++) if (u < t && l < nb.nw_fail[u] && nb.ch_s[l][u] == nb.ch_s[l][t]) dup = true;
+      for (int u = 0; u < NARROW_W; u++)
+        if (u < t && l < nb.nw_fail[u] && l >= nb.nw_born[u] && nb.ch_s[l][u] == nb.ch_s[l][t]) dup = true;
       if (!dup) nn++;
     }
     nb.nw_n[l] = nn;
@@ -683,9 +726,9 @@ G2S_D int narrow_forward(const Table &T, const Slice &S, GShared &sh, NarrowBuf 
 #pragma unroll
     for (int t = 0; t < NARROW_W; t++) {
       const bool in = t < w;
-      const int fail = in ? nb.nw_fail[t] : 0;
-      al[t] = in && l < fail;
-      pal[t] = in && (l == 0 || l - 1 < fail);
+      const int fail = in ? nb.nw_fail[t] : 0, born = in ? nb.nw_born[t] : 0;
+      al[t] = in && l < fail && l >= born;
+      pal[t] = in && (l == 0 ? born == 0 : (l - 1 < fail && l - 1 >= born));
       st[t] = nb.ch_s[l][t];
       ps[t] = l ? nb.ch_s[l - 1][t] : nb.nw_x0[t];
       av[t] = nb.ch_a[l][t]; ev[t] = nb.ch_e[l][t]; c0[t] = nb.nw_cnt0[t];
