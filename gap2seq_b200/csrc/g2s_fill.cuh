@@ -145,6 +145,14 @@ struct FillParams {
 static const int CHAIN_LEN = G2S_CHAIN_LEN;   // levels a narrow batch looks ahead
 static const int NARROW_W = 4;     // widest border handled in narrow mode
 
+static const int SCOUT_SEGS = 40;   // segments a chain may record per batch (a batch ends early beyond that)
+struct ScoutSeg {      // one gather of a scout: tip x, then hl hinted states on levels l0 .. l0 + hl - 1
+  uint64_t x;
+  uint32_t hb;         // the hinted bases, first base highest
+  uint16_t l0;
+  uint8_t hl, end_mask;   // end_mask: out-mask (walk orientation) of the state the hint ends at
+};
+
 struct NarrowBuf {     // look-ahead state of one pass (the right pass and the forward pass own one each, so that two warps
                        // can run them concurrently)
   uint32_t nnext;
@@ -158,6 +166,8 @@ struct NarrowBuf {     // look-ahead state of one pass (the right pass and the f
   uint32_t nw_n[CHAIN_LEN + 1], nw_off[CHAIN_LEN + 1], nw_run[CHAIN_LEN], nw_poff[CHAIN_LEN];
   uint32_t bk_p[NARROW_W][4];   // backward batches: predecessor cells of the batch's lowest level
   int32_t bk_len, scout_len;
+  uint32_t nseg[NARROW_W];
+  ScoutSeg seg[NARROW_W][SCOUT_SEGS];
   uint64_t ch_s[CHAIN_LEN][NARROW_W];
   uint32_t ch_a[CHAIN_LEN][NARROW_W], ch_e[CHAIN_LEN][NARROW_W];
 };
@@ -409,120 +419,129 @@ G2S_D bool found_scan(const Slice &S, const GapDev &gd, GShared &sh, int lo, int
 // Scout phase shared by both passes.  Returns the number of levels looked ahead (0: a border state branches).
 // ch_s[l][t] / ch_a[l][t] receive chain t's state and (adj | strand << 8 | 1 << 16) on level l, ch_a == 0: no state.
 #ifdef G2S_DEVICE_BUILD
-// Warp flavour of the scout.  Lane t < w owns chain t (tip, mask, hint in registers).  A round emits r levels at
-// once, r = the shortest remaining hint among the living chains: the state i steps past a tip is
-// ((tip << 2i) | (hint >> 2(j-i))) & kmask, so the lanes compute the w*r states of the round in parallel; a chain
-// gathers (one table probe) only when its hint is used up.  Shared memory only receives the emitted states.
-// SPLIT (forward pass only): a tip with several neighbours does not end the look-ahead while free chain slots remain:
-// the extra neighbours become new chains, born on this level, that carry their parent's initial count and - for the
-// levels before their birth - a copy of its states, so that the layout finds their predecessor cell like any other's.
+// Warp flavour of the scout.  Lane t owns chain t and runs nothing but the chain of dependent gathers: a gather
+// returns the out-mask of the tip and its skip hint, i.e. the next j <= HINT_MAX states without looking at the table;
+// the lane records that as ONE segment (tip, hint, first level), jumps to the node the hint ends at and gathers
+// again.  Chains advance independently of each other.  The states of all segments are then computed by every thread
+// of the group in parallel (expand_segments): the per-level work is off the serial path.
+// SPLIT (forward pass only): a tip with several neighbours does not end the look-ahead while free chain slots
+// remain: the extra neighbours become new chains, born on that level, that carry their parent's initial count; the
+// layout finds their predecessor cell through nw_par.  Without a free slot (or without SPLIT) the batch ends before
+// the level of the branch.
 template <bool FORWARD, bool SPLIT>
 __device__ __forceinline__ int narrow_scout_warp(const Table &T, GShared &sh, NarrowBuf &nb, int w, int maxlen) {
   const int k = T.k;
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
-  uint64_t x = 0; uint32_t mask = 0xFF, hb = 0, hl = 0;
-  if (lane < w) { x = nb.nw_x[lane]; mask = nb.nw_m[lane]; }
-  int len = 0;
-  while (len < maxlen) {
-    if (mask == 0) mask = 0xFF;                                      // dead end
-    bool ended = mask == 0xFF;
-    const bool branch = !ended && (mask & (mask - 1)) != 0;
-    if (__any_sync(FULL, branch)) {
-      if (!SPLIT) break;                                             // a branch ends the look-ahead BEFORE this level
-      const int extra = branch ? __popc(mask) - 1 : 0;
-      int total = extra;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) total += __shfl_xor_sync(FULL, total, o);
-      if (w + total > NARROW_W) break;
+  uint64_t x = 0; uint32_t mask = 0;
+  int lv = 0;                 // levels of the batch this chain has covered: its next state belongs to level lv
+  int stop = maxlen;          // the batch must end before this level because of this chain
+  int endlv = -1;             // first level without a state of this chain (dead end), -1: none
+  int nseg = 0;
+  bool active = lane < w;
+  if (active) { x = nb.nw_x[lane]; mask = nb.nw_m[lane]; }
+  uint32_t hb = 0, hl = 0;    // hint of the tip (0: none)
+  while (__any_sync(FULL, active)) {
+    // ---- branches: split into new chains while slots remain
+    const bool branch = active && (mask & (mask - 1)) != 0;
+    const uint32_t bvote = __ballot_sync(FULL, branch);
+    if (bvote) {
       int slot = w;
-      for (int p = 0; p < w; p++) {                                  // w <= 4 parents, in chain order
+      for (int p = 0; p < NARROW_W; p++) {                           // parents in chain order
+        if (!((bvote >> p) & 1)) continue;
         const uint32_t mp = __shfl_sync(FULL, mask, p);
         const uint64_t xp = __shfl_sync(FULL, x, p);
-        if (mp == 0xFF || mp == 0 || !(mp & (mp - 1))) continue;
+        const int lp = __shfl_sync(FULL, lv, p);
+        const int extra = __popc(mp) - 1;
+        if (!SPLIT || slot + extra > NARROW_W) {                     // no room: the batch ends before this level
+          if (lane == p) { stop = lv; active = false; }
+          continue;
+        }
         uint32_t rest = mp & (mp - 1);                               // every neighbour but the first
         if (lane == p) { mask = mp & (0u - mp); hl = 0; }            // the parent keeps the first
         while (rest) {
           const uint32_t bit = rest & (0u - rest);
           rest &= rest - 1;
-          if (lane == slot) { x = xp; mask = bit; hl = 0; hb = 0; }
-          if (lane == 0) { nb.nw_x0[slot] = nb.nw_x0[p]; nb.nw_cnt0[slot] = nb.nw_cnt0[p]; nb.nw_born[slot] = len; nb.nw_par[slot] = (uint32_t)p; }
-          for (int lv = lane; lv < len; lv += 32) { nb.ch_s[lv][slot] = nb.ch_s[lv][p]; nb.ch_a[lv][slot] = 0; }
+          if (lane == slot) { x = xp; mask = bit; hl = 0; lv = lp; active = true; stop = maxlen; endlv = -1; nseg = 0; }
+          if (lane == p) { nb.nw_x0[slot] = nb.nw_x0[p]; nb.nw_cnt0[slot] = nb.nw_cnt0[p]; nb.nw_born[slot] = lp; nb.nw_par[slot] = (uint32_t)p; }
           slot++;
         }
       }
-      w += total;
-      ended = mask == 0xFF;
-      __syncwarp();
+      w = slot;
     }
-    if (!__any_sync(FULL, !ended)) {                                 // every chain ended: keep the empty level
-      if (lane < w) nb.ch_a[len][lane] = 0;
-      len++;
-      break;
+    if (active) {
+      if (mask == 0) { endlv = lv; active = false; }                 // dead end: no state from level lv on
+      else if (lv >= maxlen) active = false;
+      else if (nseg >= SCOUT_SEGS) { stop = lv; active = false; }    // out of segment slots: a shorter batch
     }
-    if (!ended && hl == 0) { hb = mask == 1 ? 0 : mask == 2 ? 1 : mask == 4 ? 2 : 3; hl = 1; }   // no hint: one known step
-    int r = (int)__reduce_min_sync(FULL, ended ? 0xFFFFu : hl);
-    if (r > maxlen - len) r = maxlen - len;
-    // parallel emission of w * r states (<= 48): two fixed sweeps so that every lane takes part in the shuffles
-#pragma unroll
-    for (int sweep = 0; sweep < 2; sweep++) {
-      const int q = lane + 32 * sweep;
-      const int t = q / r, i = q - t * r + 1;                         // chain, steps past the tip (1..r)
-      const int src = t < w ? t : 0;
-      const uint64_t xt = __shfl_sync(FULL, x, src);
-      const uint32_t bt = __shfl_sync(FULL, hb, src), lt = __shfl_sync(FULL, hl, src), mt = __shfl_sync(FULL, mask, src);
-      if (t < w) {
-        const int lvl = len + i - 1;
-        if (mt == 0xFF) nb.ch_a[lvl][t] = 0;
-        else {
-          const uint64_t y = ((xt << (2 * i)) | (uint64_t)((bt >> (2 * (lt - i))) & ((1u << (2 * i)) - 1))) & T.kmask;
-          const Canon cy = canonical(y, k);
-          const uint32_t nmask = (uint32_t)i < lt ? 1u << ((bt >> (2 * (lt - i - 1))) & 3) : 0u;   // hint end: patched below
-          if (FORWARD) { nb.ch_s[lvl][t] = y; nb.ch_a[lvl][t] = nmask | (cy.strand << 8) | (1u << 16); }
-          else { nb.ch_s[lvl][t] = revcomp(y, k); nb.ch_a[lvl][t] = swap2(nmask) | ((cy.strand ^ 1u) << 8) | (1u << 16); }
-        }
-      }
+    if (active) {
+      if (hl == 0) { hb = mask == 1 ? 0 : mask == 2 ? 1 : mask == 4 ? 2 : 3; hl = 1; }   // no hint: one known step
+      // the node the hint ends at
+      const uint64_t xe = ((x << (2 * hl)) | (uint64_t)hb) & T.kmask;
+      const Canon ce = canonical(xe, k);
+      uint64_t val = 0;
+      uint32_t emask = 0;
+      if (table_find_val(T, ce.key, &val) < 0) a_or(&sh.status, GS_INTERNAL);
+      else emask = out_mask((uint32_t)(val & 0xFF), ce.strand);
+      ScoutSeg &sg = nb.seg[lane][nseg++];
+      sg.x = x; sg.hb = hb; sg.hl = (uint8_t)hl; sg.l0 = (uint16_t)lv; sg.end_mask = (uint8_t)emask;
+      x = xe; lv += (int)hl; mask = emask;
+      const uint32_t h = hint_of(val, ce.strand);
+      hb = h & 0xFFFFFFu; hl = h >> 24;
+      if (mask == 0 || (mask & (mask - 1))) hl = 0;
     }
-    __syncwarp();
-    // owners advance their tips; a used-up hint costs one gather
-    if (lane < w && !ended) {
-      x = ((x << (2 * r)) | (uint64_t)((hb >> (2 * (hl - r))) & ((1u << (2 * r)) - 1))) & T.kmask;
-      hl -= r;
-      if (hl == 0) {
-        const Canon cx = canonical(x, k);
-        uint64_t val = 0;
-        if (table_find_val(T, cx.key, &val) < 0) { a_or(&sh.status, GS_INTERNAL); mask = 0xFF; }
-        else {
-          mask = out_mask((uint32_t)(val & 0xFF), cx.strand);
-          const uint32_t h = hint_of(val, cx.strand);
-          hb = h & 0xFFFFFFu; hl = h >> 24;
-          const int lvl = len + r - 1;
-          nb.ch_a[lvl][lane] = (nb.ch_a[lvl][lane] & ~0xFFu) | (FORWARD ? mask : swap2(mask));
-        }
-      } else {
-        mask = 1u << ((hb >> (2 * (hl - 1))) & 3);
-      }
-    }
-    len += r;
   }
-  if (lane == 0) nb.nw_w = (uint32_t)w;
+  if (lane < NARROW_W) nb.nseg[lane] = lane < w ? (uint32_t)nseg : 0u;
+  // length of the batch: up to the first level a chain has to stop before; if every chain ran into a dead end
+  // earlier, one empty level is kept so that the caller sees the border die
+  int st = lane < w ? stop : maxlen;
+  int en = lane < w ? (endlv >= 0 ? endlv : 0x7fffffff) : -1;       // lanes without a chain do not keep the batch alive
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    st = min(st, __shfl_xor_sync(FULL, st, o));
+    en = max(en, __shfl_xor_sync(FULL, en, o));
+  }
+  int len = st;
+  if (en != 0x7fffffff && en < len) len = en + 1 < maxlen ? en + 1 : maxlen;
+  if (lane == 0) { nb.nw_w = (uint32_t)w; nb.scout_len = len; }
   __syncwarp();
   return len;
+}
+
+// States of the scouted segments, one (segment, step) per thread; ch_a of the covered levels was zeroed before.
+template <class G, bool FORWARD>
+__device__ __forceinline__ void expand_segments(const Table &T, NarrowBuf &nb, int w, int len) {
+  const int k = T.k;
+  for (int q = G::rank(); q < w * SCOUT_SEGS * HINT_MAX; q += G::size()) {
+    const int i = q % HINT_MAX, sq = q / HINT_MAX;
+    const int t = sq / SCOUT_SEGS, si = sq - t * SCOUT_SEGS;
+    if ((uint32_t)si >= nb.nseg[t]) continue;
+    const ScoutSeg sg = nb.seg[t][si];
+    const int hl = sg.hl, lvl = sg.l0 + i;
+    if (i >= hl || lvl >= len) continue;
+    const int j = i + 1;                                              // steps past the segment's tip
+    const uint64_t y = ((sg.x << (2 * j)) | (uint64_t)((sg.hb >> (2 * (hl - j))) & ((1u << (2 * j)) - 1))) & T.kmask;
+    const Canon cy = canonical(y, k);
+    const uint32_t nmask = j < hl ? 1u << ((sg.hb >> (2 * (hl - j - 1))) & 3) : (uint32_t)sg.end_mask;
+    if (FORWARD) { nb.ch_s[lvl][t] = y; nb.ch_a[lvl][t] = nmask | (cy.strand << 8) | (1u << 16); }
+    else { nb.ch_s[lvl][t] = revcomp(y, k); nb.ch_a[lvl][t] = swap2(nmask) | ((cy.strand ^ 1u) << 8) | (1u << 16); }
+  }
 }
 #endif
 
 template <class G, bool FORWARD>
 G2S_D int narrow_scout(const Table &T, GShared &sh, NarrowBuf &nb, int w, int maxlen) {
 #ifdef G2S_DEVICE_BUILD
-  if (G::kWarp) { G::sync(); return narrow_scout_warp<FORWARD, FORWARD>(T, sh, nb, w, maxlen); }
-  if (G::kWarpScout) {   // several warps: the first one scouts, the others wait for the emitted states
+  if (G::kWarp || G::kWarpScout) {   // the group's first warp scouts, then every thread expands the segments
     G::sync();
-    if (G::rank() < 32) {
-      const int l = narrow_scout_warp<FORWARD, FORWARD>(T, sh, nb, w, maxlen);
-      if (G::rank() == 0) nb.scout_len = l;
-    }
+    if (G::rank() < 32) narrow_scout_warp<FORWARD, FORWARD>(T, sh, nb, w, maxlen);
     G::sync();
-    return ld_sh(&nb.scout_len);
+    const int len = ld_sh(&nb.scout_len), w2 = (int)ld_sh(&nb.nw_w);
+    for (int q = G::rank(); q < len * NARROW_W; q += G::size()) nb.ch_a[q / NARROW_W][q % NARROW_W] = 0;
+    G::sync();
+    expand_segments<G, FORWARD>(T, nb, w2, len);
+    G::sync();
+    return len;
   }
 #endif
   // Per-chain state lives in shared memory so that any group size, including the size-1 host emulation, can play the
@@ -730,7 +749,7 @@ G2S_D int narrow_forward(const Table &T, const Slice &S, GShared &sh, NarrowBuf 
       al[t] = in && l < fail && l >= born;
       pal[t] = in && (l == 0 ? born == 0 : (l - 1 < fail && l - 1 >= born));
       st[t] = nb.ch_s[l][t];
-      ps[t] = l ? nb.ch_s[l - 1][t] : nb.nw_x0[t];
+      ps[t] = l ? nb.ch_s[l - 1][in && l == born && born > 0 ? nb.nw_par[t] : t] : nb.nw_x0[t];   // a new chain descends from its parent's state
       av[t] = nb.ch_a[l][t]; ev[t] = nb.ch_e[l][t]; c0[t] = nb.nw_cnt0[t];
     }
     const uint32_t off_l = nb.nw_off[l], off_p = l ? nb.nw_off[l - 1] : 0u, nn = nb.nw_n[l];
