@@ -588,21 +588,57 @@ inline void trace_many(const std::vector<TraceJob> &jobs, std::vector<g2s_result
     jobs[j].hb->trace_at(jobs[j].idx, res[j], &arena[fill_off[j]], rc, scratch);
     act[j] = rc.pos - off[j];
   };
+  // Segments: the gaps up to and including the next uncertain one.  A segment's stream position is known once the
+  // previous segment's uncertain gap has been traced, so those gaps form the only sequential chain; they are handed
+  // out first (work items are taken in this order) and the certain gaps fill the other threads in the meantime.
+  {
+    std::vector<size_t> seg_of(n), seg_first, seg_last, order;
+    order.reserve(n);
+    size_t sidx = 0;
+    for (size_t lo = 0; lo < n;) {
+      size_t hi = lo;
+      while (hi + 1 < n && certain[hi]) hi++;
+      seg_first.push_back(lo);
+      seg_last.push_back(hi);
+      order.push_back(hi);
+      for (size_t j = lo; j < hi; j++) order.push_back(j);
+      for (size_t j = lo; j <= hi; j++) seg_of[j] = sidx;
+      sidx++;
+      lo = hi + 1;
+    }
+    const size_t nseg = seg_first.size();
+    std::vector<size_t> seg_base(nseg + 1, 0);
+    std::atomic<size_t> ready{1};          // segments whose stream position is known
+    trace_stats().rounds += nseg;
+    pool->parallel_for(n, 1, [&](size_t q) {
+      static thread_local std::vector<char> scratch;
+      const size_t j = order[q], sg = seg_of[j];
+      while (ready.load(std::memory_order_acquire) <= sg) { /* the chain of uncertain gaps is being traced */ }
+      size_t o = seg_base[sg];
+      for (size_t i = seg_first[sg]; i < j; i++) o += pred[i];
+      off[j] = o;
+      trace_one(j, scratch);
+      if (j == seg_last[sg]) {   // the segment's last gap: it fixes where the next segment starts
+        seg_base[sg + 1] = o + act[j];
+        ready.store(sg + 2, std::memory_order_release);
+      }
+    });
+    // every certain gap must have consumed what was predicted; otherwise everything behind it is traced again
+    size_t bad = n;
+    for (size_t j = 0; j < n && bad == n; j++) if (act[j] != pred[j] && certain[j]) bad = j;
+    if (bad == n) { final_upto = n; base = seg_base[nseg]; }
+    else { final_upto = bad + 1; base = off[bad] + act[bad]; trace_stats().retraced += n - bad - 1; }
+  }
   std::vector<char> my_scratch;
-  while (final_upto < n) {
-    trace_stats().rounds++;
+  while (final_upto < n) {   // only after a wrong prediction: rounds up to the next uncertain gap
     const size_t lo = final_upto;
-    size_t hi = lo;                       // last gap of the round: the first one whose consumption is uncertain
+    size_t hi = lo;
     while (hi + 1 < n && certain[hi]) hi++;
     off[lo] = base;
     for (size_t j = lo; j < hi; j++) off[j + 1] = off[j] + pred[j];
-    if (hi - lo + 1 < 4) for (size_t j = lo; j <= hi; j++) trace_one(j, my_scratch);
-    else pool->parallel_for(hi - lo + 1, 2, [&](size_t q) {
-      static thread_local std::vector<char> scratch;
-      trace_one(lo + q, scratch);
-    });
-    size_t bad = hi;                      // the first gap that did not consume what was predicted ends the round
-    for (size_t j = lo; j < hi; j++) if (act[j] != pred[j]) { bad = j; trace_stats().retraced += hi - j; break; }
+    for (size_t j = lo; j <= hi; j++) trace_one(j, my_scratch);
+    size_t bad = hi;
+    for (size_t j = lo; j < hi; j++) if (act[j] != pred[j]) { bad = j; break; }
     base = off[bad] + act[bad];
     final_upto = bad + 1;
   }

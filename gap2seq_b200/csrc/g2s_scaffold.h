@@ -92,7 +92,6 @@ struct ScaffoldRun {
   RunOptions opt;
   std::vector<RecScan> recs;
   std::vector<std::unique_ptr<HostBatch>> batches;
-  std::vector<std::vector<std::string>> flank_keep;   // flank strings of each batch (the gap structs point into them)
   double phase1_ms = 0, phase2_ms = 0, trace_ms = 0;  // wall time of the two phases of run() (profiling aid)
   ThreadPool *pool = nullptr;                         // host threads for the tracebacks and the per-record replay
   RandAhead ahead;                                    // the libc rand() values the tracebacks will consume
@@ -165,26 +164,32 @@ struct ScaffoldRun {
     for (;;) {
       std::vector<std::pair<size_t, int>> wave;
       bool any_open = false;
-      for (size_t r = 0; r < recs.size(); r++) {
-        if (recs[r].done) continue;
-        scan(r, wave);
-        if (!recs[r].done) any_open = true;
+      if (pool && batches.empty() && recs.size() >= 16) {   // first wave: nothing to look up, records scan in parallel
+        std::vector<std::vector<std::pair<size_t, int>>> part(recs.size());
+        pool->parallel_for(recs.size(), 4, [&](size_t r) { scan(r, part[r]); });
+        for (size_t r = 0; r < recs.size(); r++) {
+          wave.insert(wave.end(), part[r].begin(), part[r].end());
+          if (!recs[r].done) any_open = true;
+        }
+      } else {
+        for (size_t r = 0; r < recs.size(); r++) {
+          if (recs[r].done) continue;
+          scan(r, wave);
+          if (!recs[r].done) any_open = true;
+        }
       }
       if (wave.empty()) { if (any_open) { if (pool) pool->wait_async(); return -1; } break; }
       const int b = (int)batches.size();
       batches.emplace_back(new HostBatch());
-      flank_keep.emplace_back();
-      std::vector<std::string> &keep = flank_keep.back();
-      keep.reserve(wave.size() * 2);
       std::vector<g2s_gap> gaps(wave.size());
       for (size_t j = 0; j < wave.size(); j++) {
         GapReq &q = recs[wave[j].first].reqs[wave[j].second];
         const std::string &seq = seqs[wave[j].first];
         q.batch = b; q.idx = (int)j;
-        keep.push_back(seq.substr(q.kmer_start, (size_t)k + q.lmf));
-        keep.push_back(seq.substr(q.i_after, (size_t)k + q.rmf));
         g2s_gap &g = gaps[j];
-        g.kmer_left = keep[2 * j].data(); g.kmer_right = keep[2 * j + 1].data();
+        g.kmer_left = seq.data() + q.kmer_start;   // k + lmf / k + rmf characters inside the record (not NUL terminated)
+        g.kmer_right = seq.data() + q.i_after;
+        g.kmer_right_starts = nullptr;
         g.gap_len = q.gap; g.gap_err = opt.d_err; g.left_max_fuz = q.lmf; g.right_max_fuz = q.rmf;
         g.flags = (opt.skip_confident ? G2S_GAP_SKIP_CONFIDENT : 0) | (opt.all_paths ? G2S_GAP_ALL_PATHS : 0);
         g.reserved = 0;

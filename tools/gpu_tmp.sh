@@ -1,5 +1,3 @@
-timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-for sh in 0 1 2; do G2S_THIN_SHAPE=$sh timeout 300 python tools/gpu_check_oracle.py cfg2 1.0 2>&1 | tail -4; done
-timeout 300 python tools/gpu_check_oracle.py cfg3 0.3 2>&1 | tail -3
-timeout 300 python tools/gpu_check_oracle.py cfg4 0.05 2>&1 | tail -3
-bash tools/gpu_variants.sh "base"
+for mb in 16 1000; do echo "== G2S_FLUSH_MB=$mb"
+G2S_FLUSH_MB=$mb G2S_HOST_PROF=1 python tools/gpu_hostthreads.py cfg4 0.1 2>&1 | grep "host_threads=16\|host_threads= 8\|fill_records" | tail -4
+done
