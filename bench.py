@@ -54,6 +54,17 @@ def parse_args():
     return ap.parse_args()
 
 
+def measured_traffic(workload: str, scale: float):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of this workload
+    (profiles/ncu_traffic.json, written from the capture named there), or None when there is no capture for it."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        ent = json.load(open(p)).get(f"{workload}@{scale:g}")
+        return (float(ent["dram_bytes_per_launch"]), ent.get("source")) if ent else (None, None)
+    except Exception:
+        return None, None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -320,6 +331,7 @@ def main():
     if rank == 0:
         peak, peak_src = measured_peaks()
         achieved = cells * BYTES_PER_CELL / (ms_step / 1e3) / 1e9     # this rank's kernel, GB/s
+        traffic, traffic_src = measured_traffic(args.workload, args.scale)
         line = {
             "metric": "gaps_per_s", "value": all_gaps / (ms_step / 1e3), "unit": "gaps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
@@ -338,7 +350,8 @@ def main():
             "gpu_launches": int(all_launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "k_fill_thin", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                         "algorithmic_bytes_per_launch": cells * BYTES_PER_CELL, "peak_source": peak_src,
                          "algorithmic_bytes_per_cell": BYTES_PER_CELL,
                          "note": "thin gaps are chains of dependent gathers (1 cell per level): latency bound, see DESIGN.md"},
             "timed_region_wall_s": t_region,

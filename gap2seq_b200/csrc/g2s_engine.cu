@@ -399,9 +399,18 @@ static int do_run(g2s_engine *e) {
   e->out_pass.assign(n, -1);
   if (n == 0) { e->ran = true; return G2S_OK; }
   CUDA_TRY(cudaMemsetAsync(e->d_outs.p, 0, n * sizeof(GapOut), e->st));
-  std::vector<uint32_t> todo(n);
-  for (size_t i = 0; i < n; i++) todo[i] = (uint32_t)i;
-  for (int tier = 0; !todo.empty(); tier++) {
+  // Tiers: a gap that outgrows its scratch slice is run again in a 16x larger one.  How far it got tells how much
+  // larger: a gap that overflowed before half of its levels skips a tier (on the repeat-rich workload nearly every gap
+  // that fails the first tier also fails the second, which was a quarter of the device time).
+  std::vector<int> want(n, 0);
+  std::vector<uint8_t> done(n, 0);
+  int max_tier = 0;
+  { Pass probe; probe.order.push_back(0); for (int t = 1; t < 8; t++) { probe.tier = t; if (plan_pass(e, probe) != 0) break; max_tier = t; } }
+  size_t pending = n;
+  for (int tier = 0; pending > 0; tier++) {
+    std::vector<uint32_t> todo;
+    for (size_t i = 0; i < n; i++) if (!done[i] && want[i] <= tier) todo.push_back((uint32_t)i);
+    if (todo.empty()) continue;
     e->passes.emplace_back();
     Pass &p = e->passes.back();
     p.tier = tier;
@@ -409,23 +418,28 @@ static int do_run(g2s_engine *e) {
     p.order = todo;
     std::stable_sort(p.order.begin(), p.order.end(),
                      [&](uint32_t a, uint32_t b) { return dmax_of(e->gaps[a]) > dmax_of(e->gaps[b]); });
-    if (plan_pass(e, p) != 0) {   // no larger tier fits the memory budget: the gaps are reported, not filled
-      for (uint32_t gi : todo) { e->outs[gi] = GapOut{}; e->outs[gi].status = GS_OVERFLOW | GS_DONE; e->out_pass[gi] = -2; }
+    if (tier > max_tier || plan_pass(e, p) != 0) {   // no larger tier fits the memory budget: the gaps are reported, not filled
+      for (size_t i = 0; i < n; i++)
+        if (!done[i]) { e->outs[i] = GapOut{}; e->outs[i].status = GS_OVERFLOW | GS_DONE; e->out_pass[i] = -2; }
       e->passes.pop_back();
       break;
     }
     int rc = run_pass(e, p);
     if (rc != G2S_OK) return rc;
     const GapOut *ho = (const GapOut *)e->h_outs.p;
-    std::vector<uint32_t> next;
+    size_t failed = 0;
     for (uint32_t gi : todo) {
       if (!(ho[gi].status & GS_DONE)) return fail(G2S_E_CUDA, "device pass did not finish a gap");
       if (ho[gi].status & GS_INTERNAL) return fail(G2S_E_CUDA, "device table inconsistent with its adjacency bytes");
-      if (ho[gi].status & (GS_OVERFLOW | GS_OUT_FULL)) next.push_back(gi);
-      else { e->outs[gi] = ho[gi]; e->out_pass[gi] = (int)e->passes.size() - 1; }
+      if (ho[gi].status & (GS_OVERFLOW | GS_OUT_FULL)) {
+        failed++;
+        const g2s_gap &g = e->gaps[gi];
+        const double levels = (double)dmax_of(g) + g.right_max_fuz + (g.gap_len + g.gap_err + 1) / 2;   // forward + right pass
+        const bool early = !(ho[gi].status & GS_OUT_FULL) && (double)ho[gi].levels_r + ho[gi].levels_f < 0.5 * levels;
+        want[gi] = std::min(tier + (early ? 2 : 1), std::max(max_tier, tier + 1));
+      } else { e->outs[gi] = ho[gi]; e->out_pass[gi] = (int)e->passes.size() - 1; done[gi] = 1; pending--; }
     }
-    if (tier > 0) e->tm.gaps_big_tier += (uint32_t)(todo.size() - next.size());
-    todo.swap(next);
+    if (tier > 0) e->tm.gaps_big_tier += (uint32_t)(todo.size() - failed);
   }
   e->ran = true;
   return G2S_OK;

@@ -69,11 +69,20 @@ struct PairWait {
 };
 
 template <int HW, int MW>
-static __device__ __forceinline__ void process_gap_pair(const FillParams &P, const GapDev &gd, const Slice &S, GShared &sh,
+static __device__ __forceinline__ void process_gap_pair(const FillParams &P, const GapDev &gd, const Slice &Sfull, GShared &sh,
                                                         GapOut *out) {
   typedef SubGroup<3, 0, HW> HelperGroup;     // right pass
   typedef SubGroup<2, HW, MW> MainGroup;      // forward pass, backward marking, pack
   const GapCtx cx = make_ctx(P, gd);
+  // The slice's node table is sized for the longest gap of the pass; this gap clears and uses only what its own
+  // number of levels calls for (the same rule the engine applies to the pass: 3 entries per level, power of two),
+  // which is what keeps the DRAM write traffic of a pass of mostly short gaps near its algorithmic bytes.
+  Slice S = Sfull;
+  {
+    uint32_t want = 3u * ((uint32_t)cx.Dmax + 64u), cap = 256;
+    while (cap < want) cap <<= 1;
+    if (cap < S.hcap) { S.hcap = cap; S.hmask = cap - 1; }
+  }
   unsigned long long t[5];
   t[0] = now_cycles();
   gap_init<BlockGroup>(P, cx, S, sh);

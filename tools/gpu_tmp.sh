@@ -1,3 +1,5 @@
-for mb in 16 1000; do echo "== G2S_FLUSH_MB=$mb"
-G2S_FLUSH_MB=$mb G2S_HOST_PROF=1 python tools/gpu_hostthreads.py cfg4 0.1 2>&1 | grep "host_threads=16\|host_threads= 8\|fill_records" | tail -4
-done
+timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+timeout 300 python tools/gpu_check_oracle.py cfg3 1.0 2>&1 | tail -3
+timeout 300 python tools/gpu_check_oracle.py cfg2 1.0 2>&1 | tail -3
+G2S_HOST_PROF=1 timeout 200 python bench.py --workload cfg3 --scale 1.0 --steps 3 --warmup 1 --cpu-seconds 2 2>&1 | grep "g2s: pass\|fill_records" | tail -4
+bash tools/gpu_variants.sh "base"
