@@ -243,7 +243,9 @@ def main():
         torch.cuda.synchronize()
 
     w = make_workload(args.workload, args.scale, rank)
-    eng = engine.Engine(k=w.k, max_fuz=w.fuz, device=local_rank)
+    # host threads of the engine (tracebacks, splice): the box's cores are shared by the ranks of this node
+    host_threads = max(2, min(16, (os.cpu_count() or 2) // max(1, world)))
+    eng = engine.Engine(k=w.k, max_fuz=w.fuz, device=local_rank, host_threads=host_threads)
     t0 = time.perf_counter()
     if rank == 0 or world == 1:
         eng.build_from_reads(w.reads, w.solid)
@@ -339,7 +341,7 @@ def main():
             "config": {"workload": WORKLOAD_DESC.get(args.workload, args.workload), "scale": args.scale,
                        "gaps_per_gpu": n_gaps, "filled": filled, "fills_equal_to_removed_bases": exact, "solid_kmers": n_kmers,
                        "l2": "256 MiB device buffer rewritten between timed iterations",
-                       "graph_build_s_untimed": round(t_graph, 3), "gaps_in_wide_tier": big,
+                       "graph_build_s_untimed": round(t_graph, 3), "gaps_in_wide_tier": big, "host_threads_per_rank": host_threads,
                        "parallelism": f"{world} x (one process per GPU, replicated k-mer table, disjoint gap batches)",
                        "table_broadcast_s_untimed": round(t_bcast, 4), "table_bytes": table_bytes},
             "dp_cells_per_s": all_cells / (ms_step / 1e3), "dp_cells_per_step": all_cells,

@@ -13,7 +13,7 @@
 
 namespace g2s {
 
-static const int CTA_THREADS = 512;
+static const int CTA_THREADS = 1024;
 // Thin-tier shapes (helper warps for the right pass, main warps for everything else).  A gap's latency falls with more
 // warps (the per-level work of a narrow batch is instruction bound on one warp) but fewer gaps are resident then; the
 // engine picks per pass: wide shapes for small batches (latency), the two-warp shape for large ones (throughput).

@@ -889,6 +889,59 @@ G2S_D int narrow_backward(const Slice &S, GShared &sh, NarrowBuf &nb, int d, int
     if (M != 1u || n != 1u) a_or(&nb.nw_stop, 1u);   // not a pure chain level
   }
   G::sync();
+#if defined(G2S_DEVICE_BUILD) && !defined(G2S_SERIAL_BACK)
+  // Push the marks down the batch.  Level t maps the marks x that reach it to F_t(own_t | x) on the level below, F_t
+  // = union of predecessor sets (flow_down).  Such maps compose - (A, c): x -> c | A x with a 4 x 4 boolean matrix A,
+  // applied to the B and the T nibble alike - so the group's first warp scans them: every lane composes its
+  // consecutive levels, one warp scan yields the marks entering each lane's levels, and the lanes finish their levels.
+  if (rank < 32) {
+    const unsigned FULL = 0xffffffffu;
+    const int LPL = (CHAIN_LEN + 31) / 32;
+    uint32_t own[LPL], Mx[LPL];
+    uint32_t A = 0x8421u, cB = 0, cT = 0;   // identity, no marks
+#pragma unroll
+    for (int j = 0; j < LPL; j++) {
+      const int t = rank * LPL + j;
+      own[j] = 0; Mx[j] = 0x8421u;
+      if (t < len) { const uint32_t w0 = nb.ch_a[t][0]; own[j] = w0 & 0xFFu; Mx[j] = w0 >> 8; }
+      cB = flow_down(Mx[j], (own[j] & 15u) | cB);
+      cT = flow_down(Mx[j], (own[j] >> 4) | cT);
+      A = flow_down(Mx[j], A & 15u) | (flow_down(Mx[j], (A >> 4) & 15u) << 4) | (flow_down(Mx[j], (A >> 8) & 15u) << 8) |
+          (flow_down(Mx[j], (A >> 12) & 15u) << 12);
+    }
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {      // inclusive scan: (lanes before) then mine
+      const uint32_t Ap = __shfl_up_sync(FULL, A, o), cBp = __shfl_up_sync(FULL, cB, o), cTp = __shfl_up_sync(FULL, cT, o);
+      if (rank >= o) {
+        cB |= flow_down(A, cBp);
+        cT |= flow_down(A, cTp);
+        A = flow_down(A, Ap & 15u) | (flow_down(A, (Ap >> 4) & 15u) << 4) | (flow_down(A, (Ap >> 8) & 15u) << 8) |
+            (flow_down(A, (Ap >> 12) & 15u) << 12);
+      }
+    }
+    uint32_t xB = __shfl_up_sync(FULL, cB, 1), xT = __shfl_up_sync(FULL, cT, 1);
+    if (rank == 0) { xB = 0; xT = 0; }
+    uint32_t mrk[LPL], cnt = 0;
+#pragma unroll
+    for (int j = 0; j < LPL; j++) {
+      const uint32_t mB = (own[j] & 15u) | xB, mT = (own[j] >> 4) | xT;
+      mrk[j] = rank * LPL + j < len ? mB | (mT << 4) : 0u;   // levels past the batch hold no cells
+      cnt += popc32((mrk[j] | (mrk[j] >> 4)) & 15u);
+      xB = flow_down(Mx[j], mB); xT = flow_down(Mx[j], mT);
+    }
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(FULL, incl, o); if (rank >= o) incl += v; }
+    uint32_t run = incl - cnt;
+#pragma unroll
+    for (int j = 0; j < LPL; j++) {
+      const int t = rank * LPL + j;
+      if (t < len) { nb.nw_run[t] = mrk[j]; nb.nw_poff[t] = run; }
+      run += popc32((mrk[j] | (mrk[j] >> 4)) & 15u);
+    }
+    if (rank == 31) { nb.ch_base = sh.npack; sh.npack += incl; }
+  }
+#else
   if (rank == 0) {   // push the marks down the batch
     uint32_t x = 0, npk = 0;
     if (nb.nw_stop == 0) {
@@ -911,6 +964,7 @@ G2S_D int narrow_backward(const Slice &S, GShared &sh, NarrowBuf &nb, int d, int
     nb.ch_base = sh.npack;
     sh.npack += npk;
   }
+#endif
   G::sync();
   const uint32_t base = ld_sh(&nb.ch_base);
   uint32_t nbt = 0, ned = 0;

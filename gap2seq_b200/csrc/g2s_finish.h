@@ -613,7 +613,8 @@ inline void trace_many(const std::vector<TraceJob> &jobs, std::vector<g2s_result
     pool->parallel_for(n, 1, [&](size_t q) {
       static thread_local std::vector<char> scratch;
       const size_t j = order[q], sg = seg_of[j];
-      while (ready.load(std::memory_order_acquire) <= sg) { /* the chain of uncertain gaps is being traced */ }
+      for (unsigned spins = 0; ready.load(std::memory_order_acquire) <= sg; spins++)   // the chain of uncertain gaps is
+        if (spins > 2000) std::this_thread::yield();                                   // being traced by another thread
       size_t o = seg_base[sg];
       for (size_t i = seg_first[sg]; i < j; i++) o += pred[i];
       off[j] = o;
