@@ -76,6 +76,7 @@ struct Pass {                   // one device pass over a subset of the batch
   unsigned long long pack_cap = 0;
   unsigned long long pack_used = 0;
   int pack_slot = 0;            // index into the engine's persistent device pack buffers
+  unsigned long long fill_cap = 0, fill_used = 0;   // fill arena of the device-side tracebacks (bytes)
 };
 
 struct PinPool {                // pinned host staging for pack arenas, shared by the engine and its detached batches
@@ -103,10 +104,14 @@ struct g2s_engine {
   bool uploaded = false, ran = false;
   DevBuf d_flanks, d_gaps, d_order, d_outs, d_scratch, d_counters;
   std::vector<DevBuf> d_pack;          // persistent (grow-only) pack arena per pass ordinal
+  std::vector<DevBuf> d_fill;          // fill arena per pass ordinal
+  bool device_trace = true;            // G2S_NO_DEVICE_TRACE=1: every traceback on the host (A/B measurements)
   std::shared_ptr<PinPool> pin = std::make_shared<PinPool>();
   PinBuf h_outs, h_stage;
   g2s_timing tm{};
   int max_dmax = 0, max_rmf = 0;
+  RandAhead ahead;                     // persistent host buffers of the traceback stage
+  RawBuf<char> trace_arena;
   std::unique_ptr<ThreadPool> pool;    // host threads (g2s_config.host_threads) for the stages after a device pass
 };
 
@@ -136,6 +141,7 @@ extern "C" int g2s_create(const g2s_config *cfg, g2s_engine **out) {
   e->budget = cfg->max_mem_bytes > 0 ? (size_t)cfg->max_mem_bytes : (size_t)(fr * 0.6);
   CUDA_TRY(e->d_counters.reserve(64));
   e->pool.reset(new ThreadPool(cfg->host_threads));
+  e->device_trace = getenv("G2S_NO_DEVICE_TRACE") == nullptr;
   *out = e;
   return G2S_OK;
 }
@@ -144,6 +150,7 @@ extern "C" void g2s_destroy(g2s_engine *e) {
   if (!e) return;
   cudaSetDevice(e->cfg.device);
   for (auto &b : e->d_pack) b.release();
+  for (auto &b : e->d_fill) b.release();
   e->d_flanks.release(); e->d_gaps.release(); e->d_order.release(); e->d_outs.release();
   e->d_scratch.release(); e->d_counters.release(); e->h_outs.release(); e->h_stage.release();
   if (e->table.slots) cudaFree(e->table.slots);
@@ -286,6 +293,12 @@ static int run_pass(g2s_engine *e, Pass &p) {
   if ((size_t)p.pack_slot >= e->d_pack.size()) e->d_pack.resize(p.pack_slot + 1);
   if (e->d_pack[p.pack_slot].cap < p.pack_cap * sizeof(PackRec)) CUDA_TRY(e->d_pack[p.pack_slot].reserve(p.pack_cap * sizeof(PackRec)));
   else p.pack_cap = e->d_pack[p.pack_slot].cap / sizeof(PackRec);   // use all of a buffer that is already there
+  if ((size_t)p.pack_slot >= e->d_fill.size()) e->d_fill.resize(p.pack_slot + 1);
+  p.fill_cap = 0;
+  if (e->device_trace) {
+    for (uint32_t gi : p.order) p.fill_cap += (unsigned long long)dmax_of(e->gaps[gi]) + 2;
+    CUDA_TRY(e->d_fill[p.pack_slot].reserve((size_t)p.fill_cap + 16));
+  }
   CUDA_TRY(e->d_order.reserve(p.order.size() * 4));
   CUDA_TRY(cudaMemcpyAsync(e->d_order.p, p.order.data(), p.order.size() * 4, cudaMemcpyHostToDevice, e->st));
   CUDA_TRY(cudaMemsetAsync(e->d_counters.p, 0, 64, e->st));
@@ -302,6 +315,9 @@ static int run_pass(g2s_engine *e, Pass &p) {
   P.pack_cap = p.pack_cap;
   P.pack_cursor = (unsigned long long *)((char *)e->d_counters.p + 8);
   P.queue_head = (uint32_t *)e->d_counters.p;
+  P.fills = e->device_trace ? (char *)e->d_fill[p.pack_slot].p : nullptr;
+  P.fill_cap = p.fill_cap;
+  P.fill_cursor = (unsigned long long *)((char *)e->d_counters.p + 16);
   CUDA_TRY(cudaEventRecord(e->ev[0], e->st));
   if (p.tier == 0) CUDA_TRY(launch_fill_thin(P, p.groups, p.shape, e->st));
   else CUDA_TRY(launch_fill_cta(P, p.groups, e->st));
@@ -309,8 +325,9 @@ static int run_pass(g2s_engine *e, Pass &p) {
   e->tm.launches++;
   // the per-gap summaries decide whether another tier is needed
   CUDA_TRY(cudaMemcpyAsync(e->h_outs.p, e->d_outs.p, e->gaps.size() * sizeof(GapOut), cudaMemcpyDeviceToHost, e->st));
-  unsigned long long used = 0;
+  unsigned long long used = 0, fused = 0;
   CUDA_TRY(cudaMemcpyAsync(&used, (char *)e->d_counters.p + 8, 8, cudaMemcpyDeviceToHost, e->st));
+  CUDA_TRY(cudaMemcpyAsync(&fused, (char *)e->d_counters.p + 16, 8, cudaMemcpyDeviceToHost, e->st));
   CUDA_TRY(cudaStreamSynchronize(e->st));
   float ms = 0;
   CUDA_TRY(cudaEventElapsedTime(&ms, e->ev[0], e->ev[1]));
@@ -320,6 +337,7 @@ static int run_pass(g2s_engine *e, Pass &p) {
             p.order.size(), p.groups, p.lay.bytes / 1e6, ms);
   e->tm.d2h_bytes += e->gaps.size() * sizeof(GapOut) + 8;
   p.pack_used = std::min(used, p.pack_cap);
+  p.fill_used = std::min(fused, p.fill_cap);
   return G2S_OK;
 }
 
@@ -457,7 +475,8 @@ static int do_collect(g2s_engine *e, HostBatch &hb) {
   hb.tier.assign(n, -2);
   hb.pack_of.assign(n, 0);
   hb.pack_base.assign(e->passes.size(), nullptr);
-  auto bufs = std::make_shared<std::vector<PinBuf>>(e->passes.size());
+  hb.fill_base.assign(e->passes.size(), nullptr);
+  auto bufs = std::make_shared<std::vector<PinBuf>>(2 * e->passes.size());   // [pass]: pack records, [passes + pass]: fills
   std::shared_ptr<PinPool> pool = e->pin;
   hb.on_free = [bufs, pool]() {   // hand the pinned staging back to the pool when the batch dies
     std::lock_guard<std::mutex> lk(pool->mu);
@@ -489,6 +508,24 @@ static int do_collect(g2s_engine *e, HostBatch &hb) {
     hb.staging.emplace_back(b.p, need);
     e->tm.d2h_bytes += need;
   }
+  for (size_t pi = 0; pi < e->passes.size(); pi++) {   // the fills the device traced itself
+    Pass &p = e->passes[pi];
+    if (!p.fill_used) continue;
+    const size_t need = (size_t)p.fill_used;
+    PinBuf &b = (*bufs)[e->passes.size() + pi];
+    {
+      std::lock_guard<std::mutex> lk(pool->mu);
+      size_t best = pool->free.size();
+      for (size_t j = 0; j < pool->free.size(); j++)
+        if (pool->free[j].cap >= need && (best == pool->free.size() || pool->free[j].cap < pool->free[best].cap)) best = j;
+      if (best < pool->free.size()) { b = pool->free[best]; pool->free.erase(pool->free.begin() + best); }
+    }
+    if (!b.p) CUDA_TRY(b.reserve(need + need / 2));
+    CUDA_TRY(cudaMemcpyAsync(b.p, e->d_fill[p.pack_slot].p, need, cudaMemcpyDeviceToHost, e->st));
+    hb.fill_base[pi] = (const char *)b.p;
+    hb.staging.emplace_back(b.p, need);
+    e->tm.d2h_bytes += need;
+  }
   CUDA_TRY(cudaEventRecord(e->ev[3], e->st));
   CUDA_TRY(cudaStreamSynchronize(e->st));
   float ms = 0;
@@ -514,9 +551,10 @@ static int do_finish(g2s_engine *e, g2s_result *results, char *const *fill_out) 
   std::vector<TraceJob> jobs(hb.gaps.size());
   for (size_t i = 0; i < jobs.size(); i++) jobs[i] = TraceJob{&hb, i};
   std::vector<g2s_result> res;
-  std::vector<char> arena;
   std::vector<size_t> off;
-  trace_many(jobs, res, arena, off, e->pool.get(), nullptr);
+  if (e->pool && jobs.size() >= 4) e->ahead.begin();
+  trace_many(jobs, res, e->trace_arena, off, e->pool.get(), e->ahead.ok() ? &e->ahead : nullptr);
+  const char *arena = e->trace_arena.p;
   for (size_t i = 0; i < jobs.size(); i++) {
     results[i] = res[i];
     if (fill_out && fill_out[i]) memcpy(fill_out[i], &arena[off[i]], (size_t)res[i].fill_len + 1);
@@ -574,13 +612,17 @@ extern "C" int g2s_fill_records(g2s_engine *e, const char *const *seqs, const ch
   if (!e || !opt || (n_records && (!seqs || !comments || !filled_out))) return fail(G2S_E_ARG, "g2s_fill_records: null argument");
   if (opt->k != e->cfg.k) return fail(G2S_E_ARG, "g2s_fill_records: k differs from the engine's k");
   if (opt->fuz < 0 || opt->fuz > e->cfg.max_fuz) return fail(G2S_E_ARG, "g2s_fill_records: fuz exceeds g2s_config.max_fuz");
-  std::vector<std::string> s(n_records), c(n_records);
-  for (size_t i = 0; i < n_records; i++) { s[i] = seqs[i]; c[i] = comments[i] ? comments[i] : ""; }
+  std::vector<StrRef> s(n_records), c(n_records);   // the caller's strings, not copied
+  auto ref_one = [&](size_t i) { s[i] = StrRef(seqs[i]); c[i] = StrRef(comments[i]); };
+  if (e->pool) e->pool->parallel_for(n_records, 64, ref_one);
+  else for (size_t i = 0; i < n_records; i++) ref_one(i);
   RunOptions ro;
   ro.k = opt->k; ro.d_err = opt->dist_error; ro.max_fuz = opt->fuz;
   ro.skip_confident = opt->skip_confident != 0; ro.unique_paths = opt->unique_paths != 0; ro.all_paths = opt->all_paths != 0;
   ScaffoldRun run(s, c, ro);
   run.pool = e->pool.get();
+  run.aheadp = &e->ahead;
+  run.arenap = &e->trace_arena;
   g2s_timing total{};
   int err = G2S_OK;
   double w_upload = 0, w_run = 0, w_collect = 0;
@@ -613,9 +655,11 @@ extern "C" int g2s_fill_records(g2s_engine *e, const char *const *seqs, const ch
   e->tm = total;
   if (getenv("G2S_HOST_PROF"))   // profiling aid: where the wall time of this call went
     fprintf(stderr, "g2s_fill_records: wall %.3f ms = scan+flanks %.3f | upload %.3f | run %.3f (kernel %.3f) | collect %.3f "
-            "(d2h %.3f) | trace %.3f | splice+log %.3f\n", wall, run.phase1_ms - w_upload - w_run - w_collect, w_upload, w_run,
-            total.kernel_ms, w_collect, total.d2h_ms, run.trace_ms, run.phase2_ms - run.trace_ms);
-  for (size_t i = 0; i < n_records; i++) filled_out[i] = strdup(filled[i].c_str());
+            "(d2h %.3f) | trace %.3f (rand wait %.3f, flush %.3f) | splice+log %.3f\n", wall, run.phase1_ms - w_upload - w_run - w_collect, w_upload, w_run,
+            total.kernel_ms, w_collect, total.d2h_ms, run.trace_ms, run.wait_ms, run.flush_ms, run.phase2_ms - run.trace_ms);
+  auto dup_one = [&](size_t i) { filled_out[i] = strdup(filled[i].c_str()); };
+  if (e->pool) e->pool->parallel_for(n_records, 16, dup_one);
+  else for (size_t i = 0; i < n_records; i++) dup_one(i);
   if (log_out) *log_out = strdup(log.c_str());
   if (gapcount) *gapcount = gc;
   if (filledcount) *filledcount = fc;

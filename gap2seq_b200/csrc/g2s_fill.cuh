@@ -95,10 +95,10 @@ struct GapDev {        // 32 B input descriptor
 };
 
 enum {  // GapOut.status (device side)
-  GS_ORDER_DEPENDENT = 1, GS_OVERFLOW = 2, GS_GENERAL = 4, GS_OUT_FULL = 8, GS_INTERNAL = 16, GS_DONE = 0x100
+  GS_ORDER_DEPENDENT = 1, GS_OVERFLOW = 2, GS_GENERAL = 4, GS_OUT_FULL = 8, GS_INTERNAL = 16, GS_TRACED = 32, GS_DONE = 0x100
 };
 
-struct GapOut {        // 160 B
+struct GapOut {        // 184 B
   uint32_t status;
   uint32_t count_fwd, count_all;
   uint32_t n_plen;
@@ -112,6 +112,11 @@ struct GapOut {        // 160 B
   uint32_t top_level;
   unsigned long long pack_off;
   uint32_t levels_r, levels_f;
+  // GS_TRACED: the traceback had no choice to make, the device wrote the fill (case = safe / unsafe) itself
+  unsigned long long fill_off;   // into the pass's fill arena
+  uint32_t fill_len;             // characters, ends with the right k-mer (what the reference leaves at &fill[lmf - left_fuz])
+  int32_t left_fuz;
+  uint32_t rand_calls, pad0;
   uint32_t cyc[6];     // SM cycles (>> 4) spent in: init, right pass, forward pass, backward marking, pack, total
   uint32_t prof[8];    // forward pass detail (>> 4): scout, node phase, layout, found scan, general levels; [5] narrow batches,
                        // [6] narrow levels, [7] general levels
@@ -121,7 +126,7 @@ struct SliceLayout {   // byte offsets inside one scratch slice; identical for e
   unsigned long long bytes;
   uint32_t cap_cells, hash_log2, max_levels, max_fuz1;
   unsigned long long off_hash, off_ck, off_cc, off_cn, off_cp, off_cflags, off_packidx, off_packlist, off_packlevel,
-      off_lstart, off_nB, off_thit, off_lk, off_rk, off_rbk[2], off_rbm[2];
+      off_lstart, off_nB, off_nT, off_tcell, off_thit, off_lk, off_rk, off_rbk[2], off_rbm[2];
 };
 
 struct FillParams {
@@ -137,6 +142,9 @@ struct FillParams {
   unsigned long long pack_cap;
   unsigned long long *pack_cursor;
   uint32_t *queue_head;
+  char *fills;                 // fill arena of the device-side tracebacks (may be null: every gap is packed)
+  unsigned long long fill_cap;
+  unsigned long long *fill_cursor;
 };
 
 #ifndef G2S_CHAIN_LEN
@@ -191,6 +199,9 @@ struct GShared {       // per group, in shared memory
   uint32_t trow;        // entries per target row: Dmax - tlo + 1
   // handed from the right pass / the forward pass to the rest of the gap (the two may run on different warps)
   int32_t levels_r, levels_f, top_level, fwd_overflow;
+  // device-side traceback
+  int32_t t_lo, t_left_fuz; uint32_t t_cnt, t_bad, t_ok;
+  unsigned long long fill_off;
   unsigned long long cyc_right;
   NarrowBuf nbuf[2];    // [0] right pass, [1] forward pass and backward marking
 };
@@ -202,6 +213,7 @@ struct Slice {         // typed view of one scratch slice
   uint32_t *cc, *cn;
   uint32_t *cp;        // 4 per cell
   uint32_t *cflags, *packidx, *packlist, *packlevel, *lstart, *nB, *thit;
+  uint32_t *nT, *tcell;   // trellis (CF_T) cells per level and one of them: a level-by-level chain needs no random choice
   uint64_t *lk, *rk;   // oriented flank k-mers; bit 63 set = present in the graph; bits 62..: unused
   uint32_t cap_cells, max_levels;
   // right-border ping-pong buffers (oriented k-mer, in-mask); their own arrays: the right pass may run concurrently
@@ -225,6 +237,8 @@ G2S_HD Slice make_slice(unsigned char *base, const SliceLayout &L) {
   s.packlevel = (uint32_t *)(base + L.off_packlevel);
   s.lstart = (uint32_t *)(base + L.off_lstart);
   s.nB = (uint32_t *)(base + L.off_nB);
+  s.nT = (uint32_t *)(base + L.off_nT);
+  s.tcell = (uint32_t *)(base + L.off_tcell);
   s.thit = (uint32_t *)(base + L.off_thit);
   s.lk = (uint64_t *)(base + L.off_lk);
   s.rk = (uint64_t *)(base + L.off_rk);
@@ -256,6 +270,8 @@ inline SliceLayout make_layout(uint64_t cap_cells, uint32_t hash_log2, uint32_t 
   L.off_packlevel = take(cap_cells * 4);
   L.off_lstart = take(((size_t)max_levels + 3) * 4);
   L.off_nB = take(((size_t)max_levels + 3) * 4);
+  L.off_nT = take(((size_t)max_levels + 3) * 4);
+  L.off_tcell = take(((size_t)max_levels + 3) * 4);
   L.off_thit = take((size_t)max_fuz1 * ((size_t)max_levels + 1) * 4);
   L.off_lk = take((size_t)max_fuz1 * 8);
   L.off_rk = take((size_t)max_fuz1 * 8);
@@ -809,8 +825,10 @@ G2S_D int narrow_forward(const Table &T, const Slice &S, GShared &sh, NarrowBuf 
 // bits are not read any more once the backward sweep runs).  A node marked on two levels makes the path subgraph a
 // general graph (vertex identity is the node, Gap2Seq.cpp:1222-1297); the pack phase sees that as a marked cell whose
 // level differs from its node's.  No value is returned, so the sweep never waits for the atomic.
-G2S_D void mark_node_level(const Slice &S, uint32_t en, int level) {
-  a_max(&S.ent[en].flags, ((uint32_t)(level + 1) << 8) | 0xFFu);
+G2S_D void mark_node_level(const Slice &S, GShared &sh, uint32_t en, int level) {
+  const uint32_t old = a_max(&S.ent[en].flags, ((uint32_t)(level + 1) << 8) | 0xFFu);
+  // the sweep runs top down: a mark already there comes from a higher level -> the node is a vertex of two levels
+  if ((old >> 8) != 0 && (old >> 8) != (uint32_t)(level + 1)) a_or(&sh.status, GS_GENERAL);
 }
 
 G2S_D uint32_t popc32(uint32_t x) {
@@ -818,6 +836,14 @@ G2S_D uint32_t popc32(uint32_t x) {
   return (uint32_t)__popc(x);
 #else
   return (uint32_t)__builtin_popcount(x);
+#endif
+}
+
+G2S_D uint32_t low_bit(uint32_t x) {   // index of the lowest set bit, x != 0
+#ifdef __CUDA_ARCH__
+  return (uint32_t)__ffs((int)x) - 1u;
+#else
+  return (uint32_t)__builtin_ctz(x);
 #endif
 }
 
@@ -974,6 +1000,7 @@ G2S_D int narrow_backward(const Slice &S, GShared &sh, NarrowBuf &nb, int d, int
     const int level = d - t;
     const uint32_t lo = nb.nw_off[t], npw = nb.ch_a[t][1];
     if (mB) { S.nB[level] = popc32(mB); nbt += popc32(mB); }
+    if (mT) { S.nT[level] = popc32(mT); S.tcell[level] = lo + low_bit(mT); }
     uint32_t pi = base + nb.nw_poff[t];
 #pragma unroll
     for (int i = 0; i < NARROW_W; i++) {
@@ -983,7 +1010,7 @@ G2S_D int narrow_backward(const Slice &S, GShared &sh, NarrowBuf &nb, int d, int
       a_or(&S.cflags[idx], bits);
       S.packidx[idx] = pi; S.packlist[pi] = idx; S.packlevel[pi] = (uint32_t)level;
       pi++;
-      if (bits & CF_B) { mark_node_level(S, nb.ch_e[t][i], level); ned += (npw >> (4 * i)) & 15u; }
+      if (bits & CF_B) { mark_node_level(S, sh, nb.ch_e[t][i], level); ned += (npw >> (4 * i)) & 15u; }
       if (t == len - 1) {
 #pragma unroll
         for (int z = 0; z < 4; z++) { const uint32_t p = nb.bk_p[i][z]; if (p != NONE32) a_or(&S.cflags[p], bits); }
@@ -1039,7 +1066,7 @@ G2S_D void gap_init(const FillParams &P, const GapCtx &cx, const Slice &S, GShar
   for (uint32_t i = rank; i < S.hcap; i += gsz) { hz[2 * i] = z0; hz[2 * i + 1] = z1; }
   const size_t nth = cx.trow * (size_t)(cx.rmf + 1);
   for (size_t i = rank; i < nth; i += gsz) S.thit[i] = 0;
-  for (int i = rank; i <= cx.Dmax + 1; i += gsz) { S.nB[i] = 0; S.lstart[i] = 0; }
+  for (int i = rank; i <= cx.Dmax + 1; i += gsz) { S.nB[i] = 0; S.nT[i] = 0; S.lstart[i] = 0; }
   for (int d = rank; d <= cx.lmf; d += gsz) {
     uint64_t x = kmer_from_ascii(cx.lstr + d, k);
     uint32_t adj;
@@ -1424,7 +1451,7 @@ G2S_D unsigned long long gap_backward_pack(const FillParams &P, const GapCtx &cx
         if (f & CF_B) {
           a_add(&S.nB[d], 1);
           a_add(&sh.nB, 1);
-          mark_node_level(S, en, d);
+          mark_node_level(S, sh, en, d);
           if (start) { a_add(&sh.n_src, 1); a_maxi(&sh.max_src_level, d); }
           else {
             uint32_t np = 0;
@@ -1433,6 +1460,7 @@ G2S_D unsigned long long gap_backward_pack(const FillParams &P, const GapCtx &cx
             a_add(&sh.n_edges, np);
           }
         }
+        if (f & CF_T) { a_add(&S.nT[d], 1); S.tcell[d] = i; }
         if ((f & CF_T) && !start) {
 #pragma unroll
           for (int q = 0; q < 4; q++) if (p[q] != NONE32) a_or(&S.cflags[p[q]], CF_T);
@@ -1441,6 +1469,71 @@ G2S_D unsigned long long gap_backward_pack(const FillParams &P, const GapCtx &cx
       G::sync();
     }
     t_back = now_cycles();
+
+    // ---- traceback on the device.  The reference's random traceback (Gap2Seq.cpp:1437-1517) walks the trellis of
+    // CF_T cells from the accepted target down to a start cell and draws rand() at every step; when every level of
+    // that trellis holds exactly one cell (and there is one path length) no draw can change anything: the fill is
+    // that chain's last bases, upper case within k levels below a safe vertex (or the path's end), and the number of
+    // draws is the chain's length.  The group writes the fill string itself, one level per thread, and the gap
+    // needs neither pack records nor a host traceback - the host only advances rand() by the reported count.
+    const int max_src_t = ld_sh(&sh.max_src_level), min_sink_t = ld_sh(&sh.min_sink_level);
+    const bool sink_safe_t = ld_sh(&sh.n_sink) > 0;
+    const bool general_now = G::any((ld_sh(&sh.status) & GS_GENERAL) != 0);
+    if (P.fills != nullptr && n_plen == 1 && (skip_confident || !general_now)) {
+      const int d0 = p0;
+      if (rank == 0) { sh.t_lo = 0x7fffffff; sh.t_cnt = 0; sh.t_bad = 0; sh.t_ok = 0; }
+      G::sync();
+      int lo_l = 0x7fffffff; uint32_t c1 = 0, bad = 0;
+      for (int d = rank; d <= d0; d += gsz) {
+        const uint32_t n = ld_cg(&S.nT[d]);
+        if (n) lo_l = d < lo_l ? d : lo_l;
+        c1 += n == 1 ? 1u : 0u;
+        bad |= n > 1 ? 1u : 0u;
+      }
+      if (lo_l != 0x7fffffff) a_mini(&sh.t_lo, lo_l);
+      if (c1) a_add(&sh.t_cnt, c1);
+      if (bad) a_or(&sh.t_bad, 1u);
+      G::sync();
+      if (rank == 0) {
+        const int d_end = sh.t_lo;
+        bool ok = !sh.t_bad && d_end <= lmf && d_end <= d0 && sh.t_cnt == (uint32_t)(d0 - d_end + 1);
+        if (ok) {   // the chain must end on a start cell (otherwise: "Unable to backtrace", left to the host)
+          const uint32_t idx = ld_cg(&S.tcell[d_end]);
+          ok = ld_cg(&S.ent[ld_cg(&S.cn[idx])].key) == canonical(S.lk[d_end] & FLANK_KMER, k).key;
+        }
+        if (ok) {
+          const unsigned long long need = (unsigned long long)(d0 - d_end) + 1;
+          const unsigned long long off = a_add64(P.fill_cursor, need);
+          if (off + need > P.fill_cap) ok = false;
+          else { sh.fill_off = off; sh.t_left_fuz = lmf - d_end; }
+        }
+        sh.t_ok = ok ? 1u : 0u;
+      }
+      G::sync();
+      if (ld_sh(&sh.t_ok)) {
+        const int d_end = ld_sh(&sh.t_lo);
+        for (int d = d_end + 1 + rank; d <= d0; d += gsz) {   // safe vertex? (the rule of the pack records below)
+          bool safe = skip_confident;
+          if (!safe) {
+            const uint32_t lv = ld_cg(&S.ent[ld_cg(&S.cn[ld_cg(&S.tcell[d])])].flags) >> 8;
+            if (lv == 0) safe = sink_safe_t;
+            else { const int bl = (int)lv - 1; safe = ld_cg(&S.nB[bl]) == 1 && bl >= max_src_t && bl <= min_sink_t; }
+          }
+          S.nT[d] = safe ? 2u : 1u;
+        }
+        G::sync();
+        char *outc = P.fills + ld_sh(&sh.fill_off);
+        for (int d = d_end + 1 + rank; d <= d0; d += gsz) {
+          bool up = d0 - d < k;
+          for (int z = d; !up && z <= d0 && z < d + k; z++) up = ld_cg(&S.nT[z]) == 2u;
+          const uint32_t b = (uint32_t)(ld_cg(&S.ck[ld_cg(&S.tcell[d])]) & 3u);
+          const char ch = b == 0 ? 'A' : b == 1 ? 'C' : b == 2 ? 'T' : 'G';
+          outc[d - 1 - d_end] = up ? ch : (char)(ch | 0x20);
+        }
+        if (rank == 0) { outc[d0 - d_end] = 0; sh.npack = 0; a_or(&sh.status, GS_TRACED); }
+        G::sync();
+      }
+    }
 
     // ---- pack: append the marked cells to the output arena
     const uint32_t npack = ld_sh(&sh.npack);
@@ -1516,6 +1609,13 @@ G2S_D void gap_finish(const Slice &S, GShared &sh, GapOut *out, const unsigned l
     o.top_level = (uint32_t)sh.top_level;
     o.pack_off = sh.pack_off;
     o.levels_r = (uint32_t)sh.levels_r; o.levels_f = (uint32_t)sh.levels_f;
+    o.fill_off = 0; o.fill_len = 0; o.left_fuz = 0; o.rand_calls = 0; o.pad0 = 0;
+    if (sh.status & GS_TRACED) {
+      o.fill_off = sh.fill_off; o.left_fuz = sh.t_left_fuz;
+      o.fill_len = (uint32_t)(sh.plen[0] - (sh.t_lo));
+      o.rand_calls = 1u + o.fill_len;
+      o.start_pack[0] = o.start_pack[1] = NONE32;
+    }
     const unsigned long long t_end = now_cycles();
     // t[0] start, t[1] after init, t[2] before the forward pass, t[3] after it, t[4] after the backward marking
     o.cyc[0] = (uint32_t)((t[1] - t[0]) >> 4); o.cyc[1] = (uint32_t)(sh.cyc_right >> 4);

@@ -5,6 +5,7 @@
 //                    predecessor trellis; the only consumer of libc rand()
 #pragma once
 #include <algorithm>
+#include <cstddef>
 #include <cstdlib>
 #include <cstring>
 #include <atomic>
@@ -232,36 +233,44 @@ struct LibcRand {
   int next() { return rand(); }
   void skip(size_t n) { RandSkipper::skip(n); }
 };
+// grow-only uninitialised storage that survives from call to call: fresh multi-megabyte allocations cost a page fault
+// per 4 KB on first touch, which on the measured host was several times the work done in them
+template <class T>
+struct RawBuf {
+  T *p = nullptr;
+  size_t cap = 0;
+  RawBuf() {}
+  RawBuf(const RawBuf &) = delete;
+  RawBuf &operator=(const RawBuf &) = delete;
+  ~RawBuf() { free(p); }
+  T *ensure(size_t n, size_t keep = 0) {   // room for n elements; the first `keep` survive a reallocation
+    if (n > cap) {
+      const size_t ncap = n + n / 2 + 64;
+      T *q = (T *)malloc(ncap * sizeof(T));
+      if (p && keep) memcpy(q, p, keep * sizeof(T));
+      free(p);
+      p = q; cap = ncap;
+    }
+    return p;
+  }
+};
+
 struct RandCursor {
-  const int32_t *vals;
+  const uint32_t *s;   // generator words of the stream (RandAhead); rand() returns word >> 1
   size_t pos;
-  int next() { return vals[pos++]; }
+  int next() { return (int)(s[pos++] >> 1); }
   void skip(size_t n) { pos += n; }
 };
 
 // The next values of libc rand(), computed from a private copy of the generator's table without consuming them.
-// extend(n) makes values [0, n) available (it can run on another thread while the device pass is in flight: it does
-// not touch libc); commit(used) finally advances libc by `used` values, restarting from a checkpoint of the private
-// table, so the application's stream continues exactly as after `used` rand() calls.  Only valid where RandSkipper's
-// self test recognised glibc's additive-feedback generator.
+// glibc's default generator is the additive feedback s[i] = s[i-3] + s[i-31] (mod 2^32), rand() = s[i] >> 1, kept in a
+// circular table of 31 words; laid out as a plain array in stream order the recurrence is one add per value with no
+// index arithmetic.  extend(n) makes words [0, n) available (it can run on another thread while the device pass is
+// in flight: it does not touch libc); commit(used) writes the last 31 words back into libc's table and moves its
+// rear index, so the application's stream continues exactly as after `used` rand() calls.  Only valid where
+// RandSkipper's self test recognised that generator; enabled() checks the whole mechanism once more.
 class RandAhead {
  public:
-  static const size_t CKPT = 4096;
-  bool begin() { return enabled() && begin_unchecked(); }
-  bool begin_unchecked() {
-    vals_.clear(); ck_.clear(); ok_ = false;
-    if (!RandSkipper::enabled()) return false;
-    int32_t *info = (int32_t *)setstate(RandSkipper::dummy());
-    if (!info) return false;
-    const int type = info[0] % 5, rear = info[0] / 5;
-    if (type == 3 && rear >= 0 && rear < 31) {
-      memcpy(st_, info + 1, sizeof st_);
-      r_ = rear; f_ = (rear + 3) % 31;
-      ok_ = true;
-    }
-    setstate((char *)info);
-    return ok_;
-  }
   // decided once, on a private generator state (the application's stream is restored): do the values computed ahead
   // equal what rand() returns, and does commit() leave libc where that many calls would have left it?
   static bool enabled() {
@@ -272,67 +281,79 @@ class RandAhead {
       static int32_t bufa[34];
       char *app = initstate(4242u, (char *)bufa, 128);
       if (!app) return;
-      const size_t n = 2 * CKPT + 77;
-      std::vector<int> ref(n + 8);
-      for (size_t i = 0; i < n + 8; i++) ref[i] = rand();
-      initstate(4242u, (char *)bufa, 128);
-      RandAhead a;
-      bool ok = a.begin_unchecked();
-      if (ok) { a.extend(100); a.extend(n + 8); }
-      for (size_t i = 0; i < n + 8 && ok; i++) ok = a.vals_[i] == ref[i];
-      if (ok) ok = a.commit(n);
-      for (size_t i = n; i < n + 8 && ok; i++) ok = rand() == ref[i];
+      bool ok = true;
+      for (size_t n : {(size_t)5, (size_t)31, (size_t)8269}) {
+        std::vector<int> ref(n + 8);
+        initstate(4242u, (char *)bufa, 128);
+        for (size_t i = 0; i < n + 8; i++) ref[i] = rand();
+        initstate(4242u, (char *)bufa, 128);
+        RandAhead a;
+        ok = ok && a.begin_unchecked();
+        if (ok) { a.extend(3); a.extend(n + 8); }
+        for (size_t i = 0; i < n + 8 && ok; i++) ok = (int)(a.data()[i] >> 1) == ref[i];
+        if (ok) ok = a.commit(n);
+        for (size_t i = n; i < n + 8 && ok; i++) ok = rand() == ref[i];
+      }
       setstate(app);
       good = ok;
     });
     return good;
   }
-  bool ok() const { return ok_; }
-  size_t size() const { return vals_.size(); }
-  const int32_t *data() const { return vals_.data(); }
-  void extend(size_t n) {
-    if (!ok_ || n <= vals_.size()) return;
-    size_t i = vals_.size();
-    vals_.resize(n);
-    int f = f_, r = r_;
-    for (; i < n; i++) {
-      if (i % CKPT == 0) { Ckpt c; memcpy(c.st, st_, sizeof st_); c.f = f; c.r = r; ck_.push_back(c); }
-      st_[f] += st_[r];
-      vals_[i] = (int32_t)(st_[f] >> 1);
-      if (++f == 31) f = 0;
-      if (++r == 31) r = 0;
+  bool begin() { return enabled() && begin_unchecked(); }
+  bool begin_unchecked() {
+    n_ = 0; ok_ = false;
+    if (!RandSkipper::enabled()) return false;
+    int32_t *info = (int32_t *)setstate(RandSkipper::dummy());
+    if (!info) return false;
+    const int type = info[0] % 5, rear = info[0] / 5;
+    if (type == 3 && rear >= 0 && rear < 31) {
+      const uint32_t *st = (const uint32_t *)(info + 1);
+      r0_ = rear; f0_ = (rear + 3) % 31;
+      uint32_t *b = buf_.ensure(31);
+      for (int j = -31; j < 0; j++) b[31 + j] = st[((f0_ + j) % 31 + 31) % 31];   // word of step j sits at (f0 + j) mod 31
+      ok_ = true;
     }
-    f_ = f; r_ = r;
+    setstate((char *)info);
+    return ok_;
+  }
+  bool ok() const { return ok_; }
+  size_t size() const { return n_; }
+  const uint32_t *data() const { return buf_.p + 31; }
+  void extend(size_t n) {
+    if (!ok_ || n <= n_) return;
+    uint32_t *b = buf_.ensure(31 + n, 31 + n_);
+    // s[i] = s[i-31] + s[i-3]: the three most recent words stay in registers, so that the loop is one load, one add
+    // and one store per word instead of a store-to-load forwarding chain
+    size_t i = n_;
+    uint32_t *w = b + 31;
+    uint32_t a0 = w[(ptrdiff_t)i - 3], a1 = w[(ptrdiff_t)i - 2], a2 = w[(ptrdiff_t)i - 1];
+    for (; i + 3 <= n; i += 3) {
+      a0 += w[(ptrdiff_t)i - 31]; a1 += w[(ptrdiff_t)i - 30]; a2 += w[(ptrdiff_t)i - 29];
+      w[i] = a0; w[i + 1] = a1; w[i + 2] = a2;
+    }
+    for (; i < n; i++) w[i] = w[(ptrdiff_t)i - 31] + w[(ptrdiff_t)i - 3];
+    n_ = n;
   }
   // advance libc's generator by `used` <= size() values
   bool commit(size_t used) {
     if (!ok_) return false;
     if (used == 0) return true;
-    if (used > vals_.size()) return false;
+    if (used > n_) return false;
     int32_t *info = (int32_t *)setstate(RandSkipper::dummy());
     if (!info) return false;
-    const Ckpt &c = ck_[used / CKPT < ck_.size() ? used / CKPT : ck_.size() - 1];
-    size_t at = (size_t)(&c - ck_.data()) * CKPT;
     uint32_t *st = (uint32_t *)(info + 1);
-    memcpy(st, c.st, sizeof c.st);
-    int f = c.f, r = c.r;
-    for (; at < used; at++) {
-      st[f] += st[r];
-      if (++f == 31) f = 0;
-      if (++r == 31) r = 0;
-    }
-    info[0] = r * 5 + 3;
+    const uint32_t *sw = data();
+    for (size_t j = used > 31 ? used - 31 : 0; j < used; j++) st[(f0_ + j) % 31] = sw[j];
+    info[0] = (int32_t)((r0_ + used) % 31) * 5 + 3;
     setstate((char *)info);
     ok_ = false;
     return true;
   }
 
  private:
-  struct Ckpt { uint32_t st[31]; int f, r; };
-  std::vector<int32_t> vals_;
-  std::vector<Ckpt> ck_;
-  uint32_t st_[31];
-  int f_ = 0, r_ = 0;
+  RawBuf<uint32_t> buf_;        // 31 words of history, then the stream; kept from call to call
+  size_t n_ = 0;
+  int f0_ = 0, r0_ = 0;
   bool ok_ = false;
 };
 
@@ -340,7 +361,7 @@ class RandAhead {
 // reference leaves at &fill[left_max_fuz - left_fuz].
 template <class RS>
 inline void finish_one(const g2s_gap &g, const GapOut &o, const PackRec *pk, int k, int tier, const GeneralResult &gen,
-                       g2s_result &r, char *fill_out, std::vector<char> &buf, RS &rs) {
+                       g2s_result &r, char *fill_out, std::vector<char> &buf, RS &rs, const char *dev_fill = nullptr) {
   static const char NT[4] = {'A', 'C', 'T', 'G'};
   memset(&r, 0, sizeof(r));
   const bool skip_confident = (g.flags & G2S_GAP_SKIP_CONFIDENT) != 0, all_paths = (g.flags & G2S_GAP_ALL_PATHS) != 0;
@@ -366,6 +387,16 @@ inline void finish_one(const g2s_gap &g, const GapOut &o, const PackRec *pk, int
     }
     r.substats_valid = 1;
     if (all_paths) count = (int)o.count_all;   // the Phase B recount replaces the first-found count (Gap2Seq.cpp:1192)
+  }
+  if (o.status & GS_TRACED) {   // no choice anywhere: the device wrote the fill, only the rand() stream moves on
+    if (!dev_fill) { r.status |= G2S_ST_UNABLE_TO_BACKTRACE; r.count = 0; return; }   // cannot happen: the arena travels with the batch
+    r.rand_calls = (int32_t)o.rand_calls;
+    rs.skip(o.rand_calls);
+    r.left_fuz = o.left_fuz;
+    r.fill_len = (int32_t)o.fill_len;
+    if (fill_out) { memcpy(fill_out, dev_fill, (size_t)o.fill_len); fill_out[o.fill_len] = 0; }
+    r.count = count;
+    return;
   }
   r.rand_calls = 1;
   size_t pending = 0;   // rand() values whose result cannot matter (a single choice): consumed in bulk
@@ -420,6 +451,7 @@ struct HostBatch {
   std::vector<GapOut> outs;
   std::vector<int> tier;                      // tier that produced the gap; -2 = outgrew the largest tier
   std::vector<int> pack_of;                   // index into packs
+  std::vector<const char *> fill_base;        // fill arena per device pass (gaps the device traced itself, GS_TRACED)
   std::vector<const PackRec *> pack_base;     // one arena per device pass (pinned staging owned by the engine's pool,
   std::vector<std::vector<PackRec>> own;      //  or `own` when the producer has no pool)
   std::function<void()> on_free;              // hands the staging buffers back
@@ -432,6 +464,9 @@ struct HostBatch {
   HostBatch &operator=(const HostBatch &) = delete;
   ~HostBatch() { if (on_free) on_free(); }
   const PackRec *pack_ptr(size_t i) const { return pack_base[pack_of[i]] + outs[i].pack_off; }
+  const char *fill_ptr(size_t i) const {
+    return (outs[i].status & GS_TRACED) && !fill_base.empty() && fill_base[pack_of[i]] ? fill_base[pack_of[i]] + outs[i].fill_off : nullptr;
+  }
   // call when the batch has been traced: the staging buffers leave the CPU caches before they are reused
   void flush_staging(ThreadPool *pool) {
     const size_t chunk = 64 << 10;
@@ -489,7 +524,7 @@ struct HostBatch {
       return;
     }
     LibcRand rs;
-    finish_one(gaps[i], outs[i], pack_ptr(i), k, tier[i], gen[i], r, fill_out, buf, rs);
+    finish_one(gaps[i], outs[i], pack_ptr(i), k, tier[i], gen[i], r, fill_out, buf, rs, fill_ptr(i));
   }
 
   // the same from a precomputed window of the rand() stream; thread safe (scratch is the caller's)
@@ -500,7 +535,7 @@ struct HostBatch {
       r.count = -1; r.status = G2S_ST_MEM_LIMIT;
       return;
     }
-    finish_one(gaps[i], outs[i], pack_ptr(i), k, tier[i], gen[i], r, fill_out, scratch, rc);
+    finish_one(gaps[i], outs[i], pack_ptr(i), k, tier[i], gen[i], r, fill_out, scratch, rc, fill_ptr(i));
   }
   // upper bound of the rand() values gap i's traceback can consume (one per step plus the length choice)
   size_t rand_bound(size_t i) const {
@@ -518,6 +553,7 @@ struct HostBatch {
     if (tier[i] == -2) return true;
     const GapOut &o = outs[i];
     if (o.count_fwd == 0 || o.n_plen == 0) return true;
+    if (o.status & GS_TRACED) { *calls = o.rand_calls; return true; }
     *calls = (size_t)std::max(1, 1 + o.plen[0] - gaps[i].left_max_fuz);
     if (o.n_plen != 1 || o.start_pack[0] == NONE32) return false;
     const PackRec *pk = pack_ptr(i);
@@ -552,7 +588,7 @@ struct TraceJob { HostBatch *hb; size_t idx; };
 struct TraceStats { std::atomic<unsigned long long> calls{0}, parallel_calls{0}, rounds{0}, retraced{0}; };
 inline TraceStats &trace_stats() { static TraceStats s; return s; }   // observability for the tests
 
-inline void trace_many(const std::vector<TraceJob> &jobs, std::vector<g2s_result> &res, std::vector<char> &arena,
+inline void trace_many(const std::vector<TraceJob> &jobs, std::vector<g2s_result> &res, RawBuf<char> &arena_buf,
                        std::vector<size_t> &fill_off, ThreadPool *pool, RandAhead *ahead) {
   const size_t n = jobs.size();
   res.resize(n);
@@ -560,7 +596,7 @@ inline void trace_many(const std::vector<TraceJob> &jobs, std::vector<g2s_result
   size_t tot = 0;
   for (size_t j = 0; j < n; j++) { fill_off[j] = tot; tot += jobs[j].hb->fill_bytes(jobs[j].idx); }
   fill_off[n] = tot;
-  arena.resize(tot + 1);
+  char *arena = arena_buf.ensure(tot + 1);
   RandAhead local;
   if (!ahead) { ahead = &local; if (pool && n >= 4) local.begin(); }
   trace_stats().calls++;
@@ -580,7 +616,7 @@ inline void trace_many(const std::vector<TraceJob> &jobs, std::vector<g2s_result
   size_t bound = 0;
   for (size_t j = 0; j < n; j++) bound += bounds[j];
   ahead->extend(bound + 1);
-  const int32_t *vals = ahead->data();
+  const uint32_t *vals = ahead->data();
   size_t final_upto = 0, base = 0;
   trace_stats().parallel_calls++;
   auto trace_one = [&](size_t j, std::vector<char> &scratch) {

@@ -14,6 +14,7 @@
 #include <cctype>
 #include <chrono>
 #include <cstdio>
+#include <cstring>
 #include <functional>
 #include <memory>
 #include <string>
@@ -22,6 +23,23 @@
 #include "g2s_finish.h"
 
 namespace g2s {
+
+// a caller's NUL-terminated string, not copied (records are megabytes per batch)
+struct StrRef {
+  const char *p = "";
+  size_t n = 0;
+  StrRef() {}
+  StrRef(const char *s) : p(s ? s : ""), n(s ? strlen(s) : 0) {}
+  StrRef(const std::string &s) : p(s.data()), n(s.size()) {}
+  size_t size() const { return n; }
+  const char *data() const { return p; }
+  char operator[](size_t i) const { return p[i]; }
+  std::string substr(size_t pos, size_t len = std::string::npos) const {
+    if (pos > n) pos = n;
+    return std::string(p + pos, std::min(len, n - pos));
+  }
+  std::string str() const { return std::string(p, n); }
+};
 
 struct RunOptions {
   int k = 31, d_err = 500, max_fuz = 10;
@@ -50,7 +68,8 @@ inline bool is_gap_char(char c) { return c == 'N' || c == 'n'; }
 // src/Gap2Seq.cpp:100-156
 inline void format_statistics(std::string &log, int filledStart, int gapStart, int gapEnd, int paths, const char *fill,
                               int fill_len, int k, int lmf, int rmf, int lf, int rf, bool skip_confident, bool unique_paths,
-                              const g2s_subgraph_stats &ss, int gap, const std::string &comment) {
+                              const g2s_subgraph_stats &ss, int gap, const StrRef &comment_ref) {
+  const std::string comment = comment_ref.str();
   char buf[1024];
   if (paths > 0 && (!unique_paths || paths == 1)) {
     const int filledLen = fill_len - k;
@@ -87,16 +106,17 @@ inline void format_statistics(std::string &log, int filledStart, int gapStart, i
 }
 
 struct ScaffoldRun {
-  const std::vector<std::string> &seqs;
-  const std::vector<std::string> &comments;
+  const std::vector<StrRef> &seqs;
+  const std::vector<StrRef> &comments;
   RunOptions opt;
   std::vector<RecScan> recs;
   std::vector<std::unique_ptr<HostBatch>> batches;
-  double phase1_ms = 0, phase2_ms = 0, trace_ms = 0;  // wall time of the two phases of run() (profiling aid)
+  double phase1_ms = 0, phase2_ms = 0, trace_ms = 0, wait_ms = 0, flush_ms = 0;  // wall time of the two phases of run() (profiling aid)
   ThreadPool *pool = nullptr;                         // host threads for the tracebacks and the per-record replay
-  RandAhead ahead;                                    // the libc rand() values the tracebacks will consume
+  RandAhead own_ahead, *aheadp = &own_ahead;          // the libc rand() values the tracebacks will consume; callers that
+  RawBuf<char> own_arena, *arenap = &own_arena;       // run many times hand in persistent ones (no page faults per call)
 
-  ScaffoldRun(const std::vector<std::string> &s, const std::vector<std::string> &c, const RunOptions &o)
+  ScaffoldRun(const std::vector<StrRef> &s, const std::vector<StrRef> &c, const RunOptions &o)
       : seqs(s), comments(c), opt(o), recs(s.size()) {}
   ~ScaffoldRun() { if (pool) pool->wait_async(); }
 
@@ -104,7 +124,7 @@ struct ScaffoldRun {
 
   // Phase 1 helper: scan record r as far as its gaps are decided, appending requests to `out`.
   void scan(size_t r, std::vector<std::pair<size_t, int>> &out) {
-    const std::string &seq = seqs[r];
+    const StrRef &seq = seqs[r];
     RecScan &rs = recs[r];
     const int k = opt.k, fuz = opt.max_fuz;
     while (rs.i < seq.size()) {
@@ -159,7 +179,7 @@ struct ScaffoldRun {
     const int k = opt.k;
     const auto t_begin = std::chrono::steady_clock::now();
     size_t rand_bound = 0;
-    if (pool) ahead.begin();
+    if (pool) aheadp->begin();
     // ---- phase 1: device waves
     for (;;) {
       std::vector<std::pair<size_t, int>> wave;
@@ -184,7 +204,7 @@ struct ScaffoldRun {
       std::vector<g2s_gap> gaps(wave.size());
       for (size_t j = 0; j < wave.size(); j++) {
         GapReq &q = recs[wave[j].first].reqs[wave[j].second];
-        const std::string &seq = seqs[wave[j].first];
+        const StrRef &seq = seqs[wave[j].first];
         q.batch = b; q.idx = (int)j;
         g2s_gap &g = gaps[j];
         g.kmer_left = seq.data() + q.kmer_start;   // k + lmf / k + rmf characters inside the record (not NUL terminated)
@@ -196,10 +216,10 @@ struct ScaffoldRun {
       }
       // the rand() values this wave's tracebacks can consume are computed while the device pass runs
       for (const g2s_gap &g : gaps) rand_bound += (size_t)g.gap_len + g.gap_err + g.left_max_fuz + g.right_max_fuz + 2;
-      if (pool && ahead.ok()) {
+      if (pool && aheadp->ok()) {
         pool->wait_async();
         const size_t want = rand_bound + 1;
-        pool->run_async([this, want] { ahead.extend(want); });
+        pool->run_async([this, want] { aheadp->extend(want); });
       }
       int rc = submit(gaps, *batches.back());
       if (rc != 0) { if (pool) pool->wait_async(); return rc; }
@@ -215,6 +235,7 @@ struct ScaffoldRun {
     const auto t_mid = std::chrono::steady_clock::now();
     phase1_ms = std::chrono::duration<double, std::milli>(t_mid - t_begin).count();
     if (pool) pool->wait_async();
+    wait_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_mid).count();
     std::vector<TraceJob> jobs;
     std::vector<size_t> first_job(seqs.size() + 1, 0);
     for (size_t r = 0; r < seqs.size(); r++) {
@@ -223,10 +244,12 @@ struct ScaffoldRun {
     }
     first_job[seqs.size()] = jobs.size();
     std::vector<g2s_result> res;
-    std::vector<char> arena;
     std::vector<size_t> fill_off;
-    trace_many(jobs, res, arena, fill_off, pool, ahead.ok() ? &ahead : nullptr);
+    trace_many(jobs, res, *arenap, fill_off, pool, aheadp->ok() ? aheadp : nullptr);
+    const char *arena = arenap->p;
+    const auto t_fl = std::chrono::steady_clock::now();
     for (auto &b : batches) if (b) b->flush_staging(pool);
+    flush_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_fl).count();
     trace_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_mid).count();
 
     filled.assign(seqs.size(), std::string());
@@ -234,8 +257,8 @@ struct ScaffoldRun {
     std::vector<int> rgc(seqs.size(), 0), rfc(seqs.size(), 0);
     std::atomic<int> bad{0};
     auto one_record = [&](size_t r) {
-      const std::string &seq = seqs[r];
-      const std::string &comment = comments[r];
+      const StrRef &seq = seqs[r];
+      const StrRef &comment = comments[r];
       std::string filledSeq;
       std::string &lg = rlog[r];
       long long prev = 0;

@@ -149,9 +149,10 @@ int emul_fill_batch(void *gp, int k, const g2s_gap *gaps, size_t n, g2s_result *
   std::vector<TraceJob> jobs(n);
   for (size_t i = 0; i < n; i++) jobs[i] = TraceJob{&hb, i};
   std::vector<g2s_result> res;
-  std::vector<char> arena;
+  RawBuf<char> arena_buf;
   std::vector<size_t> off;
-  trace_many(jobs, res, arena, off, host_pool(), nullptr);
+  trace_many(jobs, res, arena_buf, off, host_pool(), nullptr);
+  const char *arena = arena_buf.p;
   for (size_t i = 0; i < n; i++) {
     results[i] = res[i];
     if (fill_out && fill_out[i]) memcpy(fill_out[i], &arena[off[i]], (size_t)res[i].fill_len + 1);
@@ -163,8 +164,8 @@ int emul_fill_batch(void *gp, int k, const g2s_gap *gaps, size_t n, g2s_result *
 int emul_fill_records(void *gp, const char *const *seqs, const char *const *comments, size_t n_records,
                       const g2s_run_options *opt, char **filled_out, char **log_out, int32_t *gapcount, int32_t *filledcount,
                       g2s_result **gap_results, size_t *n_gap_results) {
-  std::vector<std::string> s(n_records), c(n_records);
-  for (size_t i = 0; i < n_records; i++) { s[i] = seqs[i]; c[i] = comments[i]; }
+  std::vector<StrRef> s(n_records), c(n_records);
+  for (size_t i = 0; i < n_records; i++) { s[i] = StrRef(seqs[i]); c[i] = StrRef(comments[i]); }
   RunOptions ro;
   ro.k = opt->k; ro.d_err = opt->dist_error; ro.max_fuz = opt->fuz;
   ro.skip_confident = opt->skip_confident != 0; ro.unique_paths = opt->unique_paths != 0; ro.all_paths = opt->all_paths != 0;
