@@ -390,6 +390,7 @@ inline void finish_one(const g2s_gap &g, const GapOut &o, const PackRec *pk, int
   }
   if (o.status & GS_TRACED) {   // no choice anywhere: the device wrote the fill, only the rand() stream moves on
     if (!dev_fill) { r.status |= G2S_ST_UNABLE_TO_BACKTRACE; r.count = 0; return; }   // cannot happen: the arena travels with the batch
+    r.status |= G2S_ST_DEVICE_TRACED;
     r.rand_calls = (int32_t)o.rand_calls;
     rs.skip(o.rand_calls);
     r.left_fuz = o.left_fuz;

@@ -18,6 +18,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libg2s_gpu.so")
 
 ST_ORDER_DEPENDENT, ST_MEM_LIMIT, ST_GENERAL_SUBGRAPH, ST_UNABLE_TO_BACKTRACE, ST_BIG_TIER = 1, 2, 4, 8, 16
+ST_DEVICE_TRACED = 32
 GAP_SKIP_CONFIDENT, GAP_ALL_PATHS = 1, 2
 
 

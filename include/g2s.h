@@ -42,7 +42,9 @@ enum {
                                   "Memory limit exceeded", src/Gap2Seq.cpp:147); count is -1 */
   G2S_ST_GENERAL_SUBGRAPH = 4, /* informational: the path subgraph had a k-mer at several levels, SCC analysis ran */
   G2S_ST_UNABLE_TO_BACKTRACE = 8,
-  G2S_ST_BIG_TIER = 16         /* informational: the gap was re-run in the wide (one CTA per gap) tier */
+  G2S_ST_BIG_TIER = 16,        /* informational: the gap was re-run in the wide (one CTA per gap) tier */
+  G2S_ST_DEVICE_TRACED = 32    /* informational: the traceback had no choice to make (one trellis cell per level, one path
+                                  length), the device wrote the fill itself and rand() was only advanced */
 };
 
 /* gap flags */

@@ -184,3 +184,54 @@ def test_table_replication_roundtrip(case_inputs, gpu_engine):
     r2, f2 = dst.fill_batch(specs)
     assert f1 == f2 and all(f[:-w.k] == rec.truth for f, rec in zip(f1, w.gaps))
     dst.close()
+
+
+@pytest.mark.parametrize("shape", [0, 1, 2])
+def test_every_thin_cta_shape_matches_oracle(shape, case_inputs, monkeypatch):
+    """The thin tier runs a gap on 2, 6 or 12 warps (picked per pass from the batch size); G2S_THIN_SHAPE forces one.
+    cfg2_small has read errors (bubbles: chain splitting, merged chains, uncertain tracebacks)."""
+    monkeypatch.setenv("G2S_THIN_SHAPE", str(shape))
+    for name in ["cfg2_small", "cfg1_small"]:
+        case, w, g = case_inputs(name)
+        e = engine.Engine(k=w.k, max_fuz=w.fuz)
+        e.import_kmers(g.kmers())
+        specs = [s for rec in w.gaps for s in record_gaps(rec.seq, w.k, w.fuz, 500)]
+        oracle_lib.srand(21)
+        res, fills = e.fill_batch(specs)
+        oracle_lib.srand(21)
+        for s, r, f in zip(specs, res, fills):
+            o, of = g.fill_gap(s.left, s.right, s.gap_len, s.gap_err, s.left_max_fuz, s.right_max_fuz)
+            assert not o.order_dependent
+            assert (r.count, r.left_fuz, r.right_fuz, f, r.rand_calls) == (o.count, o.left_fuz, o.right_fuz, of, o.rand_calls)
+            assert (r.cells_right, r.cells_left) == (o.cells_right, o.cells_left)
+        e.close()
+
+
+def test_device_traceback_equals_host_traceback_and_rand_stream(case_inputs, monkeypatch):
+    """Gaps whose trellis is a single chain are traced by the kernel (G2S_ST_DEVICE_TRACED): same fills, counts and
+    rand() consumption as the host walk over pack records, and libc's generator ends in the same state."""
+    libc = C.CDLL(None)
+    w = synth.make_workload("cfg4", 0.01, seed=45)
+    specs = [s for rec in w.gaps for s in record_gaps(rec.seq, w.k, w.fuz, 500)]
+    case, w2, g2 = case_inputs("cfg2_small")
+    specs2 = [s for rec in w2.gaps for s in record_gaps(rec.seq, w2.k, w2.fuz, 500)]
+    outs = []
+    for host_only in (False, True):
+        if host_only:
+            monkeypatch.setenv("G2S_NO_DEVICE_TRACE", "1")
+        row = []
+        for ww, sp in ((w, specs), (w2, specs2)):
+            e = engine.Engine(k=ww.k, max_fuz=ww.fuz)
+            e.build_from_reads(ww.reads, ww.solid)
+            oracle_lib.srand(5)
+            res, fills = e.fill_batch(sp)
+            after = [libc.rand() for _ in range(4)]
+            row.append(([(r.count, r.left_fuz, r.right_fuz, r.rand_calls, r.fill_len, r.substats.astuple()) for r in res], fills,
+                        after, sum(1 for r in res if r.status & engine.ST_DEVICE_TRACED)))
+            e.close()
+        outs.append(row)
+    for dev, host in zip(outs[0], outs[1]):
+        assert dev[0] == host[0] and dev[1] == host[1] and dev[2] == host[2]
+        assert host[3] == 0
+    assert outs[0][0][3] >= 0.9 * len(specs), "error-free gaps must be traced on the device"
+    assert all(f[:-w.k] == rec.truth for f, rec, r in zip(outs[0][0][1], w.gaps, outs[0][0][0]) if r[0] == 1)

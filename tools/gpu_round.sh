@@ -14,3 +14,7 @@ python bench.py --workload cfg5 --scale 0.2 --steps 5 --warmup 3 --cpu-seconds 5
 python __graft_entry__.py smoke 2>&1 | tail -2
 fi
 tail -3 gpurun_out/${TAG}_pytest.log; tail -4 gpurun_out/${TAG}_bench.err; cut -c1-600 gpurun_out/${TAG}_bench.json; cut -c1-400 gpurun_out/${TAG}_bench_reference.json
+if [ "$2" = "full" ]; then
+timeout 900 python bench.py --workload cfg4 --scale 1.0 --steps 3 --warmup 3 --cpu-seconds 10 > gpurun_out/${TAG}_bench_cfg4_full.json 2> gpurun_out/${TAG}_bench_cfg4_full.err
+cut -c1-300 gpurun_out/${TAG}_bench_cfg4_full.json
+fi
