@@ -27,22 +27,50 @@ static const uint32_t NONE32 = 0xFFFFFFFFu;
 static const uint32_t MAX_PATHS = 2147483647u / 2u - 1u;   // src/Gap2Seq.cpp:38
 static const int MAX_FUZ = 31;
 
-// 16-byte slot of the global open-addressing table: one 32-byte sector holds two slots, so a probe that
-// hits in the first or second position costs a single sector gather.
-struct __attribute__((aligned(16))) Slot {
+// 32-byte slot of the global open-addressing table = one sector: a probe that hits in its first position costs a
+// single sector gather and brings the node's neighbourhood AND its skip hints.
+struct __attribute__((aligned(32))) Slot {
   uint64_t key;   // canonical k-mer, KEY_EMPTY when free
   uint64_t val;   // bits 0-7: adjacency byte (low nibble out A,C,T,G, high nibble in; canonical orientation)
-                  // bits 8-35 / 36-63: skip hint of the canonical / reverse-complement orientation (see hint_of)
+                  // bits 8-13 / 14-19: hint length of the canonical / reverse-complement orientation
+                  // bits 20-35 / 36-51: bits 64-79 of that orientation's hint bases
+  uint64_t h[2];  // bits 0-63 of the hint bases, per orientation
 };
 
 // Skip hints.  For an oriented k-mer x the hint lists the next j <= HINT_MAX bases of its UNIQUE forward extension:
 // x and the j-1 nodes after it each have exactly one successor (the listed base); nothing is claimed about the node
 // the last base leads to.  A walker that holds a hint can therefore emit j levels from ONE table gather - the
 // per-level dependent gather of a chain of unitig-interior nodes disappears - while every node still becomes its
-// own DP cell.  28 bits: length j in bits 24-27, the bases as a 2j-bit big-endian string in the low bits (first base
-// highest, like a k-mer), so that the state i steps ahead is ((x << 2i) | (bases >> 2(j-i))) & kmask.
-static const int HINT_MAX = 12;
-G2S_HD uint32_t hint_of(uint64_t val, uint32_t strand) { return (uint32_t)(val >> (8 + 28 * strand)) & 0xFFFFFFFu; }
+// own DP cell.  The bases form a 2j-bit big-endian string (first base highest, like a k-mer; up to 80 bits), so that
+// the state i steps ahead is ((x << 2i) | (bases >> 2(j-i))) & kmask.
+static const int HINT_MAX = 40;
+struct Hint {
+  uint64_t lo;    // bits 0-63 of the bases
+  uint32_t hi;    // bits 64-79
+  uint32_t len;   // j
+};
+G2S_HD Hint hint_of(const Slot &s, uint32_t strand) {
+  Hint h;
+  h.lo = s.h[strand];
+  h.hi = (uint32_t)(s.val >> (20 + 16 * strand)) & 0xFFFFu;
+  h.len = (uint32_t)(s.val >> (8 + 6 * strand)) & 63u;
+  return h;
+}
+G2S_HD uint64_t hint_shr(const Hint &h, uint32_t sh) {   // low 64 bits of (bases >> sh), sh < 160
+  if (sh == 0) return h.lo;
+  if (sh < 64) return (h.lo >> sh) | ((uint64_t)h.hi << (64 - sh));
+  return sh < 96 ? (uint64_t)h.hi >> (sh - 64) : 0;
+}
+// the state j (1..len) steps past tip x, and the base of step j (0-based: the base that leads to state j+1)
+G2S_HD uint64_t hint_state(uint64_t x, const Hint &h, uint32_t j, uint64_t kmask) {
+  return ((2 * j < 64 ? x << (2 * j) : 0) | hint_shr(h, 2 * (h.len - j))) & kmask;
+}
+G2S_HD uint32_t hint_base(const Hint &h, uint32_t j) { return (uint32_t)hint_shr(h, 2 * (h.len - j - 1)) & 3u; }
+G2S_HD void hint_push(Hint &h, uint32_t nt) {   // append one base
+  h.hi = ((h.hi << 2) | (uint32_t)(h.lo >> 62)) & 0xFFFFu;
+  h.lo = (h.lo << 2) | nt;
+  h.len++;
+}
 
 struct Table {
   const Slot *slots;
@@ -119,37 +147,44 @@ G2S_D int64_t table_find(const Table &t, uint64_t canon, uint32_t *adj) {
   }
 }
 
-// same, returning the whole value word (adjacency byte + skip hints)
-G2S_D int64_t table_find_val(const Table &t, uint64_t canon, uint64_t *val) {
+// same, returning the whole slot (adjacency byte + skip hints): both halves of the sector
+G2S_D int64_t table_find_slot(const Table &t, uint64_t canon, Slot *out) {
   uint64_t h = mix64(canon) & t.cap_mask;
   for (;;) {
-    Slot s = load_slot(t.slots + h);
-    if (s.key == canon) { *val = s.val; return (int64_t)h; }
+#ifdef __CUDA_ARCH__
+    Slot s;
+    asm volatile("ld.global.nc.v2.u64 {%0, %1}, [%2];" : "=l"(s.key), "=l"(s.val) : "l"(t.slots + h));
+    asm volatile("ld.global.nc.v2.u64 {%0, %1}, [%2];" : "=l"(s.h[0]), "=l"(s.h[1]) : "l"((const char *)(t.slots + h) + 16));
+#else
+    const Slot s = t.slots[h];
+#endif
+    if (s.key == canon) { *out = s; return (int64_t)h; }
     if (s.key == KEY_EMPTY) return -1;
     h = (h + 1) & t.cap_mask;
   }
 }
 
 // Skip hints of one node, computed from the adjacency bytes by walking (used by the table build kernel and by the
-// host emulation in tests/): returns the 56 hint bits to be stored at bit 8 of Slot::val.
-G2S_D uint64_t compute_hints(const Table &t, uint64_t key, uint32_t adj) {
-  uint64_t out = 0;
+// host emulation in tests/): fills the hint fields of `out` (val bits 8-51 and h[]); the adjacency byte is kept.
+G2S_D void compute_hints(const Table &t, uint64_t key, uint32_t adj, Slot *out) {
+  uint64_t val = adj & 0xFFu;
   for (uint32_t o = 0; o < 2; o++) {
     uint64_t x = o ? revcomp(key, t.k) : key;
-    uint32_t mask = out_mask(adj, o), bits = 0, len = 0;
-    while (len < (uint32_t)HINT_MAX && mask != 0 && !(mask & (mask - 1))) {
+    uint32_t mask = out_mask(adj, o);
+    Hint h{0, 0, 0};
+    while (h.len < (uint32_t)HINT_MAX && mask != 0 && !(mask & (mask - 1))) {
       const uint32_t nt = mask == 1 ? 0 : mask == 2 ? 1 : mask == 4 ? 2 : 3;
-      bits = (bits << 2) | nt;
-      len++;
+      hint_push(h, nt);
       x = succ_kmer(x, nt, t);
       const Canon c = canonical(x, t.k);
       uint32_t a2 = 0;
       if (table_find(t, c.key, &a2) < 0) break;   // cannot happen: the adjacency byte said the neighbour exists
       mask = out_mask(a2, c.strand);
     }
-    out |= (uint64_t)((bits & 0xFFFFFFu) | (len << 24)) << (28 * o);
+    out->h[o] = h.lo;
+    val |= ((uint64_t)h.len << (8 + 6 * o)) | ((uint64_t)h.hi << (20 + 16 * o));
   }
-  return out;
+  out->val = val;
 }
 
 // ASCII -> oriented k-mer value (no validity check, exactly like Graph::buildNode, Graph.cpp:1726-1744)

@@ -153,12 +153,12 @@ struct FillParams {
 static const int CHAIN_LEN = G2S_CHAIN_LEN;   // levels a narrow batch looks ahead
 static const int NARROW_W = 4;     // widest border handled in narrow mode
 
-static const int SCOUT_SEGS = 40;   // segments a chain may record per batch (a batch ends early beyond that)
-struct ScoutSeg {      // one gather of a scout: tip x, then hl hinted states on levels l0 .. l0 + hl - 1
+static const int SCOUT_SEGS = 32;   // segments a chain may record per batch (a batch ends early beyond that)
+struct ScoutSeg {      // one gather of a scout: tip x, then the hint's states on levels l0 .. l0 + h.len - 1
   uint64_t x;
-  uint32_t hb;         // the hinted bases, first base highest
+  Hint h;              // the hinted bases, first base highest
   uint16_t l0;
-  uint8_t hl, end_mask;   // end_mask: out-mask (walk orientation) of the state the hint ends at
+  uint8_t end_mask, pad;   // end_mask: out-mask (walk orientation) of the state the hint ends at
 };
 
 struct NarrowBuf {     // look-ahead state of one pass (the right pass and the forward pass own one each, so that two warps
@@ -166,7 +166,8 @@ struct NarrowBuf {     // look-ahead state of one pass (the right pass and the f
   uint32_t nnext;
   uint32_t ch_len, ch_valid, ch_base, ch_cnt, nw_stop, nw_alive;
   uint64_t nw_x[NARROW_W], nw_x0[NARROW_W];
-  uint32_t nw_m[NARROW_W], nw_cnt0[NARROW_W], nw_hb[NARROW_W], nw_hl[NARROW_W];
+  uint32_t nw_m[NARROW_W], nw_cnt0[NARROW_W];
+  Hint nw_h[NARROW_W];   // what is left of the tip's skip hint (generic scout)
   int32_t nw_fail[NARROW_W];
   int32_t nw_born[NARROW_W];   // first level (of the batch) on which the chain exists: 0, or where it split off its parent
   uint32_t nw_w;               // chains after the scout (splits add chains)
@@ -456,7 +457,7 @@ __device__ __forceinline__ int narrow_scout_warp(const Table &T, GShared &sh, Na
   int nseg = 0;
   bool active = lane < w;
   if (active) { x = nb.nw_x[lane]; mask = nb.nw_m[lane]; }
-  uint32_t hb = 0, hl = 0;    // hint of the tip (0: none)
+  Hint hint{0, 0, 0};         // hint of the tip (len 0: none)
   while (__any_sync(FULL, active)) {
     // ---- branches: split into new chains while slots remain
     const bool branch = active && (mask & (mask - 1)) != 0;
@@ -474,11 +475,11 @@ __device__ __forceinline__ int narrow_scout_warp(const Table &T, GShared &sh, Na
           continue;
         }
         uint32_t rest = mp & (mp - 1);                               // every neighbour but the first
-        if (lane == p) { mask = mp & (0u - mp); hl = 0; }            // the parent keeps the first
+        if (lane == p) { mask = mp & (0u - mp); hint.len = 0; }      // the parent keeps the first
         while (rest) {
           const uint32_t bit = rest & (0u - rest);
           rest &= rest - 1;
-          if (lane == slot) { x = xp; mask = bit; hl = 0; lv = lp; active = true; stop = maxlen; endlv = -1; nseg = 0; }
+          if (lane == slot) { x = xp; mask = bit; hint.len = 0; lv = lp; active = true; stop = maxlen; endlv = -1; nseg = 0; }
           if (lane == p) { nb.nw_x0[slot] = nb.nw_x0[p]; nb.nw_cnt0[slot] = nb.nw_cnt0[p]; nb.nw_born[slot] = lp; nb.nw_par[slot] = (uint32_t)p; }
           slot++;
         }
@@ -491,20 +492,20 @@ __device__ __forceinline__ int narrow_scout_warp(const Table &T, GShared &sh, Na
       else if (nseg >= SCOUT_SEGS) { stop = lv; active = false; }    // out of segment slots: a shorter batch
     }
     if (active) {
-      if (hl == 0) { hb = mask == 1 ? 0 : mask == 2 ? 1 : mask == 4 ? 2 : 3; hl = 1; }   // no hint: one known step
+      if (hint.len == 0) { hint.lo = mask == 1 ? 0 : mask == 2 ? 1 : mask == 4 ? 2 : 3; hint.hi = 0; hint.len = 1; }   // no hint: one known step
       // the node the hint ends at
-      const uint64_t xe = ((x << (2 * hl)) | (uint64_t)hb) & T.kmask;
+      const uint64_t xe = hint_state(x, hint, hint.len, T.kmask);
       const Canon ce = canonical(xe, k);
-      uint64_t val = 0;
+      Slot sl;
       uint32_t emask = 0;
-      if (table_find_val(T, ce.key, &val) < 0) a_or(&sh.status, GS_INTERNAL);
-      else emask = out_mask((uint32_t)(val & 0xFF), ce.strand);
+      const bool hit = table_find_slot(T, ce.key, &sl) >= 0;
+      if (!hit) a_or(&sh.status, GS_INTERNAL);
+      else emask = out_mask((uint32_t)(sl.val & 0xFF), ce.strand);
       ScoutSeg &sg = nb.seg[lane][nseg++];
-      sg.x = x; sg.hb = hb; sg.hl = (uint8_t)hl; sg.l0 = (uint16_t)lv; sg.end_mask = (uint8_t)emask;
-      x = xe; lv += (int)hl; mask = emask;
-      const uint32_t h = hint_of(val, ce.strand);
-      hb = h & 0xFFFFFFu; hl = h >> 24;
-      if (mask == 0 || (mask & (mask - 1))) hl = 0;
+      sg.x = x; sg.h = hint; sg.l0 = (uint16_t)lv; sg.end_mask = (uint8_t)emask;
+      x = xe; lv += (int)hint.len; mask = emask;
+      hint.len = 0;
+      if (hit && mask != 0 && !(mask & (mask - 1))) hint = hint_of(sl, ce.strand);
     }
   }
   if (lane < NARROW_W) nb.nseg[lane] = lane < w ? (uint32_t)nseg : 0u;
@@ -524,21 +525,23 @@ __device__ __forceinline__ int narrow_scout_warp(const Table &T, GShared &sh, Na
   return len;
 }
 
-// States of the scouted segments, one (segment, step) per thread; ch_a of the covered levels was zeroed before.
+// States of the scouted segments, one (level, chain) per thread: binary search for the segment that covers the level.
+// ch_a of the covered levels was zeroed before.
 template <class G, bool FORWARD>
 __device__ __forceinline__ void expand_segments(const Table &T, NarrowBuf &nb, int w, int len) {
   const int k = T.k;
-  for (int q = G::rank(); q < w * SCOUT_SEGS * HINT_MAX; q += G::size()) {
-    const int i = q % HINT_MAX, sq = q / HINT_MAX;
-    const int t = sq / SCOUT_SEGS, si = sq - t * SCOUT_SEGS;
-    if ((uint32_t)si >= nb.nseg[t]) continue;
-    const ScoutSeg sg = nb.seg[t][si];
-    const int hl = sg.hl, lvl = sg.l0 + i;
-    if (i >= hl || lvl >= len) continue;
-    const int j = i + 1;                                              // steps past the segment's tip
-    const uint64_t y = ((sg.x << (2 * j)) | (uint64_t)((sg.hb >> (2 * (hl - j))) & ((1u << (2 * j)) - 1))) & T.kmask;
+  for (int q = G::rank(); q < len * w; q += G::size()) {
+    const int lvl = q / w, t = q - lvl * w;
+    const int ns = (int)nb.nseg[t];
+    if (ns == 0 || lvl < (int)nb.seg[t][0].l0) continue;            // not born yet (split chains start later)
+    int lo = 0, hi = ns - 1;                                          // last segment with l0 <= lvl
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if ((int)nb.seg[t][mid].l0 <= lvl) lo = mid; else hi = mid - 1; }
+    const ScoutSeg sg = nb.seg[t][lo];
+    const int j = lvl - (int)sg.l0 + 1;                               // steps past the segment's tip
+    if (j > (int)sg.h.len) continue;                                  // the chain ended before this level
+    const uint64_t y = hint_state(sg.x, sg.h, (uint32_t)j, T.kmask);
     const Canon cy = canonical(y, k);
-    const uint32_t nmask = j < hl ? 1u << ((sg.hb >> (2 * (hl - j - 1))) & 3) : (uint32_t)sg.end_mask;
+    const uint32_t nmask = j < (int)sg.h.len ? 1u << hint_base(sg.h, (uint32_t)j) : (uint32_t)sg.end_mask;
     if (FORWARD) { nb.ch_s[lvl][t] = y; nb.ch_a[lvl][t] = nmask | (cy.strand << 8) | (1u << 16); }
     else { nb.ch_s[lvl][t] = revcomp(y, k); nb.ch_a[lvl][t] = swap2(nmask) | ((cy.strand ^ 1u) << 8) | (1u << 16); }
   }
@@ -563,7 +566,7 @@ G2S_D int narrow_scout(const Table &T, GShared &sh, NarrowBuf &nb, int w, int ma
   // Per-chain state lives in shared memory so that any group size, including the size-1 host emulation, can play the
   // w scouts: nw_x = the chain's tip in WALK orientation (forward pass: the state itself; right pass: its reverse
   // complement, so that walking predecessors is walking successors), nw_m = its out-mask in that orientation
-  // (0xFF = chain ended), nw_hb / nw_hl = what is left of the tip's skip hint.  A gather happens only where a hint
+  // (0xFF = chain ended), nw_h = what is left of the tip's skip hint.  A gather happens only where a hint
   // ends; between gathers a level costs a shift and an insert.
   const int k = T.k, rank = G::rank(), gsz = G::size();
   if (rank == 0) { nb.nw_stop = 0; nb.nw_alive = 0; nb.nw_w = (uint32_t)w; }
@@ -591,15 +594,14 @@ G2S_D int narrow_scout(const Table &T, GShared &sh, NarrowBuf &nb, int w, int ma
       const uint64_t y = succ_kmer(nb.nw_x[t], nt, T);
       const Canon cy = canonical(y, k);
       uint32_t nmask;
-      if (nb.nw_hl[t] > 1) {           // y is an interior node of the hint: exactly one successor, its base is known
-        nb.nw_hl[t]--;
-        nmask = 1u << ((nb.nw_hb[t] >> (2 * (nb.nw_hl[t] - 1))) & 3);
+      if (nb.nw_h[t].len > 1) {        // y is an interior node of the hint: exactly one successor, its base is known
+        nb.nw_h[t].len--;               // (the remaining bases are the low 2 * len bits)
+        nmask = 1u << ((uint32_t)hint_shr(nb.nw_h[t], 2 * (nb.nw_h[t].len - 1)) & 3u);
       } else {                         // the hint ends at y (or there is none yet): gather y
-        uint64_t val = 0;
-        if (table_find_val(T, cy.key, &val) < 0) { a_or(&sh.status, GS_INTERNAL); nb.nw_m[t] = 0xFF; nb.ch_a[l][t] = 0; continue; }
-        nmask = out_mask((uint32_t)(val & 0xFF), cy.strand);
-        const uint32_t h = hint_of(val, cy.strand);
-        nb.nw_hb[t] = h & 0xFFFFFFu; nb.nw_hl[t] = h >> 24;
+        Slot sl;
+        if (table_find_slot(T, cy.key, &sl) < 0) { a_or(&sh.status, GS_INTERNAL); nb.nw_m[t] = 0xFF; nb.ch_a[l][t] = 0; continue; }
+        nmask = out_mask((uint32_t)(sl.val & 0xFF), cy.strand);
+        nb.nw_h[t] = hint_of(sl, cy.strand);
       }
       // emit the state of this level in the orientation of the pass, with its mask in the direction of the pass
       if (FORWARD) { nb.ch_s[l][t] = y; nb.ch_a[l][t] = nmask | (cy.strand << 8) | (1u << 16); }
@@ -618,7 +620,7 @@ G2S_D int narrow_scout(const Table &T, GShared &sh, NarrowBuf &nb, int w, int ma
 template <class G>
 G2S_D int narrow_right(const Table &T, const Slice &S, GShared &sh, NarrowBuf &nb, int cur, int c, int right_half, int n, uint32_t *n_out) {
   const int k = T.k, rank = G::rank(), gsz = G::size();
-  for (int t = rank; t < n; t += gsz) { nb.nw_x[t] = revcomp(S.rbk[cur][t], k); nb.nw_m[t] = swap2(S.rbm[cur][t]); nb.nw_hl[t] = 0; nb.nw_hb[t] = 0; }
+  for (int t = rank; t < n; t += gsz) { nb.nw_x[t] = revcomp(S.rbk[cur][t], k); nb.nw_m[t] = swap2(S.rbm[cur][t]); nb.nw_h[t] = Hint{0, 0, 0}; }
   const int maxlen = right_half - c + 1 < CHAIN_LEN ? right_half - c + 1 : CHAIN_LEN;
   const int len = narrow_scout<G, false>(T, sh, nb, n, maxlen);
   if (len == 0) return 0;
@@ -684,7 +686,7 @@ G2S_D int narrow_forward(const Table &T, const Slice &S, GShared &sh, NarrowBuf 
     nb.nw_x[t] = x; nb.nw_x0[t] = x;
     nb.nw_m[t] = (ld_cg(&S.cflags[lo + t]) >> CF_OMASK_SHIFT) & 15u;
     nb.nw_cnt0[t] = clamp_paths(ld_cg(&S.cc[lo + t]));
-    nb.nw_hl[t] = 0; nb.nw_hb[t] = 0;
+    nb.nw_h[t] = Hint{0, 0, 0};
   }
   const int maxlen = Dmax - c + 1 < CHAIN_LEN ? Dmax - c + 1 : CHAIN_LEN;
   const unsigned long long tp0 = now_cycles();

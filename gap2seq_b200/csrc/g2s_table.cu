@@ -15,7 +15,7 @@ namespace g2s {
 __global__ void k_clear_slots(Slot *slots, uint64_t cap) {
   uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  for (; i < cap; i += stride) { slots[i].key = KEY_EMPTY; slots[i].val = 0; }
+  for (; i < cap; i += stride) { slots[i].key = KEY_EMPTY; slots[i].val = 0; slots[i].h[0] = 0; slots[i].h[1] = 0; }
 }
 
 // insert keys[i] when its abundance passes; counts == nullptr means "insert all"
@@ -61,22 +61,25 @@ __global__ void k_adjacency(Slot *slots, Table t) {
   }
 }
 
-// skip hints of every node (g2s_common.cuh hint_of): up to 12 dependent probes per orientation, run once at import
-__global__ void k_hints(const Slot *slots, Table t, uint64_t *hints) {
+// skip hints of every node (g2s_common.cuh hint_of): up to 40 dependent probes per orientation, run once at import
+__global__ void k_hints(const Slot *slots, Table t, Slot *hints) {
   uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   const uint64_t cap = t.cap_mask + 1;
   for (; i < cap; i += stride) {
     const uint64_t key = slots[i].key;
-    hints[i] = key == KEY_EMPTY ? 0 : compute_hints(t, key, (uint32_t)(slots[i].val & 0xFF));
+    Slot o{key, 0, {0, 0}};
+    if (key != KEY_EMPTY) compute_hints(t, key, (uint32_t)(slots[i].val & 0xFF), &o);
+    hints[i] = o;
   }
 }
 
 // second step so that k_hints reads a table nobody writes (its probes use the read-only path)
-__global__ void k_apply_hints(Slot *slots, uint64_t cap, const uint64_t *hints) {
+__global__ void k_apply_hints(Slot *slots, uint64_t cap, const Slot *hints) {
   uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  for (; i < cap; i += stride) slots[i].val = (slots[i].val & 0xFF) | (hints[i] << 8);
+  for (; i < cap; i += stride)
+    if (slots[i].key != KEY_EMPTY) { slots[i].val = hints[i].val; slots[i].h[0] = hints[i].h[0]; slots[i].h[1] = hints[i].h[1]; }
 }
 
 __global__ void k_count_solid(const uint32_t *counts, const int *n_runs, const uint64_t *keys, uint32_t solid,
@@ -173,8 +176,8 @@ cudaError_t table_fill(DeviceTable *dt, const uint64_t *keys_dev, const uint32_t
   CK(cudaGetLastError());
   k_adjacency<<<grid_for(dt->cap, 256, sms), 256, 0, st>>>(dt->slots, table_view(*dt));
   CK(cudaGetLastError());
-  uint64_t *d_hints = nullptr;
-  CK(cudaMalloc(&d_hints, dt->cap * sizeof(uint64_t)));
+  Slot *d_hints = nullptr;
+  CK(cudaMalloc(&d_hints, dt->cap * sizeof(Slot)));
   k_hints<<<grid_for(dt->cap, 256, sms), 256, 0, st>>>(dt->slots, table_view(*dt), d_hints);
   CK(cudaGetLastError());
   k_apply_hints<<<grid_for(dt->cap, 256, sms), 256, 0, st>>>(dt->slots, dt->cap, d_hints);

@@ -44,7 +44,7 @@ void *emul_graph_from_kmers(int k, const uint64_t *kmers, size_t n) {
   EmulGraph *g = new EmulGraph();
   uint64_t cap = 1024;
   while (cap < 2 * n + 2) cap <<= 1;
-  g->slots.assign(cap, Slot{KEY_EMPTY, 0});
+  g->slots.assign(cap, Slot{KEY_EMPTY, 0, {0, 0}});
   g->t.slots = g->slots.data();
   g->t.cap_mask = cap - 1;
   g->t.k = k;
@@ -56,9 +56,12 @@ void *emul_graph_from_kmers(int k, const uint64_t *kmers, size_t n) {
   }
   for (uint64_t h = 0; h < cap; h++)
     if (g->slots[h].key != KEY_EMPTY) g->slots[h].val = host_adj(g->t, g->slots[h].key);
+  std::vector<Slot> hints(cap, Slot{KEY_EMPTY, 0, {0, 0}});
   for (uint64_t h = 0; h < cap; h++)
     if (g->slots[h].key != KEY_EMPTY)
-      g->slots[h].val = (g->slots[h].val & 0xFF) | (compute_hints(g->t, g->slots[h].key, (uint32_t)(g->slots[h].val & 0xFF)) << 8);
+      compute_hints(g->t, g->slots[h].key, (uint32_t)(g->slots[h].val & 0xFF), &hints[h]);
+  for (uint64_t h = 0; h < cap; h++)
+    if (g->slots[h].key != KEY_EMPTY) { g->slots[h].val = hints[h].val; g->slots[h].h[0] = hints[h].h[0]; g->slots[h].h[1] = hints[h].h[1]; }
   return g;
 }
 
@@ -196,14 +199,14 @@ void emul_free(void *p) { free(p); }
 
 }  // extern "C"
 
-// debugging aid: histogram of skip-hint lengths (13 bins per orientation) over all nodes
-extern "C" void emul_hint_hist(void *gp, uint64_t *hist26) {
+// debugging aid: histogram of skip-hint lengths (HINT_MAX + 1 bins per orientation) over all nodes
+extern "C" void emul_hint_hist(void *gp, uint64_t *hist82) {
   EmulGraph *g = (EmulGraph *)gp;
-  for (int i = 0; i < 26; i++) hist26[i] = 0;
+  for (int i = 0; i < 2 * (HINT_MAX + 1); i++) hist82[i] = 0;
   for (const Slot &s : g->slots) {
     if (s.key == KEY_EMPTY) continue;
-    hist26[hint_of(s.val, 0) >> 24]++;
-    hist26[13 + (hint_of(s.val, 1) >> 24)]++;
+    hist82[hint_of(s, 0).len]++;
+    hist82[HINT_MAX + 1 + hint_of(s, 1).len]++;
   }
 }
 
