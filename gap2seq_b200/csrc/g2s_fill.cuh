@@ -169,6 +169,7 @@ struct NarrowBuf {     // look-ahead state of one pass (the right pass and the f
   uint32_t nw_m[NARROW_W], nw_cnt0[NARROW_W];
   Hint nw_h[NARROW_W];   // what is left of the tip's skip hint (generic scout)
   int32_t nw_fail[NARROW_W];
+  int32_t nw_bad;              // first level of the batch that the narrow path cannot carry (start injection)
   int32_t nw_born[NARROW_W];   // first level (of the batch) on which the chain exists: 0, or where it split off its parent
   uint32_t nw_w;               // chains after the scout (splits add chains)
   uint32_t nw_par[NARROW_W];   // chain a split chain descends from
@@ -679,6 +680,7 @@ G2S_D int narrow_right(const Table &T, const Slice &S, GShared &sh, NarrowBuf &n
 template <class G>
 G2S_D int narrow_forward(const Table &T, const Slice &S, GShared &sh, NarrowBuf &nb, const GapDev &gd, uint32_t lo, int w, int c, int Dmax,
                          int prune_from) {
+  const int lmf = gd.lmf;
   const int k = T.k, rank = G::rank(), gsz = G::size();
   for (int t = rank; t < NARROW_W; t += gsz) nb.nw_born[t] = 0;
   for (int t = rank; t < w; t += gsz) {
@@ -696,6 +698,7 @@ G2S_D int narrow_forward(const Table &T, const Slice &S, GShared &sh, NarrowBuf 
   if (len == 0) return 0;
   w = (int)ld_sh(&nb.nw_w);   // the scout may have split chains
   for (int t = rank; t < w; t += gsz) nb.nw_fail[t] = len;
+  if (rank == 0) nb.nw_bad = len;
   G::sync();
   // node table + prune test, one (level, chain) per thread: ch_e = node entry; first failing level per chain
   for (int q = rank; q < len * w; q += gsz) {
@@ -735,13 +738,67 @@ G2S_D int narrow_forward(const Table &T, const Slice &S, GShared &sh, NarrowBuf 
       if (!dup) nn++;
     }
     nb.nw_n[l] = nn;
+    // Levels that inject a staggered left start (Gap2Seq.cpp:1082-1105: the start's count is OVERWRITTEN with 1): the
+    // batch can carry such a level only if the overwrite changes nothing - the start k-mer is the state of living
+    // chains whose counts add up to 1, i.e. of exactly one chain that counts one walk (the usual case: the flank
+    // is a path of the graph).  Otherwise the batch ends before that level and the level-by-level path injects.
+    if (c + l <= lmf) {
+      const uint64_t sk = S.lk[c + l];
+      if (sk & FLANK_PRESENT) {
+        uint32_t sum = 0;
+#pragma unroll
+        for (int t = 0; t < NARROW_W; t++)
+          if (t < w && l < nb.nw_fail[t] && l >= nb.nw_born[t] && nb.ch_s[l][t] == (sk & FLANK_KMER)) sum += nb.nw_cnt0[t] > 1 ? 2u : nb.nw_cnt0[t];
+        if (sum != 1) a_mini(&nb.nw_bad, l);
+      }
+    }
   }
   G::sync();
+#ifdef G2S_DEVICE_BUILD
+  if (rank < 32) {   // place the levels (first warp): where the batch ends, prefix sum of the level widths
+    const unsigned FULL = 0xffffffffu;
+    const int LPL = (CHAIN_LEN + 31) / 32;
+    const int bad = ld_sh(&nb.nw_bad);
+    uint32_t nn[LPL];
+    int my_end = 0x7fffffff;   // number of levels laid out if the batch ends inside this lane's levels
+#pragma unroll
+    for (int j = 0; j < LPL; j++) {
+      const int l = rank * LPL + j;
+      nn[j] = l < len ? nb.nw_n[l] : 0u;
+      if (l < len && my_end == 0x7fffffff) {
+        if (l >= bad) my_end = l;                  // a level the batch cannot carry: it ends before it
+        else if (nn[j] == 0) my_end = l + 1;       // the border died: the empty level is kept
+      }
+    }
+    int done = my_end;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) done = min(done, __shfl_xor_sync(FULL, done, o));
+    if (done > len) done = len;
+    uint32_t mine = 0;
+#pragma unroll
+    for (int j = 0; j < LPL; j++) { if (rank * LPL + j >= done) nn[j] = 0; mine += nn[j]; }
+    uint32_t incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(FULL, incl, o); if (rank >= o) incl += v; }
+    uint32_t run = incl - mine;
+#pragma unroll
+    for (int j = 0; j < LPL; j++) { const int l = rank * LPL + j; if (l < len) nb.nw_off[l] = run; run += nn[j]; }
+    if (rank == 31) {
+      const uint32_t base = sh.ncells;
+      uint32_t off = incl;
+      if ((uint64_t)base + off > S.cap_cells) { a_or(&sh.status, GS_OVERFLOW); done = 0; off = 0; }
+      nb.ch_base = base; nb.ch_len = (uint32_t)done;
+      sh.ncells = base + off;
+    }
+  }
+#else
   if (rank == 0) {   // place the levels: prefix sum, end of the border, chain runs
     const uint32_t base = sh.ncells;
     uint32_t off = 0;
     int done = len;
+    const int bad = nb.nw_bad;
     for (int l = 0; l < len; l++) {
+      if (l >= bad) { done = l; break; }
       const uint32_t nn = nb.nw_n[l];
       nb.nw_off[l] = off;
       off += nn;
@@ -751,6 +808,7 @@ G2S_D int narrow_forward(const Table &T, const Slice &S, GShared &sh, NarrowBuf 
     nb.ch_base = base; nb.ch_len = (uint32_t)done;
     sh.ncells = base + off;
   }
+#endif
   G::sync();
   const int done = (int)ld_sh(&nb.ch_len);
   const uint32_t base = ld_sh(&nb.ch_base);
@@ -1240,7 +1298,7 @@ G2S_D void gap_forward(const FillParams &P, const GapDev &gd, const GapCtx &cx, 
       const int dlim = waited ? Dmax : (prune_from - 1 < Dmax ? prune_from - 1 : Dmax);
       const uint32_t lo = ld_cg(&S.lstart[c - 1]), hi = ld_cg(&S.lstart[c]);
       const bool dead = (lo == hi) && c > lmf;   // empty border and no start left to inject
-      if (hi > lo && hi - lo <= (uint32_t)NARROW_W && c > lmf) {   // narrow border, no start left to inject
+      if (hi > lo && hi - lo <= (uint32_t)NARROW_W) {   // narrow border (start levels included, see narrow_forward)
         const int adv = narrow_forward<G>(T, S, sh, nb, gd, lo, (int)(hi - lo), c, dlim, prune_from);
         if (group_overflow<G>(sh)) { overflow = true; break; }
         if (adv > 0) {
