@@ -442,10 +442,9 @@ G2S_D bool found_scan(const Slice &S, const GapDev &gd, GShared &sh, int lo, int
 // the lane records that as ONE segment (tip, hint, first level), jumps to the node the hint ends at and gathers
 // again.  Chains advance independently of each other.  The states of all segments are then computed by every thread
 // of the group in parallel (expand_segments): the per-level work is off the serial path.
-// SPLIT (forward pass only): a tip with several neighbours does not end the look-ahead while free chain slots
-// remain: the extra neighbours become new chains, born on that level, that carry their parent's initial count; the
-// layout finds their predecessor cell through nw_par.  Without a free slot (or without SPLIT) the batch ends before
-// the level of the branch.
+// SPLIT: a tip with several neighbours does not end the look-ahead while free chain slots remain: the extra
+// neighbours become new chains, born on that level, that carry their parent's initial count (forward pass; the layout
+// finds their predecessor cell through nw_par).  Without a free slot the batch ends before the level of the branch.
 template <bool FORWARD, bool SPLIT>
 __device__ __forceinline__ int narrow_scout_warp(const Table &T, GShared &sh, NarrowBuf &nb, int w, int maxlen) {
   const int k = T.k;
@@ -554,7 +553,7 @@ G2S_D int narrow_scout(const Table &T, GShared &sh, NarrowBuf &nb, int w, int ma
 #ifdef G2S_DEVICE_BUILD
   if (G::kWarp || G::kWarpScout) {   // the group's first warp scouts, then every thread expands the segments
     G::sync();
-    if (G::rank() < 32) narrow_scout_warp<FORWARD, FORWARD>(T, sh, nb, w, maxlen);
+    if (G::rank() < 32) narrow_scout_warp<FORWARD, true>(T, sh, nb, w, maxlen);
     G::sync();
     const int len = ld_sh(&nb.scout_len), w2 = (int)ld_sh(&nb.nw_w);
     for (int q = G::rank(); q < len * NARROW_W; q += G::size()) nb.ch_a[q / NARROW_W][q % NARROW_W] = 0;
@@ -625,6 +624,7 @@ G2S_D int narrow_right(const Table &T, const Slice &S, GShared &sh, NarrowBuf &n
   const int maxlen = right_half - c + 1 < CHAIN_LEN ? right_half - c + 1 : CHAIN_LEN;
   const int len = narrow_scout<G, false>(T, sh, nb, n, maxlen);
   if (len == 0) return 0;
+  n = (int)ld_sh(&nb.nw_w);   // the scout splits chains at branches; a chain has no state before its birth level
   if (rank == 0) { nb.ch_cnt = 0; nb.nnext = 0; }
   G::sync();
   for (int q = rank; q < len * n; q += gsz) {
