@@ -885,10 +885,12 @@ G2S_D int narrow_forward(const Table &T, const Slice &S, GShared &sh, NarrowBuf 
 // bits are not read any more once the backward sweep runs).  A node marked on two levels makes the path subgraph a
 // general graph (vertex identity is the node, Gap2Seq.cpp:1222-1297); the pack phase sees that as a marked cell whose
 // level differs from its node's.  No value is returned, so the sweep never waits for the atomic.
-G2S_D void mark_node_level(const Slice &S, GShared &sh, uint32_t en, int level) {
+// Returns whether the node carried a mark of another level already: the sweep runs top down, so such a mark comes
+// from a higher level and the node is a vertex of two levels (general subgraph).  Callers collect the answers of
+// several cells before looking at them, so that the atomics are in flight together.
+G2S_D bool mark_node_level(const Slice &S, uint32_t en, int level) {
   const uint32_t old = a_max(&S.ent[en].flags, ((uint32_t)(level + 1) << 8) | 0xFFu);
-  // the sweep runs top down: a mark already there comes from a higher level -> the node is a vertex of two levels
-  if ((old >> 8) != 0 && (old >> 8) != (uint32_t)(level + 1)) a_or(&sh.status, GS_GENERAL);
+  return (old >> 8) != 0 && (old >> 8) != (uint32_t)(level + 1);
 }
 
 G2S_D uint32_t popc32(uint32_t x) {
@@ -1054,6 +1056,7 @@ G2S_D int narrow_backward(const Slice &S, GShared &sh, NarrowBuf &nb, int d, int
   G::sync();
   const uint32_t base = ld_sh(&nb.ch_base);
   uint32_t nbt = 0, ned = 0;
+  bool two_levels = false;
   for (int t = rank; t < len; t += gsz) {
     const uint32_t m = nb.nw_run[t], mB = m & 15u, mT = m >> 4, mk = mB | mT;
     if (!mk) continue;
@@ -1070,13 +1073,14 @@ G2S_D int narrow_backward(const Slice &S, GShared &sh, NarrowBuf &nb, int d, int
       a_or(&S.cflags[idx], bits);
       S.packidx[idx] = pi; S.packlist[pi] = idx; S.packlevel[pi] = (uint32_t)level;
       pi++;
-      if (bits & CF_B) { mark_node_level(S, sh, nb.ch_e[t][i], level); ned += (npw >> (4 * i)) & 15u; }
+      if (bits & CF_B) { two_levels |= mark_node_level(S, nb.ch_e[t][i], level); ned += (npw >> (4 * i)) & 15u; }
       if (t == len - 1) {
 #pragma unroll
         for (int z = 0; z < 4; z++) { const uint32_t p = nb.bk_p[i][z]; if (p != NONE32) a_or(&S.cflags[p], bits); }
       }
     }
   }
+  if (two_levels) a_or(&sh.status, GS_GENERAL);
   if (nbt) a_add(&sh.nB, nbt);
   if (ned) a_add(&sh.n_edges, ned);
   G2S_STAT(emul_stats().back_chain_levels += (unsigned long long)len);
@@ -1511,7 +1515,7 @@ G2S_D unsigned long long gap_backward_pack(const FillParams &P, const GapCtx &cx
         if (f & CF_B) {
           a_add(&S.nB[d], 1);
           a_add(&sh.nB, 1);
-          mark_node_level(S, sh, en, d);
+          if (mark_node_level(S, en, d)) a_or(&sh.status, GS_GENERAL);
           if (start) { a_add(&sh.n_src, 1); a_maxi(&sh.max_src_level, d); }
           else {
             uint32_t np = 0;
@@ -1572,21 +1576,38 @@ G2S_D unsigned long long gap_backward_pack(const FillParams &P, const GapCtx &cx
       G::sync();
       if (ld_sh(&sh.t_ok)) {
         const int d_end = ld_sh(&sh.t_lo);
-        for (int d = d_end + 1 + rank; d <= d0; d += gsz) {   // safe vertex? (the rule of the pack records below)
-          bool safe = skip_confident;
-          if (!safe) {
-            const uint32_t lv = ld_cg(&S.ent[ld_cg(&S.cn[ld_cg(&S.tcell[d])])].flags) >> 8;
-            if (lv == 0) safe = sink_safe_t;
-            else { const int bl = (int)lv - 1; safe = ld_cg(&S.nB[bl]) == 1 && bl >= max_src_t && bl <= min_sink_t; }
+        // four levels per thread and step: the dependent loads (cell -> node -> flags -> nB) of the four are in flight together
+        const int TU = 4;
+        for (int dbase = d_end + 1 + rank * TU; dbase <= d0; dbase += gsz * TU) {   // safe vertex? (the rule of the pack records below)
+          uint32_t ci[TU], en[TU], lv[TU], nb1[TU];
+          uint64_t kx[TU];
+#pragma unroll
+          for (int u = 0; u < TU; u++) ci[u] = dbase + u <= d0 ? ld_cg(&S.tcell[dbase + u]) : 0u;
+#pragma unroll
+          for (int u = 0; u < TU; u++) { en[u] = dbase + u <= d0 ? ld_cg(&S.cn[ci[u]]) : 0u; kx[u] = dbase + u <= d0 ? ld_cg(&S.ck[ci[u]]) : 0ull; }
+#pragma unroll
+          for (int u = 0; u < TU; u++) lv[u] = (dbase + u <= d0 && !skip_confident) ? ld_cg(&S.ent[en[u]].flags) >> 8 : 0u;
+#pragma unroll
+          for (int u = 0; u < TU; u++) nb1[u] = (dbase + u <= d0 && lv[u] != 0) ? ld_cg(&S.nB[lv[u] - 1]) : 0u;
+#pragma unroll
+          for (int u = 0; u < TU; u++) {
+            if (dbase + u > d0) continue;
+            bool safe = skip_confident;
+            if (!safe) {
+              if (lv[u] == 0) safe = sink_safe_t;
+              else { const int bl = (int)lv[u] - 1; safe = nb1[u] == 1 && bl >= max_src_t && bl <= min_sink_t; }
+            }
+            // nT now carries the safe bit and the level's base: (safe ? 2 : 1) | base << 2
+            S.nT[dbase + u] = (safe ? 2u : 1u) | ((uint32_t)(kx[u] & 3u) << 2);
           }
-          S.nT[d] = safe ? 2u : 1u;
         }
         G::sync();
         char *outc = P.fills + ld_sh(&sh.fill_off);
         for (int d = d_end + 1 + rank; d <= d0; d += gsz) {
-          bool up = d0 - d < k;
-          for (int z = d; !up && z <= d0 && z < d + k; z++) up = ld_cg(&S.nT[z]) == 2u;
-          const uint32_t b = (uint32_t)(ld_cg(&S.ck[ld_cg(&S.tcell[d])]) & 3u);
+          const uint32_t me = ld_cg(&S.nT[d]);
+          bool up = d0 - d < k || (me & 3u) == 2u;
+          for (int z = d + 1; !up && z <= d0 && z < d + k; z++) up = (ld_cg(&S.nT[z]) & 3u) == 2u;
+          const uint32_t b = me >> 2;
           const char ch = b == 0 ? 'A' : b == 1 ? 'C' : b == 2 ? 'T' : 'G';
           outc[d - 1 - d_end] = up ? ch : (char)(ch | 0x20);
         }
