@@ -7,6 +7,7 @@
 //      and therefore walks the device-built predecessor trellis gap after gap.
 // There is no CPU implementation of the DP here: without a CUDA device every call fails with G2S_E_CUDA.
 #include <cuda_runtime.h>
+#include <malloc.h>
 
 #include <algorithm>
 #include <atomic>
@@ -141,6 +142,10 @@ extern "C" int g2s_create(const g2s_config *cfg, g2s_engine **out) {
   e->budget = cfg->max_mem_bytes > 0 ? (size_t)cfg->max_mem_bytes : (size_t)(fr * 0.6);
   CUDA_TRY(e->d_counters.reserve(64));
   e->pool.reset(new ThreadPool(cfg->host_threads));
+  // The driver call hands megabytes of malloc'ed strings to the caller every time; with glibc's default trimming the
+  // freed memory goes back to the kernel and every call pays its page faults again (several ms per 10 000 records on
+  // the measured host).  Keep freed memory in the process unless the embedding application objects (G2S_KEEP_MALLOPT=1).
+  if (!getenv("G2S_KEEP_MALLOPT")) { mallopt(M_TRIM_THRESHOLD, 1 << 30); mallopt(M_MMAP_THRESHOLD, 1 << 28); }
   e->device_trace = getenv("G2S_NO_DEVICE_TRACE") == nullptr;
   *out = e;
   return G2S_OK;

@@ -215,7 +215,8 @@ struct ScaffoldRun {
         g.reserved = 0;
       }
       // the rand() values this wave's tracebacks can consume are computed while the device pass runs
-      for (const g2s_gap &g : gaps) rand_bound += (size_t)g.gap_len + g.gap_err + g.left_max_fuz + g.right_max_fuz + 2;
+      // (a filling path is about as long as the gap; the rare longer ones extend the window after the pass, see trace_many)
+      for (const g2s_gap &g : gaps) rand_bound += (size_t)g.gap_len + g.left_max_fuz + g.right_max_fuz + 64;
       if (pool && aheadp->ok()) {
         pool->wait_async();
         const size_t want = rand_bound + 1;
