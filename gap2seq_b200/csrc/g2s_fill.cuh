@@ -34,6 +34,16 @@ template <class T> G2S_D T ld_sh(const T *p) { return *(const volatile T *)p; }
 #ifdef G2S_DEVICE_BUILD
 template <class T> G2S_D T ld_cg(const T *p) { return __ldcg(p); }
 G2S_D uint32_t a_add(uint32_t *p, uint32_t v) { return atomicAdd(p, v); }
+// atomicAdd(p, 1) for counters that a whole CTA hammers (cell / node / border cursors in shared memory): the lanes
+// that arrive together send ONE atomic and share out the range.  Same results as per-lane atomics, in another order.
+G2S_D uint32_t a_inc(uint32_t *p) {
+  const unsigned m = __activemask();
+  const int lane = threadIdx.x & 31, leader = __ffs((int)m) - 1;
+  uint32_t base = 0;
+  if (lane == leader) base = atomicAdd(p, (uint32_t)__popc(m));
+  base = __shfl_sync(m, base, leader);
+  return base + (uint32_t)__popc(m & ((1u << lane) - 1u));
+}
 G2S_D unsigned long long a_add64(unsigned long long *p, unsigned long long v) { return atomicAdd(p, v); }
 G2S_D uint32_t a_max(uint32_t *p, uint32_t v) { return atomicMax(p, v); }
 G2S_D uint32_t a_or(uint32_t *p, uint32_t v) { return atomicOr(p, v); }
@@ -46,6 +56,7 @@ G2S_D uint64_t a_cas64(uint64_t *p, uint64_t cmp, uint64_t v) {
 #else
 template <class T> inline T ld_cg(const T *p) { return *p; }
 inline uint32_t a_add(uint32_t *p, uint32_t v) { uint32_t o = *p; *p = o + v; return o; }
+inline uint32_t a_inc(uint32_t *p) { return (*p)++; }
 inline unsigned long long a_add64(unsigned long long *p, unsigned long long v) { unsigned long long o = *p; *p = o + v; return o; }
 inline uint32_t a_max(uint32_t *p, uint32_t v) { uint32_t o = *p; if (v > o) *p = v; return o; }
 inline uint32_t a_or(uint32_t *p, uint32_t v) { uint32_t o = *p; *p = o | v; return o; }
@@ -334,12 +345,23 @@ G2S_D uint32_t node_insert(const Slice &S, GShared &sh, uint64_t key, uint32_t *
   for (;;) {
     G2S_STAT(emul_stats().insert_probes++);
     const uint64_t old = a_cas64(&S.ent[h].key, KEY_EMPTY, key);
-    if (old == KEY_EMPTY) { a_add(&sh.nnodes, 1); *flags = 0; return h; }
+    if (old == KEY_EMPTY) { a_inc(&sh.nnodes); *flags = 0; return h; }
     if (old == key) { *flags = ld_cg(&S.ent[h].flags); return h; }
     h = (h + 1) & S.hmask;
   }
 }
 G2S_D uint32_t node_insert(const Slice &S, GShared &sh, uint64_t key) { uint32_t f; return node_insert(S, sh, key, &f); }
+
+// Sum of v over the calling warp, added to *p by one lane (all 32 lanes must call; device only - the host emulation
+// has groups of one thread).  For per-level totals that every marked cell of a wide level would otherwise add itself.
+G2S_D void a_add_warp(uint32_t *p, uint32_t v) {
+#ifdef __CUDA_ARCH__
+  v = __reduce_add_sync(0xffffffffu, v);
+  if ((threadIdx.x & 31) == 0 && v) atomicAdd(p, v);
+#else
+  if (v) *p += v;
+#endif
+}
 
 // Has the gap outgrown its scratch slice?  The answer steers collective control flow (loops with group barriers), so
 // it must be the same for every thread of the group - but in the thin tier the OTHER warp of the pair may set the bit
@@ -361,7 +383,7 @@ G2S_D uint32_t clamp_paths(uint32_t c) { return c > MAX_PATHS ? MAX_PATHS : c; }
 template <class G>
 G2S_D uint32_t new_cell(const Slice &S, GShared &sh, const GapDev &gd, uint64_t s, uint32_t e, uint32_t strand,
                         uint32_t adj, uint32_t c, uint32_t count, uint32_t nflags) {
-  uint32_t idx = a_add(&sh.ncells, 1);
+  uint32_t idx = a_inc(&sh.ncells);
   if (idx >= S.cap_cells) { a_or(&sh.status, GS_OVERFLOW); return NONE32; }
   S.ck[idx] = s;
   S.cc[idx] = count;
@@ -1223,7 +1245,7 @@ G2S_D void gap_right(const FillParams &P, const GapCtx &cx, const Slice &S, GSha
         uint32_t stamp = (uint32_t)(c + 1) * 2 + cp.strand;
         uint32_t prev = a_max(&S.ent[en].rstamp, stamp);
         if ((prev >> 1) < (uint32_t)(c + 1)) {
-          uint32_t idx = a_add(&nb.nnext, 1);
+          uint32_t idx = a_inc(&nb.nnext);
           if (idx >= S.cap_cells) { a_or(&sh.status, GS_OVERFLOW); continue; }
           nk[idx] = p; nm[idx] = (unsigned char)in_mask(adj, cp.strand);
         } else if ((prev & 1) != cp.strand) {
@@ -1503,33 +1525,37 @@ G2S_D unsigned long long gap_backward_pack(const FillParams &P, const GapCtx &cx
       const uint32_t lo = ld_cg(&S.lstart[d]), hi = ld_cg(&S.lstart[d + 1]);
       G2S_STAT(emul_stats().back_general_levels++; emul_stats().width_hist[hi - lo > 7 ? 7 : hi - lo]++);
       const uint64_t lcanon = (d <= lmf) ? canonical(S.lk[d] & FLANK_KMER, k).key : KEY_EMPTY;
+      uint32_t my_b = 0, my_t = 0, my_e = 0;   // this thread's share of the level's totals, added once per warp below
+      bool two_levels = false;
       for (uint32_t i = lo + rank; i < hi; i += gsz) {
         const uint32_t f = ld_cg(&S.cflags[i]);
         if (!(f & (CF_B | CF_T))) continue;
-        const uint32_t pi = a_add(&sh.npack, 1);
+        const uint32_t pi = a_inc(&sh.npack);
         S.packidx[i] = pi; S.packlist[pi] = i; S.packlevel[pi] = (uint32_t)d;
         const uint32_t en = S.cn[i];
         const bool start = d <= lmf && ld_cg(&S.ent[en].key) == lcanon;
         uint32_t p[4];
         p[0] = ld_cg(&S.cp[4 * i]); p[1] = ld_cg(&S.cp[4 * i + 1]); p[2] = ld_cg(&S.cp[4 * i + 2]); p[3] = ld_cg(&S.cp[4 * i + 3]);
         if (f & CF_B) {
-          a_add(&S.nB[d], 1);
-          a_add(&sh.nB, 1);
-          if (mark_node_level(S, en, d)) a_or(&sh.status, GS_GENERAL);
+          my_b++;
+          two_levels |= mark_node_level(S, en, d);
           if (start) { a_add(&sh.n_src, 1); a_maxi(&sh.max_src_level, d); }
           else {
-            uint32_t np = 0;
 #pragma unroll
-            for (int q = 0; q < 4; q++) if (p[q] != NONE32) { a_or(&S.cflags[p[q]], CF_B); np++; }
-            a_add(&sh.n_edges, np);
+            for (int q = 0; q < 4; q++) if (p[q] != NONE32) { a_or(&S.cflags[p[q]], CF_B); my_e++; }
           }
         }
-        if (f & CF_T) { a_add(&S.nT[d], 1); S.tcell[d] = i; }
+        if (f & CF_T) { my_t++; S.tcell[d] = i; }
         if ((f & CF_T) && !start) {
 #pragma unroll
           for (int q = 0; q < 4; q++) if (p[q] != NONE32) a_or(&S.cflags[p[q]], CF_T);
         }
       }
+      if (two_levels) a_or(&sh.status, GS_GENERAL);
+      a_add_warp(&S.nB[d], my_b);
+      a_add_warp(&sh.nB, my_b);
+      a_add_warp(&sh.n_edges, my_e);
+      a_add_warp(&S.nT[d], my_t);
       G::sync();
     }
     t_back = now_cycles();
