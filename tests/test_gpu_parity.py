@@ -235,3 +235,29 @@ def test_device_traceback_equals_host_traceback_and_rand_stream(case_inputs, mon
         assert host[3] == 0
     assert outs[0][0][3] >= 0.9 * len(specs), "error-free gaps must be traced on the device"
     assert all(f[:-w.k] == rec.truth for f, rec, r in zip(outs[0][0][1], w.gaps, outs[0][0][0]) if r[0] == 1)
+
+
+@pytest.mark.parametrize("name,scale", [("cfg2", 0.3), ("cfg3", 0.1), ("cfg5", 0.05)])
+def test_named_workloads_match_oracle_gap_by_gap(name, scale):
+    """Every gap of a named workload at moderate size (50-250 gaps) through the engine against the oracle: thin tier with
+    chain splitting and device tracebacks (cfg2, cfg5), wide tier with general subgraphs (cfg3)."""
+    w = synth.make_workload(name, scale)
+    e = engine.Engine(k=w.k, max_fuz=w.fuz)
+    e.build_from_reads(w.reads, w.solid)
+    keys, _ = e.export_kmers()
+    og = oracle_lib.OracleGraph.from_kmers(w.k, keys)
+    specs = [s for rec in w.gaps for s in record_gaps(rec.seq, w.k, w.fuz, w.dist_error, all_paths=not w.best_only)]
+    oracle_lib.srand(13)
+    res, fills = e.fill_batch(specs)
+    oracle_lib.srand(13)
+    for s, r, f in zip(specs, res, fills):
+        o, of = og.fill_gap(s.left, s.right, s.gap_len, s.gap_err, s.left_max_fuz, s.right_max_fuz, all_paths=s.all_paths)
+        if o.order_dependent:
+            assert r.status & engine.ST_ORDER_DEPENDENT
+            break
+        assert (r.count, r.left_fuz, r.right_fuz, f, r.forward_count, r.rand_calls) == \
+            (o.count, o.left_fuz, o.right_fuz, of, o.forward_count, o.rand_calls)
+        assert (r.cells_right, r.cells_left) == (o.cells_right, o.cells_left)
+        if o.substats_valid:
+            assert r.substats.astuple() == tuple(o.substats)
+    e.close()
