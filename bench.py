@@ -120,7 +120,7 @@ class ClockSampler:
 
 def make_workload(name: str, scale: float, rank: int):
     from gap2seq_b200 import synth
-    w = synth.make_workload(name, scale)
+    w = synth.make_workload(name, scale, with_reads=(rank == 0))   # only rank 0 builds the graph (then broadcast)
     if rank > 0:   # weak scaling: every rank fills its own, equally shaped batch of gaps on the same graph
         import numpy as np
         rng = np.random.default_rng(7000 + rank)

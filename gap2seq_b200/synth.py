@@ -12,6 +12,7 @@ Pure numpy; nothing here touches the GPU or the oracle.
 """
 from __future__ import annotations
 
+import bisect
 import os
 from dataclasses import dataclass, field
 
@@ -79,10 +80,16 @@ def simulate_reads(genome: np.ndarray, coverage: float, read_len: int, err: floa
     n = genome.shape[0]
     n_reads = int(round(coverage * n / read_len))
     starts = rng.integers(0, n - read_len + 1, size=n_reads)
-    idx = starts[:, None] + np.arange(read_len)[None, :]
-    reads = genome[idx]
+    reads = np.empty((n_reads, read_len), dtype=np.uint8)
+    ar = np.arange(read_len)[None, :]
+    for lo in range(0, n_reads, 1 << 20):   # gathered in chunks: the index matrix of 30 M reads would take 24 GB
+        hi = min(n_reads, lo + (1 << 20))
+        reads[lo:hi] = genome[starts[lo:hi, None] + ar]
     flip = rng.random(n_reads) < 0.5
-    reads[flip] = _COMP[reads[flip][:, ::-1]]
+    for lo in range(0, n_reads, 1 << 20):
+        hi = min(n_reads, lo + (1 << 20))
+        f = flip[lo:hi]
+        reads[lo:hi][f] = _COMP[reads[lo:hi][f][:, ::-1]]
     if err > 0:
         hit = rng.random(reads.shape) < err
         nh = int(hit.sum())
@@ -147,7 +154,11 @@ def place_gaps(genome: np.ndarray, lengths: np.ndarray, rng: np.random.Generator
                near: list[int] | None = None, min_sep: int = 200, est_jitter: float = 0.0) -> list[GapRecord]:
     """One-gap records.  `near`: optional anchor positions, each gap starts <=150 bp upstream of one."""
     n = genome.shape[0]
-    taken: list[tuple[int, int]] = []
+    # accepted windows, sorted by start.  They are pairwise separated, hence sorted by end as well, so a candidate
+    # [a, b) conflicts with some window iff it conflicts with the last window that starts before b + min_sep
+    # (the same accept / reject decisions as testing every window, in O(log n)).
+    starts: list[int] = []
+    ends: list[int] = []
     out: list[GapRecord] = []
     for gi, L in enumerate(int(x) for x in lengths):
         for _try in range(1000):
@@ -158,11 +169,14 @@ def place_gaps(genome: np.ndarray, lengths: np.ndarray, rng: np.random.Generator
                 p = int(rng.integers(flank + 1, n - L - flank - 1))
             if p - flank < 0 or p + L + flank > n:
                 continue
-            if all(p + L + flank + min_sep <= s or e + min_sep <= p - flank for s, e in taken):
+            j = bisect.bisect_left(starts, p + L + flank + min_sep)   # windows [0, j) start before b + min_sep
+            if j == 0 or ends[j - 1] + min_sep <= p - flank:
                 break
         else:
             continue
-        taken.append((p - flank, p + L + flank))
+        j = bisect.bisect_left(starts, p - flank)
+        starts.insert(j, p - flank)
+        ends.insert(j, p + L + flank)
         est = L if est_jitter <= 0 else max(1, int(round(L * (1 + rng.uniform(-est_jitter, est_jitter)))))
         left = genome[p - flank:p].tobytes().decode()
         right = genome[p + L:p + L + flank].tobytes().decode()
@@ -175,9 +189,19 @@ def _loguniform(rng, lo, hi, n):
     return np.exp(rng.uniform(np.log(lo), np.log(hi), size=n)).astype(np.int64)
 
 
-def make_workload(name: str, scale: float = 1.0, *, inverted_copies: bool = False, seed: int | None = None) -> Workload:
+def make_workload(name: str, scale: float = 1.0, *, inverted_copies: bool = False, seed: int | None = None,
+                  with_reads: bool = True) -> Workload:
     """The five named configurations of BASELINE.json; `scale` shrinks genome and gap count
-    for tests (scale=1.0 is the full configuration)."""
+    for tests (scale=1.0 is the full configuration).  with_reads=False skips the read simulation (the genome is the
+    same, the gap list is NOT: ranks that receive the graph by broadcast place their own gaps, bench.py)."""
+    if not with_reads:
+        global simulate_reads
+        real = simulate_reads
+        simulate_reads = lambda g, cov, rl, err, rng: np.zeros((0, rl), dtype=np.uint8)   # noqa: E731
+        try:
+            return make_workload(name, scale, inverted_copies=inverted_copies, seed=seed)
+        finally:
+            simulate_reads = real
     flank = 100
     if name == "cfg1":      # 100 kbp, 30x error-free 100 bp reads, 20 gaps of 50-500 bp
         rng = np.random.default_rng(1 if seed is None else seed)
