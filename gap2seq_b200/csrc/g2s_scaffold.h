@@ -64,6 +64,17 @@ struct RecScan {
 };
 
 inline bool is_gap_char(char c) { return c == 'N' || c == 'n'; }
+// index of the next N / n at or after i (seq.size() if none).  The records are NUL-terminated strings, so libc's
+// vectorised strcspn does the scan; an embedded NUL only ends the fast scan early and the byte loop takes over.
+inline size_t next_gap_char(const StrRef &seq, size_t i) {
+  const size_t n = seq.size();
+  while (i < n) {
+    i += strcspn(seq.data() + i, "Nn");
+    if (i >= n || is_gap_char(seq[i])) break;
+    i++;   // a NUL inside the record
+  }
+  return i < n ? i : n;
+}
 
 // src/Gap2Seq.cpp:100-156
 inline void format_statistics(std::string &log, int filledStart, int gapStart, int gapEnd, int paths, const char *fill,
@@ -128,7 +139,7 @@ struct ScaffoldRun {
     RecScan &rs = recs[r];
     const int k = opt.k, fuz = opt.max_fuz;
     while (rs.i < seq.size()) {
-      if (!is_gap_char(seq[rs.i])) { rs.i++; continue; }
+      if (!is_gap_char(seq[rs.i])) { rs.i = next_gap_char(seq, rs.i + 1); continue; }
       const size_t gs = rs.i;
       bool independent = false;
       if (rs.last_attempt >= 0) {
@@ -261,11 +272,12 @@ struct ScaffoldRun {
       const StrRef &seq = seqs[r];
       const StrRef &comment = comments[r];
       std::string filledSeq;
+      filledSeq.reserve(seq.size() + 64);
       std::string &lg = rlog[r];
       long long prev = 0;
       size_t i = 0, next_req = 0;
       while (i < seq.size()) {
-        if (!is_gap_char(seq[i])) { i++; continue; }
+        if (!is_gap_char(seq[i])) { i = next_gap_char(seq, i + 1); continue; }
         rgc[r]++;
         const int lmf = (int)std::min<long long>((long long)i + k - prev, opt.max_fuz);
         const int kmer_start = (int)i - k - lmf;
@@ -289,20 +301,20 @@ struct ScaffoldRun {
           if (filled_status(s)) {
             rfc[r]++;
             // '=' not '+=': the prefix of a multi-gap record is dropped, as in the reference
-            filledSeq = seq.substr((size_t)prev, (size_t)(kmer_start + k + lmf - rs.left_fuz - prev)) +
-                        std::string(fill, (size_t)rs.fill_len);
+            filledSeq.assign(seq.data() + prev, (size_t)(kmer_start + k + lmf - rs.left_fuz - prev));
+            filledSeq.append(fill, (size_t)rs.fill_len);
             filledSeq.resize(filledSeq.size() - k);   // drop the right k-mer
             i += rs.right_fuz;
           } else {
-            filledSeq += seq.substr((size_t)prev, (size_t)(kmer_start + k + lmf + gap - prev));
+            filledSeq.append(seq.data() + prev, (size_t)(kmer_start + k + lmf + gap - prev));
           }
         } else {
-          filledSeq += seq.substr((size_t)prev, (size_t)(kmer_start + k + lmf + gap - prev));
+          filledSeq.append(seq.data() + prev, (size_t)(kmer_start + k + lmf + gap - prev));
         }
         prev = (long long)i;
       }
       if (next_req != recs[r].reqs.size()) { bad = -4; return; }
-      filledSeq += seq.substr((size_t)prev);
+      filledSeq.append(seq.data() + prev, seq.size() - (size_t)prev);
       filled[r].swap(filledSeq);
     };
     if (pool) pool->parallel_for(seqs.size(), 8, one_record);
