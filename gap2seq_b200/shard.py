@@ -57,15 +57,17 @@ def broadcast_table(engine, src: int = 0):
     import torch
     import torch.distributed as dist
     rank = dist.get_rank()
-    meta = torch.zeros(2, dtype=torch.int64, device="cuda")
+    meta = torch.zeros(3, dtype=torch.int64, device="cuda")
     if rank == src:
         ptr, cap, n, nbytes = engine.table_raw()
-        meta[0], meta[1] = cap, n
+        meta[0], meta[1], meta[2] = cap, n, nbytes
     dist.broadcast(meta, src=src)
-    cap, n = int(meta[0].item()), int(meta[1].item())
+    cap, n, nbytes = int(meta[0].item()), int(meta[1].item()), int(meta[2].item())
     if rank != src:
         ptr = engine.table_adopt(cap, n)
-        nbytes = cap * 16
+        _, cap2, _, nbytes2 = engine.table_raw()   # the receiver's own view of the buffer it just allocated
+        if (cap2, nbytes2) != (cap, nbytes):
+            raise RuntimeError(f"table replication: receiver expects {nbytes2} bytes for {cap2} slots, sender has {nbytes} for {cap}")
     t = torch.as_tensor(DeviceBytes(ptr, nbytes), device="cuda")
     dist.broadcast(t, src=src)
     torch.cuda.synchronize()
