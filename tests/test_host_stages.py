@@ -48,3 +48,44 @@ def test_sequential_and_threaded_host_stages_agree(case_inputs, monkeypatch):
         assert p.returncode == 0, p.stderr[-2000:]
         res.append(json.loads(p.stdout.strip().splitlines()[-1]))
     assert res[0] == res[1]
+
+
+def test_record_scanner_edge_cases_match_the_oracle_driver(case_inputs):
+    """The gap driver (g2s_scaffold.h: wave scan, per-record replay, splice, statistics lines) against the oracle's
+    restatement of Gap2Seq::execute() on records built to hit the scanner's corners: several gaps per record, gaps closer
+    than k + 2 fuz (dependent flanks), lower-case n, N at the very start, left flanks shorter than k, gaps of length 1,
+    records without gaps, an empty record."""
+    import numpy as np
+    import oracle_lib
+    case, w, g = case_inputs("cfg1_small")
+    eng = emul_lib.EmulEngine(w.k, g.kmers())
+    rng = np.random.default_rng(5)
+    genome = w.genome.tobytes().decode()
+    recs = []
+    for r in range(40):
+        a = int(rng.integers(0, len(genome) - 4000))
+        s = list(genome[a:a + int(rng.integers(200, 2500))])
+        for _ in range(int(rng.integers(0, 4))):
+            L = int(rng.choice([1, 2, 30, 45, 120, 300]))
+            if len(s) - L - w.k <= 0:
+                continue
+            # a right flank shorter than k is undefined behaviour in the reference (negative right_max_fuz) and fenced
+            # in the engine (DESIGN.md section 2 iv): every gap here keeps >= k characters to its right
+            p = int(rng.integers(0, len(s) - L - w.k))
+            ch = "n" if rng.random() < 0.3 else "N"
+            s[p:p + L] = ch * L
+        recs.append("".join(s))
+    recs += ["", genome[100:400], "N" * 50 + genome[500:900], genome[2000:2020] + "N" * 60 + genome[2080:2500],
+             genome[3000:3300] + "N" * 100 + genome[3400:3460] + "n" * 80 + genome[3540:3900]]
+    names = [f"rec{i} x" for i in range(len(recs))]
+    for kw in (dict(), dict(all_paths=False), dict(unique=True), dict(skip_confident=True)):
+        oracle_lib.srand(2)
+        filled, log, gc, fc, _ = eng.fill_records(recs, names, dist_error=300, fuz=10, **kw)
+        oracle_lib.srand(2)
+        ofilled, olog, ogc, ofc = [], "", 0, 0
+        for s, n in zip(recs, names):
+            f, l, a, b = g.fill_record(s, n, d_err=300, fuz=10, **kw)
+            ofilled.append(f); olog += l; ogc += a; ofc += b
+        assert (gc, fc) == (ogc, ofc)
+        assert filled == ofilled
+        assert log == olog
