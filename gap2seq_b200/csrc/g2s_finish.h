@@ -455,6 +455,7 @@ struct HostBatch {
   std::vector<const char *> fill_base;        // fill arena per device pass (gaps the device traced itself, GS_TRACED)
   std::vector<const PackRec *> pack_base;     // one arena per device pass (pinned staging owned by the engine's pool,
   std::vector<std::vector<PackRec>> own;      //  or `own` when the producer has no pool)
+  std::vector<std::vector<char>> own_fill;    // likewise for fills (host emulation)
   std::function<void()> on_free;              // hands the staging buffers back
   std::vector<std::pair<const void *, size_t>> staging;   // DMA targets to evict from the CPU caches when done
   std::vector<GeneralResult> gen;

@@ -90,6 +90,9 @@ static int emul_submit(EmulGraph *g, int k, const g2s_gap *gaps, size_t n, HostB
   hb.pack_of.assign(n, 0);
   hb.own.assign(n, std::vector<PackRec>());
   hb.pack_base.assign(n, nullptr);
+  hb.fill_base.assign(n, nullptr);
+  hb.own_fill.assign(n, std::vector<char>());   // fills of the gaps the (emulated) device traced itself
+  const bool device_trace = getenv("G2S_NO_DEVICE_TRACE") == nullptr;
   for (size_t i = 0; i < n; i++) {
     const g2s_gap &gg = gaps[i];
     std::vector<char> flanks((size_t)3 * k + gg.left_max_fuz + 2 * gg.right_max_fuz + 1);
@@ -113,16 +116,21 @@ static int emul_submit(EmulGraph *g, int k, const g2s_gap *gaps, size_t n, HostB
       SliceLayout L = make_layout(cap, hlog, (uint32_t)dmax + 1, (uint32_t)std::max(gg.left_max_fuz, gg.right_max_fuz) + 1);
       std::vector<unsigned char> scratch(L.bytes);
       pack.assign(cap, PackRec{});
-      unsigned long long cursor = 0;
+      unsigned long long cursor = 0, fcursor = 0;
+      std::vector<char> fills((size_t)dmax + 8);
       uint32_t order = 0, qh = 0;
       FillParams P{};
       P.table = g->t; P.flanks = flanks.data(); P.gaps = &gd; P.order = &order; P.n_gaps = 1; P.outs = &out;
       P.scratch = scratch.data(); P.lay = L; P.pack = pack.data(); P.pack_cap = cap; P.pack_cursor = &cursor; P.queue_head = &qh;
+      if (device_trace) { P.fills = fills.data(); P.fill_cap = fills.size(); P.fill_cursor = &fcursor; }
       GShared sh{};
       Slice S = make_slice(scratch.data(), L);
       process_gap<EmulGroup>(P, gd, S, sh, &out);
       if (out.status & GS_INTERNAL) return -100;
-      if (!(out.status & (GS_OVERFLOW | GS_OUT_FULL))) break;
+      if (!(out.status & (GS_OVERFLOW | GS_OUT_FULL))) {
+        if (out.status & GS_TRACED) { hb.own_fill[i].assign(fills.begin() + out.fill_off, fills.begin() + out.fill_off + out.fill_len + 1); out.fill_off = 0; }
+        break;
+      }
       if (cap > (1ULL << 28)) return -101;
     }
     pack.resize(out.npack + out.pack_off);
@@ -131,6 +139,7 @@ static int emul_submit(EmulGraph *g, int k, const g2s_gap *gaps, size_t n, HostB
     hb.pack_of[i] = (int)i;
     hb.own[i].swap(pack);
     hb.pack_base[i] = hb.own[i].data();
+    if (out.status & GS_TRACED) hb.fill_base[i] = hb.own_fill[i].data();
     hb.gaps[i].kmer_left = hb.gaps[i].kmer_right = nullptr;
   }
   const double t_an0 = now_s();
@@ -226,3 +235,4 @@ extern "C" void emul_trace_stats(unsigned long long *out4) {
   g2s::TraceStats &t = g2s::trace_stats();
   out4[0] = t.calls; out4[1] = t.parallel_calls; out4[2] = t.rounds; out4[3] = t.retraced;
 }
+

@@ -89,3 +89,38 @@ def test_record_scanner_edge_cases_match_the_oracle_driver(case_inputs):
         assert (gc, fc) == (ogc, ofc)
         assert filled == ofilled
         assert log == olog
+
+
+def test_emulated_device_traceback_equals_the_host_walk():
+    """The kernel's traceback (g2s_fill.cuh: single-chain trellis -> fill string with case, no pack records) runs in the host
+    emulation as well; with G2S_NO_DEVICE_TRACE=1 every gap is packed and walked on the host.  Same bytes either way."""
+    import json, os, subprocess, sys
+    code = (
+        "import sys, json; sys.path.insert(0, 'tests'); sys.path.insert(0, '.')\n"
+        "import cases, emul_lib, oracle_lib\n"
+        "from gap2seq_b200.scaffold import record_gaps\n"
+        "out = {}\n"
+        "for name in ['cfg1_small', 'cfg5_small', 'cfg2_small', 'cfg1_allupper']:\n"
+        "    case = cases.CASE_BY_NAME[name]; w = cases.build(case); o = case.opts()\n"
+        "    g = oracle_lib.OracleGraph.from_reads(w.k, w.solid, w.reads)\n"
+        "    eng = emul_lib.EmulEngine(w.k, g.kmers())\n"
+        "    specs = [s for rec in w.gaps for s in record_gaps(rec.seq, w.k, w.fuz, 500, skip_confident=o['all_upper'])]\n"
+        "    oracle_lib.srand(4)\n"
+        "    res, fills = eng.fill_batch(specs)\n"
+        "    out[name] = [[(r.count, r.left_fuz, r.right_fuz, r.rand_calls, r.fill_len, list(r.substats.astuple())) for r in res], fills,\n"
+        "                 sum(1 for r in res if r.status & 32)]\n"
+        "print(json.dumps(out))\n")
+    res = []
+    for host_only in (False, True):
+        env = dict(os.environ)
+        env.pop("G2S_NO_DEVICE_TRACE", None)
+        if host_only:
+            env["G2S_NO_DEVICE_TRACE"] = "1"
+        p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env,
+                           cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))), timeout=600)
+        assert p.returncode == 0, p.stderr[-2000:]
+        res.append(json.loads(p.stdout.strip().splitlines()[-1]))
+    for name in res[0]:
+        assert res[0][name][:2] == res[1][name][:2], name
+        assert res[1][name][2] == 0
+    assert res[0]["cfg1_small"][2] > 0 and res[0]["cfg5_small"][2] > 0 and res[0]["cfg1_allupper"][2] > 0
