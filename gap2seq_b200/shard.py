@@ -52,12 +52,15 @@ class DeviceBytes:
         self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
 
 
-def broadcast_table(engine, src: int = 0):
-    """Replicate rank `src`'s k-mer table to every rank's engine with ONE NCCL broadcast (NVLink / NVSwitch)."""
+def broadcast_table(engine, src: int = 0, device: str = "cuda", as_tensor=None):
+    """Replicate rank `src`'s k-mer table to every rank's engine with ONE NCCL broadcast (NVLink / NVSwitch).
+    `device` / `as_tensor(ptr, nbytes)` exist for the CPU test of the protocol (gloo, host buffers)."""
     import torch
     import torch.distributed as dist
     rank = dist.get_rank()
-    meta = torch.zeros(3, dtype=torch.int64, device="cuda")
+    if as_tensor is None:
+        as_tensor = lambda ptr, nbytes: torch.as_tensor(DeviceBytes(ptr, nbytes), device="cuda")   # noqa: E731
+    meta = torch.zeros(3, dtype=torch.int64, device=device)
     if rank == src:
         ptr, cap, n, nbytes = engine.table_raw()
         meta[0], meta[1], meta[2] = cap, n, nbytes
@@ -68,7 +71,8 @@ def broadcast_table(engine, src: int = 0):
         _, cap2, _, nbytes2 = engine.table_raw()   # the receiver's own view of the buffer it just allocated
         if (cap2, nbytes2) != (cap, nbytes):
             raise RuntimeError(f"table replication: receiver expects {nbytes2} bytes for {cap2} slots, sender has {nbytes} for {cap}")
-    t = torch.as_tensor(DeviceBytes(ptr, nbytes), device="cuda")
+    t = as_tensor(ptr, nbytes)
     dist.broadcast(t, src=src)
-    torch.cuda.synchronize()
+    if device == "cuda":
+        torch.cuda.synchronize()
     return nbytes
