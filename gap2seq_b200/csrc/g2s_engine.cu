@@ -290,6 +290,8 @@ static int plan_pass(g2s_engine *e, Pass &p) {
   }
   unsigned long long lim = (unsigned long long)(e->budget / 4 / sizeof(PackRec));
   p.pack_cap = std::max<unsigned long long>(std::min(want, lim), 1 << 16);
+  // diagnostic knob (tests): a deliberately small pack arena, so that the GS_OUT_FULL -> next tier path can be driven
+  if (const char *pc = getenv("G2S_PACK_CAP_RECORDS")) p.pack_cap = std::max<unsigned long long>(1, strtoull(pc, nullptr, 10));
   return 0;
 }
 
@@ -297,7 +299,7 @@ static int run_pass(g2s_engine *e, Pass &p) {
   CUDA_TRY(e->d_scratch.reserve((size_t)p.groups * p.lay.bytes));
   if ((size_t)p.pack_slot >= e->d_pack.size()) e->d_pack.resize(p.pack_slot + 1);
   if (e->d_pack[p.pack_slot].cap < p.pack_cap * sizeof(PackRec)) CUDA_TRY(e->d_pack[p.pack_slot].reserve(p.pack_cap * sizeof(PackRec)));
-  else p.pack_cap = e->d_pack[p.pack_slot].cap / sizeof(PackRec);   // use all of a buffer that is already there
+  else if (!getenv("G2S_PACK_CAP_RECORDS")) p.pack_cap = e->d_pack[p.pack_slot].cap / sizeof(PackRec);   // use all of a buffer that is already there
   if ((size_t)p.pack_slot >= e->d_fill.size()) e->d_fill.resize(p.pack_slot + 1);
   p.fill_cap = 0;
   if (e->device_trace) {
@@ -419,6 +421,7 @@ static int do_run(g2s_engine *e) {
   const size_t n = e->gaps.size();
   e->passes.clear();
   e->tm.kernel_ms = 0; e->tm.launches = 0; e->tm.gaps_big_tier = 0; e->tm.d2h_bytes = 0; e->tm.d2h_ms = 0; e->tm.host_ms = 0;
+  e->tm.max_tier_run = 0; e->tm.gaps_rerun_scratch = 0; e->tm.gaps_rerun_out_full = 0; e->tm.gaps_mem_limit = 0;
   e->out_pass.assign(n, -1);
   if (n == 0) { e->ran = true; return G2S_OK; }
   CUDA_TRY(cudaMemsetAsync(e->d_outs.p, 0, n * sizeof(GapOut), e->st));
@@ -443,7 +446,7 @@ static int do_run(g2s_engine *e) {
                      [&](uint32_t a, uint32_t b) { return dmax_of(e->gaps[a]) > dmax_of(e->gaps[b]); });
     if (tier > max_tier || plan_pass(e, p) != 0) {   // no larger tier fits the memory budget: the gaps are reported, not filled
       for (size_t i = 0; i < n; i++)
-        if (!done[i]) { e->outs[i] = GapOut{}; e->outs[i].status = GS_OVERFLOW | GS_DONE; e->out_pass[i] = -2; }
+        if (!done[i]) { e->outs[i] = GapOut{}; e->outs[i].status = GS_OVERFLOW | GS_DONE; e->out_pass[i] = -2; e->tm.gaps_mem_limit++; }
       e->passes.pop_back();
       break;
     }
@@ -456,6 +459,7 @@ static int do_run(g2s_engine *e) {
       if (ho[gi].status & GS_INTERNAL) return fail(G2S_E_CUDA, "device table inconsistent with its adjacency bytes");
       if (ho[gi].status & (GS_OVERFLOW | GS_OUT_FULL)) {
         failed++;
+        if (ho[gi].status & GS_OUT_FULL) e->tm.gaps_rerun_out_full++; else e->tm.gaps_rerun_scratch++;
         const g2s_gap &g = e->gaps[gi];
         const double levels = (double)dmax_of(g) + g.right_max_fuz + (g.gap_len + g.gap_err + 1) / 2;   // forward + right pass
         const bool early = !(ho[gi].status & GS_OUT_FULL) && (double)ho[gi].levels_r + ho[gi].levels_f < 0.5 * levels;
@@ -463,6 +467,7 @@ static int do_run(g2s_engine *e) {
       } else { e->outs[gi] = ho[gi]; e->out_pass[gi] = (int)e->passes.size() - 1; done[gi] = 1; pending--; }
     }
     if (tier > 0) e->tm.gaps_big_tier += (uint32_t)(todo.size() - failed);
+    e->tm.max_tier_run = (uint32_t)tier;
   }
   e->ran = true;
   return G2S_OK;
@@ -646,6 +651,9 @@ extern "C" int g2s_fill_records(g2s_engine *e, const char *const *seqs, const ch
     total.h2d_ms += e->tm.h2d_ms; total.kernel_ms += e->tm.kernel_ms; total.d2h_ms += e->tm.d2h_ms; total.host_ms += e->tm.host_ms;
     total.h2d_bytes += e->tm.h2d_bytes; total.d2h_bytes += e->tm.d2h_bytes; total.launches += e->tm.launches;
     total.gaps_big_tier += e->tm.gaps_big_tier;
+    total.max_tier_run = std::max(total.max_tier_run, e->tm.max_tier_run);
+    total.gaps_rerun_scratch += e->tm.gaps_rerun_scratch; total.gaps_rerun_out_full += e->tm.gaps_rerun_out_full;
+    total.gaps_mem_limit += e->tm.gaps_mem_limit;
     return rc;
   };
   std::vector<std::string> filled;

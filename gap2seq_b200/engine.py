@@ -20,6 +20,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libg2s_gpu.so")
 ST_ORDER_DEPENDENT, ST_MEM_LIMIT, ST_GENERAL_SUBGRAPH, ST_UNABLE_TO_BACKTRACE, ST_BIG_TIER = 1, 2, 4, 8, 16
 ST_DEVICE_TRACED = 32
 GAP_SKIP_CONFIDENT, GAP_ALL_PATHS = 1, 2
+ABI_VERSION = 2   # G2S_ABI_VERSION of include/g2s.h
 
 
 class G2SError(RuntimeError):
@@ -56,7 +57,8 @@ class G2SResult(C.Structure):
 class G2STiming(C.Structure):
     _fields_ = [("h2d_ms", C.c_double), ("kernel_ms", C.c_double), ("d2h_ms", C.c_double), ("host_ms", C.c_double),
                 ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("launches", C.c_uint32),
-                ("gaps_big_tier", C.c_uint32)]
+                ("gaps_big_tier", C.c_uint32), ("max_tier_run", C.c_uint32), ("gaps_rerun_scratch", C.c_uint32),
+                ("gaps_rerun_out_full", C.c_uint32), ("gaps_mem_limit", C.c_uint32)]
 
 
 class G2SRunOptions(C.Structure):
@@ -156,7 +158,7 @@ class Engine:
                  lib=None):
         self.L = lib or load_library()
         self.k = k
-        cfg = G2SConfig(1, device, k, max_fuz, max_mem_bytes, host_threads, 0)
+        cfg = G2SConfig(ABI_VERSION, device, k, max_fuz, max_mem_bytes, host_threads, 0)
         h = C.c_void_p()
         self._check(self.L.g2s_create(C.byref(cfg), C.byref(h)))
         self.h = h

@@ -190,7 +190,7 @@ def _loguniform(rng, lo, hi, n):
 
 
 def make_workload(name: str, scale: float = 1.0, *, inverted_copies: bool = False, seed: int | None = None,
-                  with_reads: bool = True) -> Workload:
+                  with_reads: bool = True, repeat_load: float = 1.0) -> Workload:
     """The five named configurations of BASELINE.json; `scale` shrinks genome and gap count
     for tests (scale=1.0 is the full configuration).  with_reads=False skips the read simulation (the genome is the
     same, the gap list is NOT: ranks that receive the graph by broadcast place their own gaps, bench.py)."""
@@ -199,7 +199,7 @@ def make_workload(name: str, scale: float = 1.0, *, inverted_copies: bool = Fals
         real = simulate_reads
         simulate_reads = lambda g, cov, rl, err, rng: np.zeros((0, rl), dtype=np.uint8)   # noqa: E731
         try:
-            return make_workload(name, scale, inverted_copies=inverted_copies, seed=seed)
+            return make_workload(name, scale, inverted_copies=inverted_copies, seed=seed, repeat_load=repeat_load)
         finally:
             simulate_reads = real
     flank = 100
@@ -221,13 +221,18 @@ def make_workload(name: str, scale: float = 1.0, *, inverted_copies: bool = Fals
         rng = np.random.default_rng(3 if seed is None else seed)
         n = max(60000, int(5_000_000 * scale)); ngap = max(4, int(round(60 * scale)))
         g = random_genome(n, rng)
+        # repeat_load (cfg3 only, default 1.0 = the configuration the goldens were made with): multiplies the number of
+        # interspersed copies, i.e. the fraction of the genome they cover (1.6 % at 1.0).  A walk that leaves one copy
+        # then runs into the next one before the DP ends and branches again: at ~20 % coverage (repeat_load 12) a gap
+        # holds 10^6 - 10^7 DP cells, the regime of the reference probe in SURVEY section 6
+        rl = float(repeat_load)
         starts = add_repeats(g, rng, n_tandem=max(2, int(40 * scale)), n_families=1,
-                             copies=(max(8, int(100 * scale)), max(12, int(300 * scale))),
+                             copies=(max(8, int(100 * scale * rl)), max(12, int(300 * scale * rl))),
                              family_len=(300, 500), divergence=(0.02, 0.05), inverted_copies=inverted_copies)
         reads = simulate_reads(g, 30, 100, 0.0, rng)
         gaps = place_gaps(g, rng.integers(100, 701, size=ngap), rng, flank=flank, near=starts)
         return Workload(name, 31, 2, 500, 10, g, reads, gaps,
-                        note=f"inverted_copies={inverted_copies}")
+                        note=f"inverted_copies={inverted_copies} repeat_load={rl:g}")
     if name == "cfg4":      # chromosome scale: 100 Mbp, 30x, 10k gaps 100 bp - 5 kbp
         rng = np.random.default_rng(4 if seed is None else seed)
         n = max(40000, int(100_000_000 * scale)); ngap = max(4, int(round(10_000 * scale)))
@@ -255,3 +260,30 @@ def make_workload(name: str, scale: float = 1.0, *, inverted_copies: bool = Fals
         reads = simulate_reads(donor, 40, 100, 0.0, rng)
         return Workload(name, 31, 2, 500, 10, donor, reads, gaps, note="-v/-R genotyping as gap records")
     raise ValueError(f"unknown workload {name!r}")
+
+
+def make_order_dependent_workload(seed: int = 77, n_plain: int = 3) -> Workload:
+    """A workload with ONE gap whose border provably receives both strands of a k-mer on one level, between
+    `n_plain` ordinary gaps before and after it.
+
+    Two copies of a 60 bp segment L are followed by equally long but different segments a / b and then by a 101 bp
+    segment S in copy 1 and by revcomp(S) in copy 2.  A walk that starts in L branches after it; 35 bases into S (its
+    middle k-mer, k = 31) the walk through copy 1 stands on k-mer K and the walk through copy 2 on revcomp(K) at the same
+    level: the reference inserts both strands of one node into one unordered_set (src/Gap2Seq.cpp:1064), its result
+    depends on hashtable order, and the engine must flag the gap G2S_ST_ORDER_DEPENDENT.  The gap starts right after
+    L of copy 1."""
+    rng = np.random.default_rng(seed)
+    g = random_genome(40_000, rng)
+    L, a, b, S = (random_genome(n, rng) for n in (60, 50, 50, 101))
+    p1, p2 = 12_000, 25_000
+    c1 = np.concatenate([L, a, S])
+    c2 = np.concatenate([L, b, revcomp(S)])
+    g[p1:p1 + c1.size] = c1
+    g[p2:p2 + c2.size] = c2
+    reads = simulate_reads(g, 30, 100, 0.0, rng)
+    plain = place_gaps(np.concatenate([g[:p1 - 500], g[p2 + 1000:]]), rng.integers(80, 400, size=2 * n_plain), rng, flank=100)
+    gs, glen = p1 + L.size, 320
+    od = GapRecord(name=f"hairpin genome:{gs}-{gs + glen}", seq=g[gs - 100:gs].tobytes().decode() + "N" * glen +
+                   g[gs + glen:gs + glen + 100].tobytes().decode(), truth=g[gs:gs + glen].tobytes().decode(), pos=gs, gap_len=glen)
+    return Workload("order_dependent", 31, 2, 500, 10, g, reads, plain[:n_plain] + [od] + plain[n_plain:],
+                    note="one Q3 gap between plain gaps")

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define G2S_ABI_VERSION 1
+#define G2S_ABI_VERSION 2
 
 enum {
   G2S_OK = 0,
@@ -102,6 +102,11 @@ typedef struct g2s_timing {
   uint64_t h2d_bytes, d2h_bytes;
   uint32_t launches;                            /* kernels launched by that call */
   uint32_t gaps_big_tier;
+  /* device-memory budget (the -max-mem analogue): what the tier ladder did in that call */
+  uint32_t max_tier_run;                        /* highest tier a pass ran in (0 = thin tier only) */
+  uint32_t gaps_rerun_scratch;                  /* gap runs that ended because the scratch slice of their tier was full */
+  uint32_t gaps_rerun_out_full;                 /* gap runs that ended because the pass's pack arena was full */
+  uint32_t gaps_mem_limit;                      /* gaps given up: no larger tier fits g2s_config.max_mem_bytes (count -1) */
 } g2s_timing;
 
 const char *g2s_last_error(void);
