@@ -422,6 +422,7 @@ static int do_run(g2s_engine *e) {
   e->passes.clear();
   e->tm.kernel_ms = 0; e->tm.launches = 0; e->tm.gaps_big_tier = 0; e->tm.d2h_bytes = 0; e->tm.d2h_ms = 0; e->tm.host_ms = 0;
   e->tm.max_tier_run = 0; e->tm.gaps_rerun_scratch = 0; e->tm.gaps_rerun_out_full = 0; e->tm.gaps_mem_limit = 0;
+  e->tm.table_lookups = 0; e->tm.node_ops = 0;
   e->out_pass.assign(n, -1);
   if (n == 0) { e->ran = true; return G2S_OK; }
   CUDA_TRY(cudaMemsetAsync(e->d_outs.p, 0, n * sizeof(GapOut), e->st));
@@ -469,6 +470,7 @@ static int do_run(g2s_engine *e) {
     if (tier > 0) e->tm.gaps_big_tier += (uint32_t)(todo.size() - failed);
     e->tm.max_tier_run = (uint32_t)tier;
   }
+  for (const GapOut &o : e->outs) { e->tm.table_lookups += o.table_lookups; e->tm.node_ops += o.node_ops; }
   e->ran = true;
   return G2S_OK;
 }
@@ -654,6 +656,7 @@ extern "C" int g2s_fill_records(g2s_engine *e, const char *const *seqs, const ch
     total.max_tier_run = std::max(total.max_tier_run, e->tm.max_tier_run);
     total.gaps_rerun_scratch += e->tm.gaps_rerun_scratch; total.gaps_rerun_out_full += e->tm.gaps_rerun_out_full;
     total.gaps_mem_limit += e->tm.gaps_mem_limit;
+    total.table_lookups += e->tm.table_lookups; total.node_ops += e->tm.node_ops;
     return rc;
   };
   std::vector<std::string> filled;

@@ -109,7 +109,7 @@ enum {  // GapOut.status (device side)
   GS_ORDER_DEPENDENT = 1, GS_OVERFLOW = 2, GS_GENERAL = 4, GS_OUT_FULL = 8, GS_INTERNAL = 16, GS_TRACED = 32, GS_DONE = 0x100
 };
 
-struct GapOut {        // 184 B
+struct GapOut {        // 192 B
   uint32_t status;
   uint32_t count_fwd, count_all;
   uint32_t n_plen;
@@ -131,6 +131,8 @@ struct GapOut {        // 184 B
   uint32_t cyc[6];     // SM cycles (>> 4) spent in: init, right pass, forward pass, backward marking, pack, total
   uint32_t prof[8];    // forward pass detail (>> 4): scout, node phase, layout, found scan, general levels; [5] narrow batches,
                        // [6] narrow levels, [7] general levels
+  uint32_t table_lookups;   // lookups in the global k-mer table (hash-gathers: one per scout segment / expanded successor / flank k-mer)
+  uint32_t node_ops;        // find / find-or-insert operations on the gap's own node table
 };
 
 struct SliceLayout {   // byte offsets inside one scratch slice; identical for every slice of a launch
@@ -208,6 +210,7 @@ struct GShared {       // per group, in shared memory
   uint32_t fc1[MAX_FUZ + 1], fc2[MAX_FUZ + 1];
   uint32_t queue_item;
   unsigned long long prof[8];
+  uint32_t table_lookups, node_ops;   // counters of the hash work (GapOut)
   int32_t tlo;          // first level that has thit entries: max(0, g + lmf - e)
   uint32_t trow;        // entries per target row: Dmax - tlo + 1
   // handed from the right pass / the forward pass to the rest of the gap (the two may run on different warps)
@@ -570,6 +573,15 @@ __device__ __forceinline__ void expand_segments(const Table &T, NarrowBuf &nb, i
 }
 #endif
 
+// hash-gather accounting: the warp scout makes one table lookup per recorded segment
+G2S_D void count_scout_lookups(GShared &sh, const NarrowBuf &nb, int w) {
+#ifdef G2S_DEVICE_BUILD
+  uint32_t n = 0;
+  for (int t = 0; t < w && t < NARROW_W; t++) n += nb.nseg[t];
+  a_add(&sh.table_lookups, n);
+#endif
+}
+
 template <class G, bool FORWARD>
 G2S_D int narrow_scout(const Table &T, GShared &sh, NarrowBuf &nb, int w, int maxlen) {
 #ifdef G2S_DEVICE_BUILD
@@ -647,13 +659,15 @@ G2S_D int narrow_right(const Table &T, const Slice &S, GShared &sh, NarrowBuf &n
   const int len = narrow_scout<G, false>(T, sh, nb, n, maxlen);
   if (len == 0) return 0;
   n = (int)ld_sh(&nb.nw_w);   // the scout splits chains at branches; a chain has no state before its birth level
-  if (rank == 0) { nb.ch_cnt = 0; nb.nnext = 0; }
+  if (rank == 0) { nb.ch_cnt = 0; nb.nnext = 0; count_scout_lookups(sh, nb, n); }
   G::sync();
+  uint32_t my_ops = 0;
   for (int q = rank; q < len * n; q += gsz) {
     const int l = q / n, t = q - l * n;
     if (!nb.ch_a[l][t]) continue;
     const Canon cp = canonical(nb.ch_s[l][t], k);
     const uint32_t en = node_insert(S, sh, cp.key);
+    my_ops++;
     if (en == NONE32) continue;
     a_or(&S.ent[en].flags, NF_IN_RS);
     a_max(&S.ent[en].rstamp, (uint32_t)(c + l + 1) * 2 + cp.strand);
@@ -682,6 +696,7 @@ G2S_D int narrow_right(const Table &T, const Slice &S, GShared &sh, NarrowBuf &n
     a_add(&nb.ch_cnt, ns);
     if (l == len - 1) nb.nnext = ns;
   }
+  if (my_ops) a_add(&sh.node_ops, my_ops);
   G::sync();
   if (rank == 0) sh.cells_right += nb.ch_cnt;
   *n_out = ld_sh(&nb.nnext);
@@ -720,8 +735,9 @@ G2S_D int narrow_forward(const Table &T, const Slice &S, GShared &sh, NarrowBuf 
   if (len == 0) return 0;
   w = (int)ld_sh(&nb.nw_w);   // the scout may have split chains
   for (int t = rank; t < w; t += gsz) nb.nw_fail[t] = len;
-  if (rank == 0) nb.nw_bad = len;
+  if (rank == 0) { nb.nw_bad = len; count_scout_lookups(sh, nb, w); }
   G::sync();
+  uint32_t my_ops = 0;
   // node table + prune test, one (level, chain) per thread: ch_e = node entry; first failing level per chain
   for (int q = rank; q < len * w; q += gsz) {
     const int l = q / w, t = q - l * w;
@@ -732,11 +748,13 @@ G2S_D int narrow_forward(const Table &T, const Slice &S, GShared &sh, NarrowBuf 
       uint32_t nf = 0;
       if (c + l < prune_from) en = node_insert(S, sh, cs.key, &nf);
       else { en = node_find(S, cs.key, &nf); if (en != NONE32 && !(nf & NF_IN_RS)) en = NONE32; }
+      my_ops++;
       if (nf & NF_TARGET) nb.ch_a[l][t] |= 1u << 17;
     }
     nb.ch_e[l][t] = en;
     if (en == NONE32) a_mini(&nb.nw_fail[t], l);
   }
+  if (my_ops) a_add(&sh.node_ops, my_ops);
   G::sync();
   // the scout splits chains before it knows where chains get pruned: a chain whose parent failed before the split
   // level descends from a state that has no cell, so it never lives (parents have lower indices than their children)
@@ -1168,6 +1186,7 @@ G2S_D void gap_init(const FillParams &P, const GapCtx &cx, const Slice &S, GShar
   if (rank == 0) {
     sh.tlo = cx.tlo; sh.trow = (uint32_t)cx.trow;
     for (int q = 0; q < 8; q++) sh.prof[q] = 0;
+    sh.table_lookups = (uint32_t)(cx.lmf + cx.rmf + 2); sh.node_ops = 0;
     sh.ncells = 0; sh.nnodes = 0; sh.status = 0;
     sh.nbuf[0].nnext = 0; sh.nbuf[1].nnext = 0;
     sh.npack = 0; sh.nB = 0; sh.n_edges = 0; sh.n_src = 0; sh.n_sink = 0;
@@ -1198,7 +1217,7 @@ G2S_D void gap_right(const FillParams &P, const GapCtx &cx, const Slice &S, GSha
   const int k = cx.k, rank = G::rank(), gsz = G::size(), rmf = cx.rmf, right_half = cx.right_half;
   const unsigned long long t0 = now_cycles();
   int levels_r = 0;
-  uint32_t n = 0;
+  uint32_t n = 0, my_lookups = 0;   // general-path successors: one table lookup + one node operation each
   int cur = 0;
   if (rank == 0) {
     uint64_t x = kmer_from_ascii(cx.rsstr + rmf, k);
@@ -1233,6 +1252,7 @@ G2S_D void gap_right(const FillParams &P, const GapCtx &cx, const Slice &S, GSha
     for (uint32_t i = rank; i < n; i += gsz) {
       const uint64_t x = fk[i];
       uint32_t im = fm[i];
+      my_lookups += popc32(im & 15u);
       for (uint32_t nt = 0; nt < 4; nt++) {
         if (!((im >> nt) & 1)) continue;
         uint64_t p = pred_kmer(x, nt, T);
@@ -1280,6 +1300,7 @@ G2S_D void gap_right(const FillParams &P, const GapCtx &cx, const Slice &S, GSha
     if (rank == 0) sh.cells_right += n;
     cur ^= 1;
   }
+  if (my_lookups) { a_add(&sh.table_lookups, my_lookups); a_add(&sh.node_ops, my_lookups); }
   G::sync();
   if (rank == 0) { sh.levels_r = levels_r; sh.cyc_right = now_cycles() - t0; }
   G::sync();
@@ -1294,6 +1315,7 @@ G2S_D void gap_forward(const FillParams &P, const GapDev &gd, const GapCtx &cx, 
   const bool all_paths = cx.all_paths;
   int top_level = 0;       // last level that was expanded into
   int levels_f = 0;
+  uint32_t my_lookups = 0;
   bool waited = !W::kConcurrent;
   bool overflow = group_overflow<G>(sh);
   if (!overflow) {
@@ -1361,6 +1383,7 @@ G2S_D void gap_forward(const FillParams &P, const GapDev &gd, const GapCtx &cx, 
             const uint32_t om = (ld_cg(&S.cflags[i]) >> CF_OMASK_SHIFT) & 15u;
             np = clamp_paths(ld_cg(&S.cc[i]));
             u0 = (uint32_t)(x >> (2 * (k - 1))) & 3u;
+            my_lookups += popc32(om);
 #pragma unroll
             for (uint32_t nt = 0; nt < 4; nt++) {
               cand_e[nt] = NONE32;
@@ -1463,6 +1486,7 @@ G2S_D void gap_forward(const FillParams &P, const GapDev &gd, const GapCtx &cx, 
     }
   }
   if (!waited) W::wait_right();
+  if (my_lookups) { a_add(&sh.table_lookups, my_lookups); a_add(&sh.node_ops, my_lookups); }
   G::sync();
   if (rank == 0) { sh.top_level = top_level; sh.levels_f = levels_f; sh.fwd_overflow = overflow ? 1 : 0; }
   G::sync();
@@ -1730,6 +1754,7 @@ G2S_D void gap_finish(const Slice &S, GShared &sh, GapOut *out, const unsigned l
     o.cyc[4] = (uint32_t)((t_end - t[4]) >> 4); o.cyc[5] = (uint32_t)((t_end - t[0]) >> 4);
     for (int q = 0; q < 5; q++) o.prof[q] = (uint32_t)(sh.prof[q] >> 4);
     for (int q = 5; q < 8; q++) o.prof[q] = (uint32_t)sh.prof[q];
+    o.table_lookups = sh.table_lookups; o.node_ops = sh.node_ops;
     *out = o;
   }
   G::sync();

@@ -20,7 +20,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libg2s_gpu.so")
 ST_ORDER_DEPENDENT, ST_MEM_LIMIT, ST_GENERAL_SUBGRAPH, ST_UNABLE_TO_BACKTRACE, ST_BIG_TIER = 1, 2, 4, 8, 16
 ST_DEVICE_TRACED = 32
 GAP_SKIP_CONFIDENT, GAP_ALL_PATHS = 1, 2
-ABI_VERSION = 2   # G2S_ABI_VERSION of include/g2s.h
+ABI_VERSION = 3   # G2S_ABI_VERSION of include/g2s.h
 
 
 class G2SError(RuntimeError):
@@ -58,7 +58,8 @@ class G2STiming(C.Structure):
     _fields_ = [("h2d_ms", C.c_double), ("kernel_ms", C.c_double), ("d2h_ms", C.c_double), ("host_ms", C.c_double),
                 ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("launches", C.c_uint32),
                 ("gaps_big_tier", C.c_uint32), ("max_tier_run", C.c_uint32), ("gaps_rerun_scratch", C.c_uint32),
-                ("gaps_rerun_out_full", C.c_uint32), ("gaps_mem_limit", C.c_uint32)]
+                ("gaps_rerun_out_full", C.c_uint32), ("gaps_mem_limit", C.c_uint32),
+                ("table_lookups", C.c_uint64), ("node_ops", C.c_uint64)]
 
 
 class G2SRunOptions(C.Structure):

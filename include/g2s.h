@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define G2S_ABI_VERSION 2
+#define G2S_ABI_VERSION 3
 
 enum {
   G2S_OK = 0,
@@ -107,6 +107,10 @@ typedef struct g2s_timing {
   uint32_t gaps_rerun_scratch;                  /* gap runs that ended because the scratch slice of their tier was full */
   uint32_t gaps_rerun_out_full;                 /* gap runs that ended because the pass's pack arena was full */
   uint32_t gaps_mem_limit;                      /* gaps given up: no larger tier fits g2s_config.max_mem_bytes (count -1) */
+  /* hash work of the gap runs that produced the results (re-runs in a larger tier count once) */
+  uint64_t table_lookups;                       /* hash-gathers in the global k-mer table (one 32-byte sector each when the
+                                                   first probe hits): flank k-mers, scout segments, expanded successors */
+  uint64_t node_ops;                            /* find / find-or-insert operations on the per-gap node tables */
 } g2s_timing;
 
 const char *g2s_last_error(void);
