@@ -1,18 +1,27 @@
 #!/usr/bin/env python
 """bench.py - throughput of the gap-filling hot path (Gap2Seq::fill_gap, reference src/Gap2Seq.cpp:858-1556)
-on the BASELINE.json workload `configs[1]` (S. aureus-scale synthetic genome, ~170 gaps up to 3 kbp, k=31).
+on the BASELINE.json workload the metric is quoted on: `configs[3]`, the chromosome-scale synthetic genome with
+10 000 gaps of 100 bp - 5 kbp ("gaps sharded across 1/2/4/8 B200"); it fits one GPU (8.6 GB k-mer table).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2] [--scale 1.0]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg4] [--scale 1.0]
 
-One "step" = one pass of the hot path over the workload's batch of gaps.
-  value        gaps/s of the device pass with the gaps already resident in HBM (CUDA events on the engine's stream)
+One "step" = one pass of the hot path over the workload's whole gap list.
+  value        gaps/s of the device pass with the gaps already resident in HBM (CUDA events on the engine's stream).
+               N > 1 (torchrun, one process per GPU): the ONE gap list is split longest-processing-time-first over the
+               ranks (strong scaling), the k-mer table is built on rank 0 and replicated by one NCCL broadcast; the
+               step time is the max over ranks
   e2e          gaps/s through the reference-facing driver call (g2s_fill_records: host strings in, filled strings
-               out; H2D, kernels, D2H and the host traceback inside the timed region)
-  roofline     dominant kernel (k_fill_thin) against the HBM-gather roofline: 52 algorithmic bytes per DP cell
-  cpu_baseline the oracle port on a bounded sample of the same gaps (1 host core)
-`--impl reference` times the unmodified reference binary (oracle/_ref/bin/Gap2Seq-core -nb-cores <all cores>) on the
-same workload on the host CPU.  Graph construction is not part of any timed region (BASELINE.json: "timed
-separately and is not the product"); its duration is reported under config.
+               out; H2D, kernels, D2H, tracebacks and splice inside the timed region).  N > 1: rank 0 makes that call on
+               an engine that owns all N GPUs (g2s_create_multi: sharded waves, results gathered in input order, one
+               rand() stream) while the other ranks wait; its output must equal the one-GPU output byte for byte
+  roofline     the kernel with the largest share of the step against the HBM-gather roofline: 52 algorithmic bytes per
+               DP cell; kernel name = the tier that actually finished the gaps
+  cpu_baseline the oracle port on a bounded prefix of the same gaps (1 host core)
+The step's output is compared with the oracle (a prefix of the records, outside the timed regions): a mismatch is fatal.
+`--impl reference` times the unmodified reference binary (oracle/_ref/bin/Gap2Seq-core) on the host CPU at
+-nb-cores 1, 4 and all cores (the timed steps run at the fastest of the three) on a bounded sample of the workload.
+Graph construction is not part of any timed region (BASELINE.json: "timed separately and is not the product"); its
+duration is reported under config.
 """
 from __future__ import annotations
 
@@ -48,9 +57,11 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg2")
+    ap.add_argument("--workload", default="cfg4")
     ap.add_argument("--scale", type=float, default=1.0)
-    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline sample")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
+    ap.add_argument("--oracle-seconds", type=float, default=8.0, help="budget of the oracle check of the step's output")
+    ap.add_argument("--ref-gaps", type=int, default=1000, help="--impl reference: gaps in the bounded sample")
     return ap.parse_args()
 
 

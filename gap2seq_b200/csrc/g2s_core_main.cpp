@@ -5,13 +5,15 @@
 //
 //   Gap2Seq-core -k 31 -solid 2 -reads R1.fa[,R2.fa] -scaffolds gaps.fa -filled out.fa
 //                [-dist-error 500] [-fuz 10] [-max-mem 20] [-all-upper] [-best-only] [-unique] [-randseed S]
-//                [-nb-cores N] [-device D]
+//                [-nb-cores N] [-device D] [-gpus G]
 //   Gap2Seq-core ... -left L -right R -length n -filled out.fa            (single-gap mode, src/Gap2Seq.cpp:227-283)
 //
 // Differences, all deliberate: the de Bruijn graph is built on the GPU from the reads (exact solid k-mer set, no
 // Bloom filter, no ./.h5 file); -nb-cores only sets the host threads of the subgraph analysis; -max-mem bounds the
-// device scratch.  stdout carries the same parameter echo, per-gap "Scaffold:" / "SubgraphStats:" lines and the final
+// device scratch; -gpus G shards the gaps over GPUs D .. D+G-1 of the box (one k-mer table per GPU, replicated once;
+// results gathered in input order, one rand() stream - the output does not depend on G).  stdout carries the same parameter echo, per-gap "Scaffold:" / "SubgraphStats:" lines and the final
 // "Filled X gaps out of Y" as the reference.
+#include <algorithm>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -67,6 +69,7 @@ static void usage() {
                "   -k          (1 arg) :    k-mer length  [default '31']\n"
                "   -nb-cores   (1 arg) :    number of cores  [default '0']\n"
                "   -device     (1 arg) :    CUDA device ordinal  [default '0']\n"
+               "   -gpus       (1 arg) :    number of GPUs the gaps are sharded over (devices D .. D+G-1)  [default '1']\n"
                "   -verbose    (1 arg) :    verbosity level  [default '1']\n"
                "   -version    (0 arg) :    version\n"
                "   -help       (0 arg) :    help\n";
@@ -74,12 +77,12 @@ static void usage() {
 
 int main(int argc, char **argv) {
   std::map<std::string, std::string> opt = {{"-k", "31"}, {"-solid", "2"}, {"-dist-error", "500"}, {"-fuz", "10"},
-                                            {"-max-mem", "20"}, {"-randseed", "0"}, {"-nb-cores", "0"}, {"-device", "0"},
+                                            {"-max-mem", "20"}, {"-randseed", "0"}, {"-nb-cores", "0"}, {"-device", "0"}, {"-gpus", "1"},
                                             {"-verbose", "1"}, {"-scaffolds", ""}};
   std::map<std::string, bool> flag = {{"-all-upper", false}, {"-best-only", false}, {"-unique", false}};
   std::map<std::string, bool> saw;
   const char *one[] = {"-k", "-solid", "-reads", "-scaffolds", "-filled", "-dist-error", "-fuz", "-max-mem", "-randseed",
-                       "-left", "-right", "-length", "-nb-cores", "-device", "-verbose"};
+                       "-left", "-right", "-length", "-nb-cores", "-device", "-gpus", "-verbose"};
   for (int i = 1; i < argc; i++) {
     std::string a = argv[i];
     if (a == "-help" || a == "-h") { usage(); return 0; }
@@ -121,7 +124,10 @@ int main(int argc, char **argv) {
   cfg.max_mem_bytes = max_mem;
   cfg.host_threads = atoi(opt["-nb-cores"].c_str());
   g2s_engine *eng = nullptr;
-  if (g2s_create(&cfg, &eng) != G2S_OK) { std::cout << "EXCEPTION: " << g2s_last_error() << std::endl; return 1; }
+  const int n_gpus = std::max(1, atoi(opt["-gpus"].c_str()));
+  std::vector<int32_t> devices(n_gpus);
+  for (int d = 0; d < n_gpus; d++) devices[d] = cfg.device + d;
+  if (g2s_create_multi(&cfg, devices.data(), n_gpus, &eng) != G2S_OK) { std::cout << "EXCEPTION: " << g2s_last_error() << std::endl; return 1; }
 
   // ---- de Bruijn graph from the reads (stand-in for Graph::create, src/Gap2Seq.cpp:199-218); timed separately
   auto t0 = std::chrono::steady_clock::now();

@@ -7,6 +7,7 @@
 //      and therefore walks the device-built predecessor trellis gap after gap.
 // There is no CPU implementation of the DP here: without a CUDA device every call fails with G2S_E_CUDA.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #include <malloc.h>
 
 #include <algorithm>
@@ -114,6 +115,12 @@ struct g2s_engine {
   RandAhead ahead;                     // persistent host buffers of the traceback stage
   RawBuf<char> trace_arena;
   std::unique_ptr<ThreadPool> pool;    // host threads (g2s_config.host_threads) for the stages after a device pass
+  // g2s_create_multi: the engines of the other GPUs of the box.  This engine (devices[0]) owns the graph import, the
+  // sharding of every wave of gaps, the single libc rand() stream of the tracebacks and the output; a peer runs the
+  // device pass + D2H + subgraph analysis of its shard on its own host thread.
+  std::vector<g2s_engine *> peers;
+  std::string table_transport;         // how the table reached the peers ("nccl" / "peer-copy"), for the log
+  double table_replicate_ms = 0;
 };
 
 // ------------------------------------------------------------------------------------------------ C ABI: basics
@@ -153,6 +160,8 @@ extern "C" int g2s_create(const g2s_config *cfg, g2s_engine **out) {
 
 extern "C" void g2s_destroy(g2s_engine *e) {
   if (!e) return;
+  for (g2s_engine *p : e->peers) g2s_destroy(p);
+  e->peers.clear();
   cudaSetDevice(e->cfg.device);
   for (auto &b : e->d_pack) b.release();
   for (auto &b : e->d_fill) b.release();
@@ -163,6 +172,129 @@ extern "C" void g2s_destroy(g2s_engine *e) {
   if (e->st) cudaStreamDestroy(e->st);
   delete e;
 }
+
+
+// ------------------------------------------------------------------------------------------------ several GPUs
+// The k-mer table is built (or imported) on devices[0] and replicated to the peers ONCE, by one ncclBroadcast over
+// NVLink / NVSwitch.  NCCL is bound at run time (dlopen of libnccl.so.2: the library the process already
+// loaded - e.g. torch's - or the system one), so that libg2s_gpu.so itself has no link-time dependency; where no NCCL
+// library can be loaded the table travels by cudaMemcpyPeerAsync over the same links.
+namespace {
+struct NcclApi {
+  typedef struct ncclComm *comm_t;
+  int (*CommInitAll)(comm_t *, int, const int *) = nullptr;
+  int (*CommDestroy)(comm_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  int (*Broadcast)(const void *, void *, size_t, int /*ncclDataType_t*/, int, comm_t, cudaStream_t) = nullptr;
+  const char *(*GetErrorString)(int) = nullptr;
+  bool ok = false;
+  NcclApi() {
+    if (getenv("G2S_NO_NCCL")) return;
+    void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return;
+    CommInitAll = (decltype(CommInitAll))dlsym(h, "ncclCommInitAll");
+    CommDestroy = (decltype(CommDestroy))dlsym(h, "ncclCommDestroy");
+    GroupStart = (decltype(GroupStart))dlsym(h, "ncclGroupStart");
+    GroupEnd = (decltype(GroupEnd))dlsym(h, "ncclGroupEnd");
+    Broadcast = (decltype(Broadcast))dlsym(h, "ncclBroadcast");
+    GetErrorString = (decltype(GetErrorString))dlsym(h, "ncclGetErrorString");
+    ok = CommInitAll && CommDestroy && GroupStart && GroupEnd && Broadcast && GetErrorString;
+  }
+};
+NcclApi &nccl() { static NcclApi a; return a; }
+}  // namespace
+
+static int replicate_table(g2s_engine *e) {
+  if (e->peers.empty() || !e->table.slots) return G2S_OK;
+  const auto t0 = std::chrono::steady_clock::now();
+  const size_t bytes = e->table.cap * sizeof(Slot);
+  for (g2s_engine *p : e->peers) {
+    CUDA_TRY(cudaSetDevice(p->cfg.device));
+    if (p->table.slots) { cudaFree(p->table.slots); p->table.slots = nullptr; }
+    CUDA_TRY(cudaMalloc(&p->table.slots, bytes));
+    p->table.cap = e->table.cap; p->table.n = e->table.n; p->table.k = e->table.k;
+  }
+  const int n = 1 + (int)e->peers.size();
+  bool done = false, dup = false;
+  for (g2s_engine *p : e->peers) {
+    if (p->cfg.device == e->cfg.device) dup = true;
+    for (g2s_engine *q : e->peers) if (q != p && q->cfg.device == p->cfg.device) dup = true;
+  }
+  if (!dup && nccl().ok) {
+    std::vector<int> devs(n);
+    std::vector<g2s_engine *> all(n);
+    all[0] = e; devs[0] = e->cfg.device;
+    for (int i = 1; i < n; i++) { all[i] = e->peers[i - 1]; devs[i] = all[i]->cfg.device; }
+    std::vector<NcclApi::comm_t> comms(n, nullptr);
+    int rc = nccl().CommInitAll(comms.data(), n, devs.data());
+    if (rc == 0) {
+      rc = nccl().GroupStart();
+      for (int i = 0; i < n && rc == 0; i++) {
+        cudaSetDevice(devs[i]);
+        rc = nccl().Broadcast(e->table.slots, all[i]->table.slots, bytes, 0 /* ncclChar */, 0, comms[i], all[i]->st);
+      }
+      const int rc2 = nccl().GroupEnd();
+      if (rc == 0) rc = rc2;
+      for (int i = 0; i < n; i++) { cudaSetDevice(devs[i]); cudaError_t ce = cudaStreamSynchronize(all[i]->st); if (ce != cudaSuccess && rc == 0) rc = -1; }
+      for (int i = 0; i < n; i++) if (comms[i]) nccl().CommDestroy(comms[i]);
+    }
+    if (rc != 0) return fail(G2S_E_CUDA, std::string("table replication (NCCL broadcast): ") + (rc > 0 ? nccl().GetErrorString(rc) : "CUDA error"));
+    done = true;
+    e->table_transport = "nccl";
+  }
+  if (!done) {
+    for (g2s_engine *p : e->peers) {
+      CUDA_TRY(cudaSetDevice(e->cfg.device));
+      int can = 0;
+      cudaDeviceCanAccessPeer(&can, e->cfg.device, p->cfg.device);
+      if (can) { cudaError_t ce = cudaDeviceEnablePeerAccess(p->cfg.device, 0); if (ce != cudaSuccess) cudaGetLastError(); }
+      CUDA_TRY(cudaMemcpyPeerAsync(p->table.slots, p->cfg.device, e->table.slots, e->cfg.device, bytes, e->st));
+    }
+    CUDA_TRY(cudaStreamSynchronize(e->st));
+    e->table_transport = "peer-copy";
+  }
+  CUDA_TRY(cudaSetDevice(e->cfg.device));
+  e->table_replicate_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  if (getenv("G2S_HOST_PROF"))
+    fprintf(stderr, "g2s: table of %.1f MB replicated to %zu peer GPUs by %s in %.1f ms\n", bytes / 1e6, e->peers.size(),
+            e->table_transport.c_str(), e->table_replicate_ms);
+  return G2S_OK;
+}
+
+extern "C" int g2s_create_multi(const g2s_config *cfg, const int32_t *devices, int32_t n_devices, g2s_engine **out) {
+  if (!cfg || !out || !devices || n_devices < 1) return fail(G2S_E_ARG, "g2s_create_multi: bad argument");
+  // G2S_ALLOW_DUPLICATE_DEVICES=1 (tests on a one-GPU box): several engines on one GPU exercise the sharding, the
+  // gather in input order and the table replication (device-to-device copy; NCCL refuses duplicate devices)
+  bool dup = false;
+  for (int i = 0; i < n_devices; i++)
+    for (int j = 0; j < i; j++)
+      if (devices[i] == devices[j]) dup = true;
+  if (dup && !getenv("G2S_ALLOW_DUPLICATE_DEVICES")) return fail(G2S_E_ARG, "g2s_create_multi: device listed twice");
+  g2s_config c0 = *cfg;
+  c0.device = devices[0];
+  g2s_engine *e = nullptr;
+  int rc = g2s_create(&c0, &e);
+  if (rc != G2S_OK) return rc;
+  // the host threads are shared out: the primary keeps its pool for the tracebacks and the splice of the whole batch,
+  // every peer gets a share for the subgraph analysis of its shard
+  const int total = e->pool->size();
+  for (int i = 1; i < n_devices; i++) {
+    g2s_config ci = *cfg;
+    ci.device = devices[i];
+    ci.host_threads = std::max(1, total / n_devices);
+    g2s_engine *p = nullptr;
+    rc = g2s_create(&ci, &p);
+    if (rc != G2S_OK) { g2s_destroy(e); return rc; }
+    e->peers.push_back(p);
+  }
+  cudaSetDevice(e->cfg.device);
+  *out = e;
+  return G2S_OK;
+}
+
+extern "C" int g2s_num_devices(const g2s_engine *e) { return e ? 1 + (int)e->peers.size() : -1; }
 
 extern "C" int g2s_import_kmers(g2s_engine *e, const uint64_t *canon, size_t n) {
   if (!e || (!canon && n)) return fail(G2S_E_ARG, "g2s_import_kmers: null argument");
@@ -178,14 +310,14 @@ extern "C" int g2s_import_kmers(g2s_engine *e, const uint64_t *canon, size_t n) 
   } else {
     CUDA_TRY(cudaStreamSynchronize(e->st));
   }
-  return G2S_OK;
+  return replicate_table(e);
 }
 
 extern "C" int g2s_build_from_reads(g2s_engine *e, const char *bases, const uint64_t *offsets, size_t n_reads, int solid) {
   if (!e || !bases || !offsets) return fail(G2S_E_ARG, "g2s_build_from_reads: null argument");
   CUDA_TRY(cudaSetDevice(e->cfg.device));
   CUDA_TRY(table_from_reads(&e->table, e->cfg.k, bases, offsets, n_reads, solid, e->sms, e->st));
-  return G2S_OK;
+  return replicate_table(e);
 }
 
 extern "C" int g2s_table_raw(g2s_engine *e, void **device_ptr, uint64_t *capacity_slots, uint64_t *n_kmers, uint64_t *bytes) {
@@ -339,6 +471,8 @@ static int run_pass(g2s_engine *e, Pass &p) {
   float ms = 0;
   CUDA_TRY(cudaEventElapsedTime(&ms, e->ev[0], e->ev[1]));
   e->tm.kernel_ms += ms;
+  if (p.tier == 0) { e->tm.kernel_ms_thin += ms; e->tm.launches_thin++; e->tm.thin_shape = (uint32_t)p.shape; }
+  else { e->tm.kernel_ms_wide += ms; e->tm.launches_wide++; }
   if (getenv("G2S_HOST_PROF"))
     fprintf(stderr, "g2s: pass tier %d (shape %d): %zu gaps on %d groups, slice %.1f MB, %.3f ms\n", p.tier, p.shape,
             p.order.size(), p.groups, p.lay.bytes / 1e6, ms);
@@ -423,6 +557,7 @@ static int do_run(g2s_engine *e) {
   e->tm.kernel_ms = 0; e->tm.launches = 0; e->tm.gaps_big_tier = 0; e->tm.d2h_bytes = 0; e->tm.d2h_ms = 0; e->tm.host_ms = 0;
   e->tm.max_tier_run = 0; e->tm.gaps_rerun_scratch = 0; e->tm.gaps_rerun_out_full = 0; e->tm.gaps_mem_limit = 0;
   e->tm.table_lookups = 0; e->tm.node_ops = 0;
+  e->tm.kernel_ms_thin = 0; e->tm.kernel_ms_wide = 0; e->tm.launches_thin = 0; e->tm.launches_wide = 0; e->tm.thin_shape = 0;
   e->out_pass.assign(n, -1);
   if (n == 0) { e->ran = true; return G2S_OK; }
   CUDA_TRY(cudaMemsetAsync(e->d_outs.p, 0, n * sizeof(GapOut), e->st));
@@ -552,14 +687,19 @@ static int do_collect(g2s_engine *e, HostBatch &hb) {
   return G2S_OK;
 }
 
+static int trace_batch(g2s_engine *e, HostBatch &hb, g2s_result *results, char *const *fill_out);
 static int do_finish(g2s_engine *e, g2s_result *results, char *const *fill_out) {
   if (!e || !e->ran) return fail(G2S_E_STATE, "g2s_finish_resident: no device pass has run");
   if (!results && !e->gaps.empty()) return fail(G2S_E_ARG, "null results");
   HostBatch hb;
   int rc = do_collect(e, hb);
   if (rc != G2S_OK) return rc;
+  return trace_batch(e, hb, results, fill_out);
+}
+
+// tracebacks of a whole batch in input order of the libc rand() stream, its only consumer (src/Gap2Seq.cpp:1440, 1513)
+static int trace_batch(g2s_engine *e, HostBatch &hb, g2s_result *results, char *const *fill_out) {
   auto t0 = std::chrono::steady_clock::now();
-  // tracebacks in input order of the libc rand() stream, its only consumer (src/Gap2Seq.cpp:1440, 1513)
   std::vector<TraceJob> jobs(hb.gaps.size());
   for (size_t i = 0; i < jobs.size(); i++) jobs[i] = TraceJob{&hb, i};
   std::vector<g2s_result> res;
@@ -576,27 +716,147 @@ static int do_finish(g2s_engine *e, g2s_result *results, char *const *fill_out) 
   return G2S_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------ one wave of gaps
+// Longest-processing-time-first assignment of a wave's gaps to the GPUs: cost = levels of the DP
+// (g + e + lmf + rmf) x the expected border width (1: no pilot pass here); the next most expensive gap goes to the
+// GPU with the least load so far.  Each shard keeps input order.
+static void lpt_shards(const g2s_gap *gaps, size_t n, int n_dev, std::vector<std::vector<uint32_t>> &shards) {
+  shards.assign(n_dev, std::vector<uint32_t>());
+  std::vector<uint32_t> order(n);
+  for (size_t i = 0; i < n; i++) order[i] = (uint32_t)i;
+  std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return dmax_of(gaps[a]) > dmax_of(gaps[b]); });
+  std::vector<double> load(n_dev, 0.0);
+  for (uint32_t i : order) {
+    int best = 0;
+    for (int d = 1; d < n_dev; d++) if (load[d] < load[best]) best = d;
+    shards[best].push_back(i);
+    load[best] += (double)dmax_of(gaps[i]) + 64.0;
+  }
+  for (auto &sh : shards) std::sort(sh.begin(), sh.end());
+}
+
+static int do_upload(g2s_engine *e, const g2s_gap *gaps, size_t n);
+static int do_run(g2s_engine *e);
+static int do_collect(g2s_engine *e, HostBatch &hb);
+
+// device pass + D2H + subgraph analysis of one wave of gaps -> a detached host batch in the wave's order (no rand()
+// consumed).  With peers the wave is sharded over the GPUs, every GPU on its own host thread.
+static int run_wave(g2s_engine *e, const g2s_gap *gaps, size_t n, HostBatch &hb, double *w_ms /* upload, run, collect */) {
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+    return std::chrono::duration<double, std::milli>(b - a).count();
+  };
+  if (e->peers.empty()) {
+    auto t0 = now();
+    int rc = do_upload(e, gaps, n);
+    auto t1 = now();
+    if (rc == G2S_OK) rc = do_run(e);
+    auto t2 = now();
+    if (rc == G2S_OK) rc = do_collect(e, hb);
+    if (w_ms) { w_ms[0] += ms(t0, t1); w_ms[1] += ms(t1, t2); w_ms[2] += ms(t2, now()); }
+    return rc;
+  }
+  const int nd = 1 + (int)e->peers.size();
+  std::vector<g2s_engine *> eng(nd);
+  eng[0] = e;
+  for (int d = 1; d < nd; d++) eng[d] = e->peers[d - 1];
+  for (int d = 1; d < nd; d++)
+    if (!eng[d]->table.slots) return fail(G2S_E_STATE, "no graph on a peer GPU (import the graph through the multi-GPU engine)");
+  std::vector<std::vector<uint32_t>> shards;
+  lpt_shards(gaps, n, nd, shards);
+  std::vector<std::shared_ptr<HostBatch>> parts(nd);
+  std::vector<int> rcs(nd, G2S_OK);
+  std::vector<std::string> errs(nd);
+  std::vector<double> wall(3 * nd, 0.0);
+  auto one_device = [&](int d) {
+    std::vector<g2s_gap> mine(shards[d].size());
+    for (size_t j = 0; j < mine.size(); j++) mine[j] = gaps[shards[d][j]];
+    parts[d] = std::make_shared<HostBatch>();
+    auto t0 = now();
+    int rc = do_upload(eng[d], mine.data(), mine.size());
+    auto t1 = now();
+    if (rc == G2S_OK) rc = do_run(eng[d]);
+    auto t2 = now();
+    if (rc == G2S_OK) rc = do_collect(eng[d], *parts[d]);
+    wall[3 * d] = ms(t0, t1); wall[3 * d + 1] = ms(t1, t2); wall[3 * d + 2] = ms(t2, now());
+    rcs[d] = rc;
+    if (rc != G2S_OK) errs[d] = g_err;
+  };
+  {
+    std::vector<std::thread> th;
+    for (int d = 1; d < nd; d++) th.emplace_back(one_device, d);
+    one_device(0);
+    for (auto &t : th) t.join();
+  }
+  cudaSetDevice(e->cfg.device);
+  for (int d = 0; d < nd; d++) if (rcs[d] != G2S_OK) return fail(rcs[d], "GPU " + std::to_string(eng[d]->cfg.device) + ": " + errs[d]);
+  // merge in the wave's order; the parts stay alive (and their pinned staging busy) as long as the merged batch
+  hb.k = e->cfg.k;
+  hb.gaps.resize(n); hb.outs.resize(n); hb.tier.assign(n, -2); hb.pack_of.assign(n, 0); hb.gen.resize(n);
+  hb.pack_base.clear(); hb.fill_base.clear();
+  for (int d = 0; d < nd; d++) {
+    HostBatch &pt = *parts[d];
+    const int base = (int)hb.pack_base.size();
+    hb.pack_base.insert(hb.pack_base.end(), pt.pack_base.begin(), pt.pack_base.end());
+    hb.fill_base.insert(hb.fill_base.end(), pt.fill_base.begin(), pt.fill_base.end());
+    hb.staging.insert(hb.staging.end(), pt.staging.begin(), pt.staging.end());
+    pt.staging.clear();
+    for (size_t j = 0; j < shards[d].size(); j++) {
+      const uint32_t i = shards[d][j];
+      hb.gaps[i] = pt.gaps[j]; hb.outs[i] = pt.outs[j]; hb.tier[i] = pt.tier[j]; hb.pack_of[i] = base + pt.pack_of[j];
+      if (j < pt.gen.size()) hb.gen[i] = std::move(pt.gen[j]);
+    }
+  }
+  hb.parts = parts;
+  // timing of the wave: the GPUs ran side by side
+  g2s_timing t{};
+  for (int d = 0; d < nd; d++) {
+    const g2s_timing &x = eng[d]->tm;
+    t.h2d_ms = std::max(t.h2d_ms, x.h2d_ms); t.kernel_ms = std::max(t.kernel_ms, x.kernel_ms); t.d2h_ms = std::max(t.d2h_ms, x.d2h_ms);
+    t.host_ms = std::max(t.host_ms, x.host_ms);
+    t.h2d_bytes += x.h2d_bytes; t.d2h_bytes += x.d2h_bytes; t.launches += x.launches; t.gaps_big_tier += x.gaps_big_tier;
+    t.max_tier_run = std::max(t.max_tier_run, x.max_tier_run); t.gaps_rerun_scratch += x.gaps_rerun_scratch;
+    t.gaps_rerun_out_full += x.gaps_rerun_out_full; t.gaps_mem_limit += x.gaps_mem_limit;
+    t.table_lookups += x.table_lookups; t.node_ops += x.node_ops;
+    t.kernel_ms_thin = std::max(t.kernel_ms_thin, x.kernel_ms_thin); t.kernel_ms_wide = std::max(t.kernel_ms_wide, x.kernel_ms_wide);
+    t.launches_thin += x.launches_thin; t.launches_wide += x.launches_wide; t.thin_shape = std::max(t.thin_shape, x.thin_shape);
+    if (getenv("G2S_HOST_PROF"))
+      fprintf(stderr, "g2s: GPU %d: %zu gaps, upload %.3f ms, run %.3f ms (kernels %.3f), collect %.3f ms\n", eng[d]->cfg.device,
+              shards[d].size(), wall[3 * d], wall[3 * d + 1], x.kernel_ms, wall[3 * d + 2]);
+  }
+  if (w_ms)
+    for (int q = 0; q < 3; q++) { double m = 0; for (int d = 0; d < nd; d++) m = std::max(m, wall[3 * d + q]); w_ms[q] += m; }
+  e->tm = t;
+  return G2S_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ C ABI: fill
 extern "C" int g2s_upload_gaps(g2s_engine *e, const g2s_gap *gaps, size_t n) { return do_upload(e, gaps, n); }
 extern "C" int g2s_run_resident(g2s_engine *e) { return do_run(e); }
 extern "C" int g2s_finish_resident(g2s_engine *e, g2s_result *results, char *const *fill_out) { return do_finish(e, results, fill_out); }
 
 extern "C" int g2s_fill_batch(g2s_engine *e, const g2s_gap *gaps, size_t n, g2s_result *results, char *const *fill_out) {
-  int rc = do_upload(e, gaps, n);
-  if (rc == G2S_OK) rc = do_run(e);
-  if (rc == G2S_OK) rc = do_finish(e, results, fill_out);
-  return rc;
+  if (!e) return fail(G2S_E_ARG, "null engine");
+  if (e->peers.empty()) {
+    int rc = do_upload(e, gaps, n);
+    if (rc == G2S_OK) rc = do_run(e);
+    if (rc == G2S_OK) rc = do_finish(e, results, fill_out);
+    return rc;
+  }
+  if (!results && n) return fail(G2S_E_ARG, "null results");
+  HostBatch hb;
+  int rc = run_wave(e, gaps, n, hb, nullptr);
+  if (rc != G2S_OK) return rc;
+  return trace_batch(e, hb, results, fill_out);
 }
 
 struct g2s_batch { HostBatch hb; };
 
 extern "C" int g2s_submit(g2s_engine *e, const g2s_gap *gaps, size_t n, g2s_batch **out) {
-  if (!out) return fail(G2S_E_ARG, "g2s_submit: null output");
-  int rc = do_upload(e, gaps, n);
-  if (rc == G2S_OK) rc = do_run(e);
-  if (rc != G2S_OK) return rc;
+  if (!out || !e) return fail(G2S_E_ARG, "g2s_submit: null argument");
   g2s_batch *b = new g2s_batch();
-  rc = do_collect(e, b->hb);
+  int rc = run_wave(e, gaps, n, b->hb, nullptr);
   if (rc != G2S_OK) { delete b; return rc; }
   *out = b;
   return G2S_OK;
@@ -637,18 +897,10 @@ extern "C" int g2s_fill_records(g2s_engine *e, const char *const *seqs, const ch
   run.arenap = &e->trace_arena;
   g2s_timing total{};
   int err = G2S_OK;
-  double w_upload = 0, w_run = 0, w_collect = 0;
-  auto ms_since = [](std::chrono::steady_clock::time_point t) {
-    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count();
-  };
+  double w_ms[3] = {0, 0, 0};
+  double &w_upload = w_ms[0], &w_run = w_ms[1], &w_collect = w_ms[2];
   SubmitFn submit = [&](const std::vector<g2s_gap> &gaps, HostBatch &hb) -> int {
-    auto t = std::chrono::steady_clock::now();
-    int rc = do_upload(e, gaps.data(), gaps.size());
-    w_upload += ms_since(t); t = std::chrono::steady_clock::now();
-    if (rc == G2S_OK) rc = do_run(e);
-    w_run += ms_since(t); t = std::chrono::steady_clock::now();
-    if (rc == G2S_OK) rc = do_collect(e, hb);
-    w_collect += ms_since(t);
+    int rc = run_wave(e, gaps.data(), gaps.size(), hb, w_ms);
     err = rc;
     total.h2d_ms += e->tm.h2d_ms; total.kernel_ms += e->tm.kernel_ms; total.d2h_ms += e->tm.d2h_ms; total.host_ms += e->tm.host_ms;
     total.h2d_bytes += e->tm.h2d_bytes; total.d2h_bytes += e->tm.d2h_bytes; total.launches += e->tm.launches;
@@ -657,6 +909,8 @@ extern "C" int g2s_fill_records(g2s_engine *e, const char *const *seqs, const ch
     total.gaps_rerun_scratch += e->tm.gaps_rerun_scratch; total.gaps_rerun_out_full += e->tm.gaps_rerun_out_full;
     total.gaps_mem_limit += e->tm.gaps_mem_limit;
     total.table_lookups += e->tm.table_lookups; total.node_ops += e->tm.node_ops;
+    total.kernel_ms_thin += e->tm.kernel_ms_thin; total.kernel_ms_wide += e->tm.kernel_ms_wide;
+    total.launches_thin += e->tm.launches_thin; total.launches_wide += e->tm.launches_wide; total.thin_shape = e->tm.thin_shape;
     return rc;
   };
   std::vector<std::string> filled;

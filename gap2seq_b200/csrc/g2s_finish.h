@@ -10,6 +10,7 @@
 #include <cstring>
 #include <atomic>
 #include <functional>
+#include <memory>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -460,6 +461,7 @@ struct HostBatch {
   std::vector<std::pair<const void *, size_t>> staging;   // DMA targets to evict from the CPU caches when done
   std::vector<GeneralResult> gen;
   std::vector<char> buf;
+  std::vector<std::shared_ptr<HostBatch>> parts;   // a batch merged from the batches of several GPUs keeps them alive
 
   HostBatch() {}
   HostBatch(const HostBatch &) = delete;

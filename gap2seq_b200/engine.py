@@ -59,7 +59,9 @@ class G2STiming(C.Structure):
                 ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("launches", C.c_uint32),
                 ("gaps_big_tier", C.c_uint32), ("max_tier_run", C.c_uint32), ("gaps_rerun_scratch", C.c_uint32),
                 ("gaps_rerun_out_full", C.c_uint32), ("gaps_mem_limit", C.c_uint32),
-                ("table_lookups", C.c_uint64), ("node_ops", C.c_uint64)]
+                ("table_lookups", C.c_uint64), ("node_ops", C.c_uint64),
+                ("kernel_ms_thin", C.c_double), ("kernel_ms_wide", C.c_double), ("launches_thin", C.c_uint32),
+                ("launches_wide", C.c_uint32), ("thin_shape", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 class G2SRunOptions(C.Structure):
@@ -68,7 +70,7 @@ class G2SRunOptions(C.Structure):
 
 
 # every symbol include/g2s.h declares (tests check that the library exports all of them)
-ABI_SYMBOLS = ["g2s_last_error", "g2s_abi_version", "g2s_create", "g2s_destroy", "g2s_import_kmers",
+ABI_SYMBOLS = ["g2s_last_error", "g2s_abi_version", "g2s_create", "g2s_create_multi", "g2s_num_devices", "g2s_destroy", "g2s_import_kmers",
                "g2s_build_from_reads", "g2s_table_raw", "g2s_table_adopt", "g2s_num_kmers", "g2s_export_kmers", "g2s_contains", "g2s_fill_gap",
                "g2s_fill_batch", "g2s_upload_gaps", "g2s_run_resident", "g2s_finish_resident", "g2s_submit",
                "g2s_batch_peek", "g2s_batch_trace", "g2s_batch_free", "g2s_fill_records", "g2s_free",
@@ -88,6 +90,8 @@ def load_library(path: str | None = None):
     L = C.CDLL(p)
     L.g2s_last_error.restype = C.c_char_p
     L.g2s_create.argtypes = [C.POINTER(G2SConfig), C.POINTER(C.c_void_p)]
+    L.g2s_create_multi.argtypes = [C.POINTER(G2SConfig), C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_void_p)]
+    L.g2s_num_devices.argtypes = [C.c_void_p]
     L.g2s_destroy.argtypes = [C.c_void_p]
     L.g2s_import_kmers.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
     L.g2s_build_from_reads.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
@@ -156,12 +160,18 @@ class Engine:
     """One device-resident de Bruijn graph + the gap-filling passes that run against it."""
 
     def __init__(self, k: int = 31, max_fuz: int = 10, device: int = 0, max_mem_bytes: int = 0, host_threads: int = 0,
-                 lib=None):
+                 lib=None, devices: list[int] | None = None):
+        """`devices`: several GPUs of the box behind one engine (g2s_create_multi): every wave of gaps is sharded
+        over them and gathered in input order; `device` is ignored then."""
         self.L = lib or load_library()
         self.k = k
         cfg = G2SConfig(ABI_VERSION, device, k, max_fuz, max_mem_bytes, host_threads, 0)
         h = C.c_void_p()
-        self._check(self.L.g2s_create(C.byref(cfg), C.byref(h)))
+        if devices is not None:
+            arr = (C.c_int32 * len(devices))(*devices)
+            self._check(self.L.g2s_create_multi(C.byref(cfg), arr, len(devices), C.byref(h)))
+        else:
+            self._check(self.L.g2s_create(C.byref(cfg), C.byref(h)))
         self.h = h
         self._resident = None
 

@@ -80,6 +80,7 @@ def simulate_reads(genome: np.ndarray, coverage: float, read_len: int, err: floa
     n = genome.shape[0]
     n_reads = int(round(coverage * n / read_len))
     starts = rng.integers(0, n - read_len + 1, size=n_reads)
+    simulate_reads.last_starts = starts          # genome position of every read (Workload.reads_near)
     reads = np.empty((n_reads, read_len), dtype=np.uint8)
     ar = np.arange(read_len)[None, :]
     for lo in range(0, n_reads, 1 << 20):   # gathered in chunks: the index matrix of 30 M reads would take 24 GB
@@ -135,6 +136,28 @@ class Workload:
     gaps: list[GapRecord] = field(default_factory=list)
     best_only: bool = False
     note: str = ""
+    read_starts: np.ndarray | None = None   # genome position of reads[i] (set by make_workload)
+
+    def reads_near(self, gaps: list, reach: int = 300) -> np.ndarray:
+        """The reads that overlap the DP window of one of `gaps`: [pos - reach, pos + gap_len + dist_error + reach).
+        The forward pass of a gap walks at most gap_len + dist_error + 2 fuz levels from the left flank and the right
+        pass stays left of the right flank, so on a genome without long repeats the solid k-mers any of these gaps can
+        touch - and their counts - are the same as with all reads: a bounded sample of a large workload that fills to
+        the same result gap by gap (used for the CPU reference arm of bench.py; checked in tests/test_synth_sample.py)."""
+        if self.read_starts is None:
+            raise ValueError("workload without read positions")
+        n, L = self.genome.shape[0], self.reads.shape[1]
+        cover = np.zeros(n + 1, dtype=np.int32)
+        for g in gaps:
+            lo, hi = max(0, g.pos - reach), min(n, g.pos + g.gap_len + self.dist_error + reach)
+            cover[lo] += 1
+            cover[hi] -= 1
+        inside = np.cumsum(cover[:-1]) > 0
+        # a read [s, s + L) overlaps a window iff any of its positions is inside one
+        csum = np.concatenate([[0], np.cumsum(inside, dtype=np.int64)])
+        s0 = self.read_starts
+        keep = (csum[np.minimum(s0 + L, n)] - csum[s0]) > 0
+        return self.reads[keep]
 
     def write(self, outdir: str) -> dict:
         os.makedirs(outdir, exist_ok=True)
@@ -203,6 +226,12 @@ def make_workload(name: str, scale: float = 1.0, *, inverted_copies: bool = Fals
         finally:
             simulate_reads = real
     flank = 100
+    w = _make_workload(name, scale, inverted_copies, seed, repeat_load, flank)
+    w.read_starts = getattr(simulate_reads, "last_starts", None)
+    return w
+
+
+def _make_workload(name, scale, inverted_copies, seed, repeat_load, flank) -> Workload:
     if name == "cfg1":      # 100 kbp, 30x error-free 100 bp reads, 20 gaps of 50-500 bp
         rng = np.random.default_rng(1 if seed is None else seed)
         n = max(20000, int(100_000 * scale)); ngap = max(3, int(round(20 * scale)))

@@ -111,6 +111,11 @@ typedef struct g2s_timing {
   uint64_t table_lookups;                       /* hash-gathers in the global k-mer table (one 32-byte sector each when the
                                                    first probe hits): flank k-mers, scout segments, expanded successors */
   uint64_t node_ops;                            /* find / find-or-insert operations on the per-gap node tables */
+  /* which kernels ran: the thin tier (k_fill_thin<H,M>, thin_shape 0/1/2 = <1,1>/<2,4>/<4,8> warps per gap) and the
+     wide tiers (k_fill_cta, one CTA per gap) */
+  double kernel_ms_thin, kernel_ms_wide;
+  uint32_t launches_thin, launches_wide;
+  uint32_t thin_shape, reserved;
 } g2s_timing;
 
 const char *g2s_last_error(void);
@@ -118,6 +123,16 @@ int g2s_abi_version(void);
 
 int g2s_create(const g2s_config *cfg, g2s_engine **out);
 void g2s_destroy(g2s_engine *e);
+
+/* Several GPUs of one box behind ONE engine (cfg->device is ignored, devices[0] is the primary GPU).  Gaps are
+ * independent units (the reference hands records to -nb-cores Dispatcher workers, src/Gap2Seq.cpp:296-323, 426-432):
+ * every wave of gaps of g2s_fill_batch / g2s_submit / g2s_fill_records is split longest-processing-time-first by
+ * estimated cost over the GPUs, each GPU runs its shard on its own host thread, and the per-gap results are gathered in
+ * input order so that ONE libc rand() stream drives the tracebacks - the output is byte-identical to a one-GPU run.
+ * The k-mer table is built / imported on devices[0] and replicated to the others once (ncclBroadcast over NVLink; NCCL
+ * is bound at run time).  The resident split API (g2s_upload_gaps ...) and g2s_table_raw/adopt address devices[0] only. */
+int g2s_create_multi(const g2s_config *cfg, const int32_t *devices, int32_t n_devices, g2s_engine **out);
+int g2s_num_devices(const g2s_engine *e);
 
 /* Graph import: replaces the GATB neighbour queries (Graph::successors/predecessors/contains,
  * gatb-core/src/gatb/debruijn/impl/Graph.cpp:1284-1345, 2193-2213) by an open-addressing table of 2-bit
