@@ -41,6 +41,7 @@ sys.path.insert(0, ROOT)
 
 PHASES = ["init", "right", "forward", "backward", "pack", "total", "fwd_scout", "fwd_node", "fwd_layout", "fwd_found",
           "fwd_general", "n_narrow_batches", "n_narrow_levels", "n_general_levels"]
+L2_NOTE = "GPU arm: a 256 MiB device buffer is rewritten between timed iterations (L2 is 126 MB)"
 BYTES_PER_CELL = 52          # 8 B frontier read + 32 B sector gather + 4 B count update + 8 B cell write
 WORKLOAD_DESC = {
     "cfg1": "cfg1: 100 kbp random genome, 30x error-free 100 bp reads, 20 gaps 50-500 bp, k=31, dist-error 500",
@@ -61,19 +62,18 @@ def parse_args():
     ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--oracle-seconds", type=float, default=8.0, help="budget of the oracle check of the step's output")
-    ap.add_argument("--ref-gaps", type=int, default=1000, help="--impl reference: gaps in the bounded sample")
+    ap.add_argument("--ref-gaps", type=int, default=600, help="--impl reference: gaps in the bounded sample")
     return ap.parse_args()
 
 
-def measured_traffic(workload: str, scale: float):
-    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of this workload
-    (profiles/ncu_traffic.json, written from the capture named there), or None when there is no capture for it."""
+def measured_traffic(workload: str, scale: float) -> dict:
+    """DRAM bytes per launch and L1 sectors per request of the dominant kernel from the committed `ncu --set full`
+    capture of this workload (profiles/ncu_traffic.json, written from the capture named there); {} without a capture."""
     p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     try:
-        ent = json.load(open(p)).get(f"{workload}@{scale:g}")
-        return (float(ent["dram_bytes_per_launch"]), ent.get("source")) if ent else (None, None)
+        return json.load(open(p)).get(f"{workload}@{scale:g}") or {}
     except Exception:
-        return None, None
+        return {}
 
 
 def measured_peaks():
@@ -130,55 +130,73 @@ class ClockSampler:
 
 
 def make_workload(name: str, scale: float, rank: int):
+    """Every rank generates the SAME workload (seeded); only rank 0 simulates the reads (it builds the graph)."""
     from gap2seq_b200 import synth
-    w = synth.make_workload(name, scale, with_reads=(rank == 0))   # only rank 0 builds the graph (then broadcast)
-    if rank > 0:   # weak scaling: every rank fills its own, equally shaped batch of gaps on the same graph
-        import numpy as np
-        rng = np.random.default_rng(7000 + rank)
-        lens = [g.gap_len for g in w.gaps]
-        w.gaps = synth.place_gaps(w.genome, np.array(lens), rng, flank=100)
-    return w
+    return synth.make_workload(name, scale, with_reads=(rank == 0))
+
+
+def ref_sample(w, n_gaps: int):
+    """Bounded sample of the workload for the CPU arms: a prefix of the gap list and (large workloads) only the reads
+    that overlap those gaps' DP windows - they fill to the same records as with all reads (tests/test_synth_sample.py)."""
+    sub = w.gaps[:n_gaps]
+    if len(sub) < len(w.gaps) and w.read_starts is not None and w.reads.shape[0] > 4_000_000:
+        return sub, w.reads_near(sub), f"first {len(sub)} of {len(w.gaps)} gaps, reads restricted to those gaps' DP windows"
+    return sub, w.reads, (f"first {len(sub)} of {len(w.gaps)} gaps, all reads" if len(sub) < len(w.gaps) else f"all {len(sub)} gaps, all reads")
 
 
 def run_reference(args, rank: int, world: int):
-    """The reference's own CPU implementation of the path on the host cores (rank 0 only)."""
+    """The reference's own CPU implementation of the path on the host cores (rank 0 only): the unmodified binary at
+    -nb-cores 1, 4 and all; the timed steps run at the fastest of the three."""
     if rank != 0:
         return
+    from gap2seq_b200 import synth
     w = make_workload(args.workload, args.scale, 0)
     binp = os.path.join(ROOT, "oracle", "_ref", "bin", "Gap2Seq-core")
     cores = os.cpu_count() or 1
-    n_gaps = len(w.gaps)
+    sub, reads, sample = ref_sample(w, args.ref_gaps)
+    n_gaps = len(sub)
     line = {"impl": "reference", "metric": "gaps_per_s", "unit": "gaps/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
-            "data": "synthetic", "config": {"workload": WORKLOAD_DESC.get(args.workload, args.workload), "scale": args.scale}}
+            "warmup": args.warmup, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int32",
+            "data": "synthetic", "config": {"workload": WORKLOAD_DESC.get(args.workload, args.workload), "scale": args.scale, "l2": L2_NOTE}}
     if os.path.exists(binp):
         tmp = tempfile.mkdtemp(prefix="g2s_refbench_")
         try:
-            paths = w.write(tmp)
-            flags = ["-k", str(w.k), "-solid", str(w.solid), "-fuz", str(w.fuz), "-dist-error", str(w.dist_error),
-                     "-randseed", "1", "-nb-cores", str(cores)]
+            rp, gp = os.path.join(tmp, "reads.fa"), os.path.join(tmp, "gaps.fa")
+            synth.write_reads_fasta(rp, reads)
+            with open(gp, "w") as f:
+                for g in sub:
+                    f.write(f">{g.name}\n{g.seq}\n")
+            flags = ["-k", str(w.k), "-solid", str(w.solid), "-fuz", str(w.fuz), "-dist-error", str(w.dist_error), "-randseed", "1"]
+            if w.best_only:
+                flags.append("-best-only")
             nogap = os.path.join(tmp, "nogap.fa")
             with open(nogap, "w") as f:
                 f.write(">none x\n" + w.genome[:2000].tobytes().decode() + "\n")
 
-            def run(scaf, out):
+            def run(scaf, out, nb):
                 t0 = time.perf_counter()
-                subprocess.run([binp] + flags + ["-reads", paths["reads"], "-scaffolds", scaf, "-filled", out], cwd=tmp,
+                subprocess.run([binp] + flags + ["-nb-cores", str(nb), "-reads", rp, "-scaffolds", scaf, "-filled", out], cwd=tmp,
                                check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
                 return time.perf_counter() - t0
-            t_build = run(nogap, os.path.join(tmp, "o0.fa"))          # builds ./.h5 (DSK + Bloom + MPHF)
-            os.replace(os.path.join(tmp, ".h5"), paths["reads"] + ".h5")   # SURVEY Q14: reload instead of rebuild
-            t_reload = min(run(nogap, os.path.join(tmp, "o0.fa")) for _ in range(2))
+            t_build = run(nogap, os.path.join(tmp, "o0.fa"), cores)          # builds ./.h5 (DSK + Bloom + MPHF)
+            os.replace(os.path.join(tmp, ".h5"), rp + ".h5")                   # SURVEY Q14: reload instead of rebuild
+            t_reload = min(run(nogap, os.path.join(tmp, "o0.fa"), cores) for _ in range(2))
+            by_cores = {}
+            for nb in sorted({1, min(4, cores), cores}):
+                by_cores[nb] = n_gaps / max(run(gp, os.path.join(tmp, "o1.fa"), nb) - t_reload, 1e-6)
+            best = max(by_cores, key=by_cores.get)
             times = []
             for s in range(args.warmup + args.steps):
-                t = run(paths["gaps"], os.path.join(tmp, "o1.fa"))
+                t = run(gp, os.path.join(tmp, "o1.fa"), best)
                 if s >= args.warmup:
                     times.append(max(t - t_reload, 1e-6))
             ms = 1e3 * sum(times) / len(times)
             v = n_gaps / (ms / 1e3)
             line.update({"value": v, "ms_per_step": ms,
-                         "cpu_baseline": {"value": v, "unit": "gaps/s", "cores": cores, "kind": "reference",
-                                          "sample": f"all {n_gaps} gaps per step, Gap2Seq-core -nb-cores {cores}, wall minus "
+                         "cpu_baseline": {"value": v, "unit": "gaps/s", "cores": best, "kind": "reference",
+                                          "gaps_per_s_by_nb_cores": {str(k): round(x, 2) for k, x in by_cores.items()},
+                                          "host_cores": cores,
+                                          "sample": f"{sample}; one step = Gap2Seq-core -nb-cores {best} over the sample, wall minus "
                                                     f"graph reload ({t_reload:.2f} s); graph build {t_build:.1f} s untimed"},
                          "e2e": {"value": v, "unit": "gaps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
         finally:
@@ -186,43 +204,44 @@ def run_reference(args, rank: int, world: int):
     else:   # the reference binary did not travel: time the oracle port (pinned to it by tests/test_oracle_golden.py)
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         import oracle_lib
-        g = oracle_lib.OracleGraph.from_reads(w.k, w.solid, w.reads)
+        g = oracle_lib.OracleGraph.from_reads(w.k, w.solid, reads)
         times = []
         for s in range(args.warmup + args.steps):
             oracle_lib.srand(1)
             t0 = time.perf_counter()
-            for rec in w.gaps:
-                g.fill_record(rec.seq, rec.name, d_err=w.dist_error, fuz=w.fuz)
+            for rec in sub:
+                g.fill_record(rec.seq, rec.name, d_err=w.dist_error, fuz=w.fuz, all_paths=not w.best_only)
             if s >= args.warmup:
                 times.append(time.perf_counter() - t0)
         ms = 1e3 * sum(times) / len(times)
         v = n_gaps / (ms / 1e3)
         line.update({"value": v, "ms_per_step": ms,
                      "cpu_baseline": {"value": v, "unit": "gaps/s", "cores": 1, "kind": "port",
-                                      "sample": f"all {n_gaps} gaps per step, oracle port, 1 thread"},
+                                      "sample": f"{sample}; oracle port, 1 thread"},
                      "e2e": {"value": v, "unit": "gaps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
     print(json.dumps(line), flush=True)
 
 
-def cpu_baseline(w, keys, budget_s: float):
-    """Oracle port (CPU restatement pinned to the reference) on a bounded prefix of the gap list, 1 core."""
+def cpu_baseline_and_check(w, keys, engine_out, budget_s: float):
+    """Oracle port (CPU restatement pinned to the reference) on a bounded prefix of the records, 1 core - and, outside
+    every timed region of the engine, the check of the engine's step output against it: record by record, the same
+    rand() stream (srand(1), input order).  A mismatch is fatal."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib
     g = oracle_lib.OracleGraph.from_kmers(w.k, keys)
     oracle_lib.srand(1)
     t0 = time.perf_counter()
-    n = cells = 0
-    for rec in w.gaps:
-        i = rec.seq.index("N")
-        res, _ = g.fill_gap(rec.seq[i - w.k - w.fuz:i], rec.seq[i + rec.gap_len:i + rec.gap_len + w.k + w.fuz],
-                            rec.gap_len, w.dist_error, w.fuz, w.fuz, all_paths=not w.best_only)
+    n = 0
+    for rec, ours in zip(w.gaps, engine_out):
+        out = g.fill_record(rec.seq, rec.name, d_err=w.dist_error, fuz=w.fuz, all_paths=not w.best_only)
+        if out[0] != ours:
+            sys.exit(f"bench.py: record {rec.name!r} filled by the engine differs from the oracle")
         n += 1
-        cells += res.cells_left + res.cells_right
         if time.perf_counter() - t0 > budget_s:
             break
     dt = time.perf_counter() - t0
-    return {"value": n / dt, "unit": "gaps/s", "cores": 1, "kind": "port", "cells_per_s": cells / dt,
-            "sample": f"first {n} of {len(w.gaps)} gaps, oracle port (oracle/g2s_oracle.cpp), {dt:.1f} s on 1 core"}
+    return {"value": n / dt, "unit": "gaps/s", "cores": 1, "kind": "port",
+            "sample": f"first {n} of {len(w.gaps)} records, oracle port (oracle/g2s_oracle.cpp), {dt:.1f} s on 1 core"}, n
 
 
 def main():
@@ -236,17 +255,20 @@ def main():
         run_reference(args, rank, world)
         return
 
+    import ctypes
     import numpy as np
     import torch
     import torch.distributed as dist
-    from gap2seq_b200 import engine
+    from gap2seq_b200 import engine, shard
     from gap2seq_b200.scaffold import record_gaps
 
     if not torch.cuda.is_available():
         sys.exit("bench.py: no CUDA device (the engine has no CPU fallback)")
     torch.cuda.set_device(local_rank)
+    cpu_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        cpu_group = dist.new_group(backend="gloo")   # waits of idle ranks must not spin on their GPUs
 
     def barrier():
         if world > 1:
@@ -254,36 +276,42 @@ def main():
         torch.cuda.synchronize()
 
     w = make_workload(args.workload, args.scale, rank)
-    # host threads of the engine (tracebacks, splice): the box's cores are shared by the ranks of this node
-    host_threads = max(2, min(16, (os.cpu_count() or 2) // max(1, world)))
+    # host threads of the engine (subgraph analysis, tracebacks, splice)
+    cores = os.cpu_count() or 2
+    host_threads = max(2, min(16, cores // max(1, world)))
     eng = engine.Engine(k=w.k, max_fuz=w.fuz, device=local_rank, host_threads=host_threads)
     t0 = time.perf_counter()
-    if rank == 0 or world == 1:
+    if rank == 0:
         eng.build_from_reads(w.reads, w.solid)
     t_graph = time.perf_counter() - t0
     t_bcast, table_bytes = 0.0, 0
     if world > 1:   # the table is built once and replicated by ONE NCCL broadcast over NVLink (no per-gap collective)
-        from gap2seq_b200 import shard
         barrier()
         t0 = time.perf_counter()
         table_bytes = shard.broadcast_table(eng, 0)
         barrier()
         t_bcast = time.perf_counter() - t0
     n_kmers = eng.num_kmers()
-    specs = [s for rec in w.gaps for s in record_gaps(rec.seq, w.k, w.fuz, w.dist_error, all_paths=not w.best_only)]
+    per_rec = [record_gaps(rec.seq, w.k, w.fuz, w.dist_error, all_paths=not w.best_only) for rec in w.gaps]
+    specs = [s for r in per_rec for s in r]
     seqs = [g.seq for g in w.gaps]
     names = [g.name for g in w.gaps]
-    n_gaps = len(specs)
+    n_all = len(specs)
+    # strong scaling: ONE gap list, longest-processing-time-first over the ranks
+    costs = [shard.estimate_cost(s.gap_len, s.gap_err, w.fuz) for s in specs]
+    shards = shard.lpt_shards(costs, world)
+    mine = [specs[i] for i in shards[rank]]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
 
     # ---- device pass, inputs resident in HBM
-    eng.upload(specs)
+    eng.upload(mine)
     for _ in range(args.warmup):
         eng.run_resident()
     sampler = ClockSampler(local_rank)
     sampler.start()
     barrier()
     kern_ms, launches = [], 0
+    tier_ms = {"chain": 0.0, "thin": 0.0, "wide": 0.0}
     t_region = time.perf_counter()
     for _ in range(args.steps):
         flush.zero_()
@@ -292,90 +320,126 @@ def main():
         t = eng.timing()
         kern_ms.append(t.kernel_ms)
         launches += t.launches
+        tier_ms["chain"] += t.kernel_ms_chain; tier_ms["thin"] += t.kernel_ms_thin; tier_ms["wide"] += t.kernel_ms_wide
     barrier()
     t_region = time.perf_counter() - t_region
+    t_dev = eng.timing()
     phase_sum, phase_slowest = eng.phase_cycles()
     res, fills = eng.finish_resident()
     cells = sum(r.cells_left + r.cells_right for r in res)
     filled = sum(1 for r in res if r.count > 0)
-    exact = sum(1 for f, rec in zip(fills, w.gaps) if f[:-w.k] == rec.truth) if len(fills) == len(w.gaps) else None
-    big = eng.timing().gaps_big_tier
+    exact = None
+    if world == 1 and len(fills) == len(w.gaps):
+        exact = sum(1 for f, rec in zip(fills, w.gaps) if f[:-w.k] == rec.truth)
 
-    # ---- end to end through the driver call, host buffers
-    import ctypes
+    # ---- end to end through the driver call, host buffers.  N = 1: this rank's engine.  N > 1: ONE engine on rank 0 owns
+    # all N GPUs (g2s_create_multi); the other ranks free their GPUs and wait on the host.
     libc = ctypes.CDLL(None)
-    libc.srand(1)
-    ref_out = eng.fill_records(seqs, names, dist_error=w.dist_error, fuz=w.fuz, all_paths=not w.best_only)
-    prepared = eng.prepare_records(seqs, names)   # host buffers of a C caller: NUL-terminated strings
-    for _ in range(max(args.warmup, 3)):
+    ref_out = None
+    if rank == 0:
         libc.srand(1)
-        eng.fill_records_c(prepared, dist_error=w.dist_error, fuz=w.fuz, all_paths=not w.best_only)[4]()
-    barrier()
-    e2e_ms, h2d_b, d2h_b = [], 0, 0
-    e2e_same = True
-    for _ in range(args.steps):
-        flush.zero_()
-        torch.cuda.synchronize()
-        libc.srand(1)
-        t1 = time.perf_counter()
-        out = eng.fill_records_c(prepared, dist_error=w.dist_error, fuz=w.fuz, all_paths=not w.best_only)
-        e2e_ms.append(1e3 * (time.perf_counter() - t1))
-        t = eng.timing()
-        h2d_b, d2h_b = t.h2d_bytes, t.d2h_bytes
-        # outside the timed region: the timed call's output equals the driver call made through the Python binding
-        e2e_same = e2e_same and out[2:4] == ref_out[2:4] and ctypes.string_at(out[1].value).decode() == ref_out[1] and \
-            all(ctypes.string_at(out[0][i]).decode() == ref_out[0][i] for i in range(len(seqs)))
-        out[4]()
-    barrier()
+        ref_out = eng.fill_records(seqs, names, dist_error=w.dist_error, fuz=w.fuz, all_paths=not w.best_only)
+    keys = None
+    if rank == 0:
+        keys, _ = eng.export_kmers()
+    e2e_eng = eng
+    multi_note = None
+    if world > 1:
+        eng.close()
+        dist.barrier(group=cpu_group)
+        if rank == 0:
+            e2e_eng = engine.Engine(k=w.k, max_fuz=w.fuz, host_threads=min(32, cores), devices=list(range(world)))
+            t0 = time.perf_counter()
+            e2e_eng.import_kmers(keys)
+            multi_note = f"g2s_create_multi over GPUs 0..{world - 1}; table import + replication {time.perf_counter() - t0:.2f} s untimed"
+    e2e_ms, h2d_b, d2h_b, e2e_same, e2e_detail = [0.0], 0, 0, True, {}
+    if rank == 0:
+        prepared = e2e_eng.prepare_records(seqs, names)   # host buffers of a C caller: NUL-terminated strings
+        kw = dict(dist_error=w.dist_error, fuz=w.fuz, all_paths=not w.best_only)
+        for _ in range(max(args.warmup, 3)):
+            libc.srand(1)
+            e2e_eng.fill_records_c(prepared, **kw)[4]()
+        e2e_ms = []
+        for _ in range(args.steps):
+            flush.zero_()
+            torch.cuda.synchronize()
+            libc.srand(1)
+            t1 = time.perf_counter()
+            out = e2e_eng.fill_records_c(prepared, **kw)
+            e2e_ms.append(1e3 * (time.perf_counter() - t1))
+            t = e2e_eng.timing()
+            h2d_b, d2h_b = t.h2d_bytes, t.d2h_bytes
+            # outside the timed region: the timed call's output equals the one-GPU driver call made through the Python binding
+            e2e_same = e2e_same and out[2:4] == ref_out[2:4] and ctypes.string_at(out[1].value).decode() == ref_out[1] and \
+                all(ctypes.string_at(out[0][i]).decode() == ref_out[0][i] for i in range(len(seqs)))
+            out[4]()
+        e2e_detail = {"h2d_ms": t.h2d_ms, "kernel_ms": t.kernel_ms, "d2h_ms": t.d2h_ms, "host_ms": t.host_ms}
+        if not e2e_same:
+            sys.exit("bench.py: the timed driver call's output differs from the one-GPU output")
+    if world > 1:
+        dist.barrier(group=cpu_group)
     clocks = sampler.stop()
-    e2e_detail = {"h2d_ms": t.h2d_ms, "kernel_ms": t.kernel_ms, "d2h_ms": t.d2h_ms, "host_ms": t.host_ms}
 
     ms_step = sum(kern_ms) / len(kern_ms)
     ms_e2e = sum(e2e_ms) / len(e2e_ms)
-    stats = torch.tensor([ms_step, ms_e2e], dtype=torch.float64, device="cuda")
-    tot = torch.tensor([float(n_gaps), float(cells), float(launches), float(h2d_b), float(d2h_b)], dtype=torch.float64,
-                       device="cuda")
+    stats = torch.tensor([ms_step], dtype=torch.float64, device="cuda")
+    tot = torch.tensor([float(len(mine)), float(cells), float(launches), float(filled), float(t_dev.table_lookups), float(t_dev.node_ops)],
+                       dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(stats, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-    ms_step, ms_e2e = stats.tolist()
-    all_gaps, all_cells, all_launches, all_h2d, all_d2h = tot.tolist()
+    ms_max = stats.tolist()[0]
+    all_gaps, all_cells, all_launches, all_filled, all_lookups, all_nodeops = tot.tolist()
 
     if rank == 0:
         peak, peak_src = measured_peaks()
-        achieved = cells * BYTES_PER_CELL / (ms_step / 1e3) / 1e9     # this rank's kernel, GB/s
-        traffic, traffic_src = measured_traffic(args.workload, args.scale)
+        # the kernel with the largest share of this rank's step, the cells of the gaps it finished, its mean duration
+        dom = max(tier_ms, key=tier_ms.get)
+        dom_ms = tier_ms[dom] / args.steps
+        dom_cells = {"chain": t_dev.cells_chain, "thin": t_dev.cells_thin, "wide": t_dev.cells_wide}[dom]
+        shapes = {0: "k_fill_thin<1,1>", 1: "k_fill_thin<2,4>", 2: "k_fill_thin<4,8>"}
+        dom_name = {"chain": "k_chain_walk + k_chain_finish", "thin": shapes.get(t_dev.thin_shape, "k_fill_thin"), "wide": "k_fill_cta"}[dom]
+        achieved = dom_cells * BYTES_PER_CELL / (dom_ms / 1e3) / 1e9 if dom_ms > 0 else 0.0
+        traffic = measured_traffic(args.workload, args.scale)
+        cpu, n_checked = cpu_baseline_and_check(w, keys, ref_out[0], args.cpu_seconds) if world == 1 else (None, 0)
         line = {
-            "metric": "gaps_per_s", "value": all_gaps / (ms_step / 1e3), "unit": "gaps/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-            "config": {"workload": WORKLOAD_DESC.get(args.workload, args.workload), "scale": args.scale,
-                       "gaps_per_gpu": n_gaps, "filled": filled, "fills_equal_to_removed_bases": exact, "solid_kmers": n_kmers,
-                       "l2": "256 MiB device buffer rewritten between timed iterations",
-                       "graph_build_s_untimed": round(t_graph, 3), "gaps_in_wide_tier": big, "host_threads_per_rank": host_threads,
-                       "parallelism": f"{world} x (one process per GPU, replicated k-mer table, disjoint gap batches)",
-                       "table_broadcast_s_untimed": round(t_bcast, 4), "table_bytes": table_bytes},
-            "dp_cells_per_s": all_cells / (ms_step / 1e3), "dp_cells_per_step": all_cells,
-            "e2e": {"value": all_gaps / (ms_e2e / 1e3), "unit": "gaps/s", "h2d_bytes_per_step": all_h2d,
-                    "d2h_bytes_per_step": all_d2h, "ms_per_step": ms_e2e, "breakdown_ms_last_step": e2e_detail,
+            "metric": "gaps_per_s", "value": all_gaps / (ms_max / 1e3), "unit": "gaps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "config": {"workload": WORKLOAD_DESC.get(args.workload, args.workload), "scale": args.scale, "l2": L2_NOTE},
+            "run": {"gaps_total": int(all_gaps), "gaps_this_rank": len(mine), "filled": int(all_filled),
+                       "fills_equal_to_removed_bases": exact, "solid_kmers": n_kmers,
+                       "graph_build_s_untimed": round(t_graph, 3), "host_threads": host_threads if world == 1 else min(32, cores),
+                       "parallelism": f"{world} x (one process per GPU, replicated k-mer table, ONE gap list split longest-processing-time-first)",
+                       "table_broadcast_s_untimed": round(t_bcast, 4), "table_bytes": table_bytes,
+                       "records_checked_against_oracle": n_checked},
+            "dp_cells_per_s": all_cells / (ms_max / 1e3), "dp_cells_per_step": all_cells,
+            "hash_probes_per_s": (all_lookups + all_nodeops) / (ms_max / 1e3),
+            "hash_probes_per_step": {"kmer_table_gathers": all_lookups, "node_table_ops": all_nodeops},
+            "e2e": {"value": len(specs) / (ms_e2e / 1e3), "unit": "gaps/s", "h2d_bytes_per_step": h2d_b,
+                    "d2h_bytes_per_step": d2h_b, "ms_per_step": ms_e2e, "breakdown_ms_last_step": e2e_detail,
                     "call": "g2s_fill_records (C ABI) on host strings: scan, H2D, device pass, D2H, tracebacks, splice, log",
-                    "output_identical_every_step": e2e_same},
+                    "engine": multi_note or "g2s_create on GPU 0", "output_identical_every_step": e2e_same},
             "gpu_launches": int(all_launches),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "k_fill_thin", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
-                         "algorithmic_bytes_per_launch": cells * BYTES_PER_CELL, "peak_source": peak_src,
-                         "algorithmic_bytes_per_cell": BYTES_PER_CELL,
-                         "note": "thin gaps are chains of dependent gathers (1 cell per level): latency bound, see DESIGN.md"},
+            "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic.get("dram_bytes_per_launch"),
+                         "traffic_source": traffic.get("source"), "sectors_per_request": traffic.get("sectors_per_request"),
+                         "algorithmic_bytes_per_launch": dom_cells * BYTES_PER_CELL, "peak_source": peak_src,
+                         "algorithmic_bytes_per_cell": BYTES_PER_CELL, "kernel_ms_per_launch": dom_ms,
+                         "kernel_share_of_step": dom_ms / (sum(tier_ms.values()) / args.steps) if sum(tier_ms.values()) else None,
+                         "tier_ms_per_step": {k: v / args.steps for k, v in tier_ms.items()},
+                         "tier_cells": {"chain": t_dev.cells_chain, "thin": t_dev.cells_thin, "wide": t_dev.cells_wide},
+                         "note": "rank 0's kernel; thin gaps are chains of dependent gathers: latency bound, see DESIGN.md"},
             "timed_region_wall_s": t_region,
             "phase_cycles_slowest_gap": dict(zip(PHASES, phase_slowest)),
             "phase_cycles_sum": dict(zip(PHASES, phase_sum)),
         }
-        if world == 1:
-            keys, _ = eng.export_kmers()
-            line["cpu_baseline"] = cpu_baseline(w, keys, args.cpu_seconds)
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
-    eng.close()
+    if e2e_eng is not None:
+        e2e_eng.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -558,6 +558,7 @@ static int do_run(g2s_engine *e) {
   e->tm.max_tier_run = 0; e->tm.gaps_rerun_scratch = 0; e->tm.gaps_rerun_out_full = 0; e->tm.gaps_mem_limit = 0;
   e->tm.table_lookups = 0; e->tm.node_ops = 0;
   e->tm.kernel_ms_thin = 0; e->tm.kernel_ms_wide = 0; e->tm.launches_thin = 0; e->tm.launches_wide = 0; e->tm.thin_shape = 0;
+  e->tm.cells_thin = 0; e->tm.cells_wide = 0; e->tm.kernel_ms_chain = 0; e->tm.launches_chain = 0; e->tm.gaps_chain = 0; e->tm.cells_chain = 0;
   e->out_pass.assign(n, -1);
   if (n == 0) { e->ran = true; return G2S_OK; }
   CUDA_TRY(cudaMemsetAsync(e->d_outs.p, 0, n * sizeof(GapOut), e->st));
@@ -605,7 +606,14 @@ static int do_run(g2s_engine *e) {
     if (tier > 0) e->tm.gaps_big_tier += (uint32_t)(todo.size() - failed);
     e->tm.max_tier_run = (uint32_t)tier;
   }
-  for (const GapOut &o : e->outs) { e->tm.table_lookups += o.table_lookups; e->tm.node_ops += o.node_ops; }
+  for (size_t i = 0; i < n; i++) {
+    const GapOut &o = e->outs[i];
+    e->tm.table_lookups += o.table_lookups; e->tm.node_ops += o.node_ops;
+    if (e->out_pass[i] < 0) continue;
+    const int tier = e->passes[e->out_pass[i]].tier;
+    (tier < 0 ? e->tm.cells_chain : tier == 0 ? e->tm.cells_thin : e->tm.cells_wide) += (uint64_t)o.cells_right + o.cells_left;
+    if (tier < 0) e->tm.gaps_chain++;
+  }
   e->ran = true;
   return G2S_OK;
 }
@@ -821,6 +829,8 @@ static int run_wave(g2s_engine *e, const g2s_gap *gaps, size_t n, HostBatch &hb,
     t.table_lookups += x.table_lookups; t.node_ops += x.node_ops;
     t.kernel_ms_thin = std::max(t.kernel_ms_thin, x.kernel_ms_thin); t.kernel_ms_wide = std::max(t.kernel_ms_wide, x.kernel_ms_wide);
     t.launches_thin += x.launches_thin; t.launches_wide += x.launches_wide; t.thin_shape = std::max(t.thin_shape, x.thin_shape);
+    t.cells_thin += x.cells_thin; t.cells_wide += x.cells_wide; t.cells_chain += x.cells_chain; t.gaps_chain += x.gaps_chain;
+    t.kernel_ms_chain = std::max(t.kernel_ms_chain, x.kernel_ms_chain); t.launches_chain += x.launches_chain;
     if (getenv("G2S_HOST_PROF"))
       fprintf(stderr, "g2s: GPU %d: %zu gaps, upload %.3f ms, run %.3f ms (kernels %.3f), collect %.3f ms\n", eng[d]->cfg.device,
               shards[d].size(), wall[3 * d], wall[3 * d + 1], x.kernel_ms, wall[3 * d + 2]);
@@ -911,6 +921,8 @@ extern "C" int g2s_fill_records(g2s_engine *e, const char *const *seqs, const ch
     total.table_lookups += e->tm.table_lookups; total.node_ops += e->tm.node_ops;
     total.kernel_ms_thin += e->tm.kernel_ms_thin; total.kernel_ms_wide += e->tm.kernel_ms_wide;
     total.launches_thin += e->tm.launches_thin; total.launches_wide += e->tm.launches_wide; total.thin_shape = e->tm.thin_shape;
+    total.cells_thin += e->tm.cells_thin; total.cells_wide += e->tm.cells_wide; total.cells_chain += e->tm.cells_chain;
+    total.gaps_chain += e->tm.gaps_chain; total.kernel_ms_chain += e->tm.kernel_ms_chain; total.launches_chain += e->tm.launches_chain;
     return rc;
   };
   std::vector<std::string> filled;

@@ -20,7 +20,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libg2s_gpu.so")
 ST_ORDER_DEPENDENT, ST_MEM_LIMIT, ST_GENERAL_SUBGRAPH, ST_UNABLE_TO_BACKTRACE, ST_BIG_TIER = 1, 2, 4, 8, 16
 ST_DEVICE_TRACED = 32
 GAP_SKIP_CONFIDENT, GAP_ALL_PATHS = 1, 2
-ABI_VERSION = 3   # G2S_ABI_VERSION of include/g2s.h
+ABI_VERSION = 4   # G2S_ABI_VERSION of include/g2s.h
 
 
 class G2SError(RuntimeError):
@@ -61,7 +61,9 @@ class G2STiming(C.Structure):
                 ("gaps_rerun_out_full", C.c_uint32), ("gaps_mem_limit", C.c_uint32),
                 ("table_lookups", C.c_uint64), ("node_ops", C.c_uint64),
                 ("kernel_ms_thin", C.c_double), ("kernel_ms_wide", C.c_double), ("launches_thin", C.c_uint32),
-                ("launches_wide", C.c_uint32), ("thin_shape", C.c_uint32), ("reserved", C.c_uint32)]
+                ("launches_wide", C.c_uint32), ("thin_shape", C.c_uint32), ("reserved", C.c_uint32),
+                ("cells_thin", C.c_uint64), ("cells_wide", C.c_uint64), ("kernel_ms_chain", C.c_double),
+                ("launches_chain", C.c_uint32), ("gaps_chain", C.c_uint32), ("cells_chain", C.c_uint64)]
 
 
 class G2SRunOptions(C.Structure):

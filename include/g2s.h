@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define G2S_ABI_VERSION 3
+#define G2S_ABI_VERSION 4
 
 enum {
   G2S_OK = 0,
@@ -116,6 +116,12 @@ typedef struct g2s_timing {
   double kernel_ms_thin, kernel_ms_wide;
   uint32_t launches_thin, launches_wide;
   uint32_t thin_shape, reserved;
+  uint64_t cells_thin, cells_wide;              /* DP cells (right + forward) of the gaps each of them finished */
+  /* the chain tier (k_chain_walk + k_chain_finish): gaps whose borders never exceed one state are finished there
+     without per-gap scratch tables; every other gap goes on to the thin tier */
+  double kernel_ms_chain;
+  uint32_t launches_chain, gaps_chain;
+  uint64_t cells_chain;
 } g2s_timing;
 
 const char *g2s_last_error(void);

@@ -23,7 +23,7 @@ def test_header_symbols_are_all_bound_and_exported():
     lib = engine.load_library()
     for s in decl:
         assert hasattr(lib, s), s
-    assert lib.g2s_abi_version() == 3
+    assert lib.g2s_abi_version() == engine.ABI_VERSION == 4
 
 
 def test_no_cpu_fallback_without_device():
