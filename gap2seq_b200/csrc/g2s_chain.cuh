@@ -1,0 +1,339 @@
+// g2s_chain.cuh - the chain tier: gaps of Gap2Seq::fill_gap (reference src/Gap2Seq.cpp:858-1556) whose borders never
+// hold more than ONE state - the right pass walks back along a path of in-degree-1 nodes, the forward pass walks along a
+// path of out-degree-1 nodes - which is what a gap in unique sequence covered by clean reads looks like.
+//
+// For such a gap every table of the reference degenerates: the right set is a string, the forward table is a string,
+// counts are 1, the path subgraph is a path, the traceback has no choice.  The tier therefore keeps NO per-gap hash table
+// and no cell arrays.  It runs in two kernels:
+//
+//   k_chain_walk    one LANE per walk (two per gap: forward from the left flank, backward from the right flank).  A walk
+//                   is the chain of dependent gathers in the global k-mer table and nothing else: every gather returns the
+//                   skip hint of the tip (the next <= 40 bases of its unique extension), the lane appends those bases to
+//                   the walk's 2-bit packed string in HBM and jumps to the node the hint ends at.  Thousands of walks are
+//                   in flight per SM, so the pass is bound by the longest gap's gather chain, not by per-level work.
+//   k_chain_finish  one WARP per gap.  Reads the two strings and derives, level-parallel, everything fill_gap computes:
+//                   where the forward chain meets the right set (the meet-in-the-middle prune of Gap2Seq.cpp:1050), the
+//                   first-found check (Gap2Seq.cpp:1107-1159), the backward subgraph and its statistics
+//                   (Gap2Seq.cpp:1173-1435), the safe/unsafe case mask and the fill string (Gap2Seq.cpp:1437-1517; with one
+//                   trellis cell per level the random traceback has no choice to make, only rand() calls to count).
+//
+// The tier proves its own applicability.  Whenever anything could make the reference's result differ from the chain
+// reading - a border that would hold two states, a start k-mer that is not on the chain, a k-mer met twice (either
+// strand), two accepted path lengths, a forward state beyond the right flank that is in the right set again - the gap
+// is handed on (GS_NOT_CHAIN) and the thin tier runs it with the full tables.  Results of the gaps it keeps are
+// bit-identical to the thin tier's (tests/test_chain_emul.py on the CPU, the -m gpu parity tests on the device).
+#pragma once
+#include "g2s_fill.cuh"
+
+namespace g2s {
+
+enum { GS_NOT_CHAIN = 64 };   // GapOut.status: the chain tier declined the gap
+
+static const uint32_t CHAIN_END_LIMIT = 0xFFu;      // ChainWalk.end_mask: the walk reached its level limit
+static const uint32_t CHAIN_END_INTERNAL = 0x100u;  // the table contradicts its own adjacency bytes
+
+struct ChainWalk {      // what a walk left behind, 16 B
+  uint32_t n;           // states recorded (the string holds k + n - 1 bases); 0: the start k-mer is not in the graph
+  uint32_t end_mask;    // out-mask of the last state in walk orientation (0: dead end, several bits: branch), or CHAIN_END_*
+  uint32_t lookups;     // gathers in the global table
+  uint32_t pad;
+};
+
+struct ChainParams {
+  Table table;
+  const char *flanks;
+  const GapDev *gaps;
+  const uint32_t *order;      // gap ids of this pass
+  uint32_t n_gaps;
+  GapOut *outs;
+  uint64_t *strs;             // per position in `order`: f_words words of the forward string, then r_words of the right one
+  uint32_t f_words, r_words;
+  ChainWalk *walks;           // [2q] forward, [2q + 1] right
+  char *fills;                // fill arena
+  unsigned long long fill_cap;
+  unsigned long long *fill_cursor;
+};
+
+// words a walk of up to `levels` levels needs: k + levels bases, one partial word, one word of slack for str_kmer
+inline uint32_t chain_words(int k, int levels) { return (uint32_t)((2 * ((size_t)k + levels) + 63) / 64 + 2); }
+
+// ------------------------------------------------------------------------------------------------ packed strings
+// Base p of a string lives in word p / 32, bits 63 - 2 (p % 32) .. 62 - 2 (p % 32): first base highest, like a k-mer.
+struct BaseWriter {
+  uint64_t *out;
+  uint64_t acc;
+  uint32_t nb, w;       // bits held in acc (from the top), words written
+  G2S_D void init(uint64_t *p) { out = p; acc = 0; nb = 0; w = 0; }
+  G2S_D void put(uint64_t v, uint32_t n) {   // the n (1..64) low bits of v
+    if (n < 64) v &= (1ULL << n) - 1;
+    const uint32_t room = 64 - nb;
+    if (n < room) { acc |= v << (room - n); nb += n; return; }
+    const uint32_t rem = n - room;             // 0..63
+    out[w++] = acc | (v >> rem);
+    acc = rem ? v << (64 - rem) : 0;
+    nb = rem;
+  }
+  G2S_D void flush() { out[w] = acc; out[w + 1] = 0; }
+};
+
+G2S_D uint64_t str_kmer(const uint64_t *W, uint32_t p, int k) {   // bases p .. p + k - 1 as a k-mer
+  const uint32_t q = p >> 5, s = 2 * (p & 31);
+  const uint64_t hi = ld_cg(&W[q]), lo = ld_cg(&W[q + 1]);
+  const uint64_t v = s ? (hi << s) | (lo >> (64 - s)) : hi;
+  return v >> (64 - 2 * k);
+}
+G2S_D uint32_t str_base(const uint64_t *W, uint32_t p) { return (uint32_t)(ld_cg(&W[p >> 5]) >> (62 - 2 * (p & 31))) & 3u; }
+
+// ------------------------------------------------------------------------------------------------ the walk
+// One chain of dependent gathers: from x0 (walk orientation) along unique successors for at most `maxlev` levels.
+G2S_D void chain_walk(const Table &T, uint64_t x0, int maxlev, uint64_t *W, ChainWalk *out) {
+  const int k = T.k;
+  ChainWalk r{0, 0, 1, 0};
+  Canon c = canonical(x0, k);
+  Slot sl;
+  if (table_find_slot(T, c.key, &sl) < 0) { *out = r; return; }
+  BaseWriter bw;
+  bw.init(W);
+  bw.put(x0, (uint32_t)(2 * k));
+  uint64_t x = x0;
+  int lev = 0;
+  uint32_t endm = CHAIN_END_LIMIT;
+  while (lev < maxlev) {
+    const uint32_t mask = out_mask((uint32_t)(sl.val & 0xFF), c.strand);
+    if (mask == 0 || (mask & (mask - 1))) { endm = mask; break; }
+    Hint h = hint_of(sl, c.strand);
+    if (h.len == 0) { h.lo = mask == 1 ? 0 : mask == 2 ? 1 : mask == 4 ? 2 : 3; h.hi = 0; h.len = 1; }   // a table without hints
+    const uint32_t j = h.len < (uint32_t)(maxlev - lev) ? h.len : (uint32_t)(maxlev - lev);
+    const uint32_t sh = 2 * (h.len - j);                 // the first j bases = bases >> sh
+    if (2 * j > 64) bw.put(sh < 16 ? (uint64_t)(h.hi >> sh) : 0, 2 * j - 64);
+    bw.put(hint_shr(h, sh), 2 * j > 64 ? 64u : 2 * j);
+    x = hint_state(x, h, j, T.kmask);
+    lev += (int)j;
+    if (lev >= maxlev) break;
+    c = canonical(x, k);
+    r.lookups++;
+    if (table_find_slot(T, c.key, &sl) < 0) { endm = CHAIN_END_INTERNAL; break; }
+  }
+  bw.flush();
+  r.n = (uint32_t)lev + 1;
+  r.end_mask = endm;
+  *out = r;
+}
+
+// ------------------------------------------------------------------------------------------------ the finish
+// G: the thread group of one gap (a warp on the device, one thread in the host emulation) with
+//    rank(), size(), any(bool), min_i32(int), max_i32(int), add_u32(uint32_t), bcast_u64(v) (rank 0's value).
+// tk: group-shared scratch of MAX_FUZ + 1 words.
+
+// is x a node of the right chain (either strand)?
+template <class G>
+G2S_D bool chain_member(const uint64_t *WR, int nR, uint64_t x, int k) {
+  const uint64_t rx = revcomp(x, k);
+  bool hit = false;
+  for (int i = G::rank(); i < nR; i += G::size()) {
+    const uint64_t y = str_kmer(WR, (uint32_t)i, k);
+    if (y == x || y == rx) hit = true;
+  }
+  return G::any(hit);
+}
+
+template <class G>
+G2S_D void chain_finish(const ChainParams &P, const GapDev &gd, const uint64_t *WF, const uint64_t *WR, const ChainWalk wf,
+                        const ChainWalk wr, uint64_t *tk, GapOut *out) {
+  const Table &T = P.table;
+  const int k = T.k, rank = G::rank(), gsz = G::size();
+  const int g = gd.gap_len, e = gd.gap_err, lmf = gd.lmf, rmf = gd.rmf;
+  const bool all_paths = (gd.flags & 2) != 0, skip_confident = (gd.flags & 1) != 0;
+  // the walks were cut at right_half = rmf + ceil((g + e) / 2) and Dmax = g + e + lmf + rmf levels (Gap2Seq.cpp:862-863)
+  const int pf = g / 2 + e / 2 + lmf;               // first pruned level, Gap2Seq.cpp:1050
+  const char *lstr = P.flanks + gd.flank_off, *rstr = lstr + k + lmf, *rsstr = P.flanks + gd.rstart_off;
+  const int nF = (int)wf.n, nR = (int)wr.n, cw = nF - 1;
+  const int NONE = 0x7fffffff;
+
+  bool internal = ((wf.end_mask | wr.end_mask) & CHAIN_END_INTERNAL) != 0;
+  bool fb = nF == 0 || nR == 0 || internal;         // a start k-mer that is absent: the staggered starts decide, not this tier
+  const bool r_branch = wr.end_mask != CHAIN_END_LIMIT && (wr.end_mask & (wr.end_mask - 1)) != 0;
+  const bool f_branch = wf.end_mask != CHAIN_END_LIMIT && (wf.end_mask & (wf.end_mask - 1)) != 0;
+  // the right pass never prunes: a state with two predecessors below the level limit makes a border of two
+  if (r_branch) fb = true;
+  // the forward chain must cover the levels that inject starts
+  if (cw < lmf) fb = true;
+
+  // ---- staggered starts (Gap2Seq.cpp:953-968, 1082-1105): each one is either the chain's own state of its level (the
+  // injection changes nothing: same node, same strand, count already 1) or absent from the graph
+  if (!fb) {
+    bool bad = false;
+    for (int c = 1 + rank; c <= rmf; c += gsz) {            // right start of iteration c = state of index c (rmf <= right_half)
+      const uint64_t s = kmer_from_ascii(rsstr + (rmf - c), k);
+      if (c < nR && revcomp(s, k) == str_kmer(WR, (uint32_t)c, k)) continue;
+      uint32_t adj;
+      if (table_find(T, canonical(s, k).key, &adj) >= 0) bad = true;
+    }
+    for (int d = 1 + rank; d <= lmf; d += gsz) {
+      const uint64_t s = kmer_from_ascii(lstr + d, k);
+      if (s == str_kmer(WF, (uint32_t)d, k)) continue;
+      uint32_t adj;
+      if (table_find(T, canonical(s, k).key, &adj) >= 0) bad = true;
+    }
+    if (G::any(bad)) fb = true;
+  }
+
+  // ---- where the forward chain ends.  Below pf nothing is pruned.  From pf on a state survives iff its node is in the
+  // right set.  The right chain R[0], R[1], .. walks unique predecessors from R[0] = the last right start, so once the
+  // forward chain stands on R[0] at level L it stood on R[i] at level L - i for every i < nR: those levels survive
+  // without a lookup.  One membership scan settles the first level that is not covered by that argument.
+  int top = -1, L = NONE;
+  if (!fb) {
+    const uint64_t R0 = kmer_from_ascii(rsstr + rmf, k);
+    for (int c = rank; c < nF; c += gsz)
+      if (str_kmer(WF, (uint32_t)c, k) == R0) { L = c; break; }
+    L = G::min_i32(L);
+    if (cw < pf) top = cw;
+    else if (L != NONE && L >= pf && L - pf <= nR - 1) {
+      top = L;
+      if (L < cw && chain_member<G>(WR, nR, str_kmer(WF, (uint32_t)L + 1, k), k)) fb = true;
+    } else {
+      if (chain_member<G>(WR, nR, str_kmer(WF, (uint32_t)pf, k), k)) fb = true;
+      top = pf - 1;
+    }
+    if (f_branch && top == cw) fb = true;     // the branching state is expanded: a border of two
+    if (top < lmf) fb = true;                 // a start level without a chain state: injection starts a new chain
+  }
+
+  // ---- one pass over the chain's states: no node twice (either strand), target hits, all-paths seeds.
+  // A chain of forced steps that meets a node again is periodic from there on (same strand) or retraces its own reverse
+  // complement (other strand); either way its LAST state, or the reverse complement of its FIRST, shows up in the chain -
+  // so three comparisons per level prove that all nodes are distinct.
+  uint32_t best = 0xFFFFFFFFu;   // (err << 6 | j) of the first-found check
+  uint32_t n_sink = 0;
+  int min_sink = NONE, sB = -1;
+  if (!fb) {
+    for (int j = rank; j <= rmf; j += gsz) tk[j] = kmer_from_ascii(rstr + j, k);
+    G::sync();
+    const uint64_t Ftop = str_kmer(WF, (uint32_t)top, k), rcFtop = revcomp(Ftop, k), rcF0 = revcomp(str_kmer(WF, 0, k), k);
+    const int jt = rmf - 1, dlo = lmf + g - e > 0 ? lmf + g - e : 0;
+    bool rep = false;
+    for (int c = rank; c <= top; c += gsz) {
+      const uint64_t x = str_kmer(WF, (uint32_t)c, k);
+      if ((c < top && x == Ftop) || x == rcFtop || x == rcF0) rep = true;
+      for (int j = 0; j <= rmf; j++) {
+        if (x != ld_sh(&tk[j])) continue;
+        const int err = c > g + lmf + j ? c - (g + lmf + j) : g + lmf + j - c;
+        if (err <= e) { const uint32_t key = ((uint32_t)err << 6) | (uint32_t)j; best = key < best ? key : best; }
+        if (j == jt && c >= dlo) { n_sink++; min_sink = c < min_sink ? c : min_sink; sB = c > sB ? c : sB; }
+      }
+    }
+    if (G::any(rep)) fb = true;
+  }
+  // group-wide: the smallest (err, j) key (err < 2^25), the seeds
+  {
+    int b = best == 0xFFFFFFFFu ? NONE : (int)best;
+    b = G::min_i32(b);
+    best = b == NONE ? 0xFFFFFFFFu : (uint32_t)b;
+    n_sink = G::add_u32(n_sink);
+    min_sink = G::min_i32(min_sink);
+    sB = G::max_i32(sB);
+  }
+
+  bool found = false;
+  int d0 = -1, J = 0, c_found = 0;
+  if (!fb && best != 0xFFFFFFFFu) {
+    const int err = (int)(best >> 6);
+    J = (int)(best & 63u);
+    const int len1 = g + lmf + J + err, len2 = g + lmf + J - err;
+    const uint64_t t = ld_sh(&tk[J]);
+    const bool h1 = len1 <= top && str_kmer(WF, (uint32_t)len1, k) == t;
+    const bool h2 = err > 0 && len2 >= 0 && len2 <= top && str_kmer(WF, (uint32_t)len2, k) == t;
+    if (h1 && h2) fb = true;                  // two accepted lengths: rand() picks one (Gap2Seq.cpp:1440)
+    found = true;
+    d0 = h1 ? len1 : len2;
+    c_found = g + lmf + rmf + err;
+  }
+
+  // ---- backward subgraph (Gap2Seq.cpp:1173-1312) of a chain: its levels from the highest seed down to the first start
+  // cell met on the way, one vertex per level; the trellis of the traceback likewise from the accepted target
+  uint32_t nB = 0, n_edges = 0, n_src = 0;
+  int max_src = -1, dS = -1, dT = -1;
+  if (!fb && found) {
+    if (skip_confident || (all_paths && rmf < 1)) { n_sink = 0; min_sink = NONE; sB = -1; }
+    else if (!all_paths) { n_sink = 1; min_sink = d0; sB = d0; }                  // -best-only: the accepted target is the seed
+    // start cells: d <= lmf whose state is the left start of that level (checked above: the only way to share its node)
+    int s1 = -1, s2 = -1;
+    for (int d = rank; d <= lmf; d += gsz) {
+      if (kmer_from_ascii(lstr + d, k) != str_kmer(WF, (uint32_t)d, k)) continue;
+      if (d <= sB) s1 = d;
+      if (d <= d0) s2 = d;
+    }
+    dS = G::max_i32(s1);
+    dT = G::max_i32(s2);
+    if (dT < 0) fb = true;                    // cannot happen (level 0 is a start): "Unable to backtrace" is the host's to say
+    if (n_sink > 0) {
+      if (dS < 0) fb = true;
+      nB = (uint32_t)(sB - dS + 1); n_edges = (uint32_t)(sB - dS); n_src = 1; max_src = dS;
+    }
+  }
+
+  // ---- the fill (Gap2Seq.cpp:1437-1517 with one trellis cell per level): bases of levels dT+1 .. d0, upper case within k
+  // levels below a safe vertex or the path's end
+  unsigned long long fill_off = 0;
+  if (!fb && found) {
+    const unsigned long long need = (unsigned long long)(d0 - dT) + 1;
+    unsigned long long off = 0;
+    if (rank == 0) off = a_add64(P.fill_cursor, need);
+    off = G::bcast_u64(off);
+    if (P.fills == nullptr || off + need > P.fill_cap) fb = true;
+    else {
+      fill_off = off;
+      char *outc = P.fills + off;
+      for (int d = dT + 1 + rank; d <= d0; d += gsz) {
+        bool up = d0 - d < k;
+        for (int z = d; !up && z <= d0 && z < d + k; z++) {
+          bool safe;
+          if (skip_confident) safe = true;
+          else if (n_sink == 0) safe = false;
+          else if (z >= dS && z <= sB) safe = z <= min_sink;   // a vertex of the path subgraph: alone on its level; between source and sink edges?
+          else safe = true;                                      // not a vertex: node2boost hands out the sink
+          up = safe;
+        }
+        const uint32_t b = str_base(WF, (uint32_t)(d + k - 1));
+        const char ch = b == 0 ? 'A' : b == 1 ? 'C' : b == 2 ? 'T' : 'G';
+        outc[d - 1 - dT] = up ? ch : (char)(ch | 0x20);
+      }
+      if (rank == 0) outc[d0 - dT] = 0;
+    }
+  }
+
+  if (rank == 0) {
+    GapOut o;
+    memset(&o, 0, sizeof(o));
+    o.plen[0] = o.plen[1] = -1;
+    o.start_pack[0] = o.start_pack[1] = NONE32;
+    o.max_src_level = -1; o.min_sink_level = NONE;
+    o.table_lookups = wf.lookups + wr.lookups;
+    if (fb) {
+      o.status = GS_NOT_CHAIN | GS_DONE | (internal ? GS_INTERNAL : 0);
+    } else {
+      o.status = GS_DONE;
+      o.cells_right = (uint32_t)nR;
+      const int last = (!all_paths && found && c_found < top) ? c_found : top;   // -best-only ends the table at the level of the hit
+      o.cells_left = (uint32_t)(last + 1);
+      o.top_level = (uint32_t)last;
+      o.levels_r = (uint32_t)nR; o.levels_f = (uint32_t)last;
+      int shared = 0;                                                           // levels that stand on a node of the right chain
+      if (L != NONE) { const int hi = L < last ? L : last, lo = L - nR + 1 > 0 ? L - nR + 1 : 0; if (hi >= lo) shared = hi - lo + 1; }
+      o.nodes = (uint32_t)(nR + last + 1 - shared);
+      if (found) {
+        o.status |= GS_TRACED;
+        o.count_fwd = 1; o.n_plen = 1; o.plen[0] = d0; o.reached_fuz = J;
+        o.count_all = n_sink > MAX_PATHS ? MAX_PATHS : n_sink;
+        o.nB = nB; o.n_edges = n_edges; o.n_src = n_src; o.n_sink = n_sink;
+        o.max_src_level = max_src; o.min_sink_level = min_sink;
+        o.fill_off = fill_off; o.fill_len = (uint32_t)(d0 - dT); o.left_fuz = lmf - dT;
+        o.rand_calls = 1u + o.fill_len;
+      }
+    }
+    *out = o;
+  }
+}
+
+}  // namespace g2s

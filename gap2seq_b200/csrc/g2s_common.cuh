@@ -152,9 +152,8 @@ G2S_D int64_t table_find_slot(const Table &t, uint64_t canon, Slot *out) {
   uint64_t h = mix64(canon) & t.cap_mask;
   for (;;) {
 #ifdef __CUDA_ARCH__
-    Slot s;
-    asm volatile("ld.global.nc.v2.u64 {%0, %1}, [%2];" : "=l"(s.key), "=l"(s.val) : "l"(t.slots + h));
-    asm volatile("ld.global.nc.v2.u64 {%0, %1}, [%2];" : "=l"(s.h[0]), "=l"(s.h[1]) : "l"((const char *)(t.slots + h) + 16));
+    Slot s;   // the whole 32-byte slot = one sector in ONE request (sm_100 256-bit load, LDG.E.256)
+    asm volatile("ld.global.nc.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(s.key), "=l"(s.val), "=l"(s.h[0]), "=l"(s.h[1]) : "l"(t.slots + h));
 #else
     const Slot s = t.slots[h];
 #endif

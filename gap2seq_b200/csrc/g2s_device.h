@@ -24,6 +24,9 @@ cudaError_t table_export(const DeviceTable &dt, uint64_t *keys_host, uint8_t *ad
 cudaError_t table_contains(const DeviceTable &dt, const char *ascii_host, uint64_t n, uint8_t *out_host, cudaStream_t st);
 
 struct FillParams;
+struct ChainParams;
+// chain tier (g2s_chain.cuh): k_chain_walk + k_chain_finish over the gaps of p.order
+cudaError_t launch_chain(const ChainParams &p, cudaStream_t st);
 // thin tier: one CTA per gap, persistent over a device work queue; `shape` selects how many warps a gap gets
 // (0: 1 helper + 1 main, 1: 2 + 4, 2: 4 + 8).  groups = number of scratch slices.
 cudaError_t launch_fill_thin(const FillParams &p, int groups, int shape, cudaStream_t st);

@@ -25,6 +25,7 @@
 #include "../../include/g2s.h"
 #include "g2s_device.h"
 #include "g2s_fill.cuh"
+#include "g2s_chain.cuh"
 #include "g2s_finish.h"
 #include "g2s_scaffold.h"
 
@@ -105,6 +106,8 @@ struct g2s_engine {
   std::vector<Pass> passes;
   bool uploaded = false, ran = false;
   DevBuf d_flanks, d_gaps, d_order, d_outs, d_scratch, d_counters;
+  DevBuf d_chain_strs, d_chain_walks;  // chain tier: packed walk strings, walk summaries
+  bool chain_tier = true;              // G2S_NO_CHAIN=1: every gap starts in the thin tier (A/B measurements)
   std::vector<DevBuf> d_pack;          // persistent (grow-only) pack arena per pass ordinal
   std::vector<DevBuf> d_fill;          // fill arena per pass ordinal
   bool device_trace = true;            // G2S_NO_DEVICE_TRACE=1: every traceback on the host (A/B measurements)
@@ -154,6 +157,7 @@ extern "C" int g2s_create(const g2s_config *cfg, g2s_engine **out) {
   // the measured host).  Keep freed memory in the process unless the embedding application objects (G2S_KEEP_MALLOPT=1).
   if (!getenv("G2S_KEEP_MALLOPT")) { mallopt(M_TRIM_THRESHOLD, 1 << 30); mallopt(M_MMAP_THRESHOLD, 1 << 28); }
   e->device_trace = getenv("G2S_NO_DEVICE_TRACE") == nullptr;
+  e->chain_tier = e->device_trace && getenv("G2S_NO_CHAIN") == nullptr;   // the chain tier writes fills on the device
   *out = e;
   return G2S_OK;
 }
@@ -163,6 +167,7 @@ extern "C" void g2s_destroy(g2s_engine *e) {
   for (g2s_engine *p : e->peers) g2s_destroy(p);
   e->peers.clear();
   cudaSetDevice(e->cfg.device);
+  e->d_chain_strs.release(); e->d_chain_walks.release();
   for (auto &b : e->d_pack) b.release();
   for (auto &b : e->d_fill) b.release();
   e->d_flanks.release(); e->d_gaps.release(); e->d_order.release(); e->d_outs.release();
@@ -482,6 +487,57 @@ static int run_pass(g2s_engine *e, Pass &p) {
   return G2S_OK;
 }
 
+// The chain tier (g2s_chain.cuh) over the gaps of p.order: two launches per chunk of gaps (walks, finish).  The walk
+// strings are the tier's only scratch: 2 bits per level and pass, a few hundred bytes per gap.
+static int run_chain_pass(g2s_engine *e, Pass &p) {
+  const int k = e->cfg.k;
+  ChainParams P{};
+  P.table = table_view(e->table);
+  P.f_words = chain_words(k, e->max_dmax);
+  P.r_words = chain_words(k, e->max_rmf + (e->max_dmax + 1) / 2);   // right_half <= rmf + ceil((g + e) / 2)
+  const size_t stride = ((size_t)P.f_words + P.r_words) * 8;
+  size_t chunk = std::max<size_t>(1, std::min<size_t>(p.order.size(), (e->budget / 2) / stride));
+  CUDA_TRY(e->d_chain_strs.reserve(chunk * stride));
+  CUDA_TRY(e->d_chain_walks.reserve(chunk * 2 * sizeof(ChainWalk)));
+  if ((size_t)p.pack_slot >= e->d_pack.size()) e->d_pack.resize(p.pack_slot + 1);
+  if ((size_t)p.pack_slot >= e->d_fill.size()) e->d_fill.resize(p.pack_slot + 1);
+  p.fill_cap = 0;
+  for (uint32_t gi : p.order) p.fill_cap += (unsigned long long)dmax_of(e->gaps[gi]) + 2;
+  CUDA_TRY(e->d_fill[p.pack_slot].reserve((size_t)p.fill_cap + 16));
+  CUDA_TRY(e->d_order.reserve(p.order.size() * 4));
+  CUDA_TRY(cudaMemcpyAsync(e->d_order.p, p.order.data(), p.order.size() * 4, cudaMemcpyHostToDevice, e->st));
+  CUDA_TRY(cudaMemsetAsync(e->d_counters.p, 0, 64, e->st));
+  P.flanks = (const char *)e->d_flanks.p;
+  P.gaps = (const GapDev *)e->d_gaps.p;
+  P.outs = (GapOut *)e->d_outs.p;
+  P.strs = (uint64_t *)e->d_chain_strs.p;
+  P.walks = (ChainWalk *)e->d_chain_walks.p;
+  P.fills = (char *)e->d_fill[p.pack_slot].p;
+  P.fill_cap = p.fill_cap;
+  P.fill_cursor = (unsigned long long *)((char *)e->d_counters.p + 16);
+  CUDA_TRY(cudaEventRecord(e->ev[0], e->st));
+  for (size_t at = 0; at < p.order.size(); at += chunk) {
+    P.order = (const uint32_t *)e->d_order.p + at;
+    P.n_gaps = (uint32_t)std::min(chunk, p.order.size() - at);
+    CUDA_TRY(launch_chain(P, e->st));
+    e->tm.launches += 2; e->tm.launches_chain += 2;
+  }
+  CUDA_TRY(cudaEventRecord(e->ev[1], e->st));
+  CUDA_TRY(cudaMemcpyAsync(e->h_outs.p, e->d_outs.p, e->gaps.size() * sizeof(GapOut), cudaMemcpyDeviceToHost, e->st));
+  unsigned long long fused = 0;
+  CUDA_TRY(cudaMemcpyAsync(&fused, (char *)e->d_counters.p + 16, 8, cudaMemcpyDeviceToHost, e->st));
+  CUDA_TRY(cudaStreamSynchronize(e->st));
+  float ms = 0;
+  CUDA_TRY(cudaEventElapsedTime(&ms, e->ev[0], e->ev[1]));
+  e->tm.kernel_ms += ms; e->tm.kernel_ms_chain += ms;
+  if (getenv("G2S_HOST_PROF"))
+    fprintf(stderr, "g2s: chain tier: %zu gaps, strings %.1f MB, %.3f ms\n", p.order.size(), chunk * stride / 1e6, ms);
+  e->tm.d2h_bytes += e->gaps.size() * sizeof(GapOut) + 8;
+  p.pack_used = 0;
+  p.fill_used = std::min(fused, p.fill_cap);
+  return G2S_OK;
+}
+
 static int do_upload(g2s_engine *e, const g2s_gap *gaps, size_t n) {
   if (!e) return fail(G2S_E_ARG, "null engine");
   if (!e->table.slots) return fail(G2S_E_STATE, "no graph imported (g2s_import_kmers / g2s_build_from_reads)");
@@ -570,6 +626,25 @@ static int do_run(g2s_engine *e) {
   int max_tier = 0;
   { Pass probe; probe.order.push_back(0); for (int t = 1; t < 8; t++) { probe.tier = t; if (plan_pass(e, probe) != 0) break; max_tier = t; } }
   size_t pending = n;
+  if (e->chain_tier) {   // gaps whose borders never exceed one state end here; the others go on to the tiers with tables
+    e->passes.emplace_back();
+    Pass &p = e->passes.back();
+    p.tier = -1;
+    p.pack_slot = 0;
+    p.order.resize(n);
+    for (size_t i = 0; i < n; i++) p.order[i] = (uint32_t)i;
+    std::stable_sort(p.order.begin(), p.order.end(),
+                     [&](uint32_t a, uint32_t b) { return dmax_of(e->gaps[a]) > dmax_of(e->gaps[b]); });
+    int rc = run_chain_pass(e, p);
+    if (rc != G2S_OK) return rc;
+    const GapOut *ho = (const GapOut *)e->h_outs.p;
+    for (size_t i = 0; i < n; i++) {
+      if (!(ho[i].status & GS_DONE)) return fail(G2S_E_CUDA, "chain tier did not finish a gap");
+      if (ho[i].status & GS_INTERNAL) return fail(G2S_E_CUDA, "device table inconsistent with its adjacency bytes");
+      if (ho[i].status & GS_NOT_CHAIN) continue;
+      e->outs[i] = ho[i]; e->out_pass[i] = 0; done[i] = 1; pending--;
+    }
+  }
   for (int tier = 0; pending > 0; tier++) {
     std::vector<uint32_t> todo;
     for (size_t i = 0; i < n; i++) if (!done[i] && want[i] <= tier) todo.push_back((uint32_t)i);

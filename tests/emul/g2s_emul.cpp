@@ -11,6 +11,7 @@
 
 #include "../../include/g2s.h"
 #include "../../gap2seq_b200/csrc/g2s_fill.cuh"
+#include "../../gap2seq_b200/csrc/g2s_chain.cuh"
 #include "../../gap2seq_b200/csrc/g2s_finish.h"
 #include "../../gap2seq_b200/csrc/g2s_scaffold.h"
 
@@ -21,6 +22,10 @@ struct EmulGroup {
   static int size() { return 1; }
   static void sync() {}
   static bool any(bool p) { return p; }
+  static int min_i32(int v) { return v; }
+  static int max_i32(int v) { return v; }
+  static uint32_t add_u32(uint32_t v) { return v; }
+  static unsigned long long bcast_u64(unsigned long long v) { return v; }
   static constexpr bool kWarp = false, kWarpScout = false;
 };
 
@@ -74,6 +79,7 @@ void emul_adjacency(void *gp, const uint64_t *kmers, size_t n, uint8_t *out) {
 
 // device pass of a list of gaps, emulated: fills a detached HostBatch exactly like the engine's do_collect
 static double g_submit_s = 0, g_analyze_s = 0;
+static unsigned long long g_chain_gaps = 0, g_table_gaps = 0;   // gaps finished by the chain tier / by the tiers with tables
 static ThreadPool *host_pool() {   // G2S_EMUL_THREADS=1 selects the sequential host stages
   static ThreadPool *p = nullptr;
   static bool init = false;
@@ -111,6 +117,35 @@ static int emul_submit(EmulGraph *g, int k, const g2s_gap *gaps, size_t n, HostB
     GapOut out{};
     std::vector<PackRec> pack;
     int tier = 0;
+    // the chain tier first (g2s_chain.cuh); G2S_NO_CHAIN=1 leaves every gap to the tiers with tables
+    static const bool chain_on = getenv("G2S_NO_CHAIN") == nullptr;
+    if (chain_on && device_trace && cap0 == 0) {
+      const int right_half = gg.right_max_fuz + (gg.gap_len + gg.gap_err + 1) / 2;
+      ChainParams CP{};
+      CP.table = g->t; CP.flanks = flanks.data(); CP.gaps = &gd; CP.n_gaps = 1; CP.outs = &out;
+      CP.f_words = chain_words(k, dmax); CP.r_words = chain_words(k, right_half);
+      std::vector<uint64_t> strs((size_t)CP.f_words + CP.r_words, 0xDEADBEEFDEADBEEFULL);
+      ChainWalk walks[2];
+      std::vector<char> fills((size_t)dmax + 8);
+      unsigned long long fcursor = 0;
+      CP.strs = strs.data(); CP.walks = walks; CP.fills = fills.data(); CP.fill_cap = fills.size(); CP.fill_cursor = &fcursor;
+      chain_walk(g->t, kmer_from_ascii(flanks.data() + gd.flank_off, k), dmax, strs.data(), &walks[0]);
+      chain_walk(g->t, revcomp(kmer_from_ascii(flanks.data() + gd.rstart_off + gd.rmf, k), k), right_half, strs.data() + CP.f_words, &walks[1]);
+      uint64_t tk[MAX_FUZ + 1];
+      chain_finish<EmulGroup>(CP, gd, strs.data(), strs.data() + CP.f_words, walks[0], walks[1], tk, &out);
+      if (out.status & GS_INTERNAL) return -100;
+      if (!(out.status & GS_NOT_CHAIN)) {
+        g_chain_gaps++;
+        if (out.status & GS_TRACED) { hb.own_fill[i].assign(fills.begin() + out.fill_off, fills.begin() + out.fill_off + out.fill_len + 1); out.fill_off = 0; }
+        hb.outs[i] = out; hb.tier[i] = -1; hb.pack_of[i] = (int)i;
+        hb.pack_base[i] = nullptr;
+        if (out.status & GS_TRACED) hb.fill_base[i] = hb.own_fill[i].data();
+        hb.gaps[i].kmer_left = hb.gaps[i].kmer_right = nullptr;
+        continue;
+      }
+      out = GapOut{};
+    }
+    g_table_gaps++;
     for (;; tier++, cap *= 16) {
       uint32_t hlog = tier == 0 ? ceil_log2(3 * ((uint64_t)dmax + 64)) : (ceil_log2(cap / 4) > 16 ? ceil_log2(cap / 4) : 16);
       SliceLayout L = make_layout(cap, hlog, (uint32_t)dmax + 1, (uint32_t)std::max(gg.left_max_fuz, gg.right_max_fuz) + 1);
@@ -147,6 +182,10 @@ static int emul_submit(EmulGraph *g, int k, const g2s_gap *gaps, size_t n, HostB
   g_analyze_s += now_s() - t_an0;
   g_submit_s += now_s() - t_submit0;
   return 0;
+}
+extern "C" void emul_tier_counts(unsigned long long *chain, unsigned long long *table, int reset) {
+  *chain = g_chain_gaps; *table = g_table_gaps;
+  if (reset) g_chain_gaps = g_table_gaps = 0;
 }
 extern "C" void emul_times(double *submit_s, double *analyze_s, int reset) {
   *submit_s = g_submit_s; *analyze_s = g_analyze_s;

@@ -14,7 +14,7 @@ from gap2seq_b200 import engine as E
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 _SO = os.path.join(ROOT, "tests", "emul", "libg2s_emul.so")
 _SRC = [os.path.join(ROOT, "tests", "emul", "g2s_emul.cpp")] + [
-    os.path.join(ROOT, "gap2seq_b200", "csrc", f) for f in ("g2s_fill.cuh", "g2s_common.cuh", "g2s_finish.h", "g2s_scaffold.h", "g2s_pool.h")]
+    os.path.join(ROOT, "gap2seq_b200", "csrc", f) for f in ("g2s_fill.cuh", "g2s_chain.cuh", "g2s_common.cuh", "g2s_finish.h", "g2s_scaffold.h", "g2s_pool.h")]
 
 _lib = None
 
