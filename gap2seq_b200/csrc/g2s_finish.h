@@ -256,24 +256,31 @@ struct RawBuf {
   }
 };
 
+class RandAhead;
 struct RandCursor {
   const uint32_t *s;   // generator words of the stream (RandAhead); rand() returns word >> 1
   size_t pos;
-  int next() { return (int)(s[pos++] >> 1); }
+  RandAhead *owner;    // materialises the block of the stream a value is read from (skipped stretches never exist)
+  inline int next();
   void skip(size_t n) { pos += n; }
 };
 
 // The next values of libc rand(), computed from a private copy of the generator's table without consuming them.
 // glibc's default generator is the additive feedback s[i] = s[i-3] + s[i-31] (mod 2^32), rand() = s[i] >> 1, kept in a
 // circular table of 31 words; laid out as a plain array in stream order the recurrence is one add per value with no
-// index arithmetic.  extend(n) makes words [0, n) available (it can run on another thread while the device pass is
-// in flight: it does not touch libc); commit(used) writes the last 31 words back into libc's table and moves its
-// rear index, so the application's stream continues exactly as after `used` rand() calls.  Only valid where
-// RandSkipper's self test recognised that generator; enabled() checks the whole mechanism once more.
+// index arithmetic.
+// The reference draws one value per traceback step even where the step has no choice (src/Gap2Seq.cpp:1513), so a batch
+// of 10 000 gaps spans tens of millions of values of which almost none is ever looked at.  The stream is therefore laid
+// out in BLOCKS of 65 536 values that are computed only when a traceback reads from them: extend(n) merely computes the
+// 31-word generator state in front of every block - a jump by a whole block is a product with x^65536 mod the
+// generator's characteristic polynomial x^31 - x^28 - 1 over Z/2^32, 961 multiply-adds - and need(lo, hi) fills the
+// blocks that overlap [lo, hi), from any thread.  commit(used) writes the 31 words in front of position `used` back
+// into libc's table and moves its rear index, so the application's stream continues exactly as after `used` rand()
+// calls.  Only valid where RandSkipper's self test recognised that generator; enabled() checks the whole mechanism
+// (values across block boundaries, commit) once more against rand() itself.
 class RandAhead {
  public:
-  // decided once, on a private generator state (the application's stream is restored): do the values computed ahead
-  // equal what rand() returns, and does commit() leave libc where that many calls would have left it?
+  static const size_t BLOCK = (size_t)1 << 16;
   static bool enabled() {
     static std::once_flag once;
     static bool good = false;
@@ -283,7 +290,7 @@ class RandAhead {
       char *app = initstate(4242u, (char *)bufa, 128);
       if (!app) return;
       bool ok = true;
-      for (size_t n : {(size_t)5, (size_t)31, (size_t)8269}) {
+      for (size_t n : {(size_t)5, (size_t)31, (size_t)8269, 3 * BLOCK + 77}) {
         std::vector<int> ref(n + 8);
         initstate(4242u, (char *)bufa, 128);
         for (size_t i = 0; i < n + 8; i++) ref[i] = rand();
@@ -291,7 +298,15 @@ class RandAhead {
         RandAhead a;
         ok = ok && a.begin_unchecked();
         if (ok) { a.extend(3); a.extend(n + 8); }
-        for (size_t i = 0; i < n + 8 && ok; i++) ok = (int)(a.data()[i] >> 1) == ref[i];
+        if (ok && n > BLOCK) {   // blocks out of order, a block in the middle never: values and commit must not depend on it
+          a.need(2 * BLOCK + 5, n + 8);
+          for (size_t i = 2 * BLOCK + 5; i < n + 8 && ok; i++) ok = (int)(a.data()[i] >> 1) == ref[i];
+          a.need(0, 100);
+          for (size_t i = 0; i < 100 && ok; i++) ok = (int)(a.data()[i] >> 1) == ref[i];
+        } else if (ok) {
+          a.need(0, n + 8);
+          for (size_t i = 0; i < n + 8 && ok; i++) ok = (int)(a.data()[i] >> 1) == ref[i];
+        }
         if (ok) ok = a.commit(n);
         for (size_t i = n; i < n + 8 && ok; i++) ok = rand() == ref[i];
       }
@@ -310,8 +325,9 @@ class RandAhead {
     if (type == 3 && rear >= 0 && rear < 31) {
       const uint32_t *st = (const uint32_t *)(info + 1);
       r0_ = rear; f0_ = (rear + 3) % 31;
-      uint32_t *b = buf_.ensure(31);
-      for (int j = -31; j < 0; j++) b[31 + j] = st[((f0_ + j) % 31 + 31) % 31];   // word of step j sits at (f0 + j) mod 31
+      states_.assign(1, State());
+      for (int j = -31; j < 0; j++) states_[0].w[31 + j] = st[((f0_ + j) % 31 + 31) % 31];   // word of step j sits at (f0 + j) mod 31
+      nblk_ = 0;
       ok_ = true;
     }
     setstate((char *)info);
@@ -319,27 +335,46 @@ class RandAhead {
   }
   bool ok() const { return ok_; }
   size_t size() const { return n_; }
-  const uint32_t *data() const { return buf_.p + 31; }
+  const uint32_t *data() const { return buf_.p; }
+  // make positions [0, n) addressable: room in the flat array, the generator state in front of each of their blocks.
+  // Not to be called while tracebacks read (the array may move).
   void extend(size_t n) {
     if (!ok_ || n <= n_) return;
-    uint32_t *b = buf_.ensure(31 + n, 31 + n_);
-    // s[i] = s[i-31] + s[i-3]: the three most recent words stay in registers, so that the loop is one load, one add
-    // and one store per word instead of a store-to-load forwarding chain
-    size_t i = n_;
-    uint32_t *w = b + 31;
-    uint32_t a0 = w[(ptrdiff_t)i - 3], a1 = w[(ptrdiff_t)i - 2], a2 = w[(ptrdiff_t)i - 1];
-    for (; i + 3 <= n; i += 3) {
-      a0 += w[(ptrdiff_t)i - 31]; a1 += w[(ptrdiff_t)i - 30]; a2 += w[(ptrdiff_t)i - 29];
-      w[i] = a0; w[i + 1] = a1; w[i + 2] = a2;
+    const size_t nb = (n + BLOCK - 1) / BLOCK;
+    bool fresh = false;
+    if (nb * BLOCK > buf_.cap) { buf_.ensure(nb * BLOCK + BLOCK); fresh = true; }   // a new array: nothing materialised is
+    if (flags_.size() < nb) {                                                       // carried over (it is cheap to redo)
+      std::vector<std::atomic<int>> f(nb + nb / 2 + 4);
+      flags_.swap(f);
+      fresh = true;
     }
-    for (; i < n; i++) w[i] = w[(ptrdiff_t)i - 31] + w[(ptrdiff_t)i - 3];
+    for (size_t b = fresh ? 0 : nblk_; b < (fresh ? flags_.size() : nb); b++) flags_[b].store(0, std::memory_order_relaxed);
+    const uint32_t *q = jump_poly();
+    while (states_.size() < nb) {          // state in front of block b + 1 = x^BLOCK applied to the state in front of block b
+      const State &a = states_.back();
+      uint32_t w[61];
+      for (int i = 0; i < 31; i++) w[i] = a.w[i];
+      for (int i = 31; i < 61; i++) w[i] = w[i - 31] + w[i - 3];
+      State nx;
+      for (int j = 0; j < 31; j++) { uint32_t acc = 0; for (int m = 0; m < 31; m++) acc += q[m] * w[j + m]; nx.w[j] = acc; }
+      states_.push_back(nx);
+    }
+    nblk_ = nb;
     n_ = n;
   }
+  // the words of positions [lo, hi) are about to be read
+  void need(size_t lo, size_t hi) {
+    if (!ok_ || hi <= lo) return;
+    if (hi > n_) hi = n_;
+    for (size_t b = lo / BLOCK; b * BLOCK < hi; b++) fill_block(b);
+  }
+  void touch(size_t pos) { if (flag(pos / BLOCK).load(std::memory_order_acquire) != 2) fill_block(pos / BLOCK); }
   // advance libc's generator by `used` <= size() values
   bool commit(size_t used) {
     if (!ok_) return false;
     if (used == 0) return true;
     if (used > n_) return false;
+    need(used > 31 ? used - 31 : 0, used);
     int32_t *info = (int32_t *)setstate(RandSkipper::dummy());
     if (!info) return false;
     uint32_t *st = (uint32_t *)(info + 1);
@@ -352,11 +387,60 @@ class RandAhead {
   }
 
  private:
-  RawBuf<uint32_t> buf_;        // 31 words of history, then the stream; kept from call to call
-  size_t n_ = 0;
+  struct State { uint32_t w[31]; };        // the 31 words in front of a block, oldest first
+  std::atomic<int> &flag(size_t b) { return flags_[b]; }
+  // x^BLOCK mod (x^31 - x^28 - 1) over Z/2^32, by repeated squaring
+  static const uint32_t *jump_poly() {
+    static uint32_t q[31];
+    static std::once_flag once;
+    std::call_once(once, [] {
+      uint32_t r[31] = {0};
+      r[1] = 1;
+      for (size_t e = 1; e < BLOCK; e <<= 1) {
+        uint32_t t[61] = {0};
+        for (int i = 0; i < 31; i++) for (int j = 0; j < 31; j++) t[i + j] += r[i] * r[j];
+        for (int d = 60; d >= 31; d--) { const uint32_t c = t[d]; t[d - 3] += c; t[d - 31] += c; }   // x^31 = x^28 + 1
+        for (int i = 0; i < 31; i++) r[i] = t[i];
+      }
+      for (int i = 0; i < 31; i++) q[i] = r[i];
+    });
+    return q;
+  }
+  void fill_block(size_t b) {
+    std::atomic<int> &f = flag(b);
+    int st = f.load(std::memory_order_acquire);
+    if (st == 2) return;
+    int expect = 0;
+    if (!f.compare_exchange_strong(expect, 1, std::memory_order_acq_rel)) {   // another thread is at it (or done)
+      while (f.load(std::memory_order_acquire) != 2) std::this_thread::yield();
+      return;
+    }
+    uint32_t *w = buf_.p + b * BLOCK;
+    const State &h = states_[b];
+    // the first 31 words read the stored history, then the recurrence runs inside the block: the three most recent words
+    // stay in registers, so that the loop is one load, one add and one store per word
+    uint32_t tmp[62];
+    for (int i = 0; i < 31; i++) tmp[i] = h.w[i];
+    for (int i = 31; i < 62; i++) tmp[i] = tmp[i - 31] + tmp[i - 3];
+    for (int i = 0; i < 31; i++) w[i] = tmp[31 + i];
+    size_t i = 31;
+    uint32_t a0 = w[i - 3], a1 = w[i - 2], a2 = w[i - 1];
+    for (; i + 3 <= BLOCK; i += 3) {
+      a0 += w[i - 31]; a1 += w[i - 30]; a2 += w[i - 29];
+      w[i] = a0; w[i + 1] = a1; w[i + 2] = a2;
+    }
+    for (; i < BLOCK; i++) w[i] = w[i - 31] + w[i - 3];
+    f.store(2, std::memory_order_release);
+  }
+
+  RawBuf<uint32_t> buf_;        // the stream, block by block where materialised; kept from call to call
+  std::vector<State> states_;
+  std::vector<std::atomic<int>> flags_;   // per block: 0 not computed, 1 being computed, 2 there
+  size_t n_ = 0, nblk_ = 0;
   int f0_ = 0, r0_ = 0;
   bool ok_ = false;
 };
+inline int RandCursor::next() { if (owner) owner->touch(pos); return (int)(s[pos++] >> 1); }
 
 // Assemble the g2s_result of one gap and run its traceback.  `fill_out` (may be null) receives what the
 // reference leaves at &fill[left_max_fuz - left_fuz].
@@ -624,7 +708,7 @@ inline void trace_many(const std::vector<TraceJob> &jobs, std::vector<g2s_result
   size_t final_upto = 0, base = 0;
   trace_stats().parallel_calls++;
   auto trace_one = [&](size_t j, std::vector<char> &scratch) {
-    RandCursor rc{vals, off[j]};
+    RandCursor rc{vals, off[j], ahead};
     jobs[j].hb->trace_at(jobs[j].idx, res[j], &arena[fill_off[j]], rc, scratch);
     act[j] = rc.pos - off[j];
   };
