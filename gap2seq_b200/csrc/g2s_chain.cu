@@ -8,6 +8,9 @@
 namespace g2s {
 
 static const int WALK_THREADS = 64;      // small CTAs: the walks of a pass spread over all SMs
+// A warp advances at the pace of its slowest lane's gather, and a gather in a multi-gigabyte table has a long latency
+// tail (TLB misses); the walks need no issue bandwidth, so only every WALK_STRIDE-th lane carries one: 4 walks per warp.
+static const int WALK_STRIDE = 8;
 static const int FINISH_WARPS = 4;
 
 struct ChainWarp {
@@ -23,21 +26,23 @@ struct ChainWarp {
 
 // thread 2q walks forward from the left flank of gap order[q], thread 2q + 1 backward from its right flank
 __global__ void __launch_bounds__(WALK_THREADS) k_chain_walk(const __grid_constant__ ChainParams P) {
-  const uint32_t t = blockIdx.x * WALK_THREADS + threadIdx.x;
+  const uint32_t tt = blockIdx.x * WALK_THREADS + threadIdx.x;
+  if (tt % WALK_STRIDE) return;
+  const uint32_t t = tt / WALK_STRIDE;
   const uint32_t q = t >> 1;
   if (q >= P.n_gaps) return;
   const GapDev gd = P.gaps[P.order[q]];
   const int k = P.table.k;
   uint64_t *W = P.strs + (size_t)q * (P.f_words + P.r_words);
-  if ((t & 1) == 0) {
-    const int Dmax = gd.gap_len + gd.gap_err + gd.lmf + gd.rmf;
-    chain_walk(P.table, kmer_from_ascii(P.flanks + gd.flank_off, k), Dmax, W, &P.walks[2 * q]);
-  } else {
-    const int right_half = gd.rmf + (gd.gap_len + gd.gap_err + 1) / 2;
-    // walking predecessors of the last right start = walking successors of its reverse complement
-    chain_walk(P.table, revcomp(kmer_from_ascii(P.flanks + gd.rstart_off + gd.rmf, k), k), right_half, W + P.f_words,
-               &P.walks[2 * q + 1]);
-  }
+  // ONE call site for both directions: the walks of a warp stay converged (two inlined copies of the loop under an
+  // if / else would serialise the forward lanes against the backward lanes)
+  const bool fwd = (t & 1) == 0;
+  const int maxlev = fwd ? gd.gap_len + gd.gap_err + gd.lmf + gd.rmf           // Dmax
+                         : gd.rmf + (gd.gap_len + gd.gap_err + 1) / 2;        // right_half
+  uint64_t x0 = kmer_from_ascii(P.flanks + (fwd ? gd.flank_off : gd.rstart_off + gd.rmf), k);
+  // walking predecessors of the last right start = walking successors of its reverse complement
+  if (!fwd) x0 = revcomp(x0, k);
+  chain_walk(P.table, x0, maxlev, fwd ? W : W + P.f_words, &P.walks[2 * q + (fwd ? 0 : 1)]);
 }
 
 __global__ void __launch_bounds__(32 * FINISH_WARPS) k_chain_finish(const __grid_constant__ ChainParams P) {
@@ -52,7 +57,7 @@ __global__ void __launch_bounds__(32 * FINISH_WARPS) k_chain_finish(const __grid
 
 cudaError_t launch_chain(const ChainParams &p, cudaStream_t st) {
   if (p.n_gaps == 0) return cudaSuccess;
-  k_chain_walk<<<(2 * p.n_gaps + WALK_THREADS - 1) / WALK_THREADS, WALK_THREADS, 0, st>>>(p);
+  k_chain_walk<<<(2 * p.n_gaps * WALK_STRIDE + WALK_THREADS - 1) / WALK_THREADS, WALK_THREADS, 0, st>>>(p);
   k_chain_finish<<<(p.n_gaps + FINISH_WARPS - 1) / FINISH_WARPS, 32 * FINISH_WARPS, 0, st>>>(p);
   return cudaGetLastError();
 }

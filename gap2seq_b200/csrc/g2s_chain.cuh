@@ -76,22 +76,67 @@ struct BaseWriter {
   G2S_D void flush() { out[w] = acc; out[w + 1] = 0; }
 };
 
+// The finish kernel only reads the strings (the walk kernel wrote them): plain cached loads, a warp's 32 consecutive
+// levels touch two or three words.
+G2S_D uint64_t ld_ro(const uint64_t *p) {
+#ifdef __CUDA_ARCH__
+  return __ldg(p);
+#else
+  return *p;
+#endif
+}
 G2S_D uint64_t str_kmer(const uint64_t *W, uint32_t p, int k) {   // bases p .. p + k - 1 as a k-mer
   const uint32_t q = p >> 5, s = 2 * (p & 31);
-  const uint64_t hi = ld_cg(&W[q]), lo = ld_cg(&W[q + 1]);
+  const uint64_t hi = ld_ro(&W[q]), lo = ld_ro(&W[q + 1]);
   const uint64_t v = s ? (hi << s) | (lo >> (64 - s)) : hi;
   return v >> (64 - 2 * k);
 }
-G2S_D uint32_t str_base(const uint64_t *W, uint32_t p) { return (uint32_t)(ld_cg(&W[p >> 5]) >> (62 - 2 * (p & 31))) & 3u; }
+G2S_D uint32_t str_base(const uint64_t *W, uint32_t p) { return (uint32_t)(ld_ro(&W[p >> 5]) >> (62 - 2 * (p & 31))) & 3u; }
 
 // ------------------------------------------------------------------------------------------------ the walk
+// The walk's lookup: the home slot and its neighbour are requested together, so that a key one probe away from home
+// (a third of them at the table's load) does not cost a second dependent round trip.
+G2S_D bool chain_find_slot(const Table &t, uint64_t canon, Slot *out) {
+#ifdef __CUDA_ARCH__
+  uint64_t h = mix64(canon) & t.cap_mask;
+  const uint64_t h1 = (h + 1) & t.cap_mask;
+  uint64_t ak, av, a0, a1, bk, bv, b0, b1;
+  // one statement: both requests leave before either result is looked at
+  asm volatile("ld.global.nc.v4.u64 {%0, %1, %2, %3}, [%8];\n\tld.global.nc.v4.u64 {%4, %5, %6, %7}, [%9];"
+               : "=l"(ak), "=l"(av), "=l"(a0), "=l"(a1), "=l"(bk), "=l"(bv), "=l"(b0), "=l"(b1)
+               : "l"(t.slots + h), "l"(t.slots + h1));
+  // straight-line selects: the compiler must not sink the second request behind a test of the first result
+  uint64_t sv, s0, s1;
+  unsigned hit;
+  asm volatile("{\n\t.reg .pred pa, pb, pe;\n\t"
+               "setp.eq.u64 pa, %4, %10;\n\tsetp.eq.u64 pb, %7, %10;\n\tsetp.ne.u64 pe, %4, %11;\n\t"
+               "and.pred pb, pb, pe;\n\t"
+               "selp.b64 %0, %5, %8, pa;\n\tselp.b64 %1, %6, %9, pa;\n\t"
+               "selp.b64 %2, %12, %13, pa;\n\t"
+               "or.pred pa, pa, pb;\n\tselp.u32 %3, 1, 0, pa;\n\t}"
+               : "=l"(sv), "=l"(s0), "=l"(s1), "=r"(hit)
+               : "l"(ak), "l"(av), "l"(a0), "l"(bk), "l"(bv), "l"(b0), "l"(canon), "l"(KEY_EMPTY), "l"(a1), "l"(b1));
+  if (hit) { out->key = canon; out->val = sv; out->h[0] = s0; out->h[1] = s1; return true; }
+  if (ak == KEY_EMPTY || bk == KEY_EMPTY) return false;
+  h = (h1 + 1) & t.cap_mask;
+  for (;;) {
+    asm volatile("ld.global.nc.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(ak), "=l"(av), "=l"(a0), "=l"(a1) : "l"(t.slots + h));
+    if (ak == canon) { out->key = canon; out->val = av; out->h[0] = a0; out->h[1] = a1; return true; }
+    if (ak == KEY_EMPTY) return false;
+    h = (h + 1) & t.cap_mask;
+  }
+#else
+  return table_find_slot(t, canon, out) >= 0;
+#endif
+}
+
 // One chain of dependent gathers: from x0 (walk orientation) along unique successors for at most `maxlev` levels.
 G2S_D void chain_walk(const Table &T, uint64_t x0, int maxlev, uint64_t *W, ChainWalk *out) {
   const int k = T.k;
   ChainWalk r{0, 0, 1, 0};
   Canon c = canonical(x0, k);
   Slot sl;
-  if (table_find_slot(T, c.key, &sl) < 0) { *out = r; return; }
+  if (!chain_find_slot(T, c.key, &sl)) { *out = r; return; }
   BaseWriter bw;
   bw.init(W);
   bw.put(x0, (uint32_t)(2 * k));
@@ -112,7 +157,7 @@ G2S_D void chain_walk(const Table &T, uint64_t x0, int maxlev, uint64_t *W, Chai
     if (lev >= maxlev) break;
     c = canonical(x, k);
     r.lookups++;
-    if (table_find_slot(T, c.key, &sl) < 0) { endm = CHAIN_END_INTERNAL; break; }
+    if (!chain_find_slot(T, c.key, &sl)) { endm = CHAIN_END_INTERNAL; break; }
   }
   bw.flush();
   r.n = (uint32_t)lev + 1;
@@ -213,9 +258,15 @@ G2S_D void chain_finish(const ChainParams &P, const GapDev &gd, const uint64_t *
     const uint64_t Ftop = str_kmer(WF, (uint32_t)top, k), rcFtop = revcomp(Ftop, k), rcF0 = revcomp(str_kmer(WF, 0, k), k);
     const int jt = rmf - 1, dlo = lmf + g - e > 0 ? lmf + g - e : 0;
     bool rep = false;
+    // a level can hit a target only within e of the target's nominal level (and seeds start at dlo >= that bound); a
+    // 64-bit signature of the targets spares most of those levels the rmf + 1 comparisons
+    const int hit_lo = g + lmf - e > 0 ? g + lmf - e : 0;
+    uint64_t sig = 0;
+    for (int j = 0; j <= rmf; j++) sig |= 1ULL << ((ld_sh(&tk[j]) * 0x9E3779B97F4A7C15ULL) >> 58);
     for (int c = rank; c <= top; c += gsz) {
       const uint64_t x = str_kmer(WF, (uint32_t)c, k);
       if ((c < top && x == Ftop) || x == rcFtop || x == rcF0) rep = true;
+      if (c < hit_lo || !((sig >> ((x * 0x9E3779B97F4A7C15ULL) >> 58)) & 1)) continue;
       for (int j = 0; j <= rmf; j++) {
         if (x != ld_sh(&tk[j])) continue;
         const int err = c > g + lmf + j ? c - (g + lmf + j) : g + lmf + j - c;

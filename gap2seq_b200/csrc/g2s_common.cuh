@@ -51,7 +51,7 @@ struct Hint {
 };
 G2S_HD Hint hint_of(const Slot &s, uint32_t strand) {
   Hint h;
-  h.lo = s.h[strand];
+  h.lo = strand ? s.h[1] : s.h[0];   // a select, not an indexed load: the slot stays in registers
   h.hi = (uint32_t)(s.val >> (20 + 16 * strand)) & 0xFFFFu;
   h.len = (uint32_t)(s.val >> (8 + 6 * strand)) & 63u;
   return h;

@@ -133,19 +133,26 @@ __global__ void __launch_bounds__(CTA_THREADS) k_fill_cta(const __grid_constant_
 int fill_thin_shapes() { return N_THIN_SHAPES; }
 int fill_thin_threads(int shape) { return 32 * (THIN_MAIN[shape] + THIN_HELPER[shape]); }
 
+// occupancy queries cost tens of microseconds each and the answers never change: asked once per shape
 int fill_max_resident_thin_groups(int sms, int shape) {
+  static int cache[N_THIN_SHAPES] = {0, 0, 0};
+  if (shape >= 0 && shape < N_THIN_SHAPES && cache[shape] > 0) return sms * cache[shape];
   int per_sm = 0;
   cudaError_t e = shape == 0   ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fill_thin<1, 1>, 64, 0)
                   : shape == 1 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fill_thin<2, 4>, 192, 0)
                                : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fill_thin<4, 8>, 384, 0);
   if (e != cudaSuccess || per_sm < 1) per_sm = 1;
+  if (shape >= 0 && shape < N_THIN_SHAPES) cache[shape] = per_sm;
   return sms * per_sm;
 }
 
 int fill_max_resident_cta_groups(int sms) {
+  static int cached = 0;
+  if (cached > 0) return sms * cached;
   int per_sm = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fill_cta, CTA_THREADS, 0) != cudaSuccess || per_sm < 1)
     per_sm = 1;
+  cached = per_sm;
   return sms * per_sm;
 }
 
