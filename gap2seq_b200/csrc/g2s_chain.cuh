@@ -336,16 +336,14 @@ G2S_D void chain_finish(const ChainParams &P, const GapDev &gd, const uint64_t *
     else {
       fill_off = off;
       char *outc = P.fills + off;
+      // a vertex of the path subgraph (levels dS .. sB, alone on its level) is safe iff no sink edge jumps over it, i.e.
+      // up to the lowest seed; a trellis cell that is no vertex gets the sink's verdict (node2boost default):
+      // safe whenever seeds exist.  So the unsafe levels are exactly uLo .. sB, and a base is lower case iff the k levels
+      // from its own upwards all lie in there.
+      const int uLo = n_sink == 0 ? 0 : (dS > min_sink + 1 ? dS : min_sink + 1);
       for (int d = dT + 1 + rank; d <= d0; d += gsz) {
-        bool up = d0 - d < k;
-        for (int z = d; !up && z <= d0 && z < d + k; z++) {
-          bool safe;
-          if (skip_confident) safe = true;
-          else if (n_sink == 0) safe = false;
-          else if (z >= dS && z <= sB) safe = z <= min_sink;   // a vertex of the path subgraph: alone on its level; between source and sink edges?
-          else safe = true;                                      // not a vertex: node2boost hands out the sink
-          up = safe;
-        }
+        const int wend = d + k - 1 < d0 ? d + k - 1 : d0;
+        const bool up = d0 - d < k || skip_confident || (n_sink > 0 && !(d >= uLo && wend <= sB));
         const uint32_t b = str_base(WF, (uint32_t)(d + k - 1));
         const char ch = b == 0 ? 'A' : b == 1 ? 'C' : b == 2 ? 'T' : 'G';
         outc[d - 1 - dT] = up ? ch : (char)(ch | 0x20);

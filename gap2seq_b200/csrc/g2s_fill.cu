@@ -101,8 +101,10 @@ static __device__ __forceinline__ void process_gap_pair(const FillParams &P, con
   }
 }
 
+static const uint32_t WIDE_CAP = 8192;   // entries of the wide tier's per-level table in shared memory (128 KB)
+
 template <int HW, int MW>   // HW == 0: wide tier, the whole CTA runs the phases one after the other
-__device__ __forceinline__ void group_loop(const FillParams &P, GShared &sh, uint32_t group_id) {
+__device__ __forceinline__ void group_loop(const FillParams &P, GShared &sh, uint32_t group_id, const WideBuf *wb = nullptr) {
   const Slice S = make_slice(P.scratch + (size_t)group_id * P.lay.bytes, P.lay);
   for (;;) {
     __syncthreads();
@@ -113,7 +115,7 @@ __device__ __forceinline__ void group_loop(const FillParams &P, GShared &sh, uin
     const uint32_t gi = P.order[q];
     const GapDev gd = P.gaps[gi];
     if (HW > 0) process_gap_pair<(HW > 0 ? HW : 1), MW>(P, gd, S, sh, &P.outs[gi]);
-    else process_gap<BlockGroup>(P, gd, S, sh, &P.outs[gi]);
+    else process_gap<BlockGroup>(P, gd, S, sh, &P.outs[gi], wb);
   }
 }
 
@@ -126,8 +128,15 @@ __global__ void __launch_bounds__(32 * (HW + MW)) k_fill_thin(const __grid_const
 
 __global__ void __launch_bounds__(CTA_THREADS) k_fill_cta(const __grid_constant__ FillParams P, int groups) {
   __shared__ GShared sh;
+  extern __shared__ __align__(16) unsigned char wide_mem[];
   if (blockIdx.x >= (uint32_t)groups) return;
-  group_loop<0, 1>(P, sh, blockIdx.x);
+  const WideBuf wb = make_wide_buf(wide_mem, WIDE_CAP);
+  group_loop<0, 1>(P, sh, blockIdx.x, &wb);
+}
+
+static cudaError_t cta_dynamic_smem() {   // opt in to the large dynamic shared memory once
+  static cudaError_t st = cudaFuncSetAttribute(k_fill_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wide_buf_bytes(WIDE_CAP));
+  return st;
 }
 
 int fill_thin_shapes() { return N_THIN_SHAPES; }
@@ -150,7 +159,8 @@ int fill_max_resident_cta_groups(int sms) {
   static int cached = 0;
   if (cached > 0) return sms * cached;
   int per_sm = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fill_cta, CTA_THREADS, 0) != cudaSuccess || per_sm < 1)
+  if (cta_dynamic_smem() != cudaSuccess ||
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fill_cta, CTA_THREADS, wide_buf_bytes(WIDE_CAP)) != cudaSuccess || per_sm < 1)
     per_sm = 1;
   cached = per_sm;
   return sms * per_sm;
@@ -164,7 +174,9 @@ cudaError_t launch_fill_thin(const FillParams &p, int groups, int shape, cudaStr
 }
 
 cudaError_t launch_fill_cta(const FillParams &p, int groups, cudaStream_t st) {
-  k_fill_cta<<<groups, CTA_THREADS, 0, st>>>(p, groups);
+  cudaError_t e = cta_dynamic_smem();
+  if (e != cudaSuccess) return e;
+  k_fill_cta<<<groups, CTA_THREADS, wide_buf_bytes(WIDE_CAP), st>>>(p, groups);
   return cudaGetLastError();
 }
 
