@@ -103,6 +103,7 @@ struct g2s_engine {
   std::vector<GapDev> gapdev;
   std::vector<GapOut> outs;
   std::vector<int> out_pass;           // pass that produced outs[i]
+  std::vector<uint8_t> phantom;        // gaps whose g2s_gap.present_bits disagree with the table (empty: no gap carried bits)
   std::vector<Pass> passes;
   bool uploaded = false, ran = false;
   DevBuf d_flanks, d_gaps, d_order, d_outs, d_scratch, d_counters;
@@ -601,6 +602,35 @@ static int do_upload(g2s_engine *e, const g2s_gap *gaps, size_t n) {
   CUDA_TRY(cudaEventElapsedTime(&ms, e->ev[2], e->ev[3]));
   e->tm.h2d_ms = ms;
   e->tm.h2d_bytes = fbytes + n * sizeof(GapDev);
+  // callers that keep their own graph hand in its contains() answers for the flank k-mers (INTEGRATION.md form 2): every
+  // disagreement with the imported exact set is reported per gap, never silently resolved
+  e->phantom.clear();
+  bool any_bits = false;
+  for (size_t i = 0; i < n && !any_bits; i++) any_bits = (gaps[i].flags & G2S_GAP_PRESENT_BITS) != 0;
+  if (any_bits) {
+    std::string ascii;
+    std::vector<size_t> first(n + 1, 0);
+    for (size_t i = 0; i < n; i++) {
+      first[i] = ascii.size() / k;
+      if (!(gaps[i].flags & G2S_GAP_PRESENT_BITS)) continue;
+      const GapDev &d = e->gapdev[i];
+      const char *l = &e->flank_store[d.flank_off], *r = l + k + d.lmf, *rs = &e->flank_store[d.rstart_off];
+      for (int q = 0; q <= d.lmf; q++) ascii.append(l + q, (size_t)k);
+      for (int q = 0; q <= d.rmf; q++) ascii.append(r + q, (size_t)k);
+      (void)rs;
+    }
+    first[n] = ascii.size() / k;
+    std::vector<uint8_t> has(first[n] + 1, 0);
+    CUDA_TRY(table_contains(e->table, ascii.data(), first[n], has.data(), e->st));
+    e->phantom.assign(n, 0);
+    for (size_t i = 0; i < n; i++) {
+      if (!(gaps[i].flags & G2S_GAP_PRESENT_BITS)) continue;
+      const GapDev &d = e->gapdev[i];
+      size_t at = first[i];
+      for (int q = 0; q <= d.lmf; q++, at++) if (((gaps[i].present_bits >> q) & 1) != (uint64_t)(has[at] != 0)) e->phantom[i] = 1;
+      for (int q = 0; q <= d.rmf; q++, at++) if (((gaps[i].present_bits >> (32 + q)) & 1) != (uint64_t)(has[at] != 0)) e->phantom[i] = 1;
+    }
+  }
   e->uploaded = true; e->ran = false;
   return G2S_OK;
 }
@@ -703,6 +733,7 @@ static int do_collect(g2s_engine *e, HostBatch &hb) {
   hb.gaps = e->gaps;
   hb.outs = e->outs;
   hb.tier.assign(n, -2);
+  hb.phantom = e->phantom;
   hb.pack_of.assign(n, 0);
   hb.pack_base.assign(e->passes.size(), nullptr);
   hb.fill_base.assign(e->passes.size(), nullptr);
@@ -888,6 +919,7 @@ static int run_wave(g2s_engine *e, const g2s_gap *gaps, size_t n, HostBatch &hb,
     for (size_t j = 0; j < shards[d].size(); j++) {
       const uint32_t i = shards[d][j];
       hb.gaps[i] = pt.gaps[j]; hb.outs[i] = pt.outs[j]; hb.tier[i] = pt.tier[j]; hb.pack_of[i] = base + pt.pack_of[j];
+      if (j < pt.phantom.size() && pt.phantom[j]) { if (hb.phantom.empty()) hb.phantom.assign(n, 0); hb.phantom[i] = 1; }
       if (j < pt.gen.size()) hb.gen[i] = std::move(pt.gen[j]);
     }
   }
@@ -1028,9 +1060,10 @@ extern "C" int g2s_fill_records(g2s_engine *e, const char *const *seqs, const ch
   return G2S_OK;
 }
 
-extern "C" int g2s_fill_gap(g2s_engine *e, const char *kmer_left, const char *kmer_right, int gap_len, int k, int gap_err,
-                            int left_max_fuz, int right_max_fuz, int *left_fuz, int *right_fuz, long long max_mem, char *fill,
-                            int skip_confident, int all_paths, g2s_subgraph_stats *substats) {
+extern "C" int g2s_fill_gap_ex(g2s_engine *e, const char *kmer_left, const char *kmer_right, int gap_len, int k, int gap_err,
+                               int left_max_fuz, int right_max_fuz, int *left_fuz, int *right_fuz, long long max_mem, char *fill,
+                               int skip_confident, int all_paths, g2s_subgraph_stats *substats, uint64_t present_bits,
+                               int have_present_bits, int32_t *status) {
   (void)max_mem;   // the device tiers are bounded by g2s_config.max_mem_bytes
   if (!e) return fail(G2S_E_ARG, "null engine");
   if (k != e->cfg.k) return fail(G2S_E_ARG, "g2s_fill_gap: k differs from the engine's k");
@@ -1042,7 +1075,9 @@ extern "C" int g2s_fill_gap(g2s_engine *e, const char *kmer_left, const char *km
     return fail(G2S_E_ARG, "g2s_fill_gap: flank shorter than k + max_fuz");
   if (rlen > (size_t)k + right_max_fuz) g.kmer_right_starts = kmer_right + (rlen - k - right_max_fuz);
   g.gap_len = gap_len; g.gap_err = gap_err; g.left_max_fuz = left_max_fuz; g.right_max_fuz = right_max_fuz;
-  g.flags = (skip_confident ? G2S_GAP_SKIP_CONFIDENT : 0) | (all_paths ? G2S_GAP_ALL_PATHS : 0);
+  g.flags = (skip_confident ? G2S_GAP_SKIP_CONFIDENT : 0) | (all_paths ? G2S_GAP_ALL_PATHS : 0) |
+            (have_present_bits ? G2S_GAP_PRESENT_BITS : 0);
+  g.present_bits = present_bits;
   g2s_result r;
   std::vector<char> tmp((size_t)gap_len + k + gap_err + left_max_fuz + right_max_fuz + 3);
   char *fo = tmp.data();
@@ -1055,5 +1090,13 @@ extern "C" int g2s_fill_gap(g2s_engine *e, const char *kmer_left, const char *km
     *right_fuz = r.right_fuz;
   }
   if (substats && r.substats_valid) *substats = r.substats;
+  if (status) *status = r.status;
   return r.count;
+}
+
+extern "C" int g2s_fill_gap(g2s_engine *e, const char *kmer_left, const char *kmer_right, int gap_len, int k, int gap_err,
+                            int left_max_fuz, int right_max_fuz, int *left_fuz, int *right_fuz, long long max_mem, char *fill,
+                            int skip_confident, int all_paths, g2s_subgraph_stats *substats) {
+  return g2s_fill_gap_ex(e, kmer_left, kmer_right, gap_len, k, gap_err, left_max_fuz, right_max_fuz, left_fuz, right_fuz, max_mem,
+                         fill, skip_confident, all_paths, substats, 0, 0, nullptr);
 }

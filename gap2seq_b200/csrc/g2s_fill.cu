@@ -13,7 +13,16 @@
 
 namespace g2s {
 
-static const int CTA_THREADS = 1024;
+#ifndef G2S_CTA_THREADS
+#define G2S_CTA_THREADS 1024
+#endif
+#ifndef G2S_CTA_WARP_SCOUT
+#define G2S_CTA_WARP_SCOUT 1
+#endif
+#ifndef G2S_WIDE_LEVEL
+#define G2S_WIDE_LEVEL 0   // the shared-memory level step (wide_forward_level): measured slower than the general path on cfg3, off
+#endif
+static const int CTA_THREADS = G2S_CTA_THREADS;
 // Thin-tier shapes (helper warps for the right pass, main warps for everything else).  A gap's latency falls with more
 // warps (the per-level work of a narrow batch is instruction bound on one warp) but fewer gaps are resident then; the
 // engine picks per pass: wide shapes for small batches (latency), the two-warp shape for large ones (throughput).
@@ -31,7 +40,9 @@ struct WarpGroup {
 };
 struct BlockGroup {
   static constexpr bool kWarp = false;
-  static constexpr bool kWarpScout = false;
+  // narrow borders inside a wide gap: the CTA's first warp scouts a batch of levels (a group barrier per scouted LEVEL,
+  // the generic flavour, costs a 32-warp barrier pair per level)
+  static constexpr bool kWarpScout = G2S_CTA_WARP_SCOUT != 0;
   static __device__ __forceinline__ int rank() { return threadIdx.x; }
   static __device__ __forceinline__ int size() { return blockDim.x; }
   static __device__ __forceinline__ void sync() { __syncthreads(); }
@@ -131,7 +142,7 @@ __global__ void __launch_bounds__(CTA_THREADS) k_fill_cta(const __grid_constant_
   extern __shared__ __align__(16) unsigned char wide_mem[];
   if (blockIdx.x >= (uint32_t)groups) return;
   const WideBuf wb = make_wide_buf(wide_mem, WIDE_CAP);
-  group_loop<0, 1>(P, sh, blockIdx.x, &wb);
+  group_loop<0, 1>(P, sh, blockIdx.x, G2S_WIDE_LEVEL ? &wb : nullptr);
 }
 
 static cudaError_t cta_dynamic_smem() {   // opt in to the large dynamic shared memory once

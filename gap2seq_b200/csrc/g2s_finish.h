@@ -546,6 +546,7 @@ struct HostBatch {
   std::vector<GeneralResult> gen;
   std::vector<char> buf;
   std::vector<std::shared_ptr<HostBatch>> parts;   // a batch merged from the batches of several GPUs keeps them alive
+  std::vector<uint8_t> phantom;               // per gap: the caller's contains() bits disagree with the imported set (may be empty)
 
   HostBatch() {}
   HostBatch(const HostBatch &) = delete;
@@ -613,6 +614,7 @@ struct HostBatch {
     }
     LibcRand rs;
     finish_one(gaps[i], outs[i], pack_ptr(i), k, tier[i], gen[i], r, fill_out, buf, rs, fill_ptr(i));
+    if (i < phantom.size() && phantom[i]) r.status |= G2S_ST_PHANTOM_FLANK;
   }
 
   // the same from a precomputed window of the rand() stream; thread safe (scratch is the caller's)
@@ -624,6 +626,7 @@ struct HostBatch {
       return;
     }
     finish_one(gaps[i], outs[i], pack_ptr(i), k, tier[i], gen[i], r, fill_out, scratch, rc, fill_ptr(i));
+    if (i < phantom.size() && phantom[i]) r.status |= G2S_ST_PHANTOM_FLANK;
   }
   // upper bound of the rand() values gap i's traceback can consume (one per step plus the length choice)
   size_t rand_bound(size_t i) const {

@@ -43,7 +43,7 @@ class G2SSubgraphStats(C.Structure):
 class G2SGap(C.Structure):
     _fields_ = [("kmer_left", C.c_char_p), ("kmer_right", C.c_char_p), ("gap_len", C.c_int32), ("gap_err", C.c_int32),
                 ("left_max_fuz", C.c_int32), ("right_max_fuz", C.c_int32), ("flags", C.c_int32), ("reserved", C.c_int32),
-                ("kmer_right_starts", C.c_char_p)]
+                ("kmer_right_starts", C.c_char_p), ("present_bits", C.c_uint64)]
 
 
 class G2SResult(C.Structure):
@@ -73,7 +73,7 @@ class G2SRunOptions(C.Structure):
 
 # every symbol include/g2s.h declares (tests check that the library exports all of them)
 ABI_SYMBOLS = ["g2s_last_error", "g2s_abi_version", "g2s_create", "g2s_create_multi", "g2s_num_devices", "g2s_destroy", "g2s_import_kmers",
-               "g2s_build_from_reads", "g2s_table_raw", "g2s_table_adopt", "g2s_num_kmers", "g2s_export_kmers", "g2s_contains", "g2s_fill_gap",
+               "g2s_build_from_reads", "g2s_table_raw", "g2s_table_adopt", "g2s_num_kmers", "g2s_export_kmers", "g2s_contains", "g2s_fill_gap", "g2s_fill_gap_ex",
                "g2s_fill_batch", "g2s_upload_gaps", "g2s_run_resident", "g2s_finish_resident", "g2s_submit",
                "g2s_batch_peek", "g2s_batch_trace", "g2s_batch_free", "g2s_fill_records", "g2s_free",
                "g2s_get_timing", "g2s_get_phase_cycles"]
@@ -135,6 +135,7 @@ class GapSpec:
     skip_confident: bool = False
     all_paths: bool = True
     right_starts: str | None = None   # see g2s_gap.kmer_right_starts (right flank longer than k + right_max_fuz)
+    present_bits: int | None = None   # see g2s_gap.present_bits: the caller's own contains() answers for the flank k-mers
 
     def fill_capacity(self, k: int) -> int:
         return self.gap_len + k + self.gap_err + self.left_max_fuz + self.right_max_fuz + 3
@@ -151,6 +152,9 @@ def pack_gaps(gaps: list[GapSpec]):
         arr[i].gap_len, arr[i].gap_err = g.gap_len, g.gap_err
         arr[i].left_max_fuz, arr[i].right_max_fuz = g.left_max_fuz, g.right_max_fuz
         arr[i].flags = (GAP_SKIP_CONFIDENT if g.skip_confident else 0) | (GAP_ALL_PATHS if g.all_paths else 0)
+        if g.present_bits is not None:
+            arr[i].flags |= 4   # G2S_GAP_PRESENT_BITS
+            arr[i].present_bits = g.present_bits
         if g.right_starts is not None:
             rs = g.right_starts.encode()
             keep.append(rs)

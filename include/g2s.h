@@ -43,14 +43,19 @@ enum {
   G2S_ST_GENERAL_SUBGRAPH = 4, /* informational: the path subgraph had a k-mer at several levels, SCC analysis ran */
   G2S_ST_UNABLE_TO_BACKTRACE = 8,
   G2S_ST_BIG_TIER = 16,        /* informational: the gap was re-run in the wide (one CTA per gap) tier */
-  G2S_ST_DEVICE_TRACED = 32    /* informational: the traceback had no choice to make (one trellis cell per level, one path
+  G2S_ST_DEVICE_TRACED = 32,   /* informational: the traceback had no choice to make (one trellis cell per level, one path
                                   length), the device wrote the fill itself and rand() was only advanced */
+  G2S_ST_PHANTOM_FLANK = 64    /* the caller's graph (g2s_gap.present_bits: GATB's contains() per flank k-mer, Bloom AND NOT
+                                  cFP AND MPHF, Graph.hpp:1249-1272) says a flank k-mer exists that is NOT in the imported
+                                  solid set - a Bloom false positive the reference would start a walk from - or
+                                  the other way round.  The gap is filled on the exact set; the reference may differ */
 };
 
 /* gap flags */
 enum {
   G2S_GAP_SKIP_CONFIDENT = 1,  /* -all-upper: skip the safe/unsafe classification (fill_gap's skip_confident) */
-  G2S_GAP_ALL_PATHS = 2        /* default mode; cleared by -best-only (fill_gap's all_paths) */
+  G2S_GAP_ALL_PATHS = 2,       /* default mode; cleared by -best-only (fill_gap's all_paths) */
+  G2S_GAP_PRESENT_BITS = 4     /* g2s_gap.present_bits is valid */
 };
 
 typedef struct g2s_engine g2s_engine;
@@ -81,6 +86,10 @@ typedef struct g2s_gap {
                                pass.  fill_gap takes those from the END of its kmer_right string but the targets from its
                                beginning (src/Gap2Seq.cpp:871-885 vs :1119); they differ only when the caller's right flank
                                is longer than k + right_max_fuz, which single-gap mode allows (src/Gap2Seq.cpp:239-252) */
+  uint64_t present_bits;    /* with G2S_GAP_PRESENT_BITS: what the CALLER's graph answers to contains() for the flank k-mers
+                               fill_gap looks up (src/Gap2Seq.cpp:884, 957, 1000, 1086): bit d (0..left_max_fuz) = left
+                               k-mer at offset d, bit 32 + j (0..right_max_fuz) = right k-mer at offset j.  The engine
+                               compares them with its exact table and reports G2S_ST_PHANTOM_FLANK on disagreement */
 } g2s_gap;
 
 typedef struct g2s_result {
@@ -170,6 +179,13 @@ int g2s_contains(g2s_engine *e, const char *kmers_ascii, size_t n, uint8_t *out)
 int g2s_fill_gap(g2s_engine *e, const char *kmer_left, const char *kmer_right, int gap_len, int k, int gap_err,
                  int left_max_fuz, int right_max_fuz, int *left_fuz, int *right_fuz, long long max_mem, char *fill,
                  int skip_confident, int all_paths, g2s_subgraph_stats *substats);
+
+/* g2s_fill_gap for a caller that keeps its own graph (INTEGRATION.md form 2): additionally takes the caller's
+ * contains() answers for the flank k-mers (g2s_gap.present_bits) and returns the G2S_ST_* bits in *status. */
+int g2s_fill_gap_ex(g2s_engine *e, const char *kmer_left, const char *kmer_right, int gap_len, int k, int gap_err,
+                    int left_max_fuz, int right_max_fuz, int *left_fuz, int *right_fuz, long long max_mem, char *fill,
+                    int skip_confident, int all_paths, g2s_subgraph_stats *substats, uint64_t present_bits,
+                    int have_present_bits, int32_t *status);
 
 /* Batched form: n independent gaps in one device pass; the host-side random traceback then replays libc
  * rand() in array order, so the results equal n successive g2s_fill_gap calls.  fill_out[i] (may be NULL)

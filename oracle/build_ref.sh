@@ -6,6 +6,9 @@
 #   oracle/_ref/bin/Gap2Seq-core        reference binary   (-O2)
 #   oracle/_ref/bin/Gap2Seq-core-stats  same with -DSTATS  (prints DP cell counts)
 #   oracle/_ref/bin/GapCutter, GapMerger
+#   oracle/_ref/bin/Gap2Seq-core-g2s    INTEGRATION.md form 2: the reference's Gap2Seq.cpp + GATB's graph with the two
+#                                       fill_gap call sites routed to libg2s_gpu.so through integration/g2s_gatb_glue.cpp
+#                                       (needs a GPU to run; built only when gap2seq_b200/lib/libg2s_gpu.so exists)
 #
 # Sources are compiled where they lie under /root/reference; only GATB-core
 # (vendored third-party library, needs its own CMake because of the bundled
@@ -23,7 +26,9 @@ if [ ! -d "$REF/src" ]; then
   echo "build_ref: $REF not present - keeping prebuilt oracle/_ref as is" >&2
   exit 0
 fi
-if [ -x "$OUT/bin/Gap2Seq-core" ] && [ -x "$OUT/bin/Gap2Seq-core-stats" ] && [ "${FORCE:-0}" != 1 ]; then
+G2SLIB="$HERE/../gap2seq_b200/lib"
+if [ -x "$OUT/bin/Gap2Seq-core" ] && [ -x "$OUT/bin/Gap2Seq-core-stats" ] && [ "${FORCE:-0}" != 1 ] && \
+   { [ -x "$OUT/bin/Gap2Seq-core-g2s" ] || [ ! -f "$G2SLIB/libg2s_gpu.so" ]; }; then
   echo "build_ref: oracle/_ref/bin already built" >&2
   exit 0
 fi
@@ -46,6 +51,16 @@ g++ $CXXF $INC "$REF/src/Gap2Seq.cpp" "$REF/src/main.cpp" $LIB -o "$OUT/bin/Gap2
 g++ $CXXF -DSTATS $INC "$REF/src/Gap2Seq.cpp" "$REF/src/main.cpp" $LIB -o "$OUT/bin/Gap2Seq-core-stats"
 g++ $CXXF $INC "$REF/src/GapCutter.cpp" $LIB -o "$OUT/bin/GapCutter"
 g++ $CXXF $INC "$REF/src/GapMerger.cpp" $LIB -o "$OUT/bin/GapMerger"
+# form 2: the reference source is patched in a scratch copy (never committed): one #include and the two call sites
+if [ -f "$G2SLIB/libg2s_gpu.so" ]; then
+  mkdir -p "$BLD/form2"
+  sed -e 's/= fill_gap(graph,/= g2s_fill_gap_graph(graph,/' \
+      -e 's/#include "Gap2Seq.hpp"/#include "Gap2Seq.hpp"\n#include "g2s_gatb_glue.h"/' "$REF/src/Gap2Seq.cpp" > "$BLD/form2/Gap2Seq.cpp"
+  test "$(grep -c 'g2s_fill_gap_graph(graph,' "$BLD/form2/Gap2Seq.cpp")" = 2
+  g++ $CXXF $INC -I"$REF/src" -I"$HERE/../integration" -I"$HERE/../include" "$BLD/form2/Gap2Seq.cpp" "$REF/src/main.cpp" \
+      "$HERE/../integration/g2s_gatb_glue.cpp" $LIB -L"$G2SLIB" -lg2s_gpu -Wl,-rpath,'$ORIGIN/../../../gap2seq_b200/lib' \
+      -o "$OUT/bin/Gap2Seq-core-g2s"
+fi
 # the GATB build tree (200 MB of objects) is scratch: only the binaries stay
 rm -rf "$BLD"
 echo "build_ref: done -> $OUT/bin" >&2

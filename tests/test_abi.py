@@ -34,10 +34,18 @@ def test_no_cpu_fallback_without_device():
         engine.Engine(k=31)
 
 
-def test_struct_sizes_match_header():
-    assert C.sizeof(engine.G2SGap) == 48
-    assert C.sizeof(engine.G2SResult) == 48 + 48 + 24
-    assert C.sizeof(engine.G2SConfig) == 32
+def test_struct_sizes_match_header(tmp_path):
+    """sizeof of every structure that crosses the C ABI, as gcc sees include/g2s.h, against the ctypes mirror."""
+    import subprocess
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include "g2s.h"\nint main(void) { printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(g2s_gap), '
+                   'sizeof(g2s_result), sizeof(g2s_config), sizeof(g2s_timing), sizeof(g2s_run_options), sizeof(g2s_subgraph_stats)); return 0; }\n')
+    exe = tmp_path / "sz"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    sizes = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    mirror = [engine.G2SGap, engine.G2SResult, engine.G2SConfig, engine.G2STiming, engine.G2SRunOptions, engine.G2SSubgraphStats]
+    assert sizes == [C.sizeof(m) for m in mirror]
+    assert C.sizeof(engine.G2SGap) == 56 and C.sizeof(engine.G2SConfig) == 32
 
 
 def test_record_gaps_matches_reference_flank_rule():

@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def sass_lines(kernel_sub):
     tmp = tempfile.mkdtemp()
-    subprocess.run(["cuobjdump", "-xelf", "all", os.path.join(ROOT, "gap2seq_b200", "lib", "libg2s_gpu.so")], cwd=tmp,
+    subprocess.run(["cuobjdump", "-xelf", "all", os.environ.get("G2S_LIB") or os.path.join(ROOT, "gap2seq_b200", "lib", "libg2s_gpu.so")], cwd=tmp,
                    stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     out = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, "g2s_fill.sm_100a.cubin")], capture_output=True, text=True).stdout
     cur, line, inside, res = None, None, False, []
