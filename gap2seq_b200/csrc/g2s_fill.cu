@@ -13,16 +13,7 @@
 
 namespace g2s {
 
-#ifndef G2S_CTA_THREADS
-#define G2S_CTA_THREADS 1024
-#endif
-#ifndef G2S_CTA_WARP_SCOUT
-#define G2S_CTA_WARP_SCOUT 1
-#endif
-#ifndef G2S_WIDE_LEVEL
-#define G2S_WIDE_LEVEL 0   // the shared-memory level step (wide_forward_level): measured slower than the general path on cfg3, off
-#endif
-static const int CTA_THREADS = G2S_CTA_THREADS;
+static const int CTA_THREADS = 1024;
 // Thin-tier shapes (helper warps for the right pass, main warps for everything else).  A gap's latency falls with more
 // warps (the per-level work of a narrow batch is instruction bound on one warp) but fewer gaps are resident then; the
 // engine picks per pass: wide shapes for small batches (latency), the two-warp shape for large ones (throughput).
@@ -40,9 +31,7 @@ struct WarpGroup {
 };
 struct BlockGroup {
   static constexpr bool kWarp = false;
-  // narrow borders inside a wide gap: the CTA's first warp scouts a batch of levels (a group barrier per scouted LEVEL,
-  // the generic flavour, costs a 32-warp barrier pair per level)
-  static constexpr bool kWarpScout = G2S_CTA_WARP_SCOUT != 0;
+  static constexpr bool kWarpScout = false;
   static __device__ __forceinline__ int rank() { return threadIdx.x; }
   static __device__ __forceinline__ int size() { return blockDim.x; }
   static __device__ __forceinline__ void sync() { __syncthreads(); }
@@ -112,10 +101,8 @@ static __device__ __forceinline__ void process_gap_pair(const FillParams &P, con
   }
 }
 
-static const uint32_t WIDE_CAP = 8192;   // entries of the wide tier's per-level table in shared memory (128 KB)
-
 template <int HW, int MW>   // HW == 0: wide tier, the whole CTA runs the phases one after the other
-__device__ __forceinline__ void group_loop(const FillParams &P, GShared &sh, uint32_t group_id, const WideBuf *wb = nullptr) {
+__device__ __forceinline__ void group_loop(const FillParams &P, GShared &sh, uint32_t group_id) {
   const Slice S = make_slice(P.scratch + (size_t)group_id * P.lay.bytes, P.lay);
   for (;;) {
     __syncthreads();
@@ -126,7 +113,7 @@ __device__ __forceinline__ void group_loop(const FillParams &P, GShared &sh, uin
     const uint32_t gi = P.order[q];
     const GapDev gd = P.gaps[gi];
     if (HW > 0) process_gap_pair<(HW > 0 ? HW : 1), MW>(P, gd, S, sh, &P.outs[gi]);
-    else process_gap<BlockGroup>(P, gd, S, sh, &P.outs[gi], wb);
+    else process_gap<BlockGroup>(P, gd, S, sh, &P.outs[gi]);
   }
 }
 
@@ -139,15 +126,8 @@ __global__ void __launch_bounds__(32 * (HW + MW)) k_fill_thin(const __grid_const
 
 __global__ void __launch_bounds__(CTA_THREADS) k_fill_cta(const __grid_constant__ FillParams P, int groups) {
   __shared__ GShared sh;
-  extern __shared__ __align__(16) unsigned char wide_mem[];
   if (blockIdx.x >= (uint32_t)groups) return;
-  const WideBuf wb = make_wide_buf(wide_mem, WIDE_CAP);
-  group_loop<0, 1>(P, sh, blockIdx.x, G2S_WIDE_LEVEL ? &wb : nullptr);
-}
-
-static cudaError_t cta_dynamic_smem() {   // opt in to the large dynamic shared memory once
-  static cudaError_t st = cudaFuncSetAttribute(k_fill_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wide_buf_bytes(WIDE_CAP));
-  return st;
+  group_loop<0, 1>(P, sh, blockIdx.x);
 }
 
 int fill_thin_shapes() { return N_THIN_SHAPES; }
@@ -170,8 +150,7 @@ int fill_max_resident_cta_groups(int sms) {
   static int cached = 0;
   if (cached > 0) return sms * cached;
   int per_sm = 0;
-  if (cta_dynamic_smem() != cudaSuccess ||
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fill_cta, CTA_THREADS, wide_buf_bytes(WIDE_CAP)) != cudaSuccess || per_sm < 1)
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fill_cta, CTA_THREADS, 0) != cudaSuccess || per_sm < 1)
     per_sm = 1;
   cached = per_sm;
   return sms * per_sm;
@@ -185,9 +164,7 @@ cudaError_t launch_fill_thin(const FillParams &p, int groups, int shape, cudaStr
 }
 
 cudaError_t launch_fill_cta(const FillParams &p, int groups, cudaStream_t st) {
-  cudaError_t e = cta_dynamic_smem();
-  if (e != cudaSuccess) return e;
-  k_fill_cta<<<groups, CTA_THREADS, wide_buf_bytes(WIDE_CAP), st>>>(p, groups);
+  k_fill_cta<<<groups, CTA_THREADS, 0, st>>>(p, groups);
   return cudaGetLastError();
 }
 

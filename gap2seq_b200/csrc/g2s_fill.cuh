@@ -1128,180 +1128,6 @@ G2S_D int narrow_backward(const Slice &S, GShared &sh, NarrowBuf &nb, int d, int
   return len;
 }
 
-// ------------------------------------------------------------------------------------------------ wide levels
-// Level step of the forward pass for borders that are neither narrow (chains, above) nor huge: the level's candidate
-// states are de-duplicated and their counts added in a hash table in SHARED memory, so that only the level's distinct
-// new states touch HBM - one node-table operation and one k-mer table gather each, in flight together - instead of
-// every candidate going through four dependent global round trips (table gather, node CAS, stamp atomicMax, cell
-// read-back).  Three phases per level, a group barrier between them:
-//   1  thread per candidate (border cell x successor base): insert the successor state into the shared table
-//      (atomicCAS on the 64-bit oriented k-mer), add the cell's walk count to the entry (atomicAdd)
-//   2  thread per table entry: k-mer table gather (adjacency), node-table find / insert with the right-set test of
-//      Gap2Seq.cpp:1050; survivors get their cell (count = the entry's sum), stamps, target hits
-//   3  thread per candidate again: predecessor link cell(successor).cp[first base of the predecessor] = predecessor
-// A level with more candidates than the table holds is processed in hash partitions of the CANONICAL k-mer (both
-// strands of a node meet in one partition: the order-dependence detector needs them side by side); a partition that
-// still overflows is split by further hash bits before anything of it is written.  Results equal the general path's:
-// counts are sums of the same addends, links are keyed by base, the order of cells inside a level is free.
-struct WideBuf {       // shared-memory hash table of one level (device: dynamic shared memory of the CTA)
-  uint64_t *key;       // oriented k-mer of the candidate state, KEY_EMPTY = free
-  uint32_t *cnt;       // sum of the clamped counts of its predecessors on the border
-  uint32_t *idx;       // its cell, NONE32 when it was pruned
-  uint32_t cap;        // entries, power of two
-  uint32_t *stack;     // partitions still to do: (bits << 26 | value), WIDE_STACK words
-  uint32_t *ctl;       // [0] stack size, [1] overflow flag of the current partition, [2] entries in use
-};
-static const int WIDE_STACK = 96;
-static const uint32_t WIDE_MAX_PART_BITS = 20;
-
-G2S_HD size_t wide_buf_bytes(uint32_t cap) { return (size_t)cap * 16 + (WIDE_STACK + 4) * 4; }
-G2S_HD WideBuf make_wide_buf(unsigned char *mem, uint32_t cap) {
-  WideBuf w;
-  w.key = (uint64_t *)mem;
-  w.cnt = (uint32_t *)(mem + (size_t)cap * 8);
-  w.idx = w.cnt + cap;
-  w.cap = cap;
-  w.stack = w.idx + cap;
-  w.ctl = w.stack + WIDE_STACK;
-  return w;
-}
-
-G2S_D uint32_t wide_slot_hash(uint64_t s) { return (uint32_t)((s * 0x9E3779B97F4A7C15ULL) >> 32); }
-
-// Creates the cells of level c from the border [lo, hi) of level c - 1.  Returns false when the level does not fit this
-// path (nothing has been written then) and the caller must take the general path.
-template <class G>
-G2S_D bool wide_forward_level(const Table &T, const Slice &S, GShared &sh, const GapDev &gd, const WideBuf &wb, uint32_t lo,
-                              uint32_t hi, int c, int prune_from, uint32_t *lookups) {
-  const int k = T.k, rank = G::rank(), gsz = G::size();
-  const uint32_t n = hi - lo;
-  // Candidates = set bits of the border's out-masks, between n and 4 n; 2 n is a generous estimate for sizing (a
-  // partition that turns out too full is split below, so the estimate only costs time when it is wrong).
-  const uint64_t est = (uint64_t)n * 2;
-  if (est > (uint64_t)wb.cap * 8) return false;           // more than 32 partitions: the general path has the parallelism
-  // initial partitions: expected candidates per partition <= cap / 4
-  uint32_t bits0 = 0;
-  while ((est >> bits0) > wb.cap / 4) bits0++;
-  if (rank == 0) {
-    wb.ctl[0] = 1u << bits0;
-    for (uint32_t v = 0; v < (1u << bits0); v++) wb.stack[v] = (bits0 << 26) | v;
-  }
-  G::sync();
-  for (;;) {
-    const uint32_t depth = ld_sh(&wb.ctl[0]);
-    if (depth == 0) break;
-    const uint32_t item = ld_sh(&wb.stack[depth - 1]);
-    const uint32_t pbits = item >> 26, pval = item & ((1u << 26) - 1), pmask = (1u << pbits) - 1;
-    G::sync();
-    if (rank == 0) { wb.ctl[0] = depth - 1; wb.ctl[1] = 0; wb.ctl[2] = 0; }
-    // table size for this partition: a quarter full when the candidates spread evenly
-    uint32_t capeff = wb.cap < 64 ? wb.cap : 64;
-    while (capeff < wb.cap && (uint64_t)capeff < ((est >> pbits) + 1) * 4) capeff <<= 1;
-    const uint32_t hmask = capeff - 1;
-    for (uint32_t q = rank; q < capeff; q += gsz) { wb.key[q] = KEY_EMPTY; wb.cnt[q] = 0; wb.idx[q] = NONE32; }
-    G::sync();
-    // ---- phase 1: candidates -> shared table
-    for (uint64_t q = rank; q < (uint64_t)n * 4; q += gsz) {
-      const uint32_t i = lo + (uint32_t)(q >> 2), nt = (uint32_t)q & 3u;
-      const uint32_t om = (ld_cg(&S.cflags[i]) >> CF_OMASK_SHIFT) & 15u;
-      if (!((om >> nt) & 1)) continue;
-      const uint64_t x = ld_cg(&S.ck[i]);
-      const uint64_t s = succ_kmer(x, nt, T);
-      if (pbits && ((uint32_t)(mix64(canonical(s, k).key) >> 20) & pmask) != pval) continue;
-      const uint32_t np = clamp_paths(ld_cg(&S.cc[i]));
-      uint32_t h = wide_slot_hash(s) & hmask;
-      bool placed = false;
-      for (uint32_t tries = 0; tries < capeff; tries++) {
-        const uint64_t old = a_cas64(&wb.key[h], KEY_EMPTY, s);
-        if (old == KEY_EMPTY) { a_inc(&wb.ctl[2]); placed = true; break; }
-        if (old == s) { placed = true; break; }
-        h = (h + 1) & hmask;
-      }
-      if (placed) a_add(&wb.cnt[h], np);
-      else a_or(&wb.ctl[1], 1u);
-    }
-    G::sync();
-    // a table more than three quarters full (or full): split the partition by one more hash bit, nothing was written
-    if (ld_sh(&wb.ctl[1]) || ld_sh(&wb.ctl[2]) > capeff - capeff / 4) {
-      G::sync();
-      if (rank == 0) {
-        const uint32_t d = wb.ctl[0];
-        if (pbits >= WIDE_MAX_PART_BITS || d + 2 > (uint32_t)WIDE_STACK) a_or(&sh.status, GS_INTERNAL);
-        else {
-          wb.stack[d] = ((pbits + 1) << 26) | pval;
-          wb.stack[d + 1] = ((pbits + 1) << 26) | pval | (1u << pbits);
-          wb.ctl[0] = d + 2;
-        }
-      }
-      G::sync();
-      if (ld_sh(&sh.status) & GS_INTERNAL) return true;
-      continue;
-    }
-    // ---- phase 2: distinct states -> node table, k-mer table, cells
-    uint32_t my = 0;
-    for (uint32_t q = rank; q < capeff; q += gsz) {
-      const uint64_t s = ld_sh(&wb.key[q]);
-      if (s == KEY_EMPTY) continue;
-      my++;
-      const Canon cs = canonical(s, k);
-      uint32_t adj = 0;
-      if (table_find(T, cs.key, &adj) < 0) { a_or(&sh.status, GS_INTERNAL); continue; }
-      uint32_t en, nf = 0;
-      if (c < prune_from) {
-        en = node_insert(S, sh, cs.key, &nf);
-        if (en == NONE32) continue;
-      } else {   // meet in the middle: only nodes of the right set survive (Gap2Seq.cpp:1050)
-        en = node_find(S, cs.key, &nf);
-        if (en == NONE32 || !(nf & NF_IN_RS)) continue;
-      }
-      // both strands of the node on this level?  (its other strand sits in the same partition)
-      {
-        const uint64_t rs = revcomp(s, k);
-        uint32_t h = wide_slot_hash(rs) & hmask;
-        for (;;) {
-          const uint64_t o = ld_sh(&wb.key[h]);
-          if (o == rs) { a_or(&sh.status, GS_ORDER_DEPENDENT); break; }
-          if (o == KEY_EMPTY) break;
-          h = (h + 1) & hmask;
-        }
-      }
-      const uint32_t cell = a_inc(&sh.ncells);
-      if (cell >= S.cap_cells) { a_or(&sh.status, GS_OVERFLOW); continue; }
-      S.ck[cell] = s;
-      S.cc[cell] = ld_sh(&wb.cnt[q]);
-      S.cn[cell] = en;
-      *(uint4 *)(S.cp + 4 * (size_t)cell) = uint4{NONE32, NONE32, NONE32, NONE32};
-      S.cflags[cell] = out_mask(adj, cs.strand) << CF_OMASK_SHIFT;
-      a_max(&S.ent[en].fstamp[cs.strand], (uint32_t)c + 1);
-      S.ent[en].fcell[cs.strand] = cell;
-      if ((nf & NF_TARGET) && c >= sh.tlo) {
-        for (int j = 0; j <= gd.rmf; j++)
-          if ((S.rk[j] & FLANK_KMER) == s) S.thit[(size_t)j * sh.trow + ((uint32_t)c - (uint32_t)sh.tlo)] = cell + 1;
-      }
-      wb.idx[q] = cell;
-    }
-    *lookups += my;
-    G::sync();
-    // ---- phase 3: predecessor links
-    if (!(ld_sh(&sh.status) & GS_OVERFLOW)) {
-      for (uint64_t q = rank; q < (uint64_t)n * 4; q += gsz) {
-        const uint32_t i = lo + (uint32_t)(q >> 2), nt = (uint32_t)q & 3u;
-        const uint32_t om = (ld_cg(&S.cflags[i]) >> CF_OMASK_SHIFT) & 15u;
-        if (!((om >> nt) & 1)) continue;
-        const uint64_t x = ld_cg(&S.ck[i]);
-        const uint64_t s = succ_kmer(x, nt, T);
-        if (pbits && ((uint32_t)(mix64(canonical(s, k).key) >> 20) & pmask) != pval) continue;
-        uint32_t h = wide_slot_hash(s) & hmask;
-        while (ld_sh(&wb.key[h]) != s) h = (h + 1) & hmask;
-        const uint32_t cell = ld_sh(&wb.idx[h]);
-        if (cell != NONE32) S.cp[4 * (size_t)cell + ((uint32_t)(x >> (2 * (k - 1))) & 3u)] = i;
-      }
-    }
-    G::sync();
-  }
-  return true;
-}
-
 // ------------------------------------------------------------------------------------------------ one gap
 // A gap is processed in phases - init, right pass, forward pass, backward marking + pack - written as functions of
 // the executing thread group so that the kernels can map them differently: the wide tier and the host emulation
@@ -1482,8 +1308,7 @@ G2S_D void gap_right(const FillParams &P, const GapCtx &cx, const Slice &S, GSha
 
 // ---- Phase F: forward walk counts by exact length (Gap2Seq.cpp:984-1167)
 template <class G, class W>
-G2S_D void gap_forward(const FillParams &P, const GapDev &gd, const GapCtx &cx, const Slice &S, GShared &sh, NarrowBuf &nb,
-                       const WideBuf *wb = nullptr) {
+G2S_D void gap_forward(const FillParams &P, const GapDev &gd, const GapCtx &cx, const Slice &S, GShared &sh, NarrowBuf &nb) {
   const Table &T = P.table;
   const int k = cx.k, rank = G::rank(), gsz = G::size();
   const int g = cx.g, lmf = cx.lmf, rmf = cx.rmf, Dmax = cx.Dmax, prune_from = cx.prune_from;
@@ -1549,8 +1374,7 @@ G2S_D void gap_forward(const FillParams &P, const GapDev &gd, const GapCtx &cx, 
       if (!dead) {
         top_level = c;
         levels_f = c;
-        const bool wide_done = wb != nullptr && hi > lo && wide_forward_level<G>(T, S, sh, gd, *wb, lo, hi, c, prune_from, &my_lookups);
-        for (uint32_t base = lo; base < hi && !wide_done; base += gsz) {
+        for (uint32_t base = lo; base < hi; base += gsz) {
           const uint32_t i = base + rank;
           uint32_t cand_e[4];
           uint32_t cand_valid = 0, cand_strand = 0, np = 0, u0 = 0;
@@ -1938,7 +1762,7 @@ G2S_D void gap_finish(const Slice &S, GShared &sh, GapOut *out, const unsigned l
 
 // all phases on one group, one after the other (wide tier, host emulation)
 template <class G>
-G2S_D void process_gap(const FillParams &P, const GapDev &gd, const Slice &S, GShared &sh, GapOut *out, const WideBuf *wb = nullptr) {
+G2S_D void process_gap(const FillParams &P, const GapDev &gd, const Slice &S, GShared &sh, GapOut *out) {
   const GapCtx cx = make_ctx(P, gd);
   unsigned long long t[5];
   t[0] = now_cycles();
@@ -1946,7 +1770,7 @@ G2S_D void process_gap(const FillParams &P, const GapDev &gd, const Slice &S, GS
   t[1] = now_cycles();
   gap_right<G>(P, cx, S, sh, sh.nbuf[0]);
   t[2] = now_cycles();
-  gap_forward<G, NoWait>(P, gd, cx, S, sh, sh.nbuf[1], wb);
+  gap_forward<G, NoWait>(P, gd, cx, S, sh, sh.nbuf[1]);
   t[3] = now_cycles();
   t[4] = gap_backward_pack<G>(P, cx, S, sh, sh.nbuf[1]);
   gap_finish<G>(S, sh, out, t);

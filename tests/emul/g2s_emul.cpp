@@ -160,12 +160,7 @@ static int emul_submit(EmulGraph *g, int k, const g2s_gap *gaps, size_t n, HostB
       if (device_trace) { P.fills = fills.data(); P.fill_cap = fills.size(); P.fill_cursor = &fcursor; }
       GShared sh{};
       Slice S = make_slice(scratch.data(), L);
-      // the wide level step (shared-memory table on the device); G2S_EMUL_WIDE_CAP: a small table forces partitions and splits, 0 = off
-      const uint32_t wide_cap = getenv("G2S_EMUL_WIDE_CAP") ? (uint32_t)atoi(getenv("G2S_EMUL_WIDE_CAP")) : 8192u;
-      std::vector<unsigned char> wide_mem(wide_cap ? wide_buf_bytes(wide_cap) : 0);
-      WideBuf wbuf{};
-      if (wide_cap) wbuf = make_wide_buf(wide_mem.data(), wide_cap);
-      process_gap<EmulGroup>(P, gd, S, sh, &out, wide_cap ? &wbuf : nullptr);
+      process_gap<EmulGroup>(P, gd, S, sh, &out);
       if (out.status & GS_INTERNAL) return -100;
       if (!(out.status & (GS_OVERFLOW | GS_OUT_FULL))) {
         if (out.status & GS_TRACED) { hb.own_fill[i].assign(fills.begin() + out.fill_off, fills.begin() + out.fill_off + out.fill_len + 1); out.fill_off = 0; }
