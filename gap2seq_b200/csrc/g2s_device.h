@@ -32,6 +32,9 @@ cudaError_t launch_chain(const ChainParams &p, cudaStream_t st);
 cudaError_t launch_fill_thin(const FillParams &p, int groups, int shape, cudaStream_t st);
 // wide tier: one CTA (512 threads) per gap
 cudaError_t launch_fill_cta(const FillParams &p, int groups, cudaStream_t st);
+// wide tier with a thread-block cluster of `cluster` (2..8) CTAs per gap; groups = number of clusters = scratch slices
+cudaError_t launch_fill_cluster(const FillParams &p, int groups, int cluster, cudaStream_t st);
+int fill_max_resident_clusters(int cluster);
 int fill_thin_shapes();
 int fill_thin_threads(int shape);
 int fill_max_resident_thin_groups(int sms, int shape);   // occupancy-derived number of thin groups that fit the device

@@ -73,6 +73,7 @@ struct PinBuf {
 struct Pass {                   // one device pass over a subset of the batch
   int tier = 0;
   int shape = 0;                // thin tier: warps per gap (g2s_device.h)
+  int cluster = 1;              // wide tiers: CTAs (SMs) per gap
   std::vector<uint32_t> order;  // gap ids, longest first
   SliceLayout lay{};
   int groups = 0;
@@ -417,6 +418,20 @@ static int plan_pass(g2s_engine *e, Pass &p) {
       if ((force && atoi(force) == sh) || (!force && (sh == 0 || t < best))) { best = t; p.shape = sh; resident = r; }
     }
   }
+  p.cluster = 1;
+  if (p.tier > 0) {
+    // Wide tiers: a pass of few gaps leaves SMs idle while every gap is bound by what ONE SM keeps in flight - give each
+    // gap the largest cluster that still lets all gaps of the pass run at once (G2S_CLUSTER forces a size, 1 = none).
+    const size_t n_run = std::min<size_t>(p.order.size(), fit);
+    const char *force = getenv("G2S_CLUSTER");
+    for (int c : {8, 4, 2}) {
+      if (force ? atoi(force) != c : (size_t)fill_max_resident_clusters(c) < n_run) continue;
+      if (fill_max_resident_clusters(c) < 1) continue;
+      p.cluster = c;
+      resident = fill_max_resident_clusters(c);
+      break;
+    }
+  }
   size_t groups = std::min<size_t>({p.order.size(), (size_t)resident, fit});
   p.groups = (int)std::max<size_t>(groups, 1);
   // output arena
@@ -465,6 +480,7 @@ static int run_pass(g2s_engine *e, Pass &p) {
   P.fill_cursor = (unsigned long long *)((char *)e->d_counters.p + 16);
   CUDA_TRY(cudaEventRecord(e->ev[0], e->st));
   if (p.tier == 0) CUDA_TRY(launch_fill_thin(P, p.groups, p.shape, e->st));
+  else if (p.cluster > 1) CUDA_TRY(launch_fill_cluster(P, p.groups, p.cluster, e->st));
   else CUDA_TRY(launch_fill_cta(P, p.groups, e->st));
   CUDA_TRY(cudaEventRecord(e->ev[1], e->st));
   e->tm.launches++;
@@ -480,8 +496,8 @@ static int run_pass(g2s_engine *e, Pass &p) {
   if (p.tier == 0) { e->tm.kernel_ms_thin += ms; e->tm.launches_thin++; e->tm.thin_shape = (uint32_t)p.shape; }
   else { e->tm.kernel_ms_wide += ms; e->tm.launches_wide++; }
   if (getenv("G2S_HOST_PROF"))
-    fprintf(stderr, "g2s: pass tier %d (shape %d): %zu gaps on %d groups, slice %.1f MB, %.3f ms\n", p.tier, p.shape,
-            p.order.size(), p.groups, p.lay.bytes / 1e6, ms);
+    fprintf(stderr, "g2s: pass tier %d (shape %d, cluster %d): %zu gaps on %d groups, slice %.1f MB, %.3f ms\n", p.tier, p.shape,
+            p.cluster, p.order.size(), p.groups, p.lay.bytes / 1e6, ms);
   e->tm.d2h_bytes += e->gaps.size() * sizeof(GapOut) + 8;
   p.pack_used = std::min(used, p.pack_cap);
   p.fill_used = std::min(fused, p.fill_cap);

@@ -28,6 +28,7 @@ struct WarpGroup {
   static __device__ __forceinline__ int size() { return 32; }
   static __device__ __forceinline__ void sync() { __syncwarp(); }
   static __device__ __forceinline__ bool any(bool p) { return __any_sync(0xffffffffu, p) != 0; }
+  static __device__ __forceinline__ bool any_word(const uint32_t *w, uint32_t bits) { return any((ld_sh(w) & bits) != 0); }
 };
 struct BlockGroup {
   static constexpr bool kWarp = false;
@@ -36,6 +37,37 @@ struct BlockGroup {
   static __device__ __forceinline__ int size() { return blockDim.x; }
   static __device__ __forceinline__ void sync() { __syncthreads(); }
   static __device__ __forceinline__ bool any(bool p) { return __syncthreads_or(p) != 0; }
+  static __device__ __forceinline__ bool any_word(const uint32_t *w, uint32_t bits) { return any((ld_sh(w) & bits) != 0); }
+};
+// A thread-block cluster per gap: the wide tier's level step is bound by the scattered global operations one SM keeps in
+// flight (profiles/r2_summary.md), and a pass of a few dozen wide gaps leaves most SMs idle, so a gap gets the threads
+// of 2 - 8 SMs.  The gap's shared state (GShared) lives in the first CTA's shared memory and the other CTAs reach it
+// through distributed shared memory; the group barrier is the cluster barrier (release / acquire at cluster scope, which
+// also orders the group's global-memory traffic like __syncthreads does inside a CTA).
+struct ClusterGroup {
+  static constexpr bool kWarp = false;
+  static constexpr bool kWarpScout = true;    // the first warp of the first CTA scouts narrow stretches
+  static __device__ __forceinline__ int rank() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return (int)(r * blockDim.x + threadIdx.x);
+  }
+  static __device__ __forceinline__ int size() {
+    unsigned n;
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(n));
+    return (int)(n * blockDim.x);
+  }
+  static __device__ __forceinline__ void sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  }
+  // a group decision on a word of the shared state: nobody can change it between the two barriers
+  static __device__ __forceinline__ bool any_word(const uint32_t *w, uint32_t bits) {
+    sync();
+    const bool v = (ld_sh(w) & bits) != 0;
+    sync();
+    return v;
+  }
+  static __device__ __forceinline__ bool any(bool p) { return p; }   // not used: decisions go through any_word
 };
 // NWARPS consecutive warps of the CTA, starting with warp FIRST, synchronised on named barrier BAR.  The per-level
 // work of a narrow batch (node table, layout, marking) is instruction bound on one warp, so the thin tier gives each
@@ -50,6 +82,7 @@ struct SubGroup {
     if (NWARPS == 1) __syncwarp();
     else asm volatile("bar.sync %0, %1;" ::"n"(BAR), "n"(32 * NWARPS) : "memory");
   }
+  static __device__ __forceinline__ bool any_word(const uint32_t *w, uint32_t bits) { return any((ld_sh(w) & bits) != 0); }
   static __device__ __forceinline__ bool any(bool p) {
     if (NWARPS == 1) return __any_sync(0xffffffffu, p) != 0;
     unsigned r;
@@ -130,6 +163,39 @@ __global__ void __launch_bounds__(CTA_THREADS) k_fill_cta(const __grid_constant_
   group_loop<0, 1>(P, sh, blockIdx.x);
 }
 
+// wide tier on a cluster of CTAs per gap (cluster size is a launch attribute)
+__global__ void __launch_bounds__(CTA_THREADS) k_fill_cluster(const __grid_constant__ FillParams P, int groups) {
+  __shared__ GShared sh_local;
+  unsigned ncta, crank;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(ncta));
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+  const uint32_t group_id = blockIdx.x / ncta;
+  // the first CTA's copy is the gap's shared state
+  GShared *shp;
+  {
+    unsigned long long local = (unsigned long long)__cvta_generic_to_shared(&sh_local), remote;
+    asm volatile("mapa.shared::cluster.u64 %0, %1, %2;" : "=l"(remote) : "l"(local), "r"(0u));
+    unsigned long long gen;
+    asm volatile("cvta.shared::cluster.u64 %0, %1;" : "=l"(gen) : "l"(remote));
+    shp = (GShared *)gen;
+  }
+  GShared &sh = *shp;
+  if (group_id < (uint32_t)groups) {
+    const Slice S = make_slice(P.scratch + (size_t)group_id * P.lay.bytes, P.lay);
+    for (;;) {
+      ClusterGroup::sync();
+      if (crank == 0 && threadIdx.x == 0) sh.queue_item = atomicAdd(P.queue_head, 1u);
+      ClusterGroup::sync();
+      const uint32_t q = ld_sh(&sh.queue_item);
+      if (q >= P.n_gaps) break;
+      const uint32_t gi = P.order[q];
+      const GapDev gd = P.gaps[gi];
+      process_gap<ClusterGroup>(P, gd, S, sh, &P.outs[gi]);
+    }
+  }
+  ClusterGroup::sync();   // no CTA leaves while another may still touch its shared memory
+}
+
 int fill_thin_shapes() { return N_THIN_SHAPES; }
 int fill_thin_threads(int shape) { return 32 * (THIN_MAIN[shape] + THIN_HELPER[shape]); }
 
@@ -161,6 +227,36 @@ cudaError_t launch_fill_thin(const FillParams &p, int groups, int shape, cudaStr
   else if (shape == 1) k_fill_thin<2, 4><<<groups, 192, 0, st>>>(p, groups);
   else k_fill_thin<4, 8><<<groups, 384, 0, st>>>(p, groups);
   return cudaGetLastError();
+}
+
+// clusters of `cluster` CTAs that can be resident at once (0: this cluster size cannot be launched)
+int fill_max_resident_clusters(int cluster) {
+  static int cache[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  if (cluster < 2 || cluster > 8) return 0;
+  if (cache[cluster] != 0) return cache[cluster] > 0 ? cache[cluster] : 0;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)cluster * 64, 1, 1);
+  cfg.blockDim = dim3(CTA_THREADS, 1, 1);
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = (unsigned)cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, k_fill_cluster, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
+  cache[cluster] = n > 0 ? n : -1;
+  return n > 0 ? n : 0;
+}
+
+cudaError_t launch_fill_cluster(const FillParams &p, int groups, int cluster, cudaStream_t st) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(groups * cluster), 1, 1);
+  cfg.blockDim = dim3(CTA_THREADS, 1, 1);
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = (unsigned)cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, k_fill_cluster, p, groups);
 }
 
 cudaError_t launch_fill_cta(const FillParams &p, int groups, cudaStream_t st) {

@@ -370,7 +370,9 @@ G2S_D void a_add_warp(uint32_t *p, uint32_t v) {
 // it must be the same for every thread of the group - but in the thin tier the OTHER warp of the pair may set the bit
 // at any moment, and lanes reading the word one after the other could disagree.  G::any() makes it a group decision.
 template <class G>
-G2S_D bool group_overflow(GShared &sh) { return G::any((ld_sh(&sh.status) & GS_OVERFLOW) != 0); }
+G2S_D bool group_status_any(GShared &sh, uint32_t bits) { return G::any_word(&sh.status, bits); }
+template <class G>
+G2S_D bool group_overflow(GShared &sh) { return group_status_any<G>(sh, GS_OVERFLOW); }
 
 G2S_D unsigned long long now_cycles() {
 #ifdef __CUDA_ARCH__
@@ -1592,7 +1594,7 @@ G2S_D unsigned long long gap_backward_pack(const FillParams &P, const GapCtx &cx
     // needs neither pack records nor a host traceback - the host only advances rand() by the reported count.
     const int max_src_t = ld_sh(&sh.max_src_level), min_sink_t = ld_sh(&sh.min_sink_level);
     const bool sink_safe_t = ld_sh(&sh.n_sink) > 0;
-    const bool general_now = G::any((ld_sh(&sh.status) & GS_GENERAL) != 0);
+    const bool general_now = group_status_any<G>(sh, GS_GENERAL);
     if (P.fills != nullptr && n_plen == 1 && (skip_confident || !general_now)) {
       const int d0 = p0;
       if (rank == 0) { sh.t_lo = 0x7fffffff; sh.t_cnt = 0; sh.t_bad = 0; sh.t_ok = 0; }

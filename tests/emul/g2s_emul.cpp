@@ -22,6 +22,7 @@ struct EmulGroup {
   static int size() { return 1; }
   static void sync() {}
   static bool any(bool p) { return p; }
+  static bool any_word(const uint32_t *w, uint32_t bits) { return (*w & bits) != 0; }
   static int min_i32(int v) { return v; }
   static int max_i32(int v) { return v; }
   static uint32_t add_u32(uint32_t v) { return v; }
