@@ -9,8 +9,8 @@ namespace g2s {
 
 static const int WALK_THREADS = 64;      // small CTAs: the walks of a pass spread over all SMs
 // A warp advances at the pace of its slowest lane's gather, and a gather in a multi-gigabyte table has a long latency
-// tail (TLB misses); the walks need no issue bandwidth, so only every WALK_STRIDE-th lane carries one: 4 walks per warp.
-static const int WALK_STRIDE = 8;
+// tail; the walks need no issue bandwidth, so only every walk_stride-th lane carries one (ChainParams.walk_stride,
+// default 8: 4 walks per warp).
 static const int FINISH_WARPS = 4;
 
 struct ChainWarp {
@@ -27,8 +27,8 @@ struct ChainWarp {
 // thread 2q walks forward from the left flank of gap order[q], thread 2q + 1 backward from its right flank
 __global__ void __launch_bounds__(WALK_THREADS) k_chain_walk(const __grid_constant__ ChainParams P) {
   const uint32_t tt = blockIdx.x * WALK_THREADS + threadIdx.x;
-  if (tt % WALK_STRIDE) return;
-  const uint32_t t = tt / WALK_STRIDE;
+  if (tt % P.walk_stride) return;
+  const uint32_t t = tt / P.walk_stride;
   const uint32_t q = t >> 1;
   if (q >= P.n_gaps) return;
   const GapDev gd = P.gaps[P.order[q]];
@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(32 * FINISH_WARPS) k_chain_finish(const __grid
 
 cudaError_t launch_chain(const ChainParams &p, cudaStream_t st) {
   if (p.n_gaps == 0) return cudaSuccess;
-  k_chain_walk<<<(2 * p.n_gaps * WALK_STRIDE + WALK_THREADS - 1) / WALK_THREADS, WALK_THREADS, 0, st>>>(p);
+  k_chain_walk<<<(unsigned)(((size_t)2 * p.n_gaps * p.walk_stride + WALK_THREADS - 1) / WALK_THREADS), WALK_THREADS, 0, st>>>(p);
   k_chain_finish<<<(p.n_gaps + FINISH_WARPS - 1) / FINISH_WARPS, 32 * FINISH_WARPS, 0, st>>>(p);
   return cudaGetLastError();
 }

@@ -48,6 +48,7 @@ struct ChainParams {
   GapOut *outs;
   uint64_t *strs;             // per position in `order`: f_words words of the forward string, then r_words of the right one
   uint32_t f_words, r_words;
+  uint32_t walk_stride;       // every walk_stride-th lane of the walk kernel carries a walk (32 / walk_stride walks per warp)
   ChainWalk *walks;           // [2q] forward, [2q + 1] right
   char *fills;                // fill arena
   unsigned long long fill_cap;

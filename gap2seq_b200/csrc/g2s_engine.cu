@@ -510,6 +510,8 @@ static int run_chain_pass(g2s_engine *e, Pass &p) {
   const int k = e->cfg.k;
   ChainParams P{};
   P.table = table_view(e->table);
+  P.walk_stride = 8;
+  if (const char *ws = getenv("G2S_WALK_STRIDE")) { const int v = atoi(ws); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) P.walk_stride = (uint32_t)v; }
   P.f_words = chain_words(k, e->max_dmax);
   P.r_words = chain_words(k, e->max_rmf + (e->max_dmax + 1) / 2);   // right_half <= rmf + ceil((g + e) / 2)
   const size_t stride = ((size_t)P.f_words + P.r_words) * 8;
