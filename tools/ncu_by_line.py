@@ -18,7 +18,7 @@ def sass_lines(kernel_sub):
     tmp = tempfile.mkdtemp()
     subprocess.run(["cuobjdump", "-xelf", "all", os.environ.get("G2S_LIB") or os.path.join(ROOT, "gap2seq_b200", "lib", "libg2s_gpu.so")], cwd=tmp,
                    stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
-    out = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, "g2s_fill.sm_100a.cubin")], capture_output=True, text=True).stdout
+    out = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, os.environ.get("G2S_CUBIN", "g2s_fill") + ".sm_100a.cubin")], capture_output=True, text=True).stdout
     cur, line, inside, res = None, None, False, []
     for ln in out.splitlines():
         m = re.match(r"\s*\.section\s+\.text\.(\S+?),", ln)
