@@ -1013,12 +1013,13 @@ extern "C" int g2s_batch_trace(g2s_batch *b, size_t i, g2s_result *result, char 
 extern "C" void g2s_batch_free(g2s_batch *b) { delete b; }
 extern "C" void g2s_free(void *p) { free(p); }
 
-extern "C" int g2s_fill_records(g2s_engine *e, const char *const *seqs, const char *const *comments, size_t n_records,
+static int fill_records_impl(g2s_engine *e, const char *const *seqs, const char *const *comments, size_t n_records,
                                 const g2s_run_options *opt, char **filled_out, char **log_out, int32_t *gapcount,
                                 int32_t *filledcount, g2s_result **gap_results, size_t *n_gap_results) {
   if (!e || !opt || (n_records && (!seqs || !comments || !filled_out))) return fail(G2S_E_ARG, "g2s_fill_records: null argument");
   if (opt->k != e->cfg.k) return fail(G2S_E_ARG, "g2s_fill_records: k differs from the engine's k");
   if (opt->fuz < 0 || opt->fuz > e->cfg.max_fuz) return fail(G2S_E_ARG, "g2s_fill_records: fuz exceeds g2s_config.max_fuz");
+  for (size_t i = 0; i < n_records; i++) filled_out[i] = nullptr;
   std::vector<StrRef> s(n_records), c(n_records);   // the caller's strings, not copied
   auto ref_one = [&](size_t i) { s[i] = StrRef(seqs[i]); c[i] = StrRef(comments[i]); };
   if (e->pool) e->pool->parallel_for(n_records, 64, ref_one);
@@ -1030,6 +1031,7 @@ extern "C" int g2s_fill_records(g2s_engine *e, const char *const *seqs, const ch
   run.pool = e->pool.get();
   run.aheadp = &e->ahead;
   run.arenap = &e->trace_arena;
+  run.filled_c = filled_out;   // the records are written straight into the malloc'ed strings the caller receives
   g2s_timing total{};
   int err = G2S_OK;
   double w_ms[3] = {0, 0, 0};
@@ -1064,9 +1066,8 @@ extern "C" int g2s_fill_records(g2s_engine *e, const char *const *seqs, const ch
     fprintf(stderr, "g2s_fill_records: wall %.3f ms = scan+flanks %.3f | upload %.3f | run %.3f (kernel %.3f) | collect %.3f "
             "(d2h %.3f) | trace %.3f (rand wait %.3f, flush %.3f) | splice+log %.3f\n", wall, run.phase1_ms - w_upload - w_run - w_collect, w_upload, w_run,
             total.kernel_ms, w_collect, total.d2h_ms, run.trace_ms, run.wait_ms, run.flush_ms, run.phase2_ms - run.trace_ms);
-  auto dup_one = [&](size_t i) { filled_out[i] = strdup(filled[i].c_str()); };
-  if (e->pool) e->pool->parallel_for(n_records, 16, dup_one);
-  else for (size_t i = 0; i < n_records; i++) dup_one(i);
+  for (size_t i = 0; i < n_records; i++)
+    if (!filled_out[i]) return fail(G2S_E_NOMEM, "g2s_fill_records: out of host memory");
   if (log_out) *log_out = strdup(log.c_str());
   if (gapcount) *gapcount = gc;
   if (filledcount) *filledcount = fc;
@@ -1076,6 +1077,20 @@ extern "C" int g2s_fill_records(g2s_engine *e, const char *const *seqs, const ch
     memcpy(*gap_results, details.data(), details.size() * sizeof(g2s_result));
   }
   return G2S_OK;
+}
+
+extern "C" int g2s_fill_records(g2s_engine *e, const char *const *seqs, const char *const *comments, size_t n_records,
+                                const g2s_run_options *opt, char **filled_out, char **log_out, int32_t *gapcount,
+                                int32_t *filledcount, g2s_result **gap_results, size_t *n_gap_results) {
+  const auto t0 = std::chrono::steady_clock::now();
+  const int rc = fill_records_impl(e, seqs, comments, n_records, opt, filled_out, log_out, gapcount, filledcount, gap_results,
+                                   n_gap_results);
+  if (rc != G2S_OK && filled_out)   // nothing half-written is handed out
+    for (size_t i = 0; i < n_records; i++) { free(filled_out[i]); filled_out[i] = nullptr; }
+  if (getenv("G2S_HOST_PROF"))
+    fprintf(stderr, "g2s_fill_records: %.3f ms from entry to return (teardown of the run's host state included)\n",
+            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+  return rc;
 }
 
 extern "C" int g2s_fill_gap_ex(g2s_engine *e, const char *kmer_left, const char *kmer_right, int gap_len, int k, int gap_err,

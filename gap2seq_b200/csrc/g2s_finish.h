@@ -679,8 +679,11 @@ struct TraceJob { HostBatch *hb; size_t idx; };
 struct TraceStats { std::atomic<unsigned long long> calls{0}, parallel_calls{0}, rounds{0}, retraced{0}; };
 inline TraceStats &trace_stats() { static TraceStats s; return s; }   // observability for the tests
 
+// `direct` (optional): fills the device traced itself are not copied into the arena; direct[j] points at the gap's fill
+// wherever it lives (the pinned staging of its batch, or the arena) - for callers that only read the fills once.
 inline void trace_many(const std::vector<TraceJob> &jobs, std::vector<g2s_result> &res, RawBuf<char> &arena_buf,
-                       std::vector<size_t> &fill_off, ThreadPool *pool, RandAhead *ahead) {
+                       std::vector<size_t> &fill_off, ThreadPool *pool, RandAhead *ahead,
+                       std::vector<const char *> *direct = nullptr) {
   const size_t n = jobs.size();
   res.resize(n);
   fill_off.resize(n + 1);
@@ -688,12 +691,17 @@ inline void trace_many(const std::vector<TraceJob> &jobs, std::vector<g2s_result
   for (size_t j = 0; j < n; j++) { fill_off[j] = tot; tot += jobs[j].hb->fill_bytes(jobs[j].idx); }
   fill_off[n] = tot;
   char *arena = arena_buf.ensure(tot + 1);
+  if (direct) {
+    direct->resize(n);
+    for (size_t j = 0; j < n; j++) { const char *d = jobs[j].hb->fill_ptr(jobs[j].idx); (*direct)[j] = d ? d : &arena[fill_off[j]]; }
+  }
+  auto dst_of = [&](size_t j) -> char * { return direct && (*direct)[j] != &arena[fill_off[j]] ? nullptr : &arena[fill_off[j]]; };
   RandAhead local;
   if (!ahead) { ahead = &local; if (pool && n >= 4) local.begin(); }
   trace_stats().calls++;
   if (!pool || n < 4 || !ahead->ok()) {   // sequential, straight from libc
     if (ahead->ok()) ahead->commit(0);
-    for (size_t j = 0; j < n; j++) jobs[j].hb->trace(jobs[j].idx, res[j], &arena[fill_off[j]]);
+    for (size_t j = 0; j < n; j++) jobs[j].hb->trace(jobs[j].idx, res[j], dst_of(j));
     return;
   }
   std::vector<size_t> pred(n), act(n), off(n + 1);
@@ -712,7 +720,7 @@ inline void trace_many(const std::vector<TraceJob> &jobs, std::vector<g2s_result
   trace_stats().parallel_calls++;
   auto trace_one = [&](size_t j, std::vector<char> &scratch) {
     RandCursor rc{vals, off[j], ahead};
-    jobs[j].hb->trace_at(jobs[j].idx, res[j], &arena[fill_off[j]], rc, scratch);
+    jobs[j].hb->trace_at(jobs[j].idx, res[j], dst_of(j), rc, scratch);
     act[j] = rc.pos - off[j];
   };
   // Segments: the gaps up to and including the next uncertain one.  A segment's stream position is known once the

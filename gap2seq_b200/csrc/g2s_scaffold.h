@@ -85,8 +85,10 @@ inline void format_statistics(std::string &log, int filledStart, int gapStart, i
   if (paths > 0 && (!unique_paths || paths == 1)) {
     const int filledLen = fill_len - k;
     if (!skip_confident) {
-      int upper = 0, lower = 0;
-      for (int j = 0; j < filledLen; j++) { if (isupper((unsigned char)fill[j])) upper++; else lower++; }
+      // fills hold letters only (ACGT / acgt): upper case = bit 5 clear; a plain sum the compiler vectorises
+      int upper = 0;
+      for (int j = 0; j < filledLen; j++) upper += ((unsigned char)fill[j] & 0x20u) == 0;
+      const int lower = filledLen - upper;
       snprintf(buf, sizeof buf,
                " GapStart: %d GapEnd: %d GapLength: %d PathsFound: %d FilledStart: %d FilledEnd: %d FilledGapLength: %d"
                " LeftMaxFuz: %d LeftFuz: %d RightMaxFuz: %d RightFuz: %d ConfidentBases: %d TotalBases: %d\n",
@@ -126,6 +128,8 @@ struct ScaffoldRun {
   ThreadPool *pool = nullptr;                         // host threads for the tracebacks and the per-record replay
   RandAhead own_ahead, *aheadp = &own_ahead;          // the libc rand() values the tracebacks will consume; callers that
   RawBuf<char> own_arena, *arenap = &own_arena;       // run many times hand in persistent ones (no page faults per call)
+  char **filled_c = nullptr;                          // when set: record r's filled sequence goes to a malloc'ed C string
+                                                      // filled_c[r] (one copy) and `filled[r]` stays empty
 
   ScaffoldRun(const std::vector<StrRef> &s, const std::vector<StrRef> &c, const RunOptions &o)
       : seqs(s), comments(c), opt(o), recs(s.size()) {}
@@ -257,11 +261,8 @@ struct ScaffoldRun {
     first_job[seqs.size()] = jobs.size();
     std::vector<g2s_result> res;
     std::vector<size_t> fill_off;
-    trace_many(jobs, res, *arenap, fill_off, pool, aheadp->ok() ? aheadp : nullptr);
-    const char *arena = arenap->p;
-    const auto t_fl = std::chrono::steady_clock::now();
-    for (auto &b : batches) if (b) b->flush_staging(pool);
-    flush_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_fl).count();
+    std::vector<const char *> fill_at;   // device-traced fills are read where the DMA left them, not copied first
+    trace_many(jobs, res, *arenap, fill_off, pool, aheadp->ok() ? aheadp : nullptr, &fill_at);
     trace_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_mid).count();
 
     filled.assign(seqs.size(), std::string());
@@ -271,7 +272,10 @@ struct ScaffoldRun {
     auto one_record = [&](size_t r) {
       const StrRef &seq = seqs[r];
       const StrRef &comment = comments[r];
-      std::string filledSeq;
+      static thread_local std::string tl_seq;   // reused from record to record when the output is a C string
+      std::string own_seq;
+      std::string &filledSeq = filled_c ? tl_seq : own_seq;
+      filledSeq.clear();
       filledSeq.reserve(seq.size() + 64);
       std::string &lg = rlog[r];
       long long prev = 0;
@@ -292,7 +296,7 @@ struct ScaffoldRun {
           if (q.kmer_start != kmer_start || q.lmf != lmf || q.rmf != rmf || q.gap != gap || q.i_after != i) { bad = -3; return; }
           const size_t jb = first_job[r] + next_req++;
           const g2s_result &rs = res[jb];
-          const char *fill = &arena[fill_off[jb]];
+          const char *fill = fill_at[jb];
           const int s = rs.count;
           const int filledStart = (int)filledSeq.length() + kmer_start + k + lmf - rs.left_fuz - (int)prev;
           const int gapStart = kmer_start + k + lmf;
@@ -315,11 +319,20 @@ struct ScaffoldRun {
       }
       if (next_req != recs[r].reqs.size()) { bad = -4; return; }
       filledSeq.append(seq.data() + prev, seq.size() - (size_t)prev);
-      filled[r].swap(filledSeq);
+      if (filled_c) {
+        char *o = (char *)malloc(filledSeq.size() + 1);
+        if (o) memcpy(o, filledSeq.c_str(), filledSeq.size() + 1);
+        filled_c[r] = o;
+      } else {
+        filled[r].swap(filledSeq);
+      }
     };
     if (pool) pool->parallel_for(seqs.size(), 8, one_record);
     else for (size_t r = 0; r < seqs.size(); r++) one_record(r);
     if (bad.load() != 0) return bad.load();
+    const auto t_fl = std::chrono::steady_clock::now();
+    for (auto &b : batches) if (b) b->flush_staging(pool);   // after the replay: it read the fills out of the staging
+    flush_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_fl).count();
     size_t lbytes = 0;
     for (const std::string &l : rlog) lbytes += l.size();
     log.reserve(log.size() + lbytes);

@@ -44,7 +44,8 @@ def sass_lines(kernel_sub):
 def main():
     rep, ksub = sys.argv[1], sys.argv[2]
     top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
-    page = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+    sel = ["--kernel-name", "regex:" + os.environ["G2S_NCU_KERNEL"]] if os.environ.get("G2S_NCU_KERNEL") else []
+    page = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"] + sel, capture_output=True, text=True).stdout
     rows = list(csv.reader(page.splitlines()))
     hdr = rows[1]
     col = {h: i for i, h in enumerate(hdr)}
