@@ -169,7 +169,8 @@ G2S_D void chain_walk(const Table &T, uint64_t x0, int maxlev, uint64_t *W, Chai
 // ------------------------------------------------------------------------------------------------ the finish
 // G: the thread group of one gap (a warp on the device, one thread in the host emulation) with
 //    rank(), size(), any(bool), min_i32(int), max_i32(int), add_u32(uint32_t), bcast_u64(v) (rank 0's value).
-// tk: group-shared scratch of MAX_FUZ + 1 words.
+// tk: group-shared scratch of 3 * (MAX_FUZ + 1) words: the flank k-mers, parsed once - [j] right-flank target j,
+//     [32 + d] left start of level d, [64 + o] right start at offset o of the start string.
 
 // is x a node of the right chain (either strand)?
 template <class G>
@@ -196,6 +197,12 @@ G2S_D void chain_finish(const ChainParams &P, const GapDev &gd, const uint64_t *
   const int nF = (int)wf.n, nR = (int)wr.n, cw = nF - 1;
   const int NONE = 0x7fffffff;
 
+  uint64_t *lkk = tk + (MAX_FUZ + 1), *rsk = tk + 2 * (MAX_FUZ + 1);
+  for (int j = rank; j <= MAX_FUZ; j += gsz) {
+    if (j <= rmf) { tk[j] = kmer_from_ascii(rstr + j, k); rsk[j] = kmer_from_ascii(rsstr + j, k); }
+    if (j <= lmf) lkk[j] = kmer_from_ascii(lstr + j, k);
+  }
+  G::sync();
   bool internal = ((wf.end_mask | wr.end_mask) & CHAIN_END_INTERNAL) != 0;
   bool fb = nF == 0 || nR == 0 || internal;         // a start k-mer that is absent: the staggered starts decide, not this tier
   const bool r_branch = wr.end_mask != CHAIN_END_LIMIT && (wr.end_mask & (wr.end_mask - 1)) != 0;
@@ -210,13 +217,13 @@ G2S_D void chain_finish(const ChainParams &P, const GapDev &gd, const uint64_t *
   if (!fb) {
     bool bad = false;
     for (int c = 1 + rank; c <= rmf; c += gsz) {            // right start of iteration c = state of index c (rmf <= right_half)
-      const uint64_t s = kmer_from_ascii(rsstr + (rmf - c), k);
+      const uint64_t s = ld_sh(&rsk[rmf - c]);
       if (c < nR && revcomp(s, k) == str_kmer(WR, (uint32_t)c, k)) continue;
       uint32_t adj;
       if (table_find(T, canonical(s, k).key, &adj) >= 0) bad = true;
     }
     for (int d = 1 + rank; d <= lmf; d += gsz) {
-      const uint64_t s = kmer_from_ascii(lstr + d, k);
+      const uint64_t s = ld_sh(&lkk[d]);
       if (s == str_kmer(WF, (uint32_t)d, k)) continue;
       uint32_t adj;
       if (table_find(T, canonical(s, k).key, &adj) >= 0) bad = true;
@@ -230,8 +237,10 @@ G2S_D void chain_finish(const ChainParams &P, const GapDev &gd, const uint64_t *
   // without a lookup.  One membership scan settles the first level that is not covered by that argument.
   int top = -1, L = NONE;
   if (!fb) {
-    const uint64_t R0 = kmer_from_ascii(rsstr + rmf, k);
-    for (int c = rank; c < nF; c += gsz)
+    const uint64_t R0 = ld_sh(&rsk[rmf]);
+    // (only a meeting at a level >= pf matters; an earlier one as well would make the chain periodic, which the pass below
+    // detects)
+    for (int c = pf + rank; c < nF; c += gsz)
       if (str_kmer(WF, (uint32_t)c, k) == R0) { L = c; break; }
     L = G::min_i32(L);
     if (cw < pf) top = cw;
@@ -254,8 +263,6 @@ G2S_D void chain_finish(const ChainParams &P, const GapDev &gd, const uint64_t *
   uint32_t n_sink = 0;
   int min_sink = NONE, sB = -1;
   if (!fb) {
-    for (int j = rank; j <= rmf; j += gsz) tk[j] = kmer_from_ascii(rstr + j, k);
-    G::sync();
     const uint64_t Ftop = str_kmer(WF, (uint32_t)top, k), rcFtop = revcomp(Ftop, k), rcF0 = revcomp(str_kmer(WF, 0, k), k);
     const int jt = rmf - 1, dlo = lmf + g - e > 0 ? lmf + g - e : 0;
     bool rep = false;
@@ -312,7 +319,7 @@ G2S_D void chain_finish(const ChainParams &P, const GapDev &gd, const uint64_t *
     // start cells: d <= lmf whose state is the left start of that level (checked above: the only way to share its node)
     int s1 = -1, s2 = -1;
     for (int d = rank; d <= lmf; d += gsz) {
-      if (kmer_from_ascii(lstr + d, k) != str_kmer(WF, (uint32_t)d, k)) continue;
+      if (ld_sh(&lkk[d]) != str_kmer(WF, (uint32_t)d, k)) continue;
       if (d <= sB) s1 = d;
       if (d <= d0) s2 = d;
     }

@@ -6,6 +6,9 @@
 #include <cub/cub.cuh>
 #include <cuda_runtime.h>
 
+#include <algorithm>
+#include <cstdlib>
+
 #include "g2s_common.cuh"
 #include "g2s_device.h"
 
@@ -114,6 +117,58 @@ __global__ void k_extract(const char *bases, const uint64_t *offsets, const uint
   }
 }
 
+// Partitioned counting (inputs with 2^31 or more k-mer occurrences, or more than the sort buffers should hold): the
+// occurrences are split by a hash of the canonical k-mer, so every partition is counted on its own with all occurrences
+// of its k-mers present.  part = (mix64(key) >> 40) & pmask.
+__device__ __forceinline__ uint64_t kmer_at(const char *bases, const uint64_t *offsets, const uint64_t *kmer_offsets,
+                                            uint64_t n_reads, int k, uint64_t i) {
+  uint64_t lo = 0, hi = n_reads;
+  while (hi - lo > 1) { uint64_t mid = (lo + hi) >> 1; if (kmer_offsets[mid] <= i) lo = mid; else hi = mid; }
+  const char *s = bases + offsets[lo] + (i - kmer_offsets[lo]);
+  uint64_t v = 0; uint32_t bad = 0;
+  for (int j = 0; j < k; j++) {
+    const unsigned char c = (unsigned char)s[j];
+    bad |= (c >> 3) & 1;
+    v = (v << 2) | ((c >> 1) & 3);
+  }
+  return bad ? KEY_EMPTY : canonical(v, k).key;
+}
+
+__global__ void k_part_histogram(const char *bases, const uint64_t *offsets, const uint64_t *kmer_offsets, uint64_t n_reads,
+                                 int k, uint64_t total, uint32_t pmask, unsigned long long *hist) {
+  __shared__ unsigned long long sh[256];
+  for (uint32_t q = threadIdx.x; q <= pmask; q += blockDim.x) sh[q] = 0;
+  __syncthreads();
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (; i < total; i += stride) {
+    const uint64_t key = kmer_at(bases, offsets, kmer_offsets, n_reads, k, i);
+    if (key != KEY_EMPTY) atomicAdd(&sh[(uint32_t)(mix64(key) >> 40) & pmask], 1ULL);
+  }
+  __syncthreads();
+  for (uint32_t q = threadIdx.x; q <= pmask; q += blockDim.x) if (sh[q]) atomicAdd(&hist[q], sh[q]);
+}
+
+__global__ void k_extract_part(const char *bases, const uint64_t *offsets, const uint64_t *kmer_offsets, uint64_t n_reads,
+                               int k, uint64_t total, uint32_t pmask, uint32_t part, uint64_t *out, unsigned long long *cursor) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (; i < total; i += stride) {
+    const uint64_t key = kmer_at(bases, offsets, kmer_offsets, n_reads, k, i);
+    if (key != KEY_EMPTY && ((uint32_t)(mix64(key) >> 40) & pmask) == part) out[atomicAdd(cursor, 1ULL)] = key;
+  }
+}
+
+// unique k-mers of one partition with count >= solid, appended to the list of solid k-mers
+__global__ void k_append_solid(const uint64_t *keys, const uint32_t *counts, const int *n_runs, uint32_t solid,
+                               uint64_t *solid_keys, unsigned long long *cursor) {
+  const uint64_t n = (uint64_t)*n_runs;
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride)
+    if (counts[i] >= solid && keys[i] != KEY_EMPTY) solid_keys[atomicAdd(cursor, 1ULL)] = keys[i];
+}
+
 __global__ void k_compact(const Slot *slots, uint64_t cap, uint64_t *keys_out, unsigned long long *cursor) {
   uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
@@ -211,15 +266,76 @@ cudaError_t table_from_reads(DeviceTable *dt, int k, const char *bases_host, con
 #define CKG(x) do { err = (x); if (err != cudaSuccess) goto done; } while (0)
   {
     if (total == 0) { CKG(table_alloc(dt, k, 0, sms, st)); CKG(cudaStreamSynchronize(st)); goto done; }
-    if (total >= (1ULL << 31)) { err = cudaErrorInvalidValue; goto done; }   // cub run-length API counts in int
     CKG(cudaMalloc(&d_bases, nbytes + 1));
     CKG(cudaMalloc(&d_off, (n_reads + 1) * 8));
     CKG(cudaMalloc(&d_koff, (n_reads + 1) * 8));
-    CKG(cudaMalloc(&d_keys, total * 8));
-    CKG(cudaMalloc(&d_sorted, total * 8));
     CKG(cudaMemcpyAsync(d_bases, bases_host, nbytes, cudaMemcpyHostToDevice, st));
     CKG(cudaMemcpyAsync(d_off, offsets_host, (n_reads + 1) * 8, cudaMemcpyHostToDevice, st));
     CKG(cudaMemcpyAsync(d_koff, koff, (n_reads + 1) * 8, cudaMemcpyHostToDevice, st));
+    // One sort + run-length pass holds at most `limit` occurrences (cub's run-length API counts in int; the sort needs two
+    // 8-byte buffers per occurrence).  Larger inputs are counted in hash partitions of the canonical k-mer.
+    uint64_t limit = 1ULL << 30;
+    if (const char *lv = getenv("G2S_COUNT_PART_LIMIT")) { const uint64_t v = strtoull(lv, nullptr, 10); if (v >= 1024) limit = v; }
+    if (total > limit) {
+      uint32_t pbits = 1;
+      while (pbits < 8 && (total >> pbits) > limit - limit / 4) pbits++;   // a quarter of headroom for uneven partitions
+      const uint32_t nparts = 1u << pbits, pmask = nparts - 1;
+      unsigned long long *d_hist = nullptr, *d_cur = nullptr;
+      uint64_t *d_solid = nullptr;
+      unsigned long long hist[256];
+      CKG(cudaMalloc(&d_hist, nparts * 8));
+      CKG(cudaMemsetAsync(d_hist, 0, nparts * 8, st));
+      k_part_histogram<<<grid_for(total, 256, sms), 256, 0, st>>>(d_bases, d_off, d_koff, n_reads, k, total, pmask, d_hist);
+      err = cudaGetLastError();
+      if (err == cudaSuccess) err = cudaMemcpyAsync(hist, d_hist, nparts * 8, cudaMemcpyDeviceToHost, st);
+      if (err == cudaSuccess) err = cudaStreamSynchronize(st);
+      cudaFree(d_hist);
+      if (err != cudaSuccess) goto done;
+      uint64_t biggest = 0, valid = 0;
+      for (uint32_t q = 0; q < nparts; q++) { biggest = std::max<uint64_t>(biggest, hist[q]); valid += hist[q]; }
+      if (biggest >= (1ULL << 31)) { err = cudaErrorInvalidValue; goto done; }   // 256 partitions of 2^31: beyond this build
+      const uint64_t solid_cap = valid / (uint64_t)std::max(solid, 1) + 1;          // a solid k-mer has >= solid occurrences
+      CKG(cudaMalloc(&d_keys, std::max<uint64_t>(biggest, 1) * 8));
+      CKG(cudaMalloc(&d_sorted, std::max<uint64_t>(biggest, 1) * 8));
+      CKG(cudaMalloc(&d_counts, std::max<uint64_t>(biggest, 1) * 4));
+      CKG(cudaMalloc(&d_nruns, sizeof(int)));
+      CKG(cudaMalloc(&d_solid, solid_cap * 8));
+      CKG(cudaMalloc(&d_cur, 16));
+      CKG(cudaMemsetAsync(d_cur, 0, 16, st));
+      for (uint32_t q = 0; q < nparts && err == cudaSuccess; q++) {
+        if (hist[q] == 0) continue;
+        err = cudaMemsetAsync(d_cur, 0, 8, st);
+        if (err != cudaSuccess) break;
+        k_extract_part<<<grid_for(total, 256, sms), 256, 0, st>>>(d_bases, d_off, d_koff, n_reads, k, total, pmask, q, d_keys, d_cur);
+        size_t tmp_bytes = 0;
+        err = cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, d_keys, d_sorted, (int)hist[q], 0, 64, st);
+        if (err != cudaSuccess) break;
+        err = cudaMalloc(&d_tmp, tmp_bytes);
+        if (err != cudaSuccess) break;
+        err = cub::DeviceRadixSort::SortKeys(d_tmp, tmp_bytes, d_keys, d_sorted, (int)hist[q], 0, 64, st);
+        cudaFree(d_tmp); d_tmp = nullptr;
+        if (err != cudaSuccess) break;
+        tmp_bytes = 0;
+        err = cub::DeviceRunLengthEncode::Encode(nullptr, tmp_bytes, d_sorted, d_keys, d_counts, d_nruns, (int)hist[q], st);
+        if (err != cudaSuccess) break;
+        err = cudaMalloc(&d_tmp, tmp_bytes);
+        if (err != cudaSuccess) break;
+        err = cub::DeviceRunLengthEncode::Encode(d_tmp, tmp_bytes, d_sorted, d_keys, d_counts, d_nruns, (int)hist[q], st);
+        cudaFree(d_tmp); d_tmp = nullptr;
+        if (err != cudaSuccess) break;
+        k_append_solid<<<grid_for(hist[q], 256, sms), 256, 0, st>>>(d_keys, d_counts, d_nruns, (uint32_t)solid, d_solid, d_cur + 1);
+        err = cudaGetLastError();
+      }
+      unsigned long long n_solid = 0;
+      if (err == cudaSuccess) err = cudaMemcpyAsync(&n_solid, d_cur + 1, 8, cudaMemcpyDeviceToHost, st);
+      if (err == cudaSuccess) err = cudaStreamSynchronize(st);
+      if (err == cudaSuccess) err = table_alloc(dt, k, n_solid, sms, st);
+      if (err == cudaSuccess) err = table_fill(dt, d_solid, nullptr, 0, n_solid, sms, st);
+      cudaFree(d_solid); cudaFree(d_cur);
+      goto done;
+    }
+    CKG(cudaMalloc(&d_keys, total * 8));
+    CKG(cudaMalloc(&d_sorted, total * 8));
     k_extract<<<grid_for(total, 256, sms), 256, 0, st>>>(d_bases, d_off, d_koff, n_reads, k, d_keys, total);
     CKG(cudaGetLastError());
     size_t tmp_bytes = 0;

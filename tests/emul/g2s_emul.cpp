@@ -132,7 +132,7 @@ static int emul_submit(EmulGraph *g, int k, const g2s_gap *gaps, size_t n, HostB
       CP.strs = strs.data(); CP.walks = walks; CP.fills = fills.data(); CP.fill_cap = fills.size(); CP.fill_cursor = &fcursor;
       chain_walk(g->t, kmer_from_ascii(flanks.data() + gd.flank_off, k), dmax, strs.data(), &walks[0]);
       chain_walk(g->t, revcomp(kmer_from_ascii(flanks.data() + gd.rstart_off + gd.rmf, k), k), right_half, strs.data() + CP.f_words, &walks[1]);
-      uint64_t tk[MAX_FUZ + 1];
+      uint64_t tk[3 * (MAX_FUZ + 1)];
       chain_finish<EmulGroup>(CP, gd, strs.data(), strs.data() + CP.f_words, walks[0], walks[1], tk, &out);
       if (out.status & GS_INTERNAL) return -100;
       if (!(out.status & GS_NOT_CHAIN)) {

@@ -43,6 +43,22 @@ def test_device_table_equals_oracle_graph(name, case_inputs, gpu_engine):
     assert np.array_equal(adj, oadj)
 
 
+@pytest.mark.parametrize("name,limit", [("cfg2_small", 60000), ("cfg2_small_solid3", 20000), ("cfg1_k21", 1024)])
+def test_partitioned_counting_equals_oracle_graph(name, limit, case_inputs, monkeypatch):
+    """Inputs with more k-mer occurrences than one sort pass holds (2^30; cub's run-length API counts in int) are counted in
+    hash partitions of the canonical k-mer.  A tiny limit forces 2 - 256 partitions on a small read set: same solid k-mers,
+    same adjacency bytes, same hints-derived fills as the one-pass path."""
+    case, w, g = case_inputs(name)
+    monkeypatch.setenv("G2S_COUNT_PART_LIMIT", str(limit))
+    e = engine.Engine(k=w.k, max_fuz=max(w.fuz, 1))
+    e.build_from_reads(w.reads, w.solid)
+    keys, adj = e.export_kmers()
+    okeys, oadj = g.kmers(with_adjacency=True)
+    assert np.array_equal(keys, okeys)
+    assert np.array_equal(adj, oadj)
+    e.close()
+
+
 def test_import_kmers_equals_build_from_reads(case_inputs, gpu_engine):
     case, w, g = case_inputs("cfg2_small")
     e = engine.Engine(k=w.k)
