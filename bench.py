@@ -445,7 +445,7 @@ def main():
         dom_ms = tier_ms[dom] / args.steps
         dom_cells = {"chain": t_dev.cells_chain, "thin": t_dev.cells_thin, "wide": t_dev.cells_wide}[dom]
         shapes = {0: "k_fill_thin<1,1>", 1: "k_fill_thin<2,4>", 2: "k_fill_thin<4,8>"}
-        dom_name = {"chain": "k_chain_walk + k_chain_finish", "thin": shapes.get(t_dev.thin_shape, "k_fill_thin"), "wide": "k_fill_cta"}[dom]
+        dom_name = {"chain": "k_chain_walk + k_chain_finish", "thin": shapes.get(t_dev.thin_shape, "k_fill_thin"), "wide": "k_fill_cta" if t_dev.wide_cluster <= 1 else f"k_fill_cluster (cluster of {t_dev.wide_cluster} CTAs per gap)"}[dom]
         achieved = dom_cells * BYTES_PER_CELL / (dom_ms / 1e3) / 1e9 if dom_ms > 0 else 0.0
         traffic = measured_traffic(args.workload, args.scale)
         cpu, n_checked = cpu_baseline_and_check(w, keys, ref_out[0], args.cpu_seconds) if world == 1 else (None, 0)

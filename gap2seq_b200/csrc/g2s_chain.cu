@@ -37,12 +37,12 @@ __global__ void __launch_bounds__(WALK_THREADS) k_chain_walk(const __grid_consta
   // ONE call site for both directions: the walks of a warp stay converged (two inlined copies of the loop under an
   // if / else would serialise the forward lanes against the backward lanes)
   const bool fwd = (t & 1) == 0;
-  const int maxlev = fwd ? gd.gap_len + gd.gap_err + gd.lmf + gd.rmf           // Dmax
-                         : gd.rmf + (gd.gap_len + gd.gap_err + 1) / 2;        // right_half
+  const int maxlev = fwd ? gd.gap_len / 2 + gd.gap_err / 2 + gd.lmf           // the first pruned level (<= Dmax): the levels
+                         : gd.rmf + (gd.gap_len + gd.gap_err + 1) / 2;        // beyond it are read off the backward walk (right_half)
   uint64_t x0 = kmer_from_ascii(P.flanks + (fwd ? gd.flank_off : gd.rstart_off + gd.rmf), k);
   // walking predecessors of the last right start = walking successors of its reverse complement
   if (!fwd) x0 = revcomp(x0, k);
-  chain_walk(P.table, x0, maxlev, fwd ? W : W + P.f_words, &P.walks[2 * q + (fwd ? 0 : 1)]);
+  chain_walk(P.table, x0, maxlev, fwd ? W : W + P.f_words, &P.walks[2 * q + (fwd ? 0 : 1)], !fwd);
 }
 
 __global__ void __launch_bounds__(32 * FINISH_WARPS) k_chain_finish(const __grid_constant__ ChainParams P) {

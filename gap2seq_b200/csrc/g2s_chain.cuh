@@ -6,7 +6,8 @@
 // counts are 1, the path subgraph is a path, the traceback has no choice.  The tier therefore keeps NO per-gap hash table
 // and no cell arrays.  It runs in two kernels:
 //
-//   k_chain_walk    one LANE per walk (two per gap: forward from the left flank, backward from the right flank).  A walk
+//   k_chain_walk    one LANE per walk (two per gap: forward from the left flank up to the first pruned level, backward
+//                   from the right flank; the forward chain's levels beyond that ARE the backward chain, see the finish).  A walk
 //                   is the chain of dependent gathers in the global k-mer table and nothing else: every gather returns the
 //                   skip hint of the tip (the next <= 40 bases of its unique extension), the lane appends those bases to
 //                   the walk's 2-bit packed string in HBM and jumps to the node the hint ends at.  Thousands of walks are
@@ -34,10 +35,14 @@ static const uint32_t CHAIN_END_INTERNAL = 0x100u;  // the table contradicts its
 
 struct ChainWalk {      // what a walk left behind, 16 B
   uint32_t n;           // states recorded (the string holds k + n - 1 bases); 0: the start k-mer is not in the graph
-  uint32_t end_mask;    // out-mask of the last state in walk orientation (0: dead end, several bits: branch), or CHAIN_END_*
+  uint32_t end_mask;    // bits 0-15: out-mask of the last state in walk orientation (0: dead end, several bits: branch), or
+                        // CHAIN_END_*; bits 24-27 (backward walk): out-mask of the START state against the walk, i.e. the
+                        // successors of the last right start in forward orientation
   uint32_t lookups;     // gathers in the global table
-  uint32_t pad;
+  uint32_t ok_upto;     // backward walk: states 1 .. ok_upto each have exactly ONE neighbour against the walk direction (the
+                        // skip hint of the other orientation, read at every gather, covers the segment walked before it)
 };
+G2S_HD uint32_t chain_end(const ChainWalk &w) { return w.end_mask & 0xFFFFu; }
 
 struct ChainParams {
   Table table;
@@ -132,7 +137,11 @@ G2S_D bool chain_find_slot(const Table &t, uint64_t canon, Slot *out) {
 }
 
 // One chain of dependent gathers: from x0 (walk orientation) along unique successors for at most `maxlev` levels.
-G2S_D void chain_walk(const Table &T, uint64_t x0, int maxlev, uint64_t *W, ChainWalk *out) {
+// backcheck (the backward walk): every gather also reads the tip's hint of the OTHER orientation - the length of the
+// unique extension against the walk - and thereby proves that the nodes of the segment just walked have one neighbour
+// in that direction too (that is what lets the forward chain be read off the backward one); the final state is gathered
+// for that purpose even when the level limit ends the walk.
+G2S_D void chain_walk(const Table &T, uint64_t x0, int maxlev, uint64_t *W, ChainWalk *out, bool backcheck) {
   const int k = T.k;
   ChainWalk r{0, 0, 1, 0};
   Canon c = canonical(x0, k);
@@ -144,6 +153,8 @@ G2S_D void chain_walk(const Table &T, uint64_t x0, int maxlev, uint64_t *W, Chai
   uint64_t x = x0;
   int lev = 0;
   uint32_t endm = CHAIN_END_LIMIT;
+  const uint32_t aux = backcheck ? out_mask((uint32_t)(sl.val & 0xFF), c.strand ^ 1u) : 0u;
+  bool ok = true;
   while (lev < maxlev) {
     const uint32_t mask = out_mask((uint32_t)(sl.val & 0xFF), c.strand);
     if (mask == 0 || (mask & (mask - 1))) { endm = mask; break; }
@@ -155,14 +166,20 @@ G2S_D void chain_walk(const Table &T, uint64_t x0, int maxlev, uint64_t *W, Chai
     bw.put(hint_shr(h, sh), 2 * j > 64 ? 64u : 2 * j);
     x = hint_state(x, h, j, T.kmask);
     lev += (int)j;
-    if (lev >= maxlev) break;
+    const bool last = lev >= maxlev;
+    if (last && !backcheck) break;
     c = canonical(x, k);
     r.lookups++;
     if (!chain_find_slot(T, c.key, &sl)) { endm = CHAIN_END_INTERNAL; break; }
+    if (backcheck) {
+      if (ok && hint_of(sl, c.strand ^ 1u).len >= j) r.ok_upto = (uint32_t)lev;
+      else ok = false;
+    }
+    if (last) break;
   }
   bw.flush();
   r.n = (uint32_t)lev + 1;
-  r.end_mask = endm;
+  r.end_mask = endm | (aux << 24);
   *out = r;
 }
 
@@ -203,10 +220,10 @@ G2S_D void chain_finish(const ChainParams &P, const GapDev &gd, const uint64_t *
     if (j <= lmf) lkk[j] = kmer_from_ascii(lstr + j, k);
   }
   G::sync();
-  bool internal = ((wf.end_mask | wr.end_mask) & CHAIN_END_INTERNAL) != 0;
+  bool internal = ((chain_end(wf) | chain_end(wr)) & CHAIN_END_INTERNAL) != 0;
   bool fb = nF == 0 || nR == 0 || internal;         // a start k-mer that is absent: the staggered starts decide, not this tier
-  const bool r_branch = wr.end_mask != CHAIN_END_LIMIT && (wr.end_mask & (wr.end_mask - 1)) != 0;
-  const bool f_branch = wf.end_mask != CHAIN_END_LIMIT && (wf.end_mask & (wf.end_mask - 1)) != 0;
+  const bool r_branch = chain_end(wr) != CHAIN_END_LIMIT && (chain_end(wr) & (chain_end(wr) - 1)) != 0;
+  const bool f_branch = chain_end(wf) != CHAIN_END_LIMIT && (chain_end(wf) & (chain_end(wf) - 1)) != 0;
   // the right pass never prunes: a state with two predecessors below the level limit makes a border of two
   if (r_branch) fb = true;
   // the forward chain must cover the levels that inject starts
@@ -231,29 +248,51 @@ G2S_D void chain_finish(const ChainParams &P, const GapDev &gd, const uint64_t *
     if (G::any(bad)) fb = true;
   }
 
-  // ---- where the forward chain ends.  Below pf nothing is pruned.  From pf on a state survives iff its node is in the
-  // right set.  The right chain R[0], R[1], .. walks unique predecessors from R[0] = the last right start, so once the
-  // forward chain stands on R[0] at level L it stood on R[i] at level L - i for every i < nR: those levels survive
-  // without a lookup.  One membership scan settles the first level that is not covered by that argument.
+  // ---- where the forward chain ends.  Below pf nothing is pruned; the forward walk covers levels 0 .. pf.  From pf on a
+  // state survives iff its node is in the right set.  The right chain R[0], R[1], .. walks UNIQUE predecessors from R[0] =
+  // the last right start, and its gathers proved that R[1] .. R[ok_upto] have one SUCCESSOR each as well.  So if the
+  // forward chain stands on R[i0] at level pf, it walks R[i0 - 1], .. , R[0] on levels pf + 1 .. L = pf + i0 and nothing
+  // else can enter the border there: those levels need neither a walk nor a lookup - the forward chain beyond pf is the
+  // right chain read backwards.  What comes behind R[0] (one successor, from the start slot's adjacency) is settled by one
+  // membership scan.
   int top = -1, L = NONE;
   if (!fb) {
-    const uint64_t R0 = ld_sh(&rsk[rmf]);
-    // (only a meeting at a level >= pf matters; an earlier one as well would make the chain periodic, which the pass below
-    // detects)
-    for (int c = pf + rank; c < nF; c += gsz)
-      if (str_kmer(WF, (uint32_t)c, k) == R0) { L = c; break; }
-    L = G::min_i32(L);
-    if (cw < pf) top = cw;
-    else if (L != NONE && L >= pf && L - pf <= nR - 1) {
-      top = L;
-      if (L < cw && chain_member<G>(WR, nR, str_kmer(WF, (uint32_t)L + 1, k), k)) fb = true;
-    } else {
-      if (chain_member<G>(WR, nR, str_kmer(WF, (uint32_t)pf, k), k)) fb = true;
-      top = pf - 1;
+    if (cw < pf) top = cw;                    // the chain ended (dead end or branch) before the first pruned level
+    else {
+      const uint64_t fp = str_kmer(WF, (uint32_t)pf, k), want = revcomp(fp, k);   // the right string holds reverse complements
+      int i0 = NONE;
+      bool flipped = false;
+      for (int i = rank; i < nR; i += gsz) {
+        const uint64_t y = str_kmer(WR, (uint32_t)i, k);
+        if (y == want) { i0 = i < i0 ? i : i0; }
+        if (y == fp) flipped = true;           // the node is in the right set on its other strand: not a chain to read off
+      }
+      i0 = G::min_i32(i0);
+      if (G::any(flipped)) fb = true;
+      if (i0 == NONE) top = pf - 1;            // not in the right set: the border dies on level pf
+      else {
+        if ((uint32_t)i0 > wr.ok_upto) fb = true;      // a node on the way to R[0] has a second successor
+        L = pf + i0;
+        top = L;
+        const uint32_t fwd0 = (wr.end_mask >> 24) & 15u;   // successors of R[0]
+        if (fwd0 & (fwd0 - 1)) fb = true;                  // several: each would need its own test
+        else if (fwd0) {
+          const uint32_t nt = fwd0 == 1 ? 0 : fwd0 == 2 ? 1 : fwd0 == 4 ? 2 : 3;
+          const uint64_t nxt = succ_kmer(revcomp(str_kmer(WR, 0, k), k), nt, T);
+          if (chain_member<G>(WR, nR, nxt, k)) fb = true;  // the chain would go on inside the right set
+        }
+      }
     }
     if (f_branch && top == cw) fb = true;     // the branching state is expanded: a border of two
     if (top < lmf) fb = true;                 // a start level without a chain state: injection starts a new chain
   }
+  // state and last base of forward level c <= top: from the forward string up to pf, from the right string beyond
+  auto f_at = [&](int c) -> uint64_t {
+    return c <= cw ? str_kmer(WF, (uint32_t)c, k) : revcomp(str_kmer(WR, (uint32_t)(L - c), k), k);
+  };
+  auto f_base = [&](int c) -> uint32_t {
+    return c <= cw ? str_base(WF, (uint32_t)(c + k - 1)) : (str_base(WR, (uint32_t)(L - c)) ^ 2u);
+  };
 
   // ---- one pass over the chain's states: no node twice (either strand), target hits, all-paths seeds.
   // A chain of forced steps that meets a node again is periodic from there on (same strand) or retraces its own reverse
@@ -263,7 +302,7 @@ G2S_D void chain_finish(const ChainParams &P, const GapDev &gd, const uint64_t *
   uint32_t n_sink = 0;
   int min_sink = NONE, sB = -1;
   if (!fb) {
-    const uint64_t Ftop = str_kmer(WF, (uint32_t)top, k), rcFtop = revcomp(Ftop, k), rcF0 = revcomp(str_kmer(WF, 0, k), k);
+    const uint64_t Ftop = f_at(top), rcFtop = revcomp(Ftop, k), rcF0 = revcomp(str_kmer(WF, 0, k), k);
     const int jt = rmf - 1, dlo = lmf + g - e > 0 ? lmf + g - e : 0;
     bool rep = false;
     // a level can hit a target only within e of the target's nominal level (and seeds start at dlo >= that bound); a
@@ -272,7 +311,7 @@ G2S_D void chain_finish(const ChainParams &P, const GapDev &gd, const uint64_t *
     uint64_t sig = 0;
     for (int j = 0; j <= rmf; j++) sig |= 1ULL << ((ld_sh(&tk[j]) * 0x9E3779B97F4A7C15ULL) >> 58);
     for (int c = rank; c <= top; c += gsz) {
-      const uint64_t x = str_kmer(WF, (uint32_t)c, k);
+      const uint64_t x = f_at(c);
       if ((c < top && x == Ftop) || x == rcFtop || x == rcF0) rep = true;
       if (c < hit_lo || !((sig >> ((x * 0x9E3779B97F4A7C15ULL) >> 58)) & 1)) continue;
       for (int j = 0; j <= rmf; j++) {
@@ -301,8 +340,8 @@ G2S_D void chain_finish(const ChainParams &P, const GapDev &gd, const uint64_t *
     J = (int)(best & 63u);
     const int len1 = g + lmf + J + err, len2 = g + lmf + J - err;
     const uint64_t t = ld_sh(&tk[J]);
-    const bool h1 = len1 <= top && str_kmer(WF, (uint32_t)len1, k) == t;
-    const bool h2 = err > 0 && len2 >= 0 && len2 <= top && str_kmer(WF, (uint32_t)len2, k) == t;
+    const bool h1 = len1 <= top && f_at(len1) == t;
+    const bool h2 = err > 0 && len2 >= 0 && len2 <= top && f_at(len2) == t;
     if (h1 && h2) fb = true;                  // two accepted lengths: rand() picks one (Gap2Seq.cpp:1440)
     found = true;
     d0 = h1 ? len1 : len2;
@@ -352,7 +391,7 @@ G2S_D void chain_finish(const ChainParams &P, const GapDev &gd, const uint64_t *
       for (int d = dT + 1 + rank; d <= d0; d += gsz) {
         const int wend = d + k - 1 < d0 ? d + k - 1 : d0;
         const bool up = d0 - d < k || skip_confident || (n_sink > 0 && !(d >= uLo && wend <= sB));
-        const uint32_t b = str_base(WF, (uint32_t)(d + k - 1));
+        const uint32_t b = f_base(d);
         const char ch = b == 0 ? 'A' : b == 1 ? 'C' : b == 2 ? 'T' : 'G';
         outc[d - 1 - dT] = up ? ch : (char)(ch | 0x20);
       }

@@ -494,7 +494,7 @@ static int run_pass(g2s_engine *e, Pass &p) {
   CUDA_TRY(cudaEventElapsedTime(&ms, e->ev[0], e->ev[1]));
   e->tm.kernel_ms += ms;
   if (p.tier == 0) { e->tm.kernel_ms_thin += ms; e->tm.launches_thin++; e->tm.thin_shape = (uint32_t)p.shape; }
-  else { e->tm.kernel_ms_wide += ms; e->tm.launches_wide++; }
+  else { e->tm.kernel_ms_wide += ms; e->tm.launches_wide++; e->tm.wide_cluster = (uint32_t)p.cluster; }
   if (getenv("G2S_HOST_PROF"))
     fprintf(stderr, "g2s: pass tier %d (shape %d, cluster %d): %zu gaps on %d groups, slice %.1f MB, %.3f ms\n", p.tier, p.shape,
             p.cluster, p.order.size(), p.groups, p.lay.bytes / 1e6, ms);
@@ -661,7 +661,7 @@ static int do_run(g2s_engine *e) {
   e->tm.kernel_ms = 0; e->tm.launches = 0; e->tm.gaps_big_tier = 0; e->tm.d2h_bytes = 0; e->tm.d2h_ms = 0; e->tm.host_ms = 0;
   e->tm.max_tier_run = 0; e->tm.gaps_rerun_scratch = 0; e->tm.gaps_rerun_out_full = 0; e->tm.gaps_mem_limit = 0;
   e->tm.table_lookups = 0; e->tm.node_ops = 0;
-  e->tm.kernel_ms_thin = 0; e->tm.kernel_ms_wide = 0; e->tm.launches_thin = 0; e->tm.launches_wide = 0; e->tm.thin_shape = 0;
+  e->tm.kernel_ms_thin = 0; e->tm.kernel_ms_wide = 0; e->tm.launches_thin = 0; e->tm.launches_wide = 0; e->tm.thin_shape = 0; e->tm.wide_cluster = 0;
   e->tm.cells_thin = 0; e->tm.cells_wide = 0; e->tm.kernel_ms_chain = 0; e->tm.launches_chain = 0; e->tm.gaps_chain = 0; e->tm.cells_chain = 0;
   e->out_pass.assign(n, -1);
   if (n == 0) { e->ran = true; return G2S_OK; }
@@ -953,7 +953,7 @@ static int run_wave(g2s_engine *e, const g2s_gap *gaps, size_t n, HostBatch &hb,
     t.gaps_rerun_out_full += x.gaps_rerun_out_full; t.gaps_mem_limit += x.gaps_mem_limit;
     t.table_lookups += x.table_lookups; t.node_ops += x.node_ops;
     t.kernel_ms_thin = std::max(t.kernel_ms_thin, x.kernel_ms_thin); t.kernel_ms_wide = std::max(t.kernel_ms_wide, x.kernel_ms_wide);
-    t.launches_thin += x.launches_thin; t.launches_wide += x.launches_wide; t.thin_shape = std::max(t.thin_shape, x.thin_shape);
+    t.launches_thin += x.launches_thin; t.launches_wide += x.launches_wide; t.thin_shape = std::max(t.thin_shape, x.thin_shape); t.wide_cluster = std::max(t.wide_cluster, x.wide_cluster);
     t.cells_thin += x.cells_thin; t.cells_wide += x.cells_wide; t.cells_chain += x.cells_chain; t.gaps_chain += x.gaps_chain;
     t.kernel_ms_chain = std::max(t.kernel_ms_chain, x.kernel_ms_chain); t.launches_chain += x.launches_chain;
     if (getenv("G2S_HOST_PROF"))
@@ -1047,7 +1047,7 @@ static int fill_records_impl(g2s_engine *e, const char *const *seqs, const char 
     total.gaps_mem_limit += e->tm.gaps_mem_limit;
     total.table_lookups += e->tm.table_lookups; total.node_ops += e->tm.node_ops;
     total.kernel_ms_thin += e->tm.kernel_ms_thin; total.kernel_ms_wide += e->tm.kernel_ms_wide;
-    total.launches_thin += e->tm.launches_thin; total.launches_wide += e->tm.launches_wide; total.thin_shape = e->tm.thin_shape;
+    total.launches_thin += e->tm.launches_thin; total.launches_wide += e->tm.launches_wide; total.thin_shape = e->tm.thin_shape; total.wide_cluster = std::max(total.wide_cluster, e->tm.wide_cluster);
     total.cells_thin += e->tm.cells_thin; total.cells_wide += e->tm.cells_wide; total.cells_chain += e->tm.cells_chain;
     total.gaps_chain += e->tm.gaps_chain; total.kernel_ms_chain += e->tm.kernel_ms_chain; total.launches_chain += e->tm.launches_chain;
     return rc;

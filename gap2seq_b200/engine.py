@@ -61,7 +61,7 @@ class G2STiming(C.Structure):
                 ("gaps_rerun_out_full", C.c_uint32), ("gaps_mem_limit", C.c_uint32),
                 ("table_lookups", C.c_uint64), ("node_ops", C.c_uint64),
                 ("kernel_ms_thin", C.c_double), ("kernel_ms_wide", C.c_double), ("launches_thin", C.c_uint32),
-                ("launches_wide", C.c_uint32), ("thin_shape", C.c_uint32), ("reserved", C.c_uint32),
+                ("launches_wide", C.c_uint32), ("thin_shape", C.c_uint32), ("wide_cluster", C.c_uint32),
                 ("cells_thin", C.c_uint64), ("cells_wide", C.c_uint64), ("kernel_ms_chain", C.c_double),
                 ("launches_chain", C.c_uint32), ("gaps_chain", C.c_uint32), ("cells_chain", C.c_uint64)]
 

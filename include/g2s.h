@@ -124,7 +124,7 @@ typedef struct g2s_timing {
      wide tiers (k_fill_cta, one CTA per gap) */
   double kernel_ms_thin, kernel_ms_wide;
   uint32_t launches_thin, launches_wide;
-  uint32_t thin_shape, reserved;
+  uint32_t thin_shape, wide_cluster;            /* wide tiers: CTAs per gap of the last pass (1: k_fill_cta, 2-8: k_fill_cluster) */
   uint64_t cells_thin, cells_wide;              /* DP cells (right + forward) of the gaps each of them finished */
   /* the chain tier (k_chain_walk + k_chain_finish): gaps whose borders never exceed one state are finished there
      without per-gap scratch tables; every other gap goes on to the thin tier */
