@@ -260,26 +260,30 @@ G2S_D void chain_finish(const ChainParams &P, const GapDev &gd, const uint64_t *
     if (cw < pf) top = cw;                    // the chain ended (dead end or branch) before the first pruned level
     else {
       const uint64_t fp = str_kmer(WF, (uint32_t)pf, k), want = revcomp(fp, k);   // the right string holds reverse complements
+      // what follows R[0] on the forward chain, if anything: its one successor (several: each would need its own test)
+      const uint32_t fwd0 = (wr.end_mask >> 24) & 15u;
+      const bool has_next = fwd0 != 0 && !(fwd0 & (fwd0 - 1));
+      const uint64_t nxt = has_next ? succ_kmer(revcomp(str_kmer(WR, 0, k), k), fwd0 == 1 ? 0 : fwd0 == 2 ? 1 : fwd0 == 4 ? 2 : 3, T) : 0;
+      const uint64_t rnxt = revcomp(nxt, k);
       int i0 = NONE;
-      bool flipped = false;
-      for (int i = rank; i < nR; i += gsz) {
+      bool flipped = false, next_inside = false;
+      for (int i = rank; i < nR; i += gsz) {     // ONE pass over the right chain answers all three questions
         const uint64_t y = str_kmer(WR, (uint32_t)i, k);
         if (y == want) { i0 = i < i0 ? i : i0; }
-        if (y == fp) flipped = true;           // the node is in the right set on its other strand: not a chain to read off
+        if (y == fp) flipped = true;             // the node is in the right set on its other strand: not a chain to read off
+        if (has_next && (y == nxt || y == rnxt)) next_inside = true;
       }
       i0 = G::min_i32(i0);
       if (G::any(flipped)) fb = true;
-      if (i0 == NONE) top = pf - 1;            // not in the right set: the border dies on level pf
+      next_inside = G::any(next_inside);
+      if (i0 == NONE) top = pf - 1;              // not in the right set: the border dies on level pf
       else {
-        if ((uint32_t)i0 > wr.ok_upto) fb = true;      // a node on the way to R[0] has a second successor
+        if ((uint32_t)i0 > wr.ok_upto) fb = true;        // a node on the way to R[0] has a second successor
         L = pf + i0;
         top = L;
-        const uint32_t fwd0 = (wr.end_mask >> 24) & 15u;   // successors of R[0]
-        if (fwd0 & (fwd0 - 1)) fb = true;                  // several: each would need its own test
-        else if (fwd0) {
-          const uint32_t nt = fwd0 == 1 ? 0 : fwd0 == 2 ? 1 : fwd0 == 4 ? 2 : 3;
-          const uint64_t nxt = succ_kmer(revcomp(str_kmer(WR, 0, k), k), nt, T);
-          if (chain_member<G>(WR, nR, nxt, k)) fb = true;  // the chain would go on inside the right set
+        if (L < g + e + lmf + rmf) {                     // a level behind L exists (L < Dmax)
+          if (fwd0 & (fwd0 - 1)) fb = true;
+          else if (next_inside) fb = true;               // the chain would go on inside the right set
         }
       }
     }
