@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(WALK_THREADS) k_chain_walk(const __grid_consta
 }
 
 __global__ void __launch_bounds__(32 * FINISH_WARPS) k_chain_finish(const __grid_constant__ ChainParams P) {
-  __shared__ uint64_t tk[FINISH_WARPS][3 * (MAX_FUZ + 1)];
+  __shared__ uint64_t tk[FINISH_WARPS][4 * (MAX_FUZ + 1)];
   const uint32_t q = blockIdx.x * FINISH_WARPS + (threadIdx.x >> 5);
   if (q >= P.n_gaps) return;
   const uint32_t gi = P.order[q];

@@ -99,6 +99,21 @@ G2S_D uint64_t str_kmer(const uint64_t *W, uint32_t p, int k) {   // bases p .. 
 }
 G2S_D uint32_t str_base(const uint64_t *W, uint32_t p) { return (uint32_t)(ld_ro(&W[p >> 5]) >> (62 - 2 * (p & 31))) & 3u; }
 
+// The k-mers of 8 consecutive positions p0 .. p0 + 7 (p0 a multiple of 8) from two words and shifts by constants: the level
+// loops of the finish take their levels in such chunks (a third of the instructions of eight separate extractions).
+struct Chunk8 { uint64_t a, b; };   // the 64 bits at base p0, and the bits behind them
+G2S_D Chunk8 str_chunk(const uint64_t *W, uint32_t p0) {
+  const uint32_t q = p0 >> 5, s = 2 * (p0 & 31);
+  const uint64_t hi = ld_ro(&W[q]), lo = ld_ro(&W[q + 1]);
+  Chunk8 c;
+  c.a = s ? (hi << s) | (lo >> (64 - s)) : hi;
+  c.b = s ? lo << s : lo;
+  return c;
+}
+G2S_D uint64_t chunk_kmer(const Chunk8 &c, int i, int k) {   // i in 0..7; constant after unrolling
+  return (i ? (c.a << (2 * i)) | (c.b >> (64 - 2 * i)) : c.a) >> (64 - 2 * k);
+}
+
 // ------------------------------------------------------------------------------------------------ the walk
 // The walk's lookup: the home slot and its neighbour are requested together, so that a key one probe away from home
 // (a third of them at the table's load) does not cost a second dependent round trip.
@@ -186,8 +201,9 @@ G2S_D void chain_walk(const Table &T, uint64_t x0, int maxlev, uint64_t *W, Chai
 // ------------------------------------------------------------------------------------------------ the finish
 // G: the thread group of one gap (a warp on the device, one thread in the host emulation) with
 //    rank(), size(), any(bool), min_i32(int), max_i32(int), add_u32(uint32_t), bcast_u64(v) (rank 0's value).
-// tk: group-shared scratch of 3 * (MAX_FUZ + 1) words: the flank k-mers, parsed once - [j] right-flank target j,
-//     [32 + d] left start of level d, [64 + o] right start at offset o of the start string.
+// tk: group-shared scratch of 4 * (MAX_FUZ + 1) words: the flank k-mers, parsed once - [j] right-flank target j,
+//     [32 + d] left start of level d, [64 + o] right start at offset o of the start string, [96 + j] reverse complement of
+//     target j (what a target looks like in the right chain's string).
 
 // is x a node of the right chain (either strand)?
 template <class G>
@@ -214,9 +230,9 @@ G2S_D void chain_finish(const ChainParams &P, const GapDev &gd, const uint64_t *
   const int nF = (int)wf.n, nR = (int)wr.n, cw = nF - 1;
   const int NONE = 0x7fffffff;
 
-  uint64_t *lkk = tk + (MAX_FUZ + 1), *rsk = tk + 2 * (MAX_FUZ + 1);
+  uint64_t *lkk = tk + (MAX_FUZ + 1), *rsk = tk + 2 * (MAX_FUZ + 1), *rtk = tk + 3 * (MAX_FUZ + 1);
   for (int j = rank; j <= MAX_FUZ; j += gsz) {
-    if (j <= rmf) { tk[j] = kmer_from_ascii(rstr + j, k); rsk[j] = kmer_from_ascii(rsstr + j, k); }
+    if (j <= rmf) { tk[j] = kmer_from_ascii(rstr + j, k); rsk[j] = kmer_from_ascii(rsstr + j, k); rtk[j] = revcomp(tk[j], k); }
     if (j <= lmf) lkk[j] = kmer_from_ascii(lstr + j, k);
   }
   G::sync();
@@ -267,11 +283,17 @@ G2S_D void chain_finish(const ChainParams &P, const GapDev &gd, const uint64_t *
       const uint64_t rnxt = revcomp(nxt, k);
       int i0 = NONE;
       bool flipped = false, next_inside = false;
-      for (int i = rank; i < nR; i += gsz) {     // ONE pass over the right chain answers all three questions
-        const uint64_t y = str_kmer(WR, (uint32_t)i, k);
-        if (y == want) { i0 = i < i0 ? i : i0; }
-        if (y == fp) flipped = true;             // the node is in the right set on its other strand: not a chain to read off
-        if (has_next && (y == nxt || y == rnxt)) next_inside = true;
+      for (int base = rank * 8; base < nR; base += gsz * 8) {   // ONE pass over the right chain answers all three questions
+        const Chunk8 ch = str_chunk(WR, (uint32_t)base);
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+          const int i = base + u;
+          if (i >= nR) break;
+          const uint64_t y = chunk_kmer(ch, u, k);
+          if (y == want) { i0 = i < i0 ? i : i0; }
+          if (y == fp) flipped = true;           // the node is in the right set on its other strand: not a chain to read off
+          if (has_next && (y == nxt || y == rnxt)) next_inside = true;
+        }
       }
       i0 = G::min_i32(i0);
       if (G::any(flipped)) fb = true;
@@ -306,23 +328,50 @@ G2S_D void chain_finish(const ChainParams &P, const GapDev &gd, const uint64_t *
   uint32_t n_sink = 0;
   int min_sink = NONE, sB = -1;
   if (!fb) {
-    const uint64_t Ftop = f_at(top), rcFtop = revcomp(Ftop, k), rcF0 = revcomp(str_kmer(WF, 0, k), k);
+    const uint64_t F0 = str_kmer(WF, 0, k), Ftop = f_at(top), rcFtop = revcomp(Ftop, k), rcF0 = revcomp(F0, k);
     const int jt = rmf - 1, dlo = lmf + g - e > 0 ? lmf + g - e : 0;
     bool rep = false;
     // a level can hit a target only within e of the target's nominal level (and seeds start at dlo >= that bound); a
     // 64-bit signature of the targets spares most of those levels the rmf + 1 comparisons
     const int hit_lo = g + lmf - e > 0 ? g + lmf - e : 0;
-    uint64_t sig = 0;
-    for (int j = 0; j <= rmf; j++) sig |= 1ULL << ((ld_sh(&tk[j]) * 0x9E3779B97F4A7C15ULL) >> 58);
-    for (int c = rank; c <= top; c += gsz) {
-      const uint64_t x = f_at(c);
-      if ((c < top && x == Ftop) || x == rcFtop || x == rcF0) rep = true;
-      if (c < hit_lo || !((sig >> ((x * 0x9E3779B97F4A7C15ULL) >> 58)) & 1)) continue;
-      for (int j = 0; j <= rmf; j++) {
-        if (x != ld_sh(&tk[j])) continue;
-        const int err = c > g + lmf + j ? c - (g + lmf + j) : g + lmf + j - c;
-        if (err <= e) { const uint32_t key = ((uint32_t)err << 6) | (uint32_t)j; best = key < best ? key : best; }
-        if (j == jt && c >= dlo) { n_sink++; min_sink = c < min_sink ? c : min_sink; sB = c > sB ? c : sB; }
+    uint64_t sig = 0, rsig = 0;
+    for (int j = 0; j <= rmf; j++) {
+      sig |= 1ULL << ((ld_sh(&tk[j]) * 0x9E3779B97F4A7C15ULL) >> 58);
+      rsig |= 1ULL << ((ld_sh(&rtk[j]) * 0x9E3779B97F4A7C15ULL) >> 58);
+    }
+    auto hit = [&](int c, int j) {
+      const int err = c > g + lmf + j ? c - (g + lmf + j) : g + lmf + j - c;
+      if (err <= e) { const uint32_t key = ((uint32_t)err << 6) | (uint32_t)j; best = key < best ? key : best; }
+      if (j == jt && c >= dlo) { n_sink++; min_sink = c < min_sink ? c : min_sink; sB = c > sB ? c : sB; }
+    };
+    // levels 0 .. min(top, cw): the forward string
+    const int hiF = top < cw ? top : cw;
+    for (int base = rank * 8; base <= hiF; base += gsz * 8) {
+      const Chunk8 ch = str_chunk(WF, (uint32_t)base);
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        const int c = base + u;
+        if (c > hiF) break;
+        const uint64_t x = chunk_kmer(ch, u, k);
+        if ((c < top && x == Ftop) || x == rcFtop || x == rcF0) rep = true;
+        if (c < hit_lo || !((sig >> ((x * 0x9E3779B97F4A7C15ULL) >> 58)) & 1)) continue;
+        for (int j = 0; j <= rmf; j++) if (x == ld_sh(&tk[j])) hit(c, j);
+      }
+    }
+    // levels cw + 1 .. top: states R[L - c], read from the right string, whose k-mers are reverse complements - so the
+    // constants are turned over instead of every state
+    const int hiR = L == NONE ? -1 : L - cw - 1;          // right-chain indices 0 .. hiR <-> levels L .. cw + 1
+    for (int base = rank * 8; base <= hiR; base += gsz * 8) {
+      const Chunk8 ch = str_chunk(WR, (uint32_t)base);
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        const int i = base + u;
+        if (i > hiR) break;
+        const int c = L - i;
+        const uint64_t y = chunk_kmer(ch, u, k);           // = rc(F[c])
+        if ((c < top && y == rcFtop) || y == Ftop || y == F0) rep = true;
+        if (c < hit_lo || !((rsig >> ((y * 0x9E3779B97F4A7C15ULL) >> 58)) & 1)) continue;
+        for (int j = 0; j <= rmf; j++) if (y == ld_sh(&rtk[j])) hit(c, j);
       }
     }
     if (G::any(rep)) fb = true;
@@ -379,7 +428,7 @@ G2S_D void chain_finish(const ChainParams &P, const GapDev &gd, const uint64_t *
   // levels below a safe vertex or the path's end
   unsigned long long fill_off = 0;
   if (!fb && found) {
-    const unsigned long long need = (unsigned long long)(d0 - dT) + 1;
+    const unsigned long long need = ((unsigned long long)(d0 - dT) + 1 + 7) & ~7ULL;   // multiples of 8: aligned 8-byte stores
     unsigned long long off = 0;
     if (rank == 0) off = a_add64(P.fill_cursor, need);
     off = G::bcast_u64(off);
@@ -392,14 +441,22 @@ G2S_D void chain_finish(const ChainParams &P, const GapDev &gd, const uint64_t *
       // safe whenever seeds exist.  So the unsafe levels are exactly uLo .. sB, and a base is lower case iff the k levels
       // from its own upwards all lie in there.
       const int uLo = n_sink == 0 ? 0 : (dS > min_sink + 1 ? dS : min_sink + 1);
-      for (int d = dT + 1 + rank; d <= d0; d += gsz) {
-        const int wend = d + k - 1 < d0 ? d + k - 1 : d0;
-        const bool up = d0 - d < k || skip_confident || (n_sink > 0 && !(d >= uLo && wend <= sB));
-        const uint32_t b = f_base(d);
-        const char ch = b == 0 ? 'A' : b == 1 ? 'C' : b == 2 ? 'T' : 'G';
-        outc[d - 1 - dT] = up ? ch : (char)(ch | 0x20);
+      const int flen = d0 - dT;
+      for (int o0 = rank * 8; o0 <= flen; o0 += gsz * 8) {   // position flen holds the terminating NUL
+        uint64_t word = 0;
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+          const int o = o0 + u;
+          if (o >= flen) break;
+          const int d = dT + 1 + o;
+          const int wend = d + k - 1 < d0 ? d + k - 1 : d0;
+          const bool up = d0 - d < k || skip_confident || (n_sink > 0 && !(d >= uLo && wend <= sB));
+          const uint32_t b = f_base(d);
+          const uint32_t ch = (b == 0 ? 'A' : b == 1 ? 'C' : b == 2 ? 'T' : 'G') | (up ? 0u : 0x20u);
+          word |= (uint64_t)ch << (8 * u);
+        }
+        *(uint64_t *)(outc + o0) = word;
       }
-      if (rank == 0) outc[d0 - dT] = 0;
     }
   }
 

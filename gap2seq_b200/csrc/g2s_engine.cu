@@ -521,7 +521,7 @@ static int run_chain_pass(g2s_engine *e, Pass &p) {
   if ((size_t)p.pack_slot >= e->d_pack.size()) e->d_pack.resize(p.pack_slot + 1);
   if ((size_t)p.pack_slot >= e->d_fill.size()) e->d_fill.resize(p.pack_slot + 1);
   p.fill_cap = 0;
-  for (uint32_t gi : p.order) p.fill_cap += (unsigned long long)dmax_of(e->gaps[gi]) + 2;
+  for (uint32_t gi : p.order) p.fill_cap += (unsigned long long)dmax_of(e->gaps[gi]) + 16;   // the tier allocates fills in multiples of 8 bytes
   CUDA_TRY(e->d_fill[p.pack_slot].reserve((size_t)p.fill_cap + 16));
   CUDA_TRY(e->d_order.reserve(p.order.size() * 4));
   CUDA_TRY(cudaMemcpyAsync(e->d_order.p, p.order.data(), p.order.size() * 4, cudaMemcpyHostToDevice, e->st));

@@ -127,12 +127,12 @@ static int emul_submit(EmulGraph *g, int k, const g2s_gap *gaps, size_t n, HostB
       CP.f_words = chain_words(k, dmax); CP.r_words = chain_words(k, right_half);
       std::vector<uint64_t> strs((size_t)CP.f_words + CP.r_words, 0xDEADBEEFDEADBEEFULL);
       ChainWalk walks[2];
-      std::vector<char> fills((size_t)dmax + 8);
+      std::vector<char> fills((size_t)dmax + 24);
       unsigned long long fcursor = 0;
       CP.strs = strs.data(); CP.walks = walks; CP.fills = fills.data(); CP.fill_cap = fills.size(); CP.fill_cursor = &fcursor;
       chain_walk(g->t, kmer_from_ascii(flanks.data() + gd.flank_off, k), gg.gap_len / 2 + gg.gap_err / 2 + gg.left_max_fuz, strs.data(), &walks[0], false);
       chain_walk(g->t, revcomp(kmer_from_ascii(flanks.data() + gd.rstart_off + gd.rmf, k), k), right_half, strs.data() + CP.f_words, &walks[1], true);
-      uint64_t tk[3 * (MAX_FUZ + 1)];
+      uint64_t tk[4 * (MAX_FUZ + 1)];
       chain_finish<EmulGroup>(CP, gd, strs.data(), strs.data() + CP.f_words, walks[0], walks[1], tk, &out);
       if (out.status & GS_INTERNAL) return -100;
       if (!(out.status & GS_NOT_CHAIN)) {
