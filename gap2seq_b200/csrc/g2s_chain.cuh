@@ -99,33 +99,28 @@ G2S_D uint64_t str_kmer(const uint64_t *W, uint32_t p, int k) {   // bases p .. 
 }
 G2S_D uint32_t str_base(const uint64_t *W, uint32_t p) { return (uint32_t)(ld_ro(&W[p >> 5]) >> (62 - 2 * (p & 31))) & 3u; }
 
-// The k-mers of 8 consecutive positions p0 .. p0 + 7 (p0 a multiple of 8) from two words and shifts by constants: the level
-// loops of the finish take their levels in such chunks (a third of the instructions of eight separate extractions).
-struct Chunk8 { uint64_t a, b; };   // the 64 bits at base p0, and the bits behind them
-G2S_D Chunk8 str_chunk(const uint64_t *W, uint32_t p0) {
-  const uint32_t q = p0 >> 5, s = 2 * (p0 & 31);
-  const uint64_t hi = ld_ro(&W[q]), lo = ld_ro(&W[q + 1]);
-  Chunk8 c;
-  c.a = s ? (hi << s) | (lo >> (64 - s)) : hi;
-  c.b = s ? lo << s : lo;
-  return c;
-}
-G2S_D uint64_t chunk_kmer(const Chunk8 &c, int i, int k) {   // i in 0..7; constant after unrolling
-  return (i ? (c.a << (2 * i)) | (c.b >> (64 - 2 * i)) : c.a) >> (64 - 2 * k);
-}
-
 // ------------------------------------------------------------------------------------------------ the walk
 // The walk's lookup: the home slot and its neighbour are requested together, so that a key one probe away from home
 // (a third of them at the table's load) does not cost a second dependent round trip.
-G2S_D bool chain_find_slot(const Table &t, uint64_t canon, Slot *out) {
+struct ChainProbe {     // the two requests of a lookup in flight
+  uint64_t h, h1, ak, av, a0, a1, bk, bv, b0, b1;
+};
+G2S_D void chain_probe_issue(const Table &t, uint64_t canon, ChainProbe &p) {
+  p.h = mix64(canon) & t.cap_mask;
+  p.h1 = (p.h + 1) & t.cap_mask;
 #ifdef __CUDA_ARCH__
-  uint64_t h = mix64(canon) & t.cap_mask;
-  const uint64_t h1 = (h + 1) & t.cap_mask;
-  uint64_t ak, av, a0, a1, bk, bv, b0, b1;
   // one statement: both requests leave before either result is looked at
   asm volatile("ld.global.nc.v4.u64 {%0, %1, %2, %3}, [%8];\n\tld.global.nc.v4.u64 {%4, %5, %6, %7}, [%9];"
-               : "=l"(ak), "=l"(av), "=l"(a0), "=l"(a1), "=l"(bk), "=l"(bv), "=l"(b0), "=l"(b1)
-               : "l"(t.slots + h), "l"(t.slots + h1));
+               : "=l"(p.ak), "=l"(p.av), "=l"(p.a0), "=l"(p.a1), "=l"(p.bk), "=l"(p.bv), "=l"(p.b0), "=l"(p.b1)
+               : "l"(t.slots + p.h), "l"(t.slots + p.h1));
+#else
+  const Slot a = t.slots[p.h], b = t.slots[p.h1];
+  p.ak = a.key; p.av = a.val; p.a0 = a.h[0]; p.a1 = a.h[1];
+  p.bk = b.key; p.bv = b.val; p.b0 = b.h[0]; p.b1 = b.h[1];
+#endif
+}
+G2S_D bool chain_probe_resolve(const Table &t, uint64_t canon, const ChainProbe &p, Slot *out) {
+#ifdef __CUDA_ARCH__
   // straight-line selects: the compiler must not sink the second request behind a test of the first result
   uint64_t sv, s0, s1;
   unsigned hit;
@@ -136,19 +131,25 @@ G2S_D bool chain_find_slot(const Table &t, uint64_t canon, Slot *out) {
                "selp.b64 %2, %12, %13, pa;\n\t"
                "or.pred pa, pa, pb;\n\tselp.u32 %3, 1, 0, pa;\n\t}"
                : "=l"(sv), "=l"(s0), "=l"(s1), "=r"(hit)
-               : "l"(ak), "l"(av), "l"(a0), "l"(bk), "l"(bv), "l"(b0), "l"(canon), "l"(KEY_EMPTY), "l"(a1), "l"(b1));
+               : "l"(p.ak), "l"(p.av), "l"(p.a0), "l"(p.bk), "l"(p.bv), "l"(p.b0), "l"(canon), "l"(KEY_EMPTY), "l"(p.a1), "l"(p.b1));
   if (hit) { out->key = canon; out->val = sv; out->h[0] = s0; out->h[1] = s1; return true; }
-  if (ak == KEY_EMPTY || bk == KEY_EMPTY) return false;
-  h = (h1 + 1) & t.cap_mask;
+#else
+  if (p.ak == canon) { out->key = canon; out->val = p.av; out->h[0] = p.a0; out->h[1] = p.a1; return true; }
+  if (p.ak != KEY_EMPTY && p.bk == canon) { out->key = canon; out->val = p.bv; out->h[0] = p.b0; out->h[1] = p.b1; return true; }
+#endif
+  if (p.ak == KEY_EMPTY || p.bk == KEY_EMPTY) return false;
+  uint64_t h = (p.h1 + 1) & t.cap_mask;
   for (;;) {
-    asm volatile("ld.global.nc.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(ak), "=l"(av), "=l"(a0), "=l"(a1) : "l"(t.slots + h));
-    if (ak == canon) { out->key = canon; out->val = av; out->h[0] = a0; out->h[1] = a1; return true; }
-    if (ak == KEY_EMPTY) return false;
+    const Slot s = load_slot32(t.slots + h);
+    if (s.key == canon) { *out = s; return true; }
+    if (s.key == KEY_EMPTY) return false;
     h = (h + 1) & t.cap_mask;
   }
-#else
-  return table_find_slot(t, canon, out) >= 0;
-#endif
+}
+G2S_D bool chain_find_slot(const Table &t, uint64_t canon, Slot *out) {
+  ChainProbe p;
+  chain_probe_issue(t, canon, p);
+  return chain_probe_resolve(t, canon, p, out);
 }
 
 // One chain of dependent gathers: from x0 (walk orientation) along unique successors for at most `maxlev` levels.
@@ -177,15 +178,18 @@ G2S_D void chain_walk(const Table &T, uint64_t x0, int maxlev, uint64_t *W, Chai
     if (h.len == 0) { h.lo = mask == 1 ? 0 : mask == 2 ? 1 : mask == 4 ? 2 : 3; h.hi = 0; h.len = 1; }   // a table without hints
     const uint32_t j = h.len < (uint32_t)(maxlev - lev) ? h.len : (uint32_t)(maxlev - lev);
     const uint32_t sh = 2 * (h.len - j);                 // the first j bases = bases >> sh
-    if (2 * j > 64) bw.put(sh < 16 ? (uint64_t)(h.hi >> sh) : 0, 2 * j - 64);
-    bw.put(hint_shr(h, sh), 2 * j > 64 ? 64u : 2 * j);
+    // the next lookup leaves first: writing this segment's bases overlaps its latency
     x = hint_state(x, h, j, T.kmask);
     lev += (int)j;
     const bool last = lev >= maxlev;
-    if (last && !backcheck) break;
-    c = canonical(x, k);
+    const bool look = !last || backcheck;
+    ChainProbe pr;
+    if (look) { c = canonical(x, k); chain_probe_issue(T, c.key, pr); }
+    if (2 * j > 64) bw.put(sh < 16 ? (uint64_t)(h.hi >> sh) : 0, 2 * j - 64);
+    bw.put(hint_shr(h, sh), 2 * j > 64 ? 64u : 2 * j);
+    if (!look) break;
     r.lookups++;
-    if (!chain_find_slot(T, c.key, &sl)) { endm = CHAIN_END_INTERNAL; break; }
+    if (!chain_probe_resolve(T, c.key, pr, &sl)) { endm = CHAIN_END_INTERNAL; break; }
     if (backcheck) {
       if (ok && hint_of(sl, c.strand ^ 1u).len >= j) r.ok_upto = (uint32_t)lev;
       else ok = false;
@@ -283,17 +287,11 @@ G2S_D void chain_finish(const ChainParams &P, const GapDev &gd, const uint64_t *
       const uint64_t rnxt = revcomp(nxt, k);
       int i0 = NONE;
       bool flipped = false, next_inside = false;
-      for (int base = rank * 8; base < nR; base += gsz * 8) {   // ONE pass over the right chain answers all three questions
-        const Chunk8 ch = str_chunk(WR, (uint32_t)base);
-#pragma unroll
-        for (int u = 0; u < 8; u++) {
-          const int i = base + u;
-          if (i >= nR) break;
-          const uint64_t y = chunk_kmer(ch, u, k);
-          if (y == want) { i0 = i < i0 ? i : i0; }
-          if (y == fp) flipped = true;           // the node is in the right set on its other strand: not a chain to read off
-          if (has_next && (y == nxt || y == rnxt)) next_inside = true;
-        }
+      for (int i = rank; i < nR; i += gsz) {     // ONE pass over the right chain answers all three questions
+        const uint64_t y = str_kmer(WR, (uint32_t)i, k);
+        if (y == want) { i0 = i < i0 ? i : i0; }
+        if (y == fp) flipped = true;             // the node is in the right set on its other strand: not a chain to read off
+        if (has_next && (y == nxt || y == rnxt)) next_inside = true;
       }
       i0 = G::min_i32(i0);
       if (G::any(flipped)) fb = true;
@@ -339,39 +337,22 @@ G2S_D void chain_finish(const ChainParams &P, const GapDev &gd, const uint64_t *
       sig |= 1ULL << ((ld_sh(&tk[j]) * 0x9E3779B97F4A7C15ULL) >> 58);
       rsig |= 1ULL << ((ld_sh(&rtk[j]) * 0x9E3779B97F4A7C15ULL) >> 58);
     }
-    auto hit = [&](int c, int j) {
-      const int err = c > g + lmf + j ? c - (g + lmf + j) : g + lmf + j - c;
-      if (err <= e) { const uint32_t key = ((uint32_t)err << 6) | (uint32_t)j; best = key < best ? key : best; }
-      if (j == jt && c >= dlo) { n_sink++; min_sink = c < min_sink ? c : min_sink; sB = c > sB ? c : sB; }
-    };
-    // levels 0 .. min(top, cw): the forward string
+    // levels 0 .. min(top, cw) come from the forward string; levels cw + 1 .. top are the states R[L - c], read from the
+    // right string, whose k-mers are reverse complements - there the constants are turned over instead of every state.
+    // One loop over both ranges: lane steps of 32 levels, a level is 2 loads, a funnel shift and a handful of compares.
     const int hiF = top < cw ? top : cw;
-    for (int base = rank * 8; base <= hiF; base += gsz * 8) {
-      const Chunk8 ch = str_chunk(WF, (uint32_t)base);
-#pragma unroll
-      for (int u = 0; u < 8; u++) {
-        const int c = base + u;
-        if (c > hiF) break;
-        const uint64_t x = chunk_kmer(ch, u, k);
-        if ((c < top && x == Ftop) || x == rcFtop || x == rcF0) rep = true;
-        if (c < hit_lo || !((sig >> ((x * 0x9E3779B97F4A7C15ULL) >> 58)) & 1)) continue;
-        for (int j = 0; j <= rmf; j++) if (x == ld_sh(&tk[j])) hit(c, j);
-      }
-    }
-    // levels cw + 1 .. top: states R[L - c], read from the right string, whose k-mers are reverse complements - so the
-    // constants are turned over instead of every state
-    const int hiR = L == NONE ? -1 : L - cw - 1;          // right-chain indices 0 .. hiR <-> levels L .. cw + 1
-    for (int base = rank * 8; base <= hiR; base += gsz * 8) {
-      const Chunk8 ch = str_chunk(WR, (uint32_t)base);
-#pragma unroll
-      for (int u = 0; u < 8; u++) {
-        const int i = base + u;
-        if (i > hiR) break;
-        const int c = L - i;
-        const uint64_t y = chunk_kmer(ch, u, k);           // = rc(F[c])
-        if ((c < top && y == rcFtop) || y == Ftop || y == F0) rep = true;
-        if (c < hit_lo || !((rsig >> ((y * 0x9E3779B97F4A7C15ULL) >> 58)) & 1)) continue;
-        for (int j = 0; j <= rmf; j++) if (y == ld_sh(&rtk[j])) hit(c, j);
+    const uint64_t c_top = Ftop, c_rtop = rcFtop, c_rf0 = rcF0;
+    for (int c = rank; c <= top; c += gsz) {
+      const bool fwd = c <= hiF;
+      const uint64_t x = fwd ? str_kmer(WF, (uint32_t)c, k) : str_kmer(WR, (uint32_t)(L - c), k);   // fwd: F[c], else rc(F[c])
+      if (fwd ? ((c < top && x == c_top) || x == c_rtop || x == c_rf0) : ((c < top && x == c_rtop) || x == c_top || x == F0)) rep = true;
+      if (c < hit_lo || !(((fwd ? sig : rsig) >> ((x * 0x9E3779B97F4A7C15ULL) >> 58)) & 1)) continue;
+      const uint64_t *tt = fwd ? tk : rtk;
+      for (int j = 0; j <= rmf; j++) {
+        if (x != ld_sh(&tt[j])) continue;
+        const int err = c > g + lmf + j ? c - (g + lmf + j) : g + lmf + j - c;
+        if (err <= e) { const uint32_t key = ((uint32_t)err << 6) | (uint32_t)j; best = key < best ? key : best; }
+        if (j == jt && c >= dlo) { n_sink++; min_sink = c < min_sink ? c : min_sink; sB = c > sB ? c : sB; }
       }
     }
     if (G::any(rep)) fb = true;
@@ -441,22 +422,14 @@ G2S_D void chain_finish(const ChainParams &P, const GapDev &gd, const uint64_t *
       // safe whenever seeds exist.  So the unsafe levels are exactly uLo .. sB, and a base is lower case iff the k levels
       // from its own upwards all lie in there.
       const int uLo = n_sink == 0 ? 0 : (dS > min_sink + 1 ? dS : min_sink + 1);
-      const int flen = d0 - dT;
-      for (int o0 = rank * 8; o0 <= flen; o0 += gsz * 8) {   // position flen holds the terminating NUL
-        uint64_t word = 0;
-#pragma unroll
-        for (int u = 0; u < 8; u++) {
-          const int o = o0 + u;
-          if (o >= flen) break;
-          const int d = dT + 1 + o;
-          const int wend = d + k - 1 < d0 ? d + k - 1 : d0;
-          const bool up = d0 - d < k || skip_confident || (n_sink > 0 && !(d >= uLo && wend <= sB));
-          const uint32_t b = f_base(d);
-          const uint32_t ch = (b == 0 ? 'A' : b == 1 ? 'C' : b == 2 ? 'T' : 'G') | (up ? 0u : 0x20u);
-          word |= (uint64_t)ch << (8 * u);
-        }
-        *(uint64_t *)(outc + o0) = word;
+      for (int d = dT + 1 + rank; d <= d0; d += gsz) {
+        const int wend = d + k - 1 < d0 ? d + k - 1 : d0;
+        const bool up = d0 - d < k || skip_confident || (n_sink > 0 && !(d >= uLo && wend <= sB));
+        const uint32_t b = f_base(d);
+        const char ch = b == 0 ? 'A' : b == 1 ? 'C' : b == 2 ? 'T' : 'G';
+        outc[d - 1 - dT] = up ? ch : (char)(ch | 0x20);
       }
+      if (rank == 0) outc[d0 - dT] = 0;
     }
   }
 

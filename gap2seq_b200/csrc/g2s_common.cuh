@@ -136,6 +136,17 @@ G2S_D Slot load_slot(const Slot *p) {
 #endif
 }
 
+// the whole 32-byte slot = one sector in ONE request (sm_100 256-bit load, LDG.E.256)
+G2S_D Slot load_slot32(const Slot *p) {
+#ifdef __CUDA_ARCH__
+  Slot s;
+  asm volatile("ld.global.nc.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(s.key), "=l"(s.val), "=l"(s.h[0]), "=l"(s.h[1]) : "l"(p));
+  return s;
+#else
+  return *p;
+#endif
+}
+
 // Graph::contains + adjacency fetch.  Returns the slot index or -1.
 G2S_D int64_t table_find(const Table &t, uint64_t canon, uint32_t *adj) {
   uint64_t h = mix64(canon) & t.cap_mask;
