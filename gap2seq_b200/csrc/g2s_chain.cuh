@@ -332,10 +332,12 @@ G2S_D void chain_finish(const ChainParams &P, const GapDev &gd, const uint64_t *
     // a level can hit a target only within e of the target's nominal level (and seeds start at dlo >= that bound); a
     // 64-bit signature of the targets spares most of those levels the rmf + 1 comparisons
     const int hit_lo = g + lmf - e > 0 ? g + lmf - e : 0;
-    uint64_t sig = 0, rsig = 0;
+    // (two 64-bit signatures from different bits of one product: ~3 % of the levels pass both by chance)
+    uint64_t sig = 0, rsig = 0, sig2 = 0, rsig2 = 0;
     for (int j = 0; j <= rmf; j++) {
-      sig |= 1ULL << ((ld_sh(&tk[j]) * 0x9E3779B97F4A7C15ULL) >> 58);
-      rsig |= 1ULL << ((ld_sh(&rtk[j]) * 0x9E3779B97F4A7C15ULL) >> 58);
+      const uint64_t ha = ld_sh(&tk[j]) * 0x9E3779B97F4A7C15ULL, hb = ld_sh(&rtk[j]) * 0x9E3779B97F4A7C15ULL;
+      sig |= 1ULL << (ha >> 58); sig2 |= 1ULL << ((ha >> 52) & 63);
+      rsig |= 1ULL << (hb >> 58); rsig2 |= 1ULL << ((hb >> 52) & 63);
     }
     // levels 0 .. min(top, cw) come from the forward string; levels cw + 1 .. top are the states R[L - c], read from the
     // right string, whose k-mers are reverse complements - there the constants are turned over instead of every state.
@@ -346,7 +348,8 @@ G2S_D void chain_finish(const ChainParams &P, const GapDev &gd, const uint64_t *
       const bool fwd = c <= hiF;
       const uint64_t x = fwd ? str_kmer(WF, (uint32_t)c, k) : str_kmer(WR, (uint32_t)(L - c), k);   // fwd: F[c], else rc(F[c])
       if (fwd ? ((c < top && x == c_top) || x == c_rtop || x == c_rf0) : ((c < top && x == c_rtop) || x == c_top || x == F0)) rep = true;
-      if (c < hit_lo || !(((fwd ? sig : rsig) >> ((x * 0x9E3779B97F4A7C15ULL) >> 58)) & 1)) continue;
+      const uint64_t hx = x * 0x9E3779B97F4A7C15ULL;
+      if (c < hit_lo || !(((fwd ? sig : rsig) >> (hx >> 58)) & ((fwd ? sig2 : rsig2) >> ((hx >> 52) & 63)) & 1)) continue;
       const uint64_t *tt = fwd ? tk : rtk;
       for (int j = 0; j <= rmf; j++) {
         if (x != ld_sh(&tt[j])) continue;
@@ -425,9 +428,8 @@ G2S_D void chain_finish(const ChainParams &P, const GapDev &gd, const uint64_t *
       for (int d = dT + 1 + rank; d <= d0; d += gsz) {
         const int wend = d + k - 1 < d0 ? d + k - 1 : d0;
         const bool up = d0 - d < k || skip_confident || (n_sink > 0 && !(d >= uLo && wend <= sB));
-        const uint32_t b = f_base(d);
-        const char ch = b == 0 ? 'A' : b == 1 ? 'C' : b == 2 ? 'T' : 'G';
-        outc[d - 1 - dT] = up ? ch : (char)(ch | 0x20);
+        // 'A' 'C' 'T' 'G' (GATB's 2-bit order) as the bytes of one word, lower case = bit 5: no branches
+        outc[d - 1 - dT] = (char)(((0x47544341u >> (8 * f_base(d))) & 0xFFu) | (up ? 0u : 0x20u));
       }
       if (rank == 0) outc[d0 - dT] = 0;
     }
