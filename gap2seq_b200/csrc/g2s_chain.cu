@@ -42,7 +42,7 @@ __global__ void __launch_bounds__(WALK_THREADS) k_chain_walk(const __grid_consta
   uint64_t x0 = kmer_from_ascii(P.flanks + (fwd ? gd.flank_off : gd.rstart_off + gd.rmf), k);
   // walking predecessors of the last right start = walking successors of its reverse complement
   if (!fwd) x0 = revcomp(x0, k);
-  chain_walk(P.table, x0, maxlev, fwd ? W : W + P.f_words, &P.walks[2 * q + (fwd ? 0 : 1)], !fwd);
+  chain_walk(gap_table(P.table, P.tables, P.graph_of, gd.id), x0, maxlev, fwd ? W : W + P.f_words, &P.walks[2 * q + (fwd ? 0 : 1)], !fwd);
 }
 
 __global__ void __launch_bounds__(32 * FINISH_WARPS) k_chain_finish(const __grid_constant__ ChainParams P) {

@@ -46,6 +46,8 @@ G2S_HD uint32_t chain_end(const ChainWalk &w) { return w.end_mask & 0xFFFFu; }
 
 struct ChainParams {
   Table table;
+  const Table *tables;        // per-gap graphs (FillParams)
+  const uint32_t *graph_of;
   const char *flanks;
   const GapDev *gaps;
   const uint32_t *order;      // gap ids of this pass
@@ -224,7 +226,7 @@ G2S_D bool chain_member(const uint64_t *WR, int nR, uint64_t x, int k) {
 template <class G>
 G2S_D void chain_finish(const ChainParams &P, const GapDev &gd, const uint64_t *WF, const uint64_t *WR, const ChainWalk wf,
                         const ChainWalk wr, uint64_t *tk, GapOut *out) {
-  const Table &T = P.table;
+  const Table T = gap_table(P.table, P.tables, P.graph_of, gd.id);
   const int k = T.k, rank = G::rank(), gsz = G::size();
   const int g = gd.gap_len, e = gd.gap_err, lmf = gd.lmf, rmf = gd.rmf;
   const bool all_paths = (gd.flags & 2) != 0, skip_confident = (gd.flags & 1) != 0;

@@ -9,7 +9,7 @@
 //   Gap2Seq-core ... -left L -right R -length n -filled out.fa            (single-gap mode, src/Gap2Seq.cpp:227-283)
 //
 // Differences, all deliberate: the de Bruijn graph is built on the GPU from the reads (exact solid k-mer set, no
-// Bloom filter, no ./.h5 file); -nb-cores only sets the host threads of the subgraph analysis; -max-mem bounds the
+// Bloom filter, no ./.h5 file is written - an existing <reads>.h5 of GATB is loaded like the reference does); -nb-cores only sets the host threads of the subgraph analysis; -max-mem bounds the
 // device scratch; -gpus G shards the gaps over GPUs D .. D+G-1 of the box (one k-mer table per GPU, replicated once;
 // results gathered in input order, one rand() stream - the output does not depend on G).  stdout carries the same parameter echo, per-gap "Scaffold:" / "SubgraphStats:" lines and the final
 // "Filled X gaps out of Y" as the reference.
@@ -131,7 +131,13 @@ int main(int argc, char **argv) {
 
   // ---- de Bruijn graph from the reads (stand-in for Graph::create, src/Gap2Seq.cpp:199-218); timed separately
   auto t0 = std::chrono::steady_clock::now();
-  {
+  const std::string reads_graph = reads + ".h5";
+  if (std::ifstream(reads_graph.c_str()).good()) {
+    // a GATB graph file next to the reads is loaded instead (src/Gap2Seq.cpp:171, 195-197): its dsk/solid partitions are
+    // the node set; they are read from the HDF5 container directly and imported into the device table
+    std::cout << "Loading from " << reads_graph << std::endl;
+    if (g2s_import_h5(eng, reads_graph.c_str()) != G2S_OK) { std::cout << "EXCEPTION: " << g2s_last_error() << std::endl; return 1; }
+  } else {
     std::vector<std::string> rn, rs;
     std::stringstream ss(reads);
     std::string file;

@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <vector>
+
 #include "g2s_common.cuh"
 
 namespace g2s {
@@ -22,6 +24,19 @@ cudaError_t table_from_reads(DeviceTable *dt, int k, const char *bases_host, con
                              uint64_t n_reads, int solid, int sms, cudaStream_t st);
 cudaError_t table_export(const DeviceTable &dt, uint64_t *keys_host, uint8_t *adj_host, int sms, cudaStream_t st);
 cudaError_t table_contains(const DeviceTable &dt, const char *ascii_host, uint64_t n, uint8_t *out_host, cudaStream_t st);
+
+// many small graphs in one slot arena (per-gap filtered-reads mode, g2s_table.cu tables_from_reads)
+struct MultiTable {
+  Slot *slots = nullptr;          // the arena
+  Table *d_tables = nullptr;      // device array, one view per graph
+  std::vector<Table> h_tables;
+  std::vector<uint32_t> h_sizes;  // solid k-mers per graph
+  uint64_t total_slots = 0, n_kmers = 0, n_graphs = 0;
+};
+void multi_table_release(MultiTable *mt);
+// graph g is built from reads graph_first_read[g] .. graph_first_read[g + 1] - 1 of the concatenated reads
+cudaError_t tables_from_reads(MultiTable *mt, int k, const char *bases_host, const uint64_t *offsets_host, uint64_t n_reads,
+                              const uint64_t *graph_first_read, uint64_t n_graphs, int solid, int sms, cudaStream_t st);
 
 struct FillParams;
 struct ChainParams;

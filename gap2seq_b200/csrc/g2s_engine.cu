@@ -27,6 +27,7 @@
 #include "g2s_fill.cuh"
 #include "g2s_chain.cuh"
 #include "g2s_finish.h"
+#include "g2s_h5.h"
 #include "g2s_scaffold.h"
 
 using namespace g2s;
@@ -108,6 +109,8 @@ struct g2s_engine {
   std::vector<Pass> passes;
   bool uploaded = false, ran = false;
   DevBuf d_flanks, d_gaps, d_order, d_outs, d_scratch, d_counters;
+  MultiTable multi;                    // per-gap filtered-reads mode: one graph per gap group (g2s_build_graphs_from_reads)
+  DevBuf d_graph_of;                   // graph of gap i of the uploaded batch
   DevBuf d_chain_strs, d_chain_walks;  // chain tier: packed walk strings, walk summaries
   bool chain_tier = true;              // G2S_NO_CHAIN=1: every gap starts in the thin tier (A/B measurements)
   std::vector<DevBuf> d_pack;          // persistent (grow-only) pack arena per pass ordinal
@@ -175,6 +178,7 @@ extern "C" void g2s_destroy(g2s_engine *e) {
   e->d_flanks.release(); e->d_gaps.release(); e->d_order.release(); e->d_outs.release();
   e->d_scratch.release(); e->d_counters.release(); e->h_outs.release(); e->h_stage.release();
   if (e->table.slots) cudaFree(e->table.slots);
+  multi_table_release(&e->multi); e->d_graph_of.release();
   for (auto &v : e->ev) if (v) cudaEventDestroy(v);
   if (e->st) cudaStreamDestroy(e->st);
   delete e;
@@ -307,6 +311,7 @@ extern "C" int g2s_import_kmers(g2s_engine *e, const uint64_t *canon, size_t n) 
   if (!e || (!canon && n)) return fail(G2S_E_ARG, "g2s_import_kmers: null argument");
   CUDA_TRY(cudaSetDevice(e->cfg.device));
   uint64_t *d_keys = nullptr;
+  multi_table_release(&e->multi);
   CUDA_TRY(table_alloc(&e->table, e->cfg.k, n, e->sms, e->st));
   if (n) {
     CUDA_TRY(cudaMalloc(&d_keys, n * 8));
@@ -320,11 +325,70 @@ extern "C" int g2s_import_kmers(g2s_engine *e, const uint64_t *canon, size_t n) 
   return replicate_table(e);
 }
 
+extern "C" int g2s_h5_read_solid(const char *path, uint64_t **canon_out, size_t *n_out, int32_t *kmer_size_out) {
+  if (!path || !canon_out || !n_out) return fail(G2S_E_ARG, "g2s_h5_read_solid: null argument");
+  *canon_out = nullptr; *n_out = 0;
+  FILE *f = fopen(path, "rb");
+  if (!f) return fail(G2S_E_ARG, std::string("g2s_h5_read_solid: cannot open ") + path);
+  std::vector<uint8_t> data;
+  {
+    fseek(f, 0, SEEK_END);
+    const long sz = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    data.resize(sz > 0 ? (size_t)sz : 0);
+    const size_t got = data.empty() ? 0 : fread(data.data(), 1, data.size(), f);
+    fclose(f);
+    if (got != data.size()) return fail(G2S_E_ARG, std::string("g2s_h5_read_solid: short read of ") + path);
+  }
+  std::vector<uint64_t> kmers;
+  int ks = 0;
+  try { h5::read_solid_kmers(data.data(), data.size(), kmers, nullptr, &ks); }
+  catch (const std::exception &ex) { return fail(G2S_E_ARG, std::string(ex.what()) + " (" + path + ")"); }
+  if (kmer_size_out) *kmer_size_out = ks;
+  uint64_t *out = (uint64_t *)malloc(std::max<size_t>(kmers.size(), 1) * 8);
+  if (!out) return fail(G2S_E_ARG, "g2s_h5_read_solid: out of memory");
+  if (!kmers.empty()) memcpy(out, kmers.data(), kmers.size() * 8);
+  *canon_out = out; *n_out = kmers.size();
+  return G2S_OK;
+}
+
+extern "C" int g2s_import_h5(g2s_engine *e, const char *path) {
+  if (!e) return fail(G2S_E_ARG, "g2s_import_h5: null argument");
+  uint64_t *canon = nullptr; size_t n = 0; int32_t ks = 0;
+  const int rc = g2s_h5_read_solid(path, &canon, &n, &ks);
+  if (rc != G2S_OK) return rc;
+  int out = G2S_OK;
+  if (ks != 0 && ks != e->cfg.k) out = fail(G2S_E_ARG, "g2s_import_h5: the graph file holds " + std::to_string(ks) + "-mers, the engine was created for k = " + std::to_string(e->cfg.k));
+  else out = g2s_import_kmers(e, canon, n);
+  free(canon);
+  return out;
+}
+
 extern "C" int g2s_build_from_reads(g2s_engine *e, const char *bases, const uint64_t *offsets, size_t n_reads, int solid) {
   if (!e || !bases || !offsets) return fail(G2S_E_ARG, "g2s_build_from_reads: null argument");
   CUDA_TRY(cudaSetDevice(e->cfg.device));
+  multi_table_release(&e->multi);
   CUDA_TRY(table_from_reads(&e->table, e->cfg.k, bases, offsets, n_reads, solid, e->sms, e->st));
   return replicate_table(e);
+}
+
+extern "C" int g2s_build_graphs_from_reads(g2s_engine *e, const char *bases, const uint64_t *offsets, size_t n_reads,
+                                           const uint64_t *graph_first_read, size_t n_graphs, int solid) {
+  if (!e || !offsets || !graph_first_read || (!bases && n_reads)) return fail(G2S_E_ARG, "g2s_build_graphs_from_reads: null argument");
+  if (!e->peers.empty()) return fail(G2S_E_STATE, "g2s_build_graphs_from_reads: per-gap graphs are built on a one-GPU engine");
+  if (n_graphs == 0) return fail(G2S_E_ARG, "g2s_build_graphs_from_reads: no graph");
+  CUDA_TRY(cudaSetDevice(e->cfg.device));
+  if (e->table.slots) { cudaFree(e->table.slots); e->table = DeviceTable{}; }   // the engine holds one kind of graph at a time
+  const cudaError_t er = tables_from_reads(&e->multi, e->cfg.k, bases, offsets, n_reads, graph_first_read, n_graphs, solid, e->sms, e->st);
+  if (er == cudaErrorInvalidValue) return fail(G2S_E_ARG, "g2s_build_graphs_from_reads: read ranges must tile the reads in order, fewer than 2^31 k-mer occurrences per call");
+  CUDA_TRY(er);
+  e->uploaded = false; e->ran = false;
+  return G2S_OK;
+}
+
+extern "C" int64_t g2s_graph_num_kmers(const g2s_engine *e, size_t graph) {
+  if (!e || graph >= e->multi.h_sizes.size()) return -1;
+  return (int64_t)e->multi.h_sizes[graph];
 }
 
 extern "C" int g2s_table_raw(g2s_engine *e, void **device_ptr, uint64_t *capacity_slots, uint64_t *n_kmers, uint64_t *bytes) {
@@ -464,6 +528,7 @@ static int run_pass(g2s_engine *e, Pass &p) {
   CUDA_TRY(cudaMemsetAsync(e->d_counters.p, 0, 64, e->st));
   FillParams P{};
   P.table = table_view(e->table);
+  if (e->multi.d_tables) { P.table = e->multi.h_tables[0]; P.tables = e->multi.d_tables; P.graph_of = (const uint32_t *)e->d_graph_of.p; }
   P.flanks = (const char *)e->d_flanks.p;
   P.gaps = (const GapDev *)e->d_gaps.p;
   P.order = (const uint32_t *)e->d_order.p;
@@ -510,6 +575,7 @@ static int run_chain_pass(g2s_engine *e, Pass &p) {
   const int k = e->cfg.k;
   ChainParams P{};
   P.table = table_view(e->table);
+  if (e->multi.d_tables) { P.table = e->multi.h_tables[0]; P.tables = e->multi.d_tables; P.graph_of = (const uint32_t *)e->d_graph_of.p; }
   P.walk_stride = 8;
   if (const char *ws = getenv("G2S_WALK_STRIDE")) { const int v = atoi(ws); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) P.walk_stride = (uint32_t)v; }
   P.f_words = chain_words(k, e->max_dmax);
@@ -559,9 +625,21 @@ static int run_chain_pass(g2s_engine *e, Pass &p) {
 
 static int do_upload(g2s_engine *e, const g2s_gap *gaps, size_t n) {
   if (!e) return fail(G2S_E_ARG, "null engine");
-  if (!e->table.slots) return fail(G2S_E_STATE, "no graph imported (g2s_import_kmers / g2s_build_from_reads)");
+  const bool multi = e->multi.d_tables != nullptr;
+  if (!e->table.slots && !multi) return fail(G2S_E_STATE, "no graph imported (g2s_import_kmers / g2s_build_from_reads)");
   if (!gaps && n) return fail(G2S_E_ARG, "null gaps");
   CUDA_TRY(cudaSetDevice(e->cfg.device));
+  if (multi) {   // per-gap graphs: g2s_gap.graph selects the gap's graph
+    std::vector<uint32_t> graph_of(std::max<size_t>(n, 1), 0);
+    for (size_t i = 0; i < n; i++) {
+      if (gaps[i].graph < 0 || (uint64_t)gaps[i].graph >= e->multi.n_graphs) return fail(G2S_E_ARG, "g2s_gap.graph out of range");
+      if (gaps[i].flags & G2S_GAP_PRESENT_BITS) return fail(G2S_E_ARG, "present_bits are not supported with per-gap graphs");
+      graph_of[i] = (uint32_t)gaps[i].graph;
+    }
+    CUDA_TRY(e->d_graph_of.reserve(graph_of.size() * 4));
+    CUDA_TRY(cudaMemcpyAsync(e->d_graph_of.p, graph_of.data(), graph_of.size() * 4, cudaMemcpyHostToDevice, e->st));
+    CUDA_TRY(cudaStreamSynchronize(e->st));
+  }
   const int k = e->cfg.k;
   e->tm = g2s_timing{};
   e->passes.clear();

@@ -145,7 +145,7 @@ __device__ __forceinline__ void group_loop(const FillParams &P, GShared &sh, uin
     if (q >= P.n_gaps) break;
     const uint32_t gi = P.order[q];
     const GapDev gd = P.gaps[gi];
-    if (HW > 0) process_gap_pair<(HW > 0 ? HW : 1), MW>(P, gd, S, sh, &P.outs[gi]);
+    if constexpr (HW > 0) process_gap_pair<(HW > 0 ? HW : 1), MW>(P, gd, S, sh, &P.outs[gi]);
     else process_gap<BlockGroup>(P, gd, S, sh, &P.outs[gi]);
   }
 }

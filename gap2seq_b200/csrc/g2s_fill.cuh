@@ -144,6 +144,8 @@ struct SliceLayout {   // byte offsets inside one scratch slice; identical for e
 
 struct FillParams {
   Table table;
+  const Table *tables;         // null, or one table per graph (per-gap filtered-reads mode): gap i uses tables[graph_of[i]]
+  const uint32_t *graph_of;
   const char *flanks;
   const GapDev *gaps;
   const uint32_t *order;       // gap indices, longest first
@@ -402,6 +404,113 @@ G2S_D uint32_t new_cell(const Slice &S, GShared &sh, const GapDev &gd, uint64_t 
   }
   return idx;
 }
+
+// same, into a cell the caller has already reserved (warp-aggregated reservation in the pair step below)
+G2S_D void new_cell_at(const Slice &S, const GShared &sh, const GapDev &gd, uint32_t idx, uint64_t s, uint32_t e, uint32_t strand,
+                       uint32_t adj, uint32_t c, uint32_t count, uint32_t nflags) {
+  S.ck[idx] = s;
+  S.cc[idx] = count;
+  S.cn[idx] = e;
+  const uint4 none4 = {NONE32, NONE32, NONE32, NONE32};
+  *(uint4 *)&S.cp[4 * idx] = none4;
+  S.cflags[idx] = out_mask(adj, strand) << CF_OMASK_SHIFT;
+  S.ent[e].fcell[strand] = idx;
+  if ((nflags & NF_TARGET) && (int)c >= sh.tlo) {
+    for (int j = 0; j <= gd.rmf; j++)
+      if ((S.rk[j] & FLANK_KMER) == s) S.thit[(size_t)j * sh.trow + (c - (uint32_t)sh.tlo)] = idx + 1;
+  }
+}
+
+#ifdef G2S_DEVICE_BUILD
+// ---- the pair step of a wide level.  A border element has up to four neighbours and each of them costs a chain of
+// dependent memory operations (k-mer table gather, node-table operation, stamp, cell).  With one thread per element a
+// warp walks that chain once per base - four times in a row, because some lane always has the base - and the level
+// step of a wide gap is nothing but this latency (profiles/r2_summary.md).  Here a warp takes C <= 32 elements, lays
+// their (element, base) pairs out over its lanes with a prefix sum of the neighbour counts and walks the chain once
+// per 32 PAIRS: one pass for most warps.
+struct PairSrc {
+  uint32_t incl, excl, total;
+};
+G2S_D PairSrc pair_scan(uint32_t cnt) {
+  const uint32_t lane = threadIdx.x & 31;
+  uint32_t v = cnt;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, v, d);
+    if (lane >= (uint32_t)d) v += t;
+  }
+  PairSrc r;
+  r.incl = v; r.excl = v - cnt; r.total = __shfl_sync(0xffffffffu, v, 31);
+  return r;
+}
+// lane that owns pair p (all lanes call): the last lane whose exclusive prefix is <= p - lanes without pairs share the
+// prefix of the next lane, so the last one of a run is the one that has pairs.  Five shuffles.
+G2S_D uint32_t pair_owner(const PairSrc &ps, uint32_t p, uint32_t C) {
+  (void)C;
+  uint32_t src = 0;
+#pragma unroll
+  for (uint32_t st = 16; st; st >>= 1) {
+    const uint32_t t = __shfl_sync(0xffffffffu, ps.excl, src + st);
+    if (t <= p) src += st;
+  }
+  return src;
+}
+G2S_D uint32_t nth_bit(uint32_t m, uint32_t r) {   // index of the r-th (0-based) set bit of a 4-bit mask
+  for (; r; r--) m &= m - 1;
+  return (uint32_t)__ffs((int)m) - 1u;
+}
+G2S_D uint64_t shfl64(uint64_t v, uint32_t src) {
+  const uint32_t lo = __shfl_sync(0xffffffffu, (uint32_t)v, src), hi = __shfl_sync(0xffffffffu, (uint32_t)(v >> 32), src);
+  return (uint64_t)lo | ((uint64_t)hi << 32);
+}
+// 16-byte compare-and-swap on the head of a node entry (key, rstamp, flags): claims a free entry for `key` or returns
+// what is there - the flag word included - in ONE round trip (ATOMG.E.CAS.128)
+G2S_D void ent_cas_head(NodeEnt *p, uint64_t key, uint64_t *okey, uint32_t *oflags) {
+  uint64_t olo, ohi;
+  asm volatile("{\n\t.reg .b128 c, s, d;\n\tmov.b128 c, {%3, %4};\n\tmov.b128 s, {%5, %6};\n\tatom.global.cas.b128 d, [%2], c, s;\n\tmov.b128 {%0, %1}, d;\n\t}"
+               : "=l"(olo), "=l"(ohi) : "l"(p), "l"(KEY_EMPTY), "l"(0ULL), "l"(key), "l"(0ULL) : "memory");
+  *okey = olo; *oflags = (uint32_t)(ohi >> 32);
+}
+// The two first probes of a neighbour - its slot of the global k-mer table and its entry of the gap's node table -
+// depend on nothing but the canonical k-mer and are issued together.  INSERT: find or insert; else find only.
+// Returns the node entry (NONE32: absent / table full) and the adjacency byte; *nflags = the node's flag word.
+template <bool INSERT>
+G2S_D uint32_t table_and_node(const Table &T, const Slice &S, GShared &sh, uint64_t key, uint32_t nnodes_seen, uint32_t *adj, uint32_t *nflags) {
+  uint64_t ht = mix64(key) & T.cap_mask;
+  uint32_t hn = node_hash(key, S.hmask);
+  Slot ts = load_slot(T.slots + ht);
+  uint64_t nk; uint32_t nf;
+  const bool full = INSERT && nnodes_seen >= S.hcap - (S.hcap >> 2);
+  if (INSERT && !full) ent_cas_head(&S.ent[hn], key, &nk, &nf);
+  else load_ent_head(&S.ent[hn], &nk, &nf);
+  while (ts.key != key && ts.key != KEY_EMPTY) { ht = (ht + 1) & T.cap_mask; ts = load_slot(T.slots + ht); }
+  if (ts.key == KEY_EMPTY) { a_or(&sh.status, GS_INTERNAL); return NONE32; }   // the adjacency byte said it exists
+  *adj = (uint32_t)(ts.val & 0xFF);
+  for (;;) {
+    if (nk == key) break;
+    if (nk == KEY_EMPTY) {
+      if (!INSERT) return NONE32;
+      if (full) { a_or(&sh.status, GS_OVERFLOW); return NONE32; }
+      a_inc(&sh.nnodes); nf = 0; break;       // the compare-and-swap above claimed the entry
+    }
+    hn = (hn + 1) & S.hmask;
+    if (INSERT && !full) ent_cas_head(&S.ent[hn], key, &nk, &nf);
+    else load_ent_head(&S.ent[hn], &nk, &nf);
+  }
+  *nflags = nf;
+  return hn;
+}
+// reserve one item per lane that asks for it with ONE atomic per warp (all 32 lanes call)
+G2S_D uint32_t warp_reserve(uint32_t *counter, bool want) {
+  const uint32_t m = __ballot_sync(0xffffffffu, want);
+  if (!m) return 0;
+  const uint32_t lane = threadIdx.x & 31, leader = (uint32_t)__ffs((int)m) - 1u;
+  uint32_t base = 0;
+  if (lane == leader) base = atomicAdd(counter, (uint32_t)__popc(m));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  return base + (uint32_t)__popc(m & ((1u << lane) - 1u));
+}
+#endif
 
 // thit holds, for target j and level d >= tlo, the cell of (rnode(j), d) + 1.  Levels below tlo = g + lmf - e are
 // never looked up: the found check reads lengths >= g + lmf - err, the seeds levels >= lmf + g - e.
@@ -1140,10 +1249,16 @@ struct GapCtx {
   size_t trow;
   bool all_paths, skip_confident;
   const char *lstr, *rstr, *rsstr;
+  Table T;   // the gap's graph
 };
+
+G2S_D Table gap_table(const Table &one, const Table *tables, const uint32_t *graph_of, uint32_t gap_id) {
+  return tables ? tables[graph_of[gap_id]] : one;
+}
 
 G2S_D GapCtx make_ctx(const FillParams &P, const GapDev &gd) {
   GapCtx cx;
+  cx.T = gap_table(P.table, P.tables, P.graph_of, gd.id);
   cx.k = P.table.k;
   cx.g = gd.gap_len; cx.e = gd.gap_err; cx.lmf = gd.lmf; cx.rmf = gd.rmf;
   cx.all_paths = (gd.flags & 2) != 0; cx.skip_confident = (gd.flags & 1) != 0;
@@ -1165,7 +1280,7 @@ struct NoWait {
 // ---- init: clear the node table, thit and the per-level counters; parse the flanks; flag the right-flank targets
 template <class G>
 G2S_D void gap_init(const FillParams &P, const GapCtx &cx, const Slice &S, GShared &sh) {
-  const Table &T = P.table;
+  const Table &T = cx.T;
   const int k = cx.k, rank = G::rank(), gsz = G::size();
   uint4 *hz = (uint4 *)S.ent;
   const uint4 z0 = {0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u}, z1 = {0u, 0u, 0u, 0u};
@@ -1215,7 +1330,7 @@ G2S_D void gap_init(const FillParams &P, const GapCtx &cx, const Slice &S, GShar
 // Only node membership in the right set is read later (Gap2Seq.cpp:1050): nodes get NF_IN_RS, cells are counted.
 template <class G>
 G2S_D void gap_right(const FillParams &P, const GapCtx &cx, const Slice &S, GShared &sh, NarrowBuf &nb) {
-  const Table &T = P.table;
+  const Table &T = cx.T;
   const int k = cx.k, rank = G::rank(), gsz = G::size(), rmf = cx.rmf, right_half = cx.right_half;
   const unsigned long long t0 = now_cycles();
   int levels_r = 0;
@@ -1251,6 +1366,47 @@ G2S_D void gap_right(const FillParams &P, const GapCtx &cx, const Slice &S, GSha
     G::sync();
     const uint64_t *fk = S.rbk[cur]; const unsigned char *fm = S.rbm[cur];
     uint64_t *nk = S.rbk[cur ^ 1]; unsigned char *nm = S.rbm[cur ^ 1];
+#ifdef G2S_DEVICE_BUILD
+    {   // pair step (see pair_scan)
+      const uint32_t lane = (uint32_t)rank & 31u, warp = (uint32_t)rank >> 5, nwarps = (uint32_t)gsz >> 5;
+      const uint32_t C = n <= 8u * nwarps ? 8u : n <= 16u * nwarps ? 16u : 32u;
+      for (uint32_t base = 0; base < n; base += C * nwarps) {
+        const uint32_t e0 = base + warp * C;
+        uint64_t x = 0; uint32_t im = 0;
+        if (lane < C && e0 + lane < n) { x = fk[e0 + lane]; im = fm[e0 + lane] & 15u; }
+        const uint32_t nnodes_seen = ld_sh(&sh.nnodes);
+        my_lookups += popc32(im);
+        const PairSrc ps = pair_scan(popc32(im));
+        for (uint32_t it = 0; it * 32u < ps.total; it++) {
+          const uint32_t q = it * 32u + lane;
+          const uint32_t src = pair_owner(ps, q, C);
+          const uint64_t sx = shfl64(x, src);
+          const uint32_t sim = __shfl_sync(0xffffffffu, im, src), sex = __shfl_sync(0xffffffffu, ps.excl, src);
+          bool act = q < ps.total, win = false;
+          uint64_t p = 0; uint32_t adj = 0, strand = 0;
+          if (act) {
+            p = pred_kmer(sx, nth_bit(sim, q - sex), T);
+            const Canon cp = canonical(p, k);
+            strand = cp.strand;
+            uint32_t nf = 0;
+            const uint32_t en = table_and_node<true>(T, S, sh, cp.key, nnodes_seen, &adj, &nf);
+            if (en != NONE32) {
+              if (!(nf & NF_IN_RS)) a_or(&S.ent[en].flags, NF_IN_RS);
+              const uint32_t stamp = (uint32_t)(c + 1) * 2 + strand;
+              const uint32_t prev = a_max(&S.ent[en].rstamp, stamp);
+              if ((prev >> 1) < (uint32_t)(c + 1)) win = true;
+              else if ((prev & 1) != strand) a_or(&sh.status, GS_ORDER_DEPENDENT);   // both strands on one level
+            }
+          }
+          const uint32_t idx = warp_reserve(&nb.nnext, win);
+          if (win) {
+            if (idx >= S.cap_cells) a_or(&sh.status, GS_OVERFLOW);
+            else { nk[idx] = p; nm[idx] = (unsigned char)in_mask(adj, strand); }
+          }
+        }
+      }
+    }
+#else
     for (uint32_t i = rank; i < n; i += gsz) {
       const uint64_t x = fk[i];
       uint32_t im = fm[i];
@@ -1275,6 +1431,7 @@ G2S_D void gap_right(const FillParams &P, const GapCtx &cx, const Slice &S, GSha
         }
       }
     }
+#endif
     G::sync();
     if (rank == 0 && c <= rmf) {   // next staggered right start (Gap2Seq.cpp:953-968)
       uint64_t x = kmer_from_ascii(cx.rsstr + (rmf - c), k);
@@ -1311,7 +1468,7 @@ G2S_D void gap_right(const FillParams &P, const GapCtx &cx, const Slice &S, GSha
 // ---- Phase F: forward walk counts by exact length (Gap2Seq.cpp:984-1167)
 template <class G, class W>
 G2S_D void gap_forward(const FillParams &P, const GapDev &gd, const GapCtx &cx, const Slice &S, GShared &sh, NarrowBuf &nb) {
-  const Table &T = P.table;
+  const Table &T = cx.T;
   const int k = cx.k, rank = G::rank(), gsz = G::size();
   const int g = cx.g, lmf = cx.lmf, rmf = cx.rmf, Dmax = cx.Dmax, prune_from = cx.prune_from;
   const bool all_paths = cx.all_paths;
@@ -1342,11 +1499,13 @@ G2S_D void gap_forward(const FillParams &P, const GapDev &gd, const GapCtx &cx, 
     G::sync();
 
     bool found = false;
+    int known_for = -1; uint32_t known_lo = 0, known_hi = 0;
     for (int c = 1; c <= Dmax; c++) {
       if (!waited && c >= prune_from) { W::wait_right(); waited = true; }
       // until the right set is complete a look-ahead batch must end below the first pruned level
       const int dlim = waited ? Dmax : (prune_from - 1 < Dmax ? prune_from - 1 : Dmax);
-      const uint32_t lo = ld_cg(&S.lstart[c - 1]), hi = ld_cg(&S.lstart[c]);
+      // the bounds of the border: handed over in registers by the general level before, else read back
+      const uint32_t lo = known_for == c ? known_lo : ld_cg(&S.lstart[c - 1]), hi = known_for == c ? known_hi : ld_cg(&S.lstart[c]);
       const bool dead = (lo == hi) && c > lmf;   // empty border and no start left to inject
       if (hi > lo && hi - lo <= (uint32_t)NARROW_W) {   // narrow border (start levels included, see narrow_forward)
         const int adv = narrow_forward<G>(T, S, sh, nb, gd, lo, (int)(hi - lo), c, dlim, prune_from);
@@ -1376,6 +1535,76 @@ G2S_D void gap_forward(const FillParams &P, const GapDev &gd, const GapCtx &cx, 
       if (!dead) {
         top_level = c;
         levels_f = c;
+#ifdef G2S_DEVICE_BUILD
+        {   // pair step (see pair_scan): C elements per warp, the smallest C that covers the border in one round
+          const uint32_t lane = (uint32_t)rank & 31u, warp = (uint32_t)rank >> 5, nwarps = (uint32_t)gsz >> 5;
+          const uint32_t wdt = hi - lo;
+          const uint32_t C = wdt <= 8u * nwarps ? 8u : wdt <= 16u * nwarps ? 16u : 32u;
+          const uint32_t lvl = (uint32_t)c + 1;
+          for (uint32_t base = lo; base < hi; base += C * nwarps) {
+            const uint32_t cell0 = base + warp * C;
+            uint64_t x = 0; uint32_t om = 0;
+            if (lane < C && cell0 + lane < hi) {
+              x = ld_cg(&S.ck[cell0 + lane]);
+              om = (ld_cg(&S.cflags[cell0 + lane]) >> CF_OMASK_SHIFT) & 15u;
+            }
+            const uint32_t nnodes_seen = c < prune_from ? ld_sh(&sh.nnodes) : 0u;
+            my_lookups += popc32(om);
+            const PairSrc ps = pair_scan(popc32(om));
+            uint32_t rec_e[4], rec_i[4];
+#pragma unroll
+            for (uint32_t it = 0; it < 4; it++) {
+              rec_e[it] = NONE32; rec_i[it] = 0;
+              if (it * 32u < ps.total) {   // the same for the whole warp
+                const uint32_t p = it * 32u + lane;
+                const uint32_t src = pair_owner(ps, p, C);
+                const uint64_t sx = shfl64(x, src);
+                const uint32_t som = __shfl_sync(0xffffffffu, om, src), sex = __shfl_sync(0xffffffffu, ps.excl, src);
+                bool act = p < ps.total;
+                uint32_t en = NONE32, adj = 0, nf = 0, strand = 0;
+                uint64_t sk = 0;
+                if (act) {
+                  const uint32_t nt = nth_bit(som, p - sex);
+                  sk = succ_kmer(sx, nt, T);
+                  const Canon cs = canonical(sk, k);
+                  strand = cs.strand;
+                  if (c < prune_from) {
+                    en = table_and_node<true>(T, S, sh, cs.key, nnodes_seen, &adj, &nf);
+                  } else {   // meet in the middle: only nodes of the right set survive (Gap2Seq.cpp:1050)
+                    en = table_and_node<false>(T, S, sh, cs.key, 0u, &adj, &nf);
+                    if (en != NONE32 && !(nf & NF_IN_RS)) en = NONE32;
+                  }
+                  act = en != NONE32;
+                }
+                bool win = false;
+                if (act) win = a_max(&S.ent[en].fstamp[strand], lvl) < lvl;
+                const uint32_t idx = warp_reserve(&sh.ncells, win);
+                if (win) {
+                  if (idx >= S.cap_cells) { a_or(&sh.status, GS_OVERFLOW); act = false; }
+                  else new_cell_at(S, sh, gd, idx, sk, en, strand, adj, (uint32_t)c, 0, nf);
+                }
+                if (act) { rec_e[it] = en | (strand << 31); rec_i[it] = cell0 + src; }
+              }
+            }
+            G::sync();
+            if (!(ld_sh(&sh.status) & GS_OVERFLOW)) {
+#pragma unroll
+              for (uint32_t it = 0; it < 4; it++) {
+                if (rec_e[it] == NONE32) continue;
+                const uint32_t st = rec_e[it] >> 31, i = rec_i[it];
+                const NodeEnt *en = &S.ent[rec_e[it] & 0x7FFFFFFFu];
+                const uint32_t idx = ld_cg(&en->fcell[st]);
+                const uint32_t other = ld_cg(&en->fstamp[st ^ 1]);
+                const uint32_t np = clamp_paths(ld_cg(&S.cc[i]));
+                const uint32_t u0 = (uint32_t)(ld_cg(&S.ck[i]) >> (2 * (k - 1))) & 3u;
+                a_add(&S.cc[idx], np);
+                S.cp[4 * idx + u0] = i;
+                if (other == lvl) a_or(&sh.status, GS_ORDER_DEPENDENT);
+              }
+            }
+          }
+        }
+#else
         for (uint32_t base = lo; base < hi; base += gsz) {
           const uint32_t i = base + rank;
           uint32_t cand_e[4];
@@ -1425,30 +1654,43 @@ G2S_D void gap_forward(const FillParams &P, const GapDev &gd, const GapCtx &cx, 
             }
           }
         }
+#endif
         G::sync();
-        if (rank == 0 && c <= lmf) {   // staggered left start: count OVERWRITTEN with 1 (Gap2Seq.cpp:1082-1105)
-          uint64_t x = S.lk[c];
-          if (x & FLANK_PRESENT) {
-            x &= FLANK_KMER;
-            Canon cs = canonical(x, k);
-            uint32_t adj = 0;
-            table_find(T, cs.key, &adj);
-            uint32_t nf = 0;
-            uint32_t en = node_insert(S, sh, cs.key, &nf);
-            if (en != NONE32) {
-              if (S.ent[en].fstamp[cs.strand] == (uint32_t)c + 1) {
-                S.cc[S.ent[en].fcell[cs.strand]] = 1;
-              } else {
-                S.ent[en].fstamp[cs.strand] = (uint32_t)c + 1;
-                new_cell<G>(S, sh, gd, x, en, cs.strand, adj, (uint32_t)c, 1, nf);
+        bool ovf;
+        if (c <= lmf) {
+          if (rank == 0 && c <= lmf) {   // staggered left start: count OVERWRITTEN with 1 (Gap2Seq.cpp:1082-1105)
+            uint64_t x = S.lk[c];
+            if (x & FLANK_PRESENT) {
+              x &= FLANK_KMER;
+              Canon cs = canonical(x, k);
+              uint32_t adj = 0;
+              table_find(T, cs.key, &adj);
+              uint32_t nf = 0;
+              uint32_t en = node_insert(S, sh, cs.key, &nf);
+              if (en != NONE32) {
+                if (S.ent[en].fstamp[cs.strand] == (uint32_t)c + 1) {
+                  S.cc[S.ent[en].fcell[cs.strand]] = 1;
+                } else {
+                  S.ent[en].fstamp[cs.strand] = (uint32_t)c + 1;
+                  new_cell<G>(S, sh, gd, x, en, cs.strand, adj, (uint32_t)c, 1, nf);
+                }
+                if (S.ent[en].fstamp[cs.strand ^ 1] == (uint32_t)c + 1) a_or(&sh.status, GS_ORDER_DEPENDENT);
               }
-              if (S.ent[en].fstamp[cs.strand ^ 1] == (uint32_t)c + 1) a_or(&sh.status, GS_ORDER_DEPENDENT);
             }
           }
+          G::sync();
+          if (rank == 0) S.lstart[c + 1] = sh.ncells < S.cap_cells ? sh.ncells : S.cap_cells;
+          ovf = group_overflow<G>(sh);
+        } else {
+          // nobody writes the cell counter or the status word between this barrier and the next level's first phase,
+          // which lies behind the barrier of the found check: every thread reads the same values
+          const uint32_t nc = ld_sh(&sh.ncells);
+          known_for = c + 1; known_lo = hi; known_hi = nc < S.cap_cells ? nc : S.cap_cells;
+          if (rank == 0) S.lstart[c + 1] = known_hi;
+          // (the thin tier's right pass runs on other warps at the same time and may set a bit at any moment: a vote there)
+          ovf = W::kConcurrent ? group_overflow<G>(sh) : (ld_sh(&sh.status) & GS_OVERFLOW) != 0;
         }
-        G::sync();
-        if (rank == 0) S.lstart[c + 1] = sh.ncells < S.cap_cells ? sh.ncells : S.cap_cells;
-        if (group_overflow<G>(sh)) { overflow = true; break; }
+        if (ovf) { overflow = true; break; }
       } else {
         // the border died: no cell can appear any more; finish the found check for the remaining levels in
         // parallel (one level per thread) and leave the level loop

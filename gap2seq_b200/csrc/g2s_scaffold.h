@@ -227,7 +227,7 @@ struct ScaffoldRun {
         g.kmer_right_starts = nullptr;
         g.gap_len = q.gap; g.gap_err = opt.d_err; g.left_max_fuz = q.lmf; g.right_max_fuz = q.rmf;
         g.flags = (opt.skip_confident ? G2S_GAP_SKIP_CONFIDENT : 0) | (opt.all_paths ? G2S_GAP_ALL_PATHS : 0);
-        g.reserved = 0;
+        g.graph = 0;
       }
       // the rand() values this wave's tracebacks can consume are computed while the device pass runs
       // (a filling path is about as long as the gap; the rare longer ones extend the window after the pass, see trace_many)

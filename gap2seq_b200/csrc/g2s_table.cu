@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <vector>
 
 #include "g2s_common.cuh"
 #include "g2s_device.h"
@@ -367,6 +368,213 @@ done:
   free(koff);
   cudaFree(d_bases); cudaFree(d_off); cudaFree(d_koff); cudaFree(d_keys); cudaFree(d_sorted);
   cudaFree(d_counts); cudaFree(d_nruns); cudaFree(d_tmp); cudaFree(d_nsolid);
+  return err;
+}
+
+// ---------------------------------------------------------------------------------------------- many small graphs
+// Per-gap filtered-reads mode: the reference's wrapper runs one Gap2Seq-core process - one GATB
+// graph construction - per gap on the reads that map near it (src/Gap2Seq.py:132-220, src/Gap2Seq.cpp:227-283).  Here
+// the graphs of a whole batch of gaps are built in ONE device pass: every k-mer occurrence is tagged with its graph,
+// one radix sort orders them by (graph, k-mer), an occurrence that starts a run of at least `solid` equal neighbours
+// is a solid k-mer of its graph, and all tables live in one slot arena (one power-of-two region per graph).
+__global__ void k_extract_tagged(const char *bases, const uint64_t *offsets, const uint64_t *kmer_offsets, uint64_t n_reads,
+                                 const uint32_t *read_graph, int k, uint64_t *keys, uint32_t *tags, uint64_t total) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (; i < total; i += stride) {
+    uint64_t lo = 0, hi = n_reads;
+    while (hi - lo > 1) { uint64_t mid = (lo + hi) >> 1; if (kmer_offsets[mid] <= i) lo = mid; else hi = mid; }
+    const char *s = bases + offsets[lo] + (i - kmer_offsets[lo]);
+    uint64_t v = 0; uint32_t bad = 0;
+    for (int j = 0; j < k; j++) {
+      const unsigned char c = (unsigned char)s[j];
+      bad |= (c >> 3) & 1;
+      v = (v << 2) | ((c >> 1) & 3);
+    }
+    keys[i] = bad ? KEY_EMPTY : canonical(v, k).key;
+    tags[i] = read_graph[lo];
+  }
+}
+
+// occurrences sorted by (tag, key): position i starts a solid run iff it differs from i - 1 and equals i + solid - 1
+__global__ void k_solid_heads(const uint64_t *keys, const uint32_t *tags, uint64_t total, uint32_t solid, uint64_t *out_keys,
+                              uint32_t *out_tags, unsigned long long *cursor, uint32_t *per_graph) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (; i < total; i += stride) {
+    const uint64_t key = keys[i];
+    const uint32_t tag = tags[i];
+    if (key == KEY_EMPTY) continue;
+    if (i > 0 && keys[i - 1] == key && tags[i - 1] == tag) continue;
+    const uint64_t j = i + (solid > 0 ? solid - 1 : 0);
+    if (j >= total || keys[j] != key || tags[j] != tag) continue;
+    const unsigned long long pos = atomicAdd(cursor, 1ULL);
+    out_keys[pos] = key; out_tags[pos] = tag;
+    atomicAdd(&per_graph[tag], 1u);
+  }
+}
+
+__global__ void k_insert_multi(const Table *tables, const uint64_t *keys, const uint32_t *tags, uint64_t n) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    const Table t = tables[tags[i]];
+    Slot *slots = const_cast<Slot *>(t.slots);
+    const uint64_t key = keys[i];
+    uint64_t h = mix64(key) & t.cap_mask;
+    for (;;) {
+      unsigned long long old = atomicCAS((unsigned long long *)&slots[h].key, (unsigned long long)KEY_EMPTY, (unsigned long long)key);
+      if (old == KEY_EMPTY || old == key) break;
+      h = (h + 1) & t.cap_mask;
+    }
+  }
+}
+
+// adjacency byte of every solid k-mer inside ITS graph; remembers where the k-mer sits for the hint pass
+__global__ void k_adjacency_multi(const Table *tables, const uint64_t *keys, const uint32_t *tags, uint64_t n, uint64_t *slot_of) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    const Table t = tables[tags[i]];
+    const uint64_t key = keys[i];
+    uint32_t adj = 0, dummy;
+#pragma unroll
+    for (uint32_t nt = 0; nt < 4; nt++) {
+      if (table_find(t, canonical(succ_kmer(key, nt, t), t.k).key, &dummy) >= 0) adj |= 1u << nt;
+      if (table_find(t, canonical(pred_kmer(key, nt, t), t.k).key, &dummy) >= 0) adj |= 1u << (4 + nt);
+    }
+    uint64_t h = mix64(key) & t.cap_mask;
+    while (t.slots[h].key != key) h = (h + 1) & t.cap_mask;
+    slot_of[i] = h;
+    // the adjacency byte lives in the low byte of val and is only read (through the read-only path) by later launches
+    const_cast<Slot *>(t.slots)[h].val = adj;
+  }
+}
+
+__global__ void k_hints_multi(const Table *tables, const uint64_t *keys, const uint32_t *tags, uint64_t n, const uint64_t *slot_of, Slot *hints) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    const Table t = tables[tags[i]];
+    Slot o{keys[i], 0, {0, 0}};
+    compute_hints(t, keys[i], (uint32_t)(t.slots[slot_of[i]].val & 0xFF), &o);
+    hints[i] = o;
+  }
+}
+
+__global__ void k_apply_hints_multi(const Table *tables, const uint32_t *tags, uint64_t n, const uint64_t *slot_of, const Slot *hints) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    Slot *s = const_cast<Slot *>(tables[tags[i]].slots) + slot_of[i];
+    s->val = hints[i].val; s->h[0] = hints[i].h[0]; s->h[1] = hints[i].h[1];
+  }
+}
+
+void multi_table_release(MultiTable *mt) {
+  if (mt->slots) cudaFree(mt->slots);
+  if (mt->d_tables) cudaFree(mt->d_tables);
+  mt->slots = nullptr; mt->d_tables = nullptr; mt->total_slots = 0; mt->n_kmers = 0; mt->n_graphs = 0;
+  mt->h_tables.clear(); mt->h_sizes.clear();
+}
+
+cudaError_t tables_from_reads(MultiTable *mt, int k, const char *bases_host, const uint64_t *offsets_host, uint64_t n_reads,
+                              const uint64_t *graph_first_read, uint64_t n_graphs, int solid, int sms, cudaStream_t st) {
+  multi_table_release(mt);
+  if (n_graphs == 0 || n_graphs >= (1ULL << 31)) return cudaErrorInvalidValue;
+  std::vector<uint64_t> koff(n_reads + 1);
+  std::vector<uint32_t> rgraph(std::max<uint64_t>(n_reads, 1));
+  uint64_t total = 0;
+  for (uint64_t i = 0; i < n_reads; i++) {
+    koff[i] = total;
+    const uint64_t len = offsets_host[i + 1] - offsets_host[i];
+    total += len >= (uint64_t)k ? len - k + 1 : 0;
+  }
+  koff[n_reads] = total;
+  for (uint64_t g = 0; g < n_graphs; g++) {
+    if (graph_first_read[g] > graph_first_read[g + 1] || graph_first_read[g + 1] > n_reads) return cudaErrorInvalidValue;
+    for (uint64_t r = graph_first_read[g]; r < graph_first_read[g + 1]; r++) rgraph[r] = (uint32_t)g;
+  }
+  if (graph_first_read[0] != 0 || graph_first_read[n_graphs] != n_reads) return cudaErrorInvalidValue;
+  if (total >= (1ULL << 31)) return cudaErrorInvalidValue;   // one sort pass; larger batches are the caller's to split
+  const uint64_t nbytes = offsets_host[n_reads];
+  char *d_bases = nullptr; uint64_t *d_off = nullptr, *d_koff = nullptr, *d_keys = nullptr, *d_keys2 = nullptr, *d_slot_of = nullptr;
+  uint32_t *d_rgraph = nullptr, *d_tags = nullptr, *d_tags2 = nullptr, *d_per_graph = nullptr;
+  unsigned long long *d_cursor = nullptr; void *d_tmp = nullptr; Slot *d_hints = nullptr;
+  std::vector<uint32_t> sizes(n_graphs, 0);
+  cudaError_t err = cudaSuccess;
+  int tag_bits = 1;
+  while ((1ULL << tag_bits) < n_graphs) tag_bits++;
+#define CKG(x) do { err = (x); if (err != cudaSuccess) goto done; } while (0)
+  {
+    unsigned long long n_solid = 0;
+    CKG(cudaMalloc(&d_per_graph, n_graphs * 4));
+    CKG(cudaMemsetAsync(d_per_graph, 0, n_graphs * 4, st));
+    CKG(cudaMalloc(&d_cursor, 8));
+    CKG(cudaMemsetAsync(d_cursor, 0, 8, st));
+    if (total > 0) {
+      CKG(cudaMalloc(&d_bases, nbytes + 1));
+      CKG(cudaMalloc(&d_off, (n_reads + 1) * 8));
+      CKG(cudaMalloc(&d_koff, (n_reads + 1) * 8));
+      CKG(cudaMalloc(&d_rgraph, n_reads * 4));
+      CKG(cudaMemcpyAsync(d_bases, bases_host, nbytes, cudaMemcpyHostToDevice, st));
+      CKG(cudaMemcpyAsync(d_off, offsets_host, (n_reads + 1) * 8, cudaMemcpyHostToDevice, st));
+      CKG(cudaMemcpyAsync(d_koff, koff.data(), (n_reads + 1) * 8, cudaMemcpyHostToDevice, st));
+      CKG(cudaMemcpyAsync(d_rgraph, rgraph.data(), n_reads * 4, cudaMemcpyHostToDevice, st));
+      CKG(cudaMalloc(&d_keys, total * 8)); CKG(cudaMalloc(&d_keys2, total * 8));
+      CKG(cudaMalloc(&d_tags, total * 4)); CKG(cudaMalloc(&d_tags2, total * 4));
+      k_extract_tagged<<<grid_for(total, 256, sms), 256, 0, st>>>(d_bases, d_off, d_koff, n_reads, d_rgraph, k, d_keys, d_tags, total);
+      CKG(cudaGetLastError());
+      // least significant digit first: by k-mer, then (stable) by graph
+      size_t tb = 0, tb2 = 0;
+      CKG(cub::DeviceRadixSort::SortPairs(nullptr, tb, d_keys, d_keys2, d_tags, d_tags2, (int)total, 0, 64, st));
+      CKG(cub::DeviceRadixSort::SortPairs(nullptr, tb2, d_tags2, d_tags, d_keys2, d_keys, (int)total, 0, tag_bits, st));
+      CKG(cudaMalloc(&d_tmp, std::max(tb, tb2)));
+      CKG(cub::DeviceRadixSort::SortPairs(d_tmp, tb, d_keys, d_keys2, d_tags, d_tags2, (int)total, 0, 64, st));
+      CKG(cub::DeviceRadixSort::SortPairs(d_tmp, tb2, d_tags2, d_tags, d_keys2, d_keys, (int)total, 0, tag_bits, st));
+      // (d_keys, d_tags) are sorted by (graph, k-mer); the solid ones are appended to (d_keys2, d_tags2)
+      k_solid_heads<<<grid_for(total, 256, sms), 256, 0, st>>>(d_keys, d_tags, total, (uint32_t)std::max(solid, 1), d_keys2, d_tags2,
+                                                               d_cursor, d_per_graph);
+      CKG(cudaGetLastError());
+    }
+    CKG(cudaMemcpyAsync(&n_solid, d_cursor, 8, cudaMemcpyDeviceToHost, st));
+    CKG(cudaMemcpyAsync(sizes.data(), d_per_graph, n_graphs * 4, cudaMemcpyDeviceToHost, st));
+    CKG(cudaStreamSynchronize(st));
+    // geometry: one power-of-two region per graph, load <= 0.5 like the single table
+    mt->h_tables.resize(n_graphs);
+    uint64_t slots_total = 0;
+    for (uint64_t g = 0; g < n_graphs; g++) {
+      uint64_t cap = 16;
+      while (cap < 2ULL * sizes[g] + 2) cap <<= 1;
+      Table &t = mt->h_tables[g];
+      t.slots = (const Slot *)(uintptr_t)slots_total;   // offset for now
+      t.cap_mask = cap - 1; t.k = k; t.kmask = k >= 32 ? ~0ULL : ((1ULL << (2 * k)) - 1);
+      slots_total += cap;
+    }
+    CKG(cudaMalloc(&mt->slots, slots_total * sizeof(Slot)));
+    for (uint64_t g = 0; g < n_graphs; g++) mt->h_tables[g].slots = mt->slots + (uintptr_t)mt->h_tables[g].slots;
+    CKG(cudaMalloc(&mt->d_tables, n_graphs * sizeof(Table)));
+    CKG(cudaMemcpyAsync(mt->d_tables, mt->h_tables.data(), n_graphs * sizeof(Table), cudaMemcpyHostToDevice, st));
+    k_clear_slots<<<grid_for(slots_total, 256, sms), 256, 0, st>>>(mt->slots, slots_total);
+    CKG(cudaGetLastError());
+    if (n_solid > 0) {
+      CKG(cudaMalloc(&d_slot_of, n_solid * 8));
+      CKG(cudaMalloc(&d_hints, n_solid * sizeof(Slot)));
+      k_insert_multi<<<grid_for(n_solid, 256, sms), 256, 0, st>>>(mt->d_tables, d_keys2, d_tags2, n_solid);
+      k_adjacency_multi<<<grid_for(n_solid, 256, sms), 256, 0, st>>>(mt->d_tables, d_keys2, d_tags2, n_solid, d_slot_of);
+      k_hints_multi<<<grid_for(n_solid, 256, sms), 256, 0, st>>>(mt->d_tables, d_keys2, d_tags2, n_solid, d_slot_of, d_hints);
+      k_apply_hints_multi<<<grid_for(n_solid, 256, sms), 256, 0, st>>>(mt->d_tables, d_tags2, n_solid, d_slot_of, d_hints);
+      CKG(cudaGetLastError());
+    }
+    CKG(cudaStreamSynchronize(st));
+    mt->total_slots = slots_total; mt->n_kmers = n_solid; mt->n_graphs = n_graphs;
+    mt->h_sizes.assign(sizes.begin(), sizes.end());
+  }
+done:
+#undef CKG
+  cudaFree(d_bases); cudaFree(d_off); cudaFree(d_koff); cudaFree(d_rgraph); cudaFree(d_keys); cudaFree(d_keys2);
+  cudaFree(d_tags); cudaFree(d_tags2); cudaFree(d_per_graph); cudaFree(d_cursor); cudaFree(d_tmp); cudaFree(d_slot_of); cudaFree(d_hints);
+  if (err != cudaSuccess) multi_table_release(mt);
   return err;
 }
 

@@ -42,7 +42,7 @@ class G2SSubgraphStats(C.Structure):
 
 class G2SGap(C.Structure):
     _fields_ = [("kmer_left", C.c_char_p), ("kmer_right", C.c_char_p), ("gap_len", C.c_int32), ("gap_err", C.c_int32),
-                ("left_max_fuz", C.c_int32), ("right_max_fuz", C.c_int32), ("flags", C.c_int32), ("reserved", C.c_int32),
+                ("left_max_fuz", C.c_int32), ("right_max_fuz", C.c_int32), ("flags", C.c_int32), ("graph", C.c_int32),
                 ("kmer_right_starts", C.c_char_p), ("present_bits", C.c_uint64)]
 
 
@@ -72,8 +72,8 @@ class G2SRunOptions(C.Structure):
 
 
 # every symbol include/g2s.h declares (tests check that the library exports all of them)
-ABI_SYMBOLS = ["g2s_last_error", "g2s_abi_version", "g2s_create", "g2s_create_multi", "g2s_num_devices", "g2s_destroy", "g2s_import_kmers",
-               "g2s_build_from_reads", "g2s_table_raw", "g2s_table_adopt", "g2s_num_kmers", "g2s_export_kmers", "g2s_contains", "g2s_fill_gap", "g2s_fill_gap_ex",
+ABI_SYMBOLS = ["g2s_last_error", "g2s_abi_version", "g2s_create", "g2s_create_multi", "g2s_num_devices", "g2s_destroy", "g2s_import_kmers", "g2s_h5_read_solid", "g2s_import_h5",
+               "g2s_build_from_reads", "g2s_build_graphs_from_reads", "g2s_graph_num_kmers", "g2s_table_raw", "g2s_table_adopt", "g2s_num_kmers", "g2s_export_kmers", "g2s_contains", "g2s_fill_gap", "g2s_fill_gap_ex",
                "g2s_fill_batch", "g2s_upload_gaps", "g2s_run_resident", "g2s_finish_resident", "g2s_submit",
                "g2s_batch_peek", "g2s_batch_trace", "g2s_batch_free", "g2s_fill_records", "g2s_free",
                "g2s_get_timing", "g2s_get_phase_cycles"]
@@ -97,6 +97,12 @@ def load_library(path: str | None = None):
     L.g2s_destroy.argtypes = [C.c_void_p]
     L.g2s_import_kmers.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
     L.g2s_build_from_reads.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
+    L.g2s_build_graphs_from_reads.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int]
+    L.g2s_graph_num_kmers.argtypes = [C.c_void_p, C.c_size_t]
+    L.g2s_graph_num_kmers.restype = C.c_int64
+    L.g2s_h5_read_solid.argtypes = [C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.c_int32)]
+    L.g2s_import_h5.argtypes = [C.c_void_p, C.c_char_p]
+    L.g2s_free.argtypes = [C.c_void_p]
     L.g2s_table_raw.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
                                 C.POINTER(C.c_uint64)]
     L.g2s_table_adopt.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(C.c_void_p)]
@@ -136,6 +142,7 @@ class GapSpec:
     all_paths: bool = True
     right_starts: str | None = None   # see g2s_gap.kmer_right_starts (right flank longer than k + right_max_fuz)
     present_bits: int | None = None   # see g2s_gap.present_bits: the caller's own contains() answers for the flank k-mers
+    graph: int = 0                    # the gap's graph after build_graphs_from_reads (per-gap filtered-reads mode)
 
     def fill_capacity(self, k: int) -> int:
         return self.gap_len + k + self.gap_err + self.left_max_fuz + self.right_max_fuz + 3
@@ -152,6 +159,7 @@ def pack_gaps(gaps: list[GapSpec]):
         arr[i].gap_len, arr[i].gap_err = g.gap_len, g.gap_err
         arr[i].left_max_fuz, arr[i].right_max_fuz = g.left_max_fuz, g.right_max_fuz
         arr[i].flags = (GAP_SKIP_CONFIDENT if g.skip_confident else 0) | (GAP_ALL_PATHS if g.all_paths else 0)
+        arr[i].graph = g.graph
         if g.present_bits is not None:
             arr[i].flags |= 4   # G2S_GAP_PRESENT_BITS
             arr[i].present_bits = g.present_bits
@@ -191,6 +199,13 @@ class Engine:
             self.L.g2s_destroy(self.h)
             self.h = None
 
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        return False
+
     def __del__(self):
         try:
             self.close()
@@ -201,6 +216,36 @@ class Engine:
     def import_kmers(self, canon: np.ndarray) -> None:
         canon = np.ascontiguousarray(canon, dtype=np.uint64)
         self._check(self.L.g2s_import_kmers(self.h, canon.ctypes.data, canon.size))
+
+    def build_graphs_from_reads(self, read_sets: list, solid: int = 2) -> None:
+        """Per-gap filtered-reads mode: graph g is built from read_sets[g] (a [n, read_len] uint8 ASCII array, or a list
+        of byte strings); all graphs in one device pass.  Gaps then name their graph (fill_batch(..., graphs=[...]))."""
+        chunks, lens, first = [], [], [0]
+        for rs in read_sets:
+            if isinstance(rs, np.ndarray):
+                rs = np.ascontiguousarray(rs, dtype=np.uint8)
+                if rs.size:
+                    chunks.append(rs.reshape(-1))
+                    lens.extend([rs.shape[1]] * rs.shape[0])
+                first.append(first[-1] + (rs.shape[0] if rs.size else 0))
+            else:
+                for r in rs:
+                    b = r if isinstance(r, (bytes, bytearray)) else str(r).encode()
+                    chunks.append(np.frombuffer(bytes(b), dtype=np.uint8))
+                    lens.append(len(b))
+                first.append(first[-1] + len(rs))
+        bases = np.concatenate(chunks) if chunks else np.zeros(1, dtype=np.uint8)
+        off = np.concatenate([[0], np.cumsum(np.asarray(lens, dtype=np.uint64))]).astype(np.uint64)
+        first = np.asarray(first, dtype=np.uint64)
+        self._check(self.L.g2s_build_graphs_from_reads(self.h, bases.ctypes.data, off.ctypes.data, len(lens), first.ctypes.data,
+                                                       len(read_sets), solid))
+
+    def graph_num_kmers(self, graph: int) -> int:
+        return int(self.L.g2s_graph_num_kmers(self.h, graph))
+
+    def import_h5(self, path: str) -> None:
+        """Import the solid k-mers of a GATB graph file (<reads>.h5, group dsk/solid)."""
+        self._check(self.L.g2s_import_h5(self.h, path.encode()))
 
     def build_from_reads(self, reads: np.ndarray, solid: int = 2) -> None:
         """reads: [n_reads, read_len] uint8 ASCII."""
@@ -346,3 +391,16 @@ class Engine:
         t = G2STiming()
         self._check(self.L.g2s_get_timing(self.h, C.byref(t)))
         return t
+
+
+def h5_solid_kmers(path: str):
+    """(canonical k-mers as uint64 array, k-mer size) of a GATB graph file - host only, no device needed."""
+    L = load_library()
+    p, n, ks = C.c_void_p(), C.c_size_t(), C.c_int32()
+    if L.g2s_h5_read_solid(path.encode(), C.byref(p), C.byref(n), C.byref(ks)) != 0:
+        raise G2SError(L.g2s_last_error().decode())
+    try:
+        out = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint64)), shape=(max(n.value, 1),))[:n.value].copy()
+    finally:
+        L.g2s_free(p)
+    return out, ks.value

@@ -81,7 +81,7 @@ typedef struct g2s_gap {
   const char *kmer_right;   /* k + right_max_fuz characters */
   int32_t gap_len, gap_err, left_max_fuz, right_max_fuz;
   int32_t flags;            /* G2S_GAP_* */
-  int32_t reserved;
+  int32_t graph;            /* 0, or the gap's graph after g2s_build_graphs_from_reads (per-gap filtered-reads mode) */
   const char *kmer_right_starts; /* NULL (= kmer_right) or k + right_max_fuz characters whose k-mers start the right
                                pass.  fill_gap takes those from the END of its kmer_right string but the targets from its
                                beginning (src/Gap2Seq.cpp:871-885 vs :1119); they differ only when the caller's right flank
@@ -156,10 +156,30 @@ int g2s_num_devices(const g2s_engine *e);
  * solid canonical k-mers, e.g. the values of graph.iterator() (Graph.cpp:2243-2362). */
 int g2s_import_kmers(g2s_engine *e, const uint64_t *canon, size_t n);
 
+/* Graph import from a GATB graph file (<reads>.h5), the file Gap2Seq::execute loads instead of building the graph when
+ * it is readable (src/Gap2Seq.cpp:171, 195-197): the partitions of group dsk/solid are read straight from the HDF5
+ * container (gatb-core/src/gatb/debruijn/impl/Graph.cpp:171-184, 2243-2362 own the format) - no GATB, no libhdf5.
+ * g2s_h5_read_solid is host-only: *canon_out (malloc'ed, release with g2s_free) receives the n canonical k-mers,
+ * *kmer_size_out the file's "kmer_size" property (0 when absent).  g2s_import_h5 = read + g2s_import_kmers; it refuses
+ * a file whose k-mer size differs from the engine's. */
+int g2s_h5_read_solid(const char *path, uint64_t **canon_out, size_t *n_out, int32_t *kmer_size_out);
+int g2s_import_h5(g2s_engine *e, const char *path);
+
 /* Graph construction on the device, the stand-in for Graph::create(... -abundance-min solid ...)
  * (src/Gap2Seq.cpp:213-214): counts canonical k-mers of `n_reads` reads (ASCII, read i is
  * bases[offsets[i] .. offsets[i+1]) ) and keeps those seen >= solid times.  Timed separately from the fill. */
 int g2s_build_from_reads(g2s_engine *e, const char *bases, const uint64_t *offsets, size_t n_reads, int solid);
+
+/* Per-gap filtered-reads mode.  The reference's wrapper fills every gap in its own Gap2Seq-core process
+ * on the reads that map near the gap - one GATB graph construction per gap (src/Gap2Seq.py:132-220, single-gap mode
+ * src/Gap2Seq.cpp:227-283).  Here the graphs of a whole batch are built in ONE device pass: graph g is counted from reads
+ * graph_first_read[g] .. graph_first_read[g + 1] - 1 of the concatenated reads (the ranges tile the reads in order), with
+ * its own solidity filter, into its own region of one table arena.  Afterwards every gap of g2s_fill_batch / g2s_submit
+ * names its graph in g2s_gap.graph and all gaps are filled in one pass, each against its own graph.  One-GPU engines;
+ * replaces the single graph of g2s_import_kmers / g2s_build_from_reads (and is replaced by them). */
+int g2s_build_graphs_from_reads(g2s_engine *e, const char *bases, const uint64_t *offsets, size_t n_reads,
+                                const uint64_t *graph_first_read, size_t n_graphs, int solid);
+int64_t g2s_graph_num_kmers(const g2s_engine *e, size_t graph);   /* solid k-mers of one of those graphs, -1 = no such graph */
 
 /* Replication of a built table to other GPUs (one NCCL broadcast over NVLink, done by the caller - e.g.
  * torch.distributed.broadcast in bench.py): the owner exposes its device buffer, the receivers allocate an

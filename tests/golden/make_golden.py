@@ -86,13 +86,37 @@ def run_single_gap() -> None:
         shutil.rmtree(tmp, ignore_errors=True)
 
 
+def run_h5_fixture() -> None:
+    """The graph file the reference writes for cfg1_small (./.h5 of the working directory), gzip'ed: the
+    fixture of the HDF5 reader (gap2seq_b200/csrc/g2s_h5.h).  Its dsk/solid partitions hold the solid canonical k-mers."""
+    import gzip
+    case = cases.CASE_BY_NAME["cfg1_small"]
+    w = cases.build(case)
+    tmp = tempfile.mkdtemp(prefix="g2s_golden_")
+    try:
+        paths = w.write(tmp)
+        cmd = [REF_PLAIN] + cases.ref_cmd_flags(case) + ["-reads", paths["reads"], "-scaffolds", paths["gaps"], "-filled",
+                                                        os.path.join(tmp, "filled.fa")]
+        p = subprocess.run("ulimit -s unlimited; " + " ".join(cmd), shell=True, cwd=tmp, capture_output=True, text=True, timeout=600)
+        assert p.returncode == 0, p.stdout[-2000:]
+        raw = open(os.path.join(tmp, ".h5"), "rb").read()
+        out = os.path.join(HERE, "cfg1_small.h5.gz")
+        with open(out, "wb") as f:
+            f.write(gzip.compress(raw, 9, mtime=0))
+        print(f"h5: {len(raw)} bytes -> {os.path.getsize(out)} gzip'ed")
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
 def main() -> None:
     if not os.path.exists(REF):
         sys.exit("oracle/_ref is not built: run oracle/build_ref.sh in the container that has /root/reference")
-    names = sys.argv[1:] or [c.name for c in cases.CASES] + ["single_gap"]
+    names = sys.argv[1:] or [c.name for c in cases.CASES] + ["single_gap", "h5"]
     for n in names:
         if n == "single_gap":
             run_single_gap()
+        elif n == "h5":
+            run_h5_fixture()
         else:
             run_case(cases.CASE_BY_NAME[n])
 
