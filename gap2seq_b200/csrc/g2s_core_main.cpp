@@ -7,6 +7,7 @@
 //                [-dist-error 500] [-fuz 10] [-max-mem 20] [-all-upper] [-best-only] [-unique] [-randseed S]
 //                [-nb-cores N] [-device D] [-gpus G]
 //   Gap2Seq-core ... -left L -right R -length n -filled out.fa            (single-gap mode, src/Gap2Seq.cpp:227-283)
+//   Gap2Seq-core ... -gap-list gaps.tsv -filled out.fa                    (many single-gap runs at once, see below)
 //
 // Differences, all deliberate: the de Bruijn graph is built on the GPU from the reads (exact solid k-mer set, no
 // Bloom filter, no ./.h5 file is written - an existing <reads>.h5 of GATB is loaded like the reference does); -nb-cores only sets the host threads of the subgraph analysis; -max-mem bounds the
@@ -82,7 +83,7 @@ int main(int argc, char **argv) {
   std::map<std::string, bool> flag = {{"-all-upper", false}, {"-best-only", false}, {"-unique", false}};
   std::map<std::string, bool> saw;
   const char *one[] = {"-k", "-solid", "-reads", "-scaffolds", "-filled", "-dist-error", "-fuz", "-max-mem", "-randseed",
-                       "-left", "-right", "-length", "-nb-cores", "-device", "-gpus", "-verbose"};
+                       "-left", "-right", "-length", "-nb-cores", "-device", "-gpus", "-verbose", "-gap-list"};
   for (int i = 1; i < argc; i++) {
     std::string a = argv[i];
     if (a == "-help" || a == "-h") { usage(); return 0; }
@@ -94,7 +95,7 @@ int main(int argc, char **argv) {
     opt[a] = argv[++i];
     saw[a] = true;
   }
-  if (!saw["-reads"] || !saw["-filled"]) { std::cout << "ERROR: Option '-reads' and '-filled' are mandatory" << std::endl; usage(); return 1; }
+  if ((!saw["-reads"] && !saw["-gap-list"]) || !saw["-filled"]) { std::cout << "ERROR: Option '-reads' and '-filled' are mandatory" << std::endl; usage(); return 1; }
 
   const int k = atoi(opt["-k"].c_str()), solid = atoi(opt["-solid"].c_str());
   const int d_err = atoi(opt["-dist-error"].c_str()), max_fuz = atoi(opt["-fuz"].c_str());
@@ -128,6 +129,101 @@ int main(int argc, char **argv) {
   std::vector<int32_t> devices(n_gpus);
   for (int d = 0; d < n_gpus; d++) devices[d] = cfg.device + d;
   if (g2s_create_multi(&cfg, devices.data(), n_gpus, &eng) != G2S_OK) { std::cout << "EXCEPTION: " << g2s_last_error() << std::endl; return 1; }
+
+  // ---- per-gap filtered-reads mode in one process.  The reference's wrapper starts one Gap2Seq-core
+  // per gap - "-reads <the reads near the gap> -left L -right R -length n" - and GATB builds one graph per process
+  // (src/Gap2Seq.py:132-220).  A line of the gap list is such an invocation: name, left flank, right flank, length,
+  // reads file(s), tab separated.  All graphs are built in one device pass and all gaps filled in one pass, each against
+  // its own graph; the traceback of every gap starts from a freshly seeded rand() like its own process would, so that
+  // log lines and sequences equal those of the per-gap runs.
+  if (saw["-gap-list"]) {
+    if (n_gpus > 1) { std::cout << "ERROR: -gap-list runs on one GPU" << std::endl; return 1; }
+    std::ifstream lf(opt["-gap-list"].c_str());
+    if (!lf) { std::cout << "EXCEPTION: cannot read " << opt["-gap-list"] << std::endl; return 1; }
+    struct Item { std::string name, left, right; int length; };
+    std::vector<Item> items;
+    std::vector<uint64_t> off(1, 0), first(1, 0);
+    std::string bases, line;
+    while (std::getline(lf, line)) {
+      if (line.empty() || line[0] == '#') continue;
+      std::vector<std::string> f;
+      std::stringstream ls(line);
+      std::string tok;
+      while (std::getline(ls, tok, '\t')) f.push_back(tok);
+      if (f.size() < 5) { std::cout << "EXCEPTION: gap list line needs name, left, right, length, reads: " << line << std::endl; return 1; }
+      items.push_back(Item{f[0], f[1], f[2], atoi(f[3].c_str())});
+      std::vector<std::string> rn, rs;
+      std::stringstream fs(f[4]);
+      std::string file;
+      while (std::getline(fs, file, ',')) {
+        if (!read_sequences(file, rn, rs)) { std::cout << "DBG building failed: cannot read " << file << std::endl; return 1; }
+      }
+      for (auto &r : rs) { bases += r; off.push_back(bases.size()); }
+      first.push_back(off.size() - 1);
+    }
+    auto tb0 = std::chrono::steady_clock::now();
+    if (g2s_build_graphs_from_reads(eng, bases.data(), off.data(), off.size() - 1, first.data(), items.size(), solid) != G2S_OK) {
+      std::cout << "DBG building failed: " << g2s_last_error() << std::endl;
+      return 1;
+    }
+    auto tb1 = std::chrono::steady_clock::now();
+    std::vector<g2s_gap> gaps(items.size());
+    std::vector<int> lmfs(items.size()), rmfs(items.size());
+    std::vector<char> skip(items.size(), 0);
+    size_t cap = 16;
+    for (size_t i = 0; i < items.size(); i++) {
+      const Item &it = items[i];
+      g2s_gap g{};
+      if ((int)it.left.length() < k || (int)it.right.length() < k) { skip[i] = 1; }   // "Flanks need to be at least k length"
+      const int lmf = skip[i] ? 0 : std::min((int)it.left.length() - k, max_fuz), rmf = skip[i] ? 0 : std::min((int)it.right.length() - k, max_fuz);
+      lmfs[i] = lmf; rmfs[i] = rmf;
+      // like g2s_fill_gap: fill_gap takes the left k-mers and the targets from the BEGINNING of its flank strings and
+      // starts the right pass from the END of the right one (src/Gap2Seq.cpp:871-885, 1000, 1119)
+      g.kmer_left = it.left.c_str();
+      g.kmer_right = it.right.c_str();
+      g.kmer_right_starts = (!skip[i] && (int)it.right.length() > k + rmf) ? it.right.c_str() + (it.right.length() - k - rmf) : nullptr;
+      g.gap_len = it.length; g.gap_err = d_err; g.left_max_fuz = lmf; g.right_max_fuz = rmf;
+      g.flags = (skip_confident ? G2S_GAP_SKIP_CONFIDENT : 0) | (all_paths ? G2S_GAP_ALL_PATHS : 0);
+      g.graph = (int32_t)i;
+      gaps[i] = g;
+      cap = std::max(cap, (size_t)it.length + k + d_err + lmf + rmf + 3);
+    }
+    std::vector<g2s_gap> run;
+    std::vector<size_t> run_of;
+    for (size_t i = 0; i < items.size(); i++) if (!skip[i]) { run_of.push_back(i); run.push_back(gaps[i]); }
+    g2s_batch *batch = nullptr;
+    if (g2s_submit(eng, run.data(), run.size(), &batch) != G2S_OK) { std::cout << "EXCEPTION: " << g2s_last_error() << std::endl; return 1; }
+    auto tb2 = std::chrono::steady_clock::now();
+    std::ofstream output(filled_path.c_str());
+    if (!output) { std::cout << "EXCEPTION: cannot write " << filled_path << std::endl; return 1; }
+    std::vector<char> buf(cap, 0);
+    size_t at = 0;
+    int filledcount = 0;
+    for (size_t i = 0; i < items.size(); i++) {
+      const Item &it = items[i];
+      if (skip[i]) { std::cerr << "Flanks need to be at least k length" << std::endl; continue; }
+      srand(randseed > 0 ? (unsigned)randseed : (unsigned)time(NULL));   // every gap is its own run (src/Gap2Seq.cpp:178)
+      g2s_result r{};
+      buf[0] = 0;
+      if (g2s_batch_trace(batch, at++, &r, buf.data()) != G2S_OK) { std::cout << "EXCEPTION: " << g2s_last_error() << std::endl; return 1; }
+      const int lmf = lmfs[i], rmf = rmfs[i];
+      std::string log;
+      g2s::format_statistics(log, (int)it.left.length() - lmf - r.left_fuz, (int)it.left.length(), (int)it.left.length() + it.length, r.count,
+                             buf.data(), (int)strlen(buf.data()), k, lmf, rmf, r.left_fuz, r.right_fuz, skip_confident, unique_paths,
+                             r.substats, it.length, "");
+      std::cout << log;
+      std::string filledSeq;
+      if (r.count > 0 && (!unique_paths || r.count == 1)) { filledSeq = it.left.substr(0, it.left.length() - r.left_fuz) + buf.data(); filledcount++; }
+      else filledSeq = it.left + std::string((size_t)it.length, 'N') + it.right;
+      output << ">" << it.name << "\n" << filledSeq << "\n";
+    }
+    g2s_batch_free(batch);
+    std::cout << "Filled " << filledcount << " gaps out of " << items.size() << std::endl;
+    std::cerr << "g2s: " << items.size() << " graphs built in " << std::chrono::duration<double>(tb1 - tb0).count() << " s, gaps filled in "
+              << std::chrono::duration<double>(tb2 - tb1).count() << " s" << std::endl;
+    g2s_destroy(eng);
+    return 0;
+  }
 
   // ---- de Bruijn graph from the reads (stand-in for Graph::create, src/Gap2Seq.cpp:199-218); timed separately
   auto t0 = std::chrono::steady_clock::now();

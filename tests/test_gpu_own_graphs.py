@@ -84,3 +84,42 @@ def test_empty_and_tiny_graphs():
         assert e.graph_num_kmers(1) == 0 and e.graph_num_kmers(2) == 0 and e.graph_num_kmers(0) > 0 and e.graph_num_kmers(3) == -1
         res, _ = e.fill_batch(specs)
         assert res[0].count > 0 and res[1].count == 0 and res[2].count == 0
+
+
+def test_gap_list_cli_equals_one_reference_process_per_gap(tmp_path):
+    """`Gap2Seq-core -gap-list` = the wrapper's loop of single-gap runs (src/Gap2Seq.py:132-220) in one process.  Every
+    gap is compared with a run of the UNMODIFIED reference binary in single-gap mode on that gap's reads (when
+    oracle/_ref is present), else with this tool's own single-gap mode - log line and sequence."""
+    import os
+    import subprocess
+    import cases
+    from gap2seq_b200.synth import write_reads_fasta
+    ref = os.path.join(cases.ROOT, "oracle", "_ref", "bin", "Gap2Seq-core")
+    exe = os.path.join(cases.ROOT, "gap2seq_b200", "lib", "Gap2Seq-core")
+    single = ref if os.path.exists(ref) else exe
+    w = make_workload("cfg1", 1.0)
+    flank_l, flank_r = [45, 41, 60, 31, 52, 41], [41, 50, 44, 41, 38, 70]   # some longer than k + fuz, one without fuz
+    lines, want_fa, want_log = [], [], []
+    for gi, rec in enumerate(w.gaps[:6]):
+        i = rec.seq.index("N")
+        left, right = rec.seq[i - flank_l[gi]:i], rec.seq[i + rec.gap_len:i + rec.gap_len + flank_r[gi]]
+        rp = str(tmp_path / f"reads{gi}.fa")
+        write_reads_fasta(rp, w.reads_near([rec], reach=150))
+        lines.append(f"gap{gi}\t{left}\t{right}\t{rec.gap_len}\t{rp}")
+        wd = tmp_path / f"run{gi}"
+        wd.mkdir()
+        p = subprocess.run([single, "-k", "31", "-solid", "2", "-nb-cores", "1", "-randseed", "5", "-reads", rp, "-left", left, "-right", right,
+                            "-length", str(rec.gap_len), "-filled", str(wd / "f.fa")], cwd=str(wd), capture_output=True, text=True, timeout=600)
+        assert p.returncode == 0, p.stdout[-1500:] + p.stderr[-1500:]
+        want_fa.append((wd / "f.fa").read_text().splitlines()[1])
+        want_log.append(cases.filter_log(p.stdout))
+    (tmp_path / "gaps.tsv").write_text("\n".join(lines) + "\n")
+    p = subprocess.run([exe, "-k", "31", "-solid", "2", "-randseed", "5", "-gap-list", str(tmp_path / "gaps.tsv"), "-filled", str(tmp_path / "out.fa")],
+                       capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout[-1500:] + p.stderr[-1500:]
+    got = (tmp_path / "out.fa").read_text().splitlines()
+    assert got[0::2] == [f">gap{g}" for g in range(6)]
+    assert got[1::2] == want_fa
+    body = cases.filter_log(p.stdout)
+    assert body.replace("Filled 6 gaps out of 6\n", "") == "".join(want_log)   # single-gap runs print no total
+    assert sum(1 for s in want_fa if "N" not in s) >= 5
