@@ -283,6 +283,10 @@ def main():
 
     import ctypes
     import numpy as np
+    # the e2e leg receives megabytes of malloc'ed strings per call: this PROCESS keeps freed memory instead of returning
+    # it to the kernel (M_TRIM_THRESHOLD = -1, M_MMAP_THRESHOLD = -3) - an application decision, the library leaves it alone
+    ctypes.CDLL(None).mallopt(-1, 1 << 30)
+    ctypes.CDLL(None).mallopt(-3, 1 << 28)
     import torch
     import torch.distributed as dist
     from gap2seq_b200 import engine, shard

@@ -14,6 +14,8 @@
 // device scratch; -gpus G shards the gaps over GPUs D .. D+G-1 of the box (one k-mer table per GPU, replicated once;
 // results gathered in input order, one rand() stream - the output does not depend on G).  stdout carries the same parameter echo, per-gap "Scaffold:" / "SubgraphStats:" lines and the final
 // "Filled X gaps out of Y" as the reference.
+#include <malloc.h>
+
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
@@ -77,6 +79,8 @@ static void usage() {
 }
 
 int main(int argc, char **argv) {
+  // this process hands megabytes of strings around per call: keep freed memory instead of returning it to the kernel
+  mallopt(M_TRIM_THRESHOLD, 1 << 30); mallopt(M_MMAP_THRESHOLD, 1 << 28);
   std::map<std::string, std::string> opt = {{"-k", "31"}, {"-solid", "2"}, {"-dist-error", "500"}, {"-fuz", "10"},
                                             {"-max-mem", "20"}, {"-randseed", "0"}, {"-nb-cores", "0"}, {"-device", "0"}, {"-gpus", "1"},
                                             {"-verbose", "1"}, {"-scaffolds", ""}};

@@ -159,8 +159,10 @@ extern "C" int g2s_create(const g2s_config *cfg, g2s_engine **out) {
   e->pool.reset(new ThreadPool(cfg->host_threads));
   // The driver call hands megabytes of malloc'ed strings to the caller every time; with glibc's default trimming the
   // freed memory goes back to the kernel and every call pays its page faults again (several ms per 10 000 records on
-  // the measured host).  Keep freed memory in the process unless the embedding application objects (G2S_KEEP_MALLOPT=1).
-  if (!getenv("G2S_KEEP_MALLOPT")) { mallopt(M_TRIM_THRESHOLD, 1 << 30); mallopt(M_MMAP_THRESHOLD, 1 << 28); }
+  // the measured host).  Keeping freed memory in the process is a process-wide policy and therefore the APPLICATION's
+  // decision: Gap2Seq-core (g2s_core_main.cpp) and bench.py make it for themselves; a library user asks for it with
+  // G2S_TUNE_MALLOC=1.
+  if (getenv("G2S_TUNE_MALLOC")) { mallopt(M_TRIM_THRESHOLD, 1 << 30); mallopt(M_MMAP_THRESHOLD, 1 << 28); }
   e->device_trace = getenv("G2S_NO_DEVICE_TRACE") == nullptr;
   e->chain_tier = e->device_trace && getenv("G2S_NO_CHAIN") == nullptr;   // the chain tier writes fills on the device
   *out = e;

@@ -405,14 +405,16 @@ G2S_D uint32_t new_cell(const Slice &S, GShared &sh, const GapDev &gd, uint64_t 
   return idx;
 }
 
-// same, into a cell the caller has already reserved (warp-aggregated reservation in the pair step below)
+// same, into a cell the caller has already reserved (warp-aggregated reservation in the pair step below), with the
+// creating pair's walk count and predecessor link
 G2S_D void new_cell_at(const Slice &S, const GShared &sh, const GapDev &gd, uint32_t idx, uint64_t s, uint32_t e, uint32_t strand,
-                       uint32_t adj, uint32_t c, uint32_t count, uint32_t nflags) {
+                       uint32_t adj, uint32_t c, uint32_t count, uint32_t nflags, uint32_t u0, uint32_t pred) {
   S.ck[idx] = s;
   S.cc[idx] = count;
   S.cn[idx] = e;
-  const uint4 none4 = {NONE32, NONE32, NONE32, NONE32};
-  *(uint4 *)&S.cp[4 * idx] = none4;
+  // predecessor links by prepended base: the creating pair's own link is there from the start
+  const uint4 links = {u0 == 0 ? pred : NONE32, u0 == 1 ? pred : NONE32, u0 == 2 ? pred : NONE32, u0 == 3 ? pred : NONE32};
+  *(uint4 *)&S.cp[4 * idx] = links;
   S.cflags[idx] = out_mask(adj, strand) << CF_OMASK_SHIFT;
   S.ent[e].fcell[strand] = idx;
   if ((nflags & NF_TARGET) && (int)c >= sh.tlo) {
@@ -1543,14 +1545,18 @@ G2S_D void gap_forward(const FillParams &P, const GapDev &gd, const GapCtx &cx, 
           const uint32_t lvl = (uint32_t)c + 1;
           for (uint32_t base = lo; base < hi; base += C * nwarps) {
             const uint32_t cell0 = base + warp * C;
-            uint64_t x = 0; uint32_t om = 0;
+            uint64_t x = 0; uint32_t om = 0, np = 0;
             if (lane < C && cell0 + lane < hi) {
               x = ld_cg(&S.ck[cell0 + lane]);
               om = (ld_cg(&S.cflags[cell0 + lane]) >> CF_OMASK_SHIFT) & 15u;
+              np = clamp_paths(ld_cg(&S.cc[cell0 + lane]));
             }
             const uint32_t nnodes_seen = c < prune_from ? ld_sh(&sh.nnodes) : 0u;
             my_lookups += popc32(om);
             const PairSrc ps = pair_scan(popc32(om));
+            // The pair that stamps a (node, strand) first creates the cell and writes it COMPLETE - its own walk count and
+            // predecessor link included; only the pairs that find the stamp in place (two states converging on one
+            // successor: rare) add theirs after the barrier.
             uint32_t rec_e[4], rec_i[4];
 #pragma unroll
             for (uint32_t it = 0; it < 4; it++) {
@@ -1560,6 +1566,7 @@ G2S_D void gap_forward(const FillParams &P, const GapDev &gd, const GapCtx &cx, 
                 const uint32_t src = pair_owner(ps, p, C);
                 const uint64_t sx = shfl64(x, src);
                 const uint32_t som = __shfl_sync(0xffffffffu, om, src), sex = __shfl_sync(0xffffffffu, ps.excl, src);
+                const uint32_t snp = __shfl_sync(0xffffffffu, np, src);
                 bool act = p < ps.total;
                 uint32_t en = NONE32, adj = 0, nf = 0, strand = 0;
                 uint64_t sk = 0;
@@ -1577,13 +1584,21 @@ G2S_D void gap_forward(const FillParams &P, const GapDev &gd, const GapCtx &cx, 
                   act = en != NONE32;
                 }
                 bool win = false;
-                if (act) win = a_max(&S.ent[en].fstamp[strand], lvl) < lvl;
+                if (act) {
+                  const uint32_t prev = a_max(&S.ent[en].fstamp[strand], lvl);
+                  win = prev < lvl;
+                  // Both strands of the node on this level?  The other strand's stamp is read AFTER this
+                  // one is in place - the load's address is made to depend on the atomic's result - so of two pairs
+                  // that stamp the two strands at least the later one sees the other.
+                  uint32_t zero;
+                  asm volatile("and.b32 %0, %1, 0;" : "=r"(zero) : "r"(prev));
+                  if (ld_cg(&S.ent[en].fstamp[strand ^ 1] + zero) == lvl) a_or(&sh.status, GS_ORDER_DEPENDENT);
+                }
                 const uint32_t idx = warp_reserve(&sh.ncells, win);
                 if (win) {
-                  if (idx >= S.cap_cells) { a_or(&sh.status, GS_OVERFLOW); act = false; }
-                  else new_cell_at(S, sh, gd, idx, sk, en, strand, adj, (uint32_t)c, 0, nf);
-                }
-                if (act) { rec_e[it] = en | (strand << 31); rec_i[it] = cell0 + src; }
+                  if (idx >= S.cap_cells) a_or(&sh.status, GS_OVERFLOW);
+                  else new_cell_at(S, sh, gd, idx, sk, en, strand, adj, (uint32_t)c, snp, nf, (uint32_t)(sx >> (2 * (k - 1))) & 3u, cell0 + src);
+                } else if (act) { rec_e[it] = en | (strand << 31); rec_i[it] = cell0 + src; }
               }
             }
             G::sync();
@@ -1592,14 +1607,11 @@ G2S_D void gap_forward(const FillParams &P, const GapDev &gd, const GapCtx &cx, 
               for (uint32_t it = 0; it < 4; it++) {
                 if (rec_e[it] == NONE32) continue;
                 const uint32_t st = rec_e[it] >> 31, i = rec_i[it];
-                const NodeEnt *en = &S.ent[rec_e[it] & 0x7FFFFFFFu];
-                const uint32_t idx = ld_cg(&en->fcell[st]);
-                const uint32_t other = ld_cg(&en->fstamp[st ^ 1]);
-                const uint32_t np = clamp_paths(ld_cg(&S.cc[i]));
+                const uint32_t idx = ld_cg(&S.ent[rec_e[it] & 0x7FFFFFFFu].fcell[st]);
+                const uint32_t np2 = clamp_paths(ld_cg(&S.cc[i]));
                 const uint32_t u0 = (uint32_t)(ld_cg(&S.ck[i]) >> (2 * (k - 1))) & 3u;
-                a_add(&S.cc[idx], np);
+                a_add(&S.cc[idx], np2);
                 S.cp[4 * idx + u0] = i;
-                if (other == lvl) a_or(&sh.status, GS_ORDER_DEPENDENT);
               }
             }
           }
