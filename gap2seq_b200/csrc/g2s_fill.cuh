@@ -1797,12 +1797,22 @@ G2S_D unsigned long long gap_backward_pack(const FillParams &P, const GapCtx &cx
 
     // nothing above the highest seed can be marked
     const int sweep_top = ld_sh(&sh.max_seed_level) < top_level ? ld_sh(&sh.max_seed_level) : top_level;
+    // the bounds of a level are read one level ahead, so that the sweep's chain of dependent reads starts at the flags;
+    // a level wider than the narrow mode's (or empty) does not even ask for a batch (narrow_backward would decline it
+    // after two barriers)
+    uint32_t b_hi = sweep_top >= 0 ? ld_cg(&S.lstart[sweep_top + 1]) : 0u, b_lo = sweep_top >= 0 ? ld_cg(&S.lstart[sweep_top]) : 0u;
     for (int d = sweep_top; d >= 0; d--) {
-      if (d > lmf) {   // batches of narrow levels (no start cells up there)
+      const uint32_t lo = b_lo, hi = b_hi;
+      const uint32_t lo_below = d > 0 ? ld_cg(&S.lstart[d - 1]) : 0u;
+      if (d > lmf && hi - lo >= 1u && hi - lo <= (uint32_t)NARROW_W) {   // batches of narrow levels (no start cells up there)
         const int adv = narrow_backward<G>(S, sh, nb, d, lmf);
-        if (adv > 0) { d -= adv - 1; continue; }
+        if (adv > 0) {
+          d -= adv - 1;
+          b_hi = ld_cg(&S.lstart[d]); b_lo = d > 0 ? ld_cg(&S.lstart[d - 1]) : 0u;   // bounds of level d - 1, the next one
+          continue;
+        }
       }
-      const uint32_t lo = ld_cg(&S.lstart[d]), hi = ld_cg(&S.lstart[d + 1]);
+      b_hi = lo; b_lo = lo_below;
       G2S_STAT(emul_stats().back_general_levels++; emul_stats().width_hist[hi - lo > 7 ? 7 : hi - lo]++);
       const uint64_t lcanon = (d <= lmf) ? canonical(S.lk[d] & FLANK_KMER, k).key : KEY_EMPTY;
       uint32_t my_b = 0, my_t = 0, my_e = 0;   // this thread's share of the level's totals, added once per warp below
