@@ -20,6 +20,7 @@ d=json.load(open(sys.argv[1])); print('N=2', 'ms', round(d['ms_per_step'],4), 'v
 P
 timeout 900 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${TAG}_bench_reference.json 2> gpurun_out/${TAG}_bench_reference.err
 cut -c1-900 gpurun_out/${TAG}_bench_reference.json
+timeout 300 python tools/own_graphs_bench.py cfg2 1.0 > gpurun_out/${TAG}_own_graphs_cfg2.json 2> gpurun_out/${TAG}_own_graphs_cfg2.err; cut -c1-400 gpurun_out/${TAG}_own_graphs_cfg2.json
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_chain -s 6 -c 2 -o gpurun_out/${TAG}_chain_cfg4 python bench.py --steps 1 --warmup 3 --cpu-seconds 0.1 > gpurun_out/${TAG}_ncu.log 2>&1
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/${TAG}_launches_cfg4.csv python bench.py --steps 2 --warmup 1 --cpu-seconds 0.1 > /dev/null 2>&1
 ncu -i gpurun_out/${TAG}_chain_cfg4.ncu-rep --page details 2>/dev/null | grep -E "k_chain|Duration" | head -4
