@@ -61,12 +61,16 @@ struct GeneralResult {
 inline void analyze_general(const PackRec *pk, uint32_t npack, GeneralResult &R) {
   // dense vertex numbers in first-seen order (every result below is invariant under renumbering):
   // node-table entry -> vertex through a direct map, then once per record so that edges never search
+  // the B records (vertices of the subgraph) are a fraction of the pack - the rest is the traceback trellis - so they
+  // are listed once and every later pass walks the list instead of streaming all 32-byte records again
+  std::vector<uint32_t> bl;
+  bl.reserve(npack / 4 + 16);
   uint32_t maxnode = 0;
-  for (uint32_t i = 0; i < npack; i++) if ((pk[i].meta & PM_B) && pk[i].node > maxnode) maxnode = pk[i].node;
+  for (uint32_t i = 0; i < npack; i++)
+    if (pk[i].meta & PM_B) { bl.push_back(i); if (pk[i].node > maxnode) maxnode = pk[i].node; }
   std::vector<uint32_t> vmap((size_t)maxnode + 1, NONE32), vof(npack, NONE32);
   uint32_t V = 2;   // 0 = sink, 1 = source
-  for (uint32_t i = 0; i < npack; i++) {
-    if (!(pk[i].meta & PM_B)) continue;
+  for (uint32_t i : bl) {
     uint32_t &m = vmap[pk[i].node];
     if (m == NONE32) m = V++;
     vof[i] = m;
@@ -74,16 +78,14 @@ inline void analyze_general(const PackRec *pk, uint32_t npack, GeneralResult &R)
   // out-edges bucketed by source (counting sort), duplicates - the same node pair on several levels - removed per
   // bucket: the reference's `if (!edge(u,v).second) add_edge`
   std::vector<uint32_t> ostart((size_t)V + 1, 0);
-  for (uint32_t i = 0; i < npack; i++) {
-    if (!(pk[i].meta & PM_B)) continue;
+  for (uint32_t i : bl) {
     if (pk[i].meta & PM_START) ostart[1 + 1]++;
     else for (int q = 0; q < 4; q++) if (pk[i].pred[q] != NONE32) ostart[vof[pk[i].pred[q]] + 1]++;
     if (pk[i].meta & PM_SEED) ostart[vof[i] + 1]++;
   }
   for (uint32_t v = 0; v < V; v++) ostart[v + 1] += ostart[v];
   std::vector<uint32_t> otgt(ostart[V]), fillp(ostart.begin(), ostart.end() - 1);
-  for (uint32_t i = 0; i < npack; i++) {
-    if (!(pk[i].meta & PM_B)) continue;
+  for (uint32_t i : bl) {
     const uint32_t v = vof[i];
     if (pk[i].meta & PM_START) otgt[fillp[1]++] = v;
     else for (int q = 0; q < 4; q++) if (pk[i].pred[q] != NONE32) otgt[fillp[vof[pk[i].pred[q]]]++] = v;
