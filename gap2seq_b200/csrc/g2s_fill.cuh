@@ -1537,6 +1537,10 @@ G2S_D void gap_forward(const FillParams &P, const GapDev &gd, const GapCtx &cx, 
       if (!dead) {
         top_level = c;
         levels_f = c;
+        // the cell counter and the status word as of the level's last reservation: read between the last round's two
+        // barriers, when nobody writes them (the next level's first phase is a barrier away), so that the level needs no
+        // third barrier for it
+        uint32_t nc_last = 0, st_last = 0;
 #ifdef G2S_DEVICE_BUILD
         {   // pair step (see pair_scan): C elements per warp, the smallest C that covers the border in one round
           const uint32_t lane = (uint32_t)rank & 31u, warp = (uint32_t)rank >> 5, nwarps = (uint32_t)gsz >> 5;
@@ -1602,6 +1606,7 @@ G2S_D void gap_forward(const FillParams &P, const GapDev &gd, const GapCtx &cx, 
               }
             }
             G::sync();
+            if (base + C * nwarps >= hi) { nc_last = ld_sh(&sh.ncells); st_last = ld_sh(&sh.status); }
             if (!(ld_sh(&sh.status) & GS_OVERFLOW)) {
 #pragma unroll
               for (uint32_t it = 0; it < 4; it++) {
@@ -1666,6 +1671,7 @@ G2S_D void gap_forward(const FillParams &P, const GapDev &gd, const GapCtx &cx, 
             }
           }
         }
+        nc_last = sh.ncells; st_last = sh.status;
 #endif
         G::sync();
         bool ovf;
@@ -1694,13 +1700,10 @@ G2S_D void gap_forward(const FillParams &P, const GapDev &gd, const GapCtx &cx, 
           if (rank == 0) S.lstart[c + 1] = sh.ncells < S.cap_cells ? sh.ncells : S.cap_cells;
           ovf = group_overflow<G>(sh);
         } else {
-          // nobody writes the cell counter or the status word between this barrier and the next level's first phase,
-          // which lies behind the barrier of the found check: every thread reads the same values
-          const uint32_t nc = ld_sh(&sh.ncells);
-          known_for = c + 1; known_lo = hi; known_hi = nc < S.cap_cells ? nc : S.cap_cells;
+          known_for = c + 1; known_lo = hi; known_hi = nc_last < S.cap_cells ? nc_last : S.cap_cells;
           if (rank == 0) S.lstart[c + 1] = known_hi;
           // (the thin tier's right pass runs on other warps at the same time and may set a bit at any moment: a vote there)
-          ovf = W::kConcurrent ? group_overflow<G>(sh) : (ld_sh(&sh.status) & GS_OVERFLOW) != 0;
+          ovf = W::kConcurrent ? group_overflow<G>(sh) : (st_last & GS_OVERFLOW) != 0;
         }
         if (ovf) { overflow = true; break; }
       } else {
@@ -1735,7 +1738,7 @@ G2S_D void gap_forward(const FillParams &P, const GapDev &gd, const GapCtx &cx, 
         G::sync();
         found = ld_sh(&sh.n_plen) != 0;
         if (found && !all_paths) break;   // -best-only stops at the first hit (Gap2Seq.cpp:1156-1158)
-      } else {
+      } else if (c <= lmf) {
         G::sync();
       }
       if (rank == 0) sh.prof[4] += now_cycles() - tg0;
