@@ -179,6 +179,8 @@ struct ScoutSeg {      // one gather of a scout: tip x, then the hint's states o
 struct NarrowBuf {     // look-ahead state of one pass (the right pass and the forward pass own one each, so that two warps
                        // can run them concurrently)
   uint32_t nnext;
+  uint32_t rnext[3];   // right pass, general levels: entries of the next border, one counter per level in rotation (bit 31: the
+                       // level could not insert a node), so that a level needs one barrier - nobody resets the counter being read
   uint32_t ch_len, ch_valid, ch_base, ch_cnt, nw_stop, nw_alive;
   uint64_t nw_x[NARROW_W], nw_x0[NARROW_W];
   uint32_t nw_m[NARROW_W], nw_cnt0[NARROW_W];
@@ -1354,6 +1356,7 @@ G2S_D void gap_right(const FillParams &P, const GapCtx &cx, const Slice &S, GSha
   }
   G::sync();
   n = ld_sh(&nb.nnext);
+  int prepared_for = -1;
   for (int c = 1; c <= right_half; c++) {
     if (n == 0 && c > rmf) break;
     levels_r = c;
@@ -1363,9 +1366,14 @@ G2S_D void gap_right(const FillParams &P, const GapCtx &cx, const Slice &S, GSha
       if (group_overflow<G>(sh)) break;
       if (adv > 0) { n = n2; levels_r = c + adv - 1; c += adv - 1; continue; }
     }
-    G::sync();
-    if (rank == 0) nb.nnext = 0;
-    G::sync();
+    uint32_t *cnt = &nb.rnext[(uint32_t)c % 3u];
+    if (prepared_for != c) {   // first general level, or a narrow batch came before: this level's counter is stale
+      G::sync();
+      if (rank == 0) *cnt = 0;
+      G::sync();
+    }
+    if (rank == 0) nb.rnext[(uint32_t)(c + 1) % 3u] = 0;   // the next level's counter: it was last read two barriers ago
+    prepared_for = c + 1;
     const uint64_t *fk = S.rbk[cur]; const unsigned char *fm = S.rbm[cur];
     uint64_t *nk = S.rbk[cur ^ 1]; unsigned char *nm = S.rbm[cur ^ 1];
 #ifdef G2S_DEVICE_BUILD
@@ -1392,6 +1400,7 @@ G2S_D void gap_right(const FillParams &P, const GapCtx &cx, const Slice &S, GSha
             strand = cp.strand;
             uint32_t nf = 0;
             const uint32_t en = table_and_node<true>(T, S, sh, cp.key, nnodes_seen, &adj, &nf);
+            if (en == NONE32) a_or(cnt, 0x80000000u);
             if (en != NONE32) {
               if (!(nf & NF_IN_RS)) a_or(&S.ent[en].flags, NF_IN_RS);
               const uint32_t stamp = (uint32_t)(c + 1) * 2 + strand;
@@ -1400,7 +1409,7 @@ G2S_D void gap_right(const FillParams &P, const GapCtx &cx, const Slice &S, GSha
               else if ((prev & 1) != strand) a_or(&sh.status, GS_ORDER_DEPENDENT);   // both strands on one level
             }
           }
-          const uint32_t idx = warp_reserve(&nb.nnext, win);
+          const uint32_t idx = warp_reserve(cnt, win);
           if (win) {
             if (idx >= S.cap_cells) a_or(&sh.status, GS_OVERFLOW);
             else { nk[idx] = p; nm[idx] = (unsigned char)in_mask(adj, strand); }
@@ -1420,12 +1429,12 @@ G2S_D void gap_right(const FillParams &P, const GapCtx &cx, const Slice &S, GSha
         uint32_t adj = 0;
         if (table_find(T, cp.key, &adj) < 0) { a_or(&sh.status, GS_INTERNAL); continue; }
         uint32_t en = node_insert(S, sh, cp.key);
-        if (en == NONE32) continue;
+        if (en == NONE32) { a_or(cnt, 0x80000000u); continue; }
         a_or(&S.ent[en].flags, NF_IN_RS);
         uint32_t stamp = (uint32_t)(c + 1) * 2 + cp.strand;
         uint32_t prev = a_max(&S.ent[en].rstamp, stamp);
         if ((prev >> 1) < (uint32_t)(c + 1)) {
-          uint32_t idx = a_inc(&nb.nnext);
+          uint32_t idx = a_inc(cnt);
           if (idx >= S.cap_cells) { a_or(&sh.status, GS_OVERFLOW); continue; }
           nk[idx] = p; nm[idx] = (unsigned char)in_mask(adj, cp.strand);
         } else if ((prev & 1) != cp.strand) {
@@ -1435,29 +1444,36 @@ G2S_D void gap_right(const FillParams &P, const GapCtx &cx, const Slice &S, GSha
     }
 #endif
     G::sync();
-    if (rank == 0 && c <= rmf) {   // next staggered right start (Gap2Seq.cpp:953-968)
-      uint64_t x = kmer_from_ascii(cx.rsstr + (rmf - c), k);
-      Canon cs = canonical(x, k);
-      uint32_t adj = 0;
-      if (table_find(T, cs.key, &adj) >= 0) {
-        uint32_t en = node_insert(S, sh, cs.key);
-        if (en != NONE32) {
-          a_or(&S.ent[en].flags, NF_IN_RS);
-          uint32_t stamp = (uint32_t)(c + 1) * 2 + cs.strand;
-          uint32_t prev = a_max(&S.ent[en].rstamp, stamp);
-          if ((prev >> 1) < (uint32_t)(c + 1)) {
-            uint32_t idx = a_add(&nb.nnext, 1);
-            if (idx >= S.cap_cells) a_or(&sh.status, GS_OVERFLOW);
-            else { nk[idx] = x; nm[idx] = (unsigned char)in_mask(adj, cs.strand); }
-          } else if ((prev & 1) != cs.strand) {
-            a_or(&sh.status, GS_ORDER_DEPENDENT);
+    if (c <= rmf) {
+      if (rank == 0) {   // next staggered right start (Gap2Seq.cpp:953-968)
+        uint64_t x = kmer_from_ascii(cx.rsstr + (rmf - c), k);
+        Canon cs = canonical(x, k);
+        uint32_t adj = 0;
+        if (table_find(T, cs.key, &adj) >= 0) {
+          uint32_t en = node_insert(S, sh, cs.key);
+          if (en == NONE32) a_or(cnt, 0x80000000u);
+          if (en != NONE32) {
+            a_or(&S.ent[en].flags, NF_IN_RS);
+            uint32_t stamp = (uint32_t)(c + 1) * 2 + cs.strand;
+            uint32_t prev = a_max(&S.ent[en].rstamp, stamp);
+            if ((prev >> 1) < (uint32_t)(c + 1)) {
+              uint32_t idx = a_add(cnt, 1);
+              if (idx >= S.cap_cells) a_or(&sh.status, GS_OVERFLOW);
+              else { nk[idx] = x; nm[idx] = (unsigned char)in_mask(adj, cs.strand); }
+            } else if ((prev & 1) != cs.strand) {
+              a_or(&sh.status, GS_ORDER_DEPENDENT);
+            }
           }
         }
       }
+      G::sync();
     }
-    G::sync();
-    n = ld_sh(&nb.nnext);
-    if (group_overflow<G>(sh)) break;
+    const uint32_t raw = ld_sh(cnt);   // stable: the next append to this counter is three levels away
+    n = raw & 0x7FFFFFFFu;
+    if ((raw >> 31) != 0 || n > S.cap_cells) {   // this pass outgrew its slice (the bit is in the status word already)
+      if (rank == 0) a_or(&sh.status, GS_OVERFLOW);
+      break;
+    }
     if (rank == 0) sh.cells_right += n;
     cur ^= 1;
   }
