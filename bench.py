@@ -66,6 +66,7 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--oracle-seconds", type=float, default=8.0, help="budget of the oracle check of the step's output")
     ap.add_argument("--ref-gaps", type=int, default=600, help="--impl reference: gaps in the bounded sample")
+    ap.add_argument("--host-threads", type=int, default=0, help="host threads of the engine (0: min(16, cores / ranks))")
     return ap.parse_args()
 
 
@@ -308,7 +309,7 @@ def main():
     w, n_base = make_workload(args.workload, args.scale, rank, lists=world)
     # host threads of the engine (subgraph analysis, tracebacks, splice)
     cores = os.cpu_count() or 2
-    host_threads = max(2, min(16, cores // max(1, world)))
+    host_threads = args.host_threads if args.host_threads > 0 else max(2, min(16, cores // max(1, world)))
     eng = engine.Engine(k=w.k, max_fuz=w.fuz, device=local_rank, host_threads=host_threads)
     t0 = time.perf_counter()
     if rank == 0:
