@@ -33,6 +33,18 @@ def test_solid_kmers_of_the_reference_graph_file_equal_the_oracle_graph(tmp_path
     assert np.array_equal(np.sort(kmers), want)
 
 
+def test_compressed_graph_file_written_by_gatb(tmp_path):
+    """GATB's own -out-compress (shuffle + deflate on every dataset, CollectionHDF5Patch.hpp:184-187): the fixture
+    tests/golden/cfg1_small_compressed.h5.gz was written by GATB's Graph::create with that option
+    (oracle/make_h5_compressed_fixture.sh); the node set must be the same as that of the plain file."""
+    p = tmp_path / "c.h5"
+    p.write_bytes(gzip.decompress(open(os.path.join(HERE, "golden", "cfg1_small_compressed.h5.gz"), "rb").read()))
+    kc, ksize = engine.h5_solid_kmers(str(p))
+    kp, _ = engine.h5_solid_kmers(_fixture(tmp_path))
+    assert ksize == 31 and kc.size == kp.size == 19955
+    assert np.array_equal(np.sort(kc), np.sort(kp))
+
+
 def test_reader_rejects_what_it_does_not_understand(tmp_path):
     bad = tmp_path / "x.h5"
     bad.write_bytes(b"not an hdf5 file at all" * 10)
