@@ -238,18 +238,15 @@ int main(int argc, char **argv) {
     std::cout << "Loading from " << reads_graph << std::endl;
     if (g2s_import_h5(eng, reads_graph.c_str()) != G2S_OK) { std::cout << "EXCEPTION: " << g2s_last_error() << std::endl; return 1; }
   } else {
-    std::vector<std::string> rn, rs;
+    // the reads files go to the device as they are and are parsed there (g2s_build_from_read_files); text that is neither
+    // FASTA nor FASTQ is reported by the engine
+    std::vector<std::string> files;
     std::stringstream ss(reads);
     std::string file;
-    while (std::getline(ss, file, ',')) {
-      if (!read_sequences(file, rn, rs)) { std::cout << "DBG building failed: cannot read " << file << std::endl; return 1; }
-    }
-    std::vector<uint64_t> off(rs.size() + 1, 0);
-    for (size_t i = 0; i < rs.size(); i++) off[i + 1] = off[i] + rs[i].size();
-    std::string bases;
-    bases.reserve(off.back());
-    for (auto &s : rs) bases += s;
-    if (g2s_build_from_reads(eng, bases.data(), off.data(), rs.size(), solid) != G2S_OK) {
+    while (std::getline(ss, file, ',')) files.push_back(file);
+    std::vector<const char *> fp;
+    for (auto &f : files) fp.push_back(f.c_str());
+    if (g2s_build_from_read_files(eng, fp.data(), fp.size(), solid, nullptr) != G2S_OK) {
       std::cout << "DBG building failed: " << g2s_last_error() << std::endl;
       return 1;
     }

@@ -22,6 +22,10 @@ cudaError_t table_fill(DeviceTable *dt, const uint64_t *keys_dev, const uint32_t
                        int sms, cudaStream_t st);
 cudaError_t table_from_reads(DeviceTable *dt, int k, const char *bases_host, const uint64_t *offsets_host,
                              uint64_t n_reads, int solid, int sms, cudaStream_t st);
+// reads as the raw bytes of FASTA / four-line FASTQ text (several files: concatenated, each ending with a line break),
+// parsed on the device; *n_reads_out = records found
+cudaError_t table_from_read_files(DeviceTable *dt, int k, const char *bytes_host, uint64_t n, int solid, int sms, cudaStream_t st,
+                                  uint64_t *n_reads_out);
 cudaError_t table_export(const DeviceTable &dt, uint64_t *keys_host, uint8_t *adj_host, int sms, cudaStream_t st);
 cudaError_t table_contains(const DeviceTable &dt, const char *ascii_host, uint64_t n, uint8_t *out_host, cudaStream_t st);
 

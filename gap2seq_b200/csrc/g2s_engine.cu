@@ -374,6 +374,33 @@ extern "C" int g2s_build_from_reads(g2s_engine *e, const char *bases, const uint
   return replicate_table(e);
 }
 
+extern "C" int g2s_build_from_read_files(g2s_engine *e, const char *const *paths, size_t n_paths, int solid, uint64_t *n_reads_out) {
+  if (!e || !paths || n_paths == 0) return fail(G2S_E_ARG, "g2s_build_from_read_files: null argument");
+  CUDA_TRY(cudaSetDevice(e->cfg.device));
+  // the files as they are, one after the other (each made to end with a line break); the device does the parsing
+  std::vector<char> bytes;
+  for (size_t f = 0; f < n_paths; f++) {
+    FILE *fp = paths[f] ? fopen(paths[f], "rb") : nullptr;
+    if (!fp) return fail(G2S_E_ARG, std::string("g2s_build_from_read_files: cannot open ") + (paths[f] ? paths[f] : "(null)"));
+    fseek(fp, 0, SEEK_END);
+    const long sz = ftell(fp);
+    fseek(fp, 0, SEEK_SET);
+    const size_t at = bytes.size();
+    bytes.resize(at + (sz > 0 ? (size_t)sz : 0));
+    const size_t got = sz > 0 ? fread(bytes.data() + at, 1, (size_t)sz, fp) : 0;
+    fclose(fp);
+    if (got != (size_t)(sz > 0 ? sz : 0)) return fail(G2S_E_ARG, std::string("g2s_build_from_read_files: short read of ") + paths[f]);
+    if (!bytes.empty() && bytes.back() != '\n') bytes.push_back('\n');
+  }
+  multi_table_release(&e->multi);
+  uint64_t nr = 0;
+  const cudaError_t er = table_from_read_files(&e->table, e->cfg.k, bytes.data(), bytes.size(), solid, e->sms, e->st, &nr);
+  if (er == cudaErrorInvalidValue) return fail(G2S_E_ARG, "g2s_build_from_read_files: the reads are neither FASTA ('>') nor FASTQ ('@') text");
+  CUDA_TRY(er);
+  if (n_reads_out) *n_reads_out = nr;
+  return replicate_table(e);
+}
+
 extern "C" int g2s_build_graphs_from_reads(g2s_engine *e, const char *bases, const uint64_t *offsets, size_t n_reads,
                                            const uint64_t *graph_first_read, size_t n_graphs, int solid) {
   if (!e || !offsets || !graph_first_read || (!bases && n_reads)) return fail(G2S_E_ARG, "g2s_build_graphs_from_reads: null argument");

@@ -4,6 +4,7 @@
 // Graph.cpp:1284-1345) and, for stand-alone use, its construction (DSK solid k-mer counting invoked from
 // src/Gap2Seq.cpp:213-214) by sort + run-length counting on the device.
 #include <cub/cub.cuh>
+#include <thrust/iterator/transform_iterator.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -247,32 +248,17 @@ cudaError_t table_fill(DeviceTable *dt, const uint64_t *keys_dev, const uint32_t
   return cudaSuccess;
 }
 
-cudaError_t table_from_reads(DeviceTable *dt, int k, const char *bases_host, const uint64_t *offsets_host, uint64_t n_reads,
-                             int solid, int sms, cudaStream_t st) {
-  // per-read k-mer counts -> exclusive offsets (host; linear in the number of reads)
-  uint64_t *koff = (uint64_t *)malloc((n_reads + 1) * sizeof(uint64_t));
-  if (!koff) return cudaErrorMemoryAllocation;
-  uint64_t total = 0;
-  for (uint64_t i = 0; i < n_reads; i++) {
-    koff[i] = total;
-    uint64_t len = offsets_host[i + 1] - offsets_host[i];
-    total += len >= (uint64_t)k ? len - k + 1 : 0;
-  }
-  koff[n_reads] = total;
-  const uint64_t nbytes = offsets_host[n_reads];
-  char *d_bases = nullptr; uint64_t *d_off = nullptr, *d_koff = nullptr, *d_keys = nullptr, *d_sorted = nullptr;
+// counting core on device-resident reads: d_bases (concatenated bases), d_off / d_koff (n_reads + 1 exclusive offsets of
+// the reads' bases / k-mer occurrences), total = k-mer occurrences
+static cudaError_t table_from_device_reads(DeviceTable *dt, int k, const char *d_bases, const uint64_t *d_off, const uint64_t *d_koff,
+                                           uint64_t n_reads, uint64_t total, int solid, int sms, cudaStream_t st) {
+  uint64_t *d_keys = nullptr, *d_sorted = nullptr;
   uint64_t *d_unique = nullptr; uint32_t *d_counts = nullptr; int *d_nruns = nullptr; void *d_tmp = nullptr;
   unsigned long long *d_nsolid = nullptr;
   cudaError_t err = cudaSuccess;
 #define CKG(x) do { err = (x); if (err != cudaSuccess) goto done; } while (0)
   {
     if (total == 0) { CKG(table_alloc(dt, k, 0, sms, st)); CKG(cudaStreamSynchronize(st)); goto done; }
-    CKG(cudaMalloc(&d_bases, nbytes + 1));
-    CKG(cudaMalloc(&d_off, (n_reads + 1) * 8));
-    CKG(cudaMalloc(&d_koff, (n_reads + 1) * 8));
-    CKG(cudaMemcpyAsync(d_bases, bases_host, nbytes, cudaMemcpyHostToDevice, st));
-    CKG(cudaMemcpyAsync(d_off, offsets_host, (n_reads + 1) * 8, cudaMemcpyHostToDevice, st));
-    CKG(cudaMemcpyAsync(d_koff, koff, (n_reads + 1) * 8, cudaMemcpyHostToDevice, st));
     // One sort + run-length pass holds at most `limit` occurrences (cub's run-length API counts in int; the sort needs two
     // 8-byte buffers per occurrence).  Larger inputs are counted in hash partitions of the canonical k-mer.
     uint64_t limit = 1ULL << 30;
@@ -365,9 +351,193 @@ cudaError_t table_from_reads(DeviceTable *dt, int k, const char *bases_host, con
   }
 done:
 #undef CKG
-  free(koff);
-  cudaFree(d_bases); cudaFree(d_off); cudaFree(d_koff); cudaFree(d_keys); cudaFree(d_sorted);
+  cudaFree(d_keys); cudaFree(d_sorted);
   cudaFree(d_counts); cudaFree(d_nruns); cudaFree(d_tmp); cudaFree(d_nsolid);
+  return err;
+}
+
+cudaError_t table_from_reads(DeviceTable *dt, int k, const char *bases_host, const uint64_t *offsets_host, uint64_t n_reads,
+                             int solid, int sms, cudaStream_t st) {
+  // per-read k-mer counts -> exclusive offsets (host; linear in the number of reads)
+  std::vector<uint64_t> koff(n_reads + 1);
+  uint64_t total = 0;
+  for (uint64_t i = 0; i < n_reads; i++) {
+    koff[i] = total;
+    const uint64_t len = offsets_host[i + 1] - offsets_host[i];
+    total += len >= (uint64_t)k ? len - k + 1 : 0;
+  }
+  koff[n_reads] = total;
+  const uint64_t nbytes = offsets_host[n_reads];
+  char *d_bases = nullptr; uint64_t *d_off = nullptr, *d_koff = nullptr;
+  cudaError_t err = cudaMalloc(&d_bases, nbytes + 1);
+  if (err == cudaSuccess) err = cudaMalloc(&d_off, (n_reads + 1) * 8);
+  if (err == cudaSuccess) err = cudaMalloc(&d_koff, (n_reads + 1) * 8);
+  if (err == cudaSuccess) err = cudaMemcpyAsync(d_bases, bases_host, nbytes, cudaMemcpyHostToDevice, st);
+  if (err == cudaSuccess) err = cudaMemcpyAsync(d_off, offsets_host, (n_reads + 1) * 8, cudaMemcpyHostToDevice, st);
+  if (err == cudaSuccess) err = cudaMemcpyAsync(d_koff, koff.data(), (n_reads + 1) * 8, cudaMemcpyHostToDevice, st);
+  if (err == cudaSuccess) err = table_from_device_reads(dt, k, d_bases, d_off, d_koff, n_reads, total, solid, sms, st);
+  cudaFree(d_bases); cudaFree(d_off); cudaFree(d_koff);
+  return err;
+}
+
+// ---------------------------------------------------------------------------------------------- reads parsed on the device
+// The reads file(s) go to the device as raw bytes (FASTA, sequences over any number of lines, or four-line FASTQ) and
+// are parsed there: a scan labels every byte with the kind of line it is on, the sequence characters are compacted into
+// the concatenated-bases array the counting kernels read, and the read boundaries fall out of the same prefix sums.
+// (The reference reads banks through GATB's BankFasta, gatb-core/src/gatb/bank/impl/BankFasta.cpp; only the sequences
+// and their boundaries matter to the graph.)
+struct LineState {   // per byte: kind of the line that holds it, and the number of line breaks before it
+  uint32_t kind;     // 0 = unknown yet, 1 = FASTA sequence line, 2 = FASTA header line
+  __host__ __device__ LineState() : kind(0) {}
+  __host__ __device__ explicit LineState(uint32_t k) : kind(k) {}
+};
+struct LastKind {
+  __host__ __device__ LineState operator()(const LineState &a, const LineState &b) const { return b.kind ? b : a; }
+};
+
+// FASTA: kind of the line each byte is on (scan of "a line starts here: header or not")
+__global__ void k_fasta_line_starts(const char *bytes, uint64_t n, LineState *st) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    const bool line_start = i == 0 || bytes[i - 1] == '\n';
+    st[i] = LineState(line_start ? (bytes[i] == '>' ? 2u : 1u) : 0u);
+  }
+}
+// keep[i]: byte i is a sequence character; head[i]: byte i starts a record (its header line)
+__global__ void k_fasta_flags(const char *bytes, uint64_t n, const LineState *st, uint8_t *keep, uint8_t *head) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    const char c = bytes[i];
+    keep[i] = (st[i].kind == 1 && c != '\n' && c != '\r' && c != ' ' && c != '\t') ? 1 : 0;
+    head[i] = (c == '>' && (i == 0 || bytes[i - 1] == '\n')) ? 1 : 0;
+  }
+}
+// FASTQ (four lines per record): line number of every byte = line breaks before it
+__global__ void k_newline_flags(const char *bytes, uint64_t n, uint32_t *nl) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) nl[i] = bytes[i] == '\n' ? 1u : 0u;
+}
+__global__ void k_fastq_flags(const char *bytes, uint64_t n, const uint32_t *line_no, uint8_t *keep, uint8_t *head) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    const char c = bytes[i];
+    const uint32_t q = line_no[i] & 3u;
+    keep[i] = (q == 1 && c != '\n' && c != '\r') ? 1 : 0;
+    head[i] = (q == 0 && (i == 0 || bytes[i - 1] == '\n') && c != '\n') ? 1 : 0;
+  }
+}
+// offsets[r] = sequence characters before record r (kept_before at its header byte); bases compacted
+__global__ void k_scatter_parsed(const char *bytes, uint64_t n, const uint8_t *keep, const uint8_t *head, const uint64_t *kept_before,
+                                 const uint64_t *heads_before, char *bases, uint64_t *offsets) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    if (keep[i]) bases[kept_before[i]] = bytes[i];
+    if (head[i]) offsets[heads_before[i]] = kept_before[i];
+  }
+}
+__global__ void k_kmer_counts(const uint64_t *offsets, uint64_t n_reads, int k, uint64_t *cnt) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (; i <= n_reads; i += stride) {
+    if (i == n_reads) { cnt[i] = 0; continue; }
+    const uint64_t len = offsets[i + 1] - offsets[i];
+    cnt[i] = len >= (uint64_t)k ? len - k + 1 : 0;
+  }
+}
+
+struct U8ToU64 { __host__ __device__ uint64_t operator()(uint8_t v) const { return v; } };
+
+cudaError_t table_from_read_files(DeviceTable *dt, int k, const char *bytes_host, uint64_t n, int solid, int sms, cudaStream_t st,
+                                  uint64_t *n_reads_out) {
+  if (n_reads_out) *n_reads_out = 0;
+  // the first non-blank byte decides the format (BankFasta does the same)
+  uint64_t p0 = 0;
+  while (p0 < n && (bytes_host[p0] == '\n' || bytes_host[p0] == '\r' || bytes_host[p0] == ' ')) p0++;
+  if (p0 == n) { cudaError_t e0 = table_alloc(dt, k, 0, sms, st); return e0 == cudaSuccess ? cudaStreamSynchronize(st) : e0; }
+  const bool fastq = bytes_host[p0] == '@';
+  if (!fastq && bytes_host[p0] != '>') return cudaErrorInvalidValue;
+  bytes_host += p0; n -= p0;
+  char *d_bytes = nullptr, *d_bases = nullptr;
+  LineState *d_st = nullptr; uint32_t *d_nl = nullptr;
+  uint8_t *d_keep = nullptr, *d_head = nullptr;
+  uint64_t *d_kept_before = nullptr, *d_heads_before = nullptr, *d_off = nullptr, *d_koff = nullptr;
+  void *d_tmp = nullptr;
+  cudaError_t err = cudaSuccess;
+#define CKG(x) do { err = (x); if (err != cudaSuccess) goto done; } while (0)
+  {
+    CKG(cudaMalloc(&d_bytes, n + 1));
+    CKG(cudaMemcpyAsync(d_bytes, bytes_host, n, cudaMemcpyHostToDevice, st));
+    CKG(cudaMalloc(&d_keep, n)); CKG(cudaMalloc(&d_head, n));
+    size_t tb = 0;
+    if (!fastq) {
+      CKG(cudaMalloc(&d_st, n * sizeof(LineState)));
+      k_fasta_line_starts<<<grid_for(n, 256, sms), 256, 0, st>>>(d_bytes, n, d_st);
+      CKG(cub::DeviceScan::InclusiveScan(nullptr, tb, d_st, d_st, LastKind(), (int64_t)n, st));
+      CKG(cudaMalloc(&d_tmp, tb));
+      CKG(cub::DeviceScan::InclusiveScan(d_tmp, tb, d_st, d_st, LastKind(), (int64_t)n, st));
+      cudaFree(d_tmp); d_tmp = nullptr;
+      k_fasta_flags<<<grid_for(n, 256, sms), 256, 0, st>>>(d_bytes, n, d_st, d_keep, d_head);
+      CKG(cudaGetLastError());
+      cudaFree(d_st); d_st = nullptr;
+    } else {
+      CKG(cudaMalloc(&d_nl, n * 4));
+      k_newline_flags<<<grid_for(n, 256, sms), 256, 0, st>>>(d_bytes, n, d_nl);
+      CKG(cub::DeviceScan::ExclusiveSum(nullptr, tb, d_nl, d_nl, (int64_t)n, st));
+      CKG(cudaMalloc(&d_tmp, tb));
+      CKG(cub::DeviceScan::ExclusiveSum(d_tmp, tb, d_nl, d_nl, (int64_t)n, st));
+      cudaFree(d_tmp); d_tmp = nullptr;
+      k_fastq_flags<<<grid_for(n, 256, sms), 256, 0, st>>>(d_bytes, n, d_nl, d_keep, d_head);
+      CKG(cudaGetLastError());
+      cudaFree(d_nl); d_nl = nullptr;
+    }
+    // prefix sums of the two flag arrays (64-bit: files beyond 4 GB)
+    CKG(cudaMalloc(&d_kept_before, (n + 1) * 8));
+    CKG(cudaMalloc(&d_heads_before, (n + 1) * 8));
+    {
+      thrust::transform_iterator<U8ToU64, const uint8_t *> kin((const uint8_t *)d_keep, U8ToU64()), hin((const uint8_t *)d_head, U8ToU64());
+      tb = 0;
+      CKG(cub::DeviceScan::ExclusiveSum(nullptr, tb, kin, d_kept_before, (int64_t)n + 1, st));
+      CKG(cudaMalloc(&d_tmp, tb));
+      CKG(cub::DeviceScan::ExclusiveSum(d_tmp, tb, kin, d_kept_before, (int64_t)n + 1, st));
+      CKG(cub::DeviceScan::ExclusiveSum(d_tmp, tb, hin, d_heads_before, (int64_t)n + 1, st));
+      cudaFree(d_tmp); d_tmp = nullptr;
+    }
+    uint64_t n_bases = 0, n_reads = 0;
+    CKG(cudaMemcpyAsync(&n_bases, d_kept_before + n, 8, cudaMemcpyDeviceToHost, st));
+    CKG(cudaMemcpyAsync(&n_reads, d_heads_before + n, 8, cudaMemcpyDeviceToHost, st));
+    CKG(cudaStreamSynchronize(st));
+    if (n_reads_out) *n_reads_out = n_reads;
+    CKG(cudaMalloc(&d_bases, n_bases + 1));
+    CKG(cudaMalloc(&d_off, (n_reads + 1) * 8));
+    CKG(cudaMalloc(&d_koff, (n_reads + 2) * 8));
+    k_scatter_parsed<<<grid_for(n, 256, sms), 256, 0, st>>>(d_bytes, n, d_keep, d_head, d_kept_before, d_heads_before, d_bases, d_off);
+    CKG(cudaGetLastError());
+    CKG(cudaMemcpyAsync(d_off + n_reads, &n_bases, 8, cudaMemcpyHostToDevice, st));
+    CKG(cudaStreamSynchronize(st));   // n_bases lives on this stack frame
+    cudaFree(d_bytes); d_bytes = nullptr; cudaFree(d_keep); d_keep = nullptr; cudaFree(d_head); d_head = nullptr;
+    cudaFree(d_kept_before); d_kept_before = nullptr; cudaFree(d_heads_before); d_heads_before = nullptr;
+    // k-mer occurrences per read -> exclusive offsets
+    k_kmer_counts<<<grid_for(n_reads + 1, 256, sms), 256, 0, st>>>(d_off, n_reads, k, d_koff);
+    CKG(cudaGetLastError());
+    tb = 0;
+    CKG(cub::DeviceScan::ExclusiveSum(nullptr, tb, d_koff, d_koff, (int64_t)n_reads + 1, st));
+    CKG(cudaMalloc(&d_tmp, tb));
+    CKG(cub::DeviceScan::ExclusiveSum(d_tmp, tb, d_koff, d_koff, (int64_t)n_reads + 1, st));
+    cudaFree(d_tmp); d_tmp = nullptr;
+    uint64_t total = 0;
+    CKG(cudaMemcpyAsync(&total, d_koff + n_reads, 8, cudaMemcpyDeviceToHost, st));
+    CKG(cudaStreamSynchronize(st));
+    CKG(table_from_device_reads(dt, k, d_bases, d_off, d_koff, n_reads, total, solid, sms, st));
+  }
+done:
+#undef CKG
+  cudaFree(d_bytes); cudaFree(d_bases); cudaFree(d_st); cudaFree(d_nl); cudaFree(d_keep); cudaFree(d_head);
+  cudaFree(d_kept_before); cudaFree(d_heads_before); cudaFree(d_off); cudaFree(d_koff); cudaFree(d_tmp);
   return err;
 }
 

@@ -73,7 +73,7 @@ class G2SRunOptions(C.Structure):
 
 # every symbol include/g2s.h declares (tests check that the library exports all of them)
 ABI_SYMBOLS = ["g2s_last_error", "g2s_abi_version", "g2s_create", "g2s_create_multi", "g2s_num_devices", "g2s_destroy", "g2s_import_kmers", "g2s_h5_read_solid", "g2s_import_h5",
-               "g2s_build_from_reads", "g2s_build_graphs_from_reads", "g2s_graph_num_kmers", "g2s_table_raw", "g2s_table_adopt", "g2s_num_kmers", "g2s_export_kmers", "g2s_contains", "g2s_fill_gap", "g2s_fill_gap_ex",
+               "g2s_build_from_reads", "g2s_build_from_read_files", "g2s_build_graphs_from_reads", "g2s_graph_num_kmers", "g2s_table_raw", "g2s_table_adopt", "g2s_num_kmers", "g2s_export_kmers", "g2s_contains", "g2s_fill_gap", "g2s_fill_gap_ex",
                "g2s_fill_batch", "g2s_upload_gaps", "g2s_run_resident", "g2s_finish_resident", "g2s_submit",
                "g2s_batch_peek", "g2s_batch_trace", "g2s_batch_free", "g2s_fill_records", "g2s_free",
                "g2s_get_timing", "g2s_get_phase_cycles"]
@@ -97,6 +97,7 @@ def load_library(path: str | None = None):
     L.g2s_destroy.argtypes = [C.c_void_p]
     L.g2s_import_kmers.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
     L.g2s_build_from_reads.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
+    L.g2s_build_from_read_files.argtypes = [C.c_void_p, C.POINTER(C.c_char_p), C.c_size_t, C.c_int, C.POINTER(C.c_uint64)]
     L.g2s_build_graphs_from_reads.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int]
     L.g2s_graph_num_kmers.argtypes = [C.c_void_p, C.c_size_t]
     L.g2s_graph_num_kmers.restype = C.c_int64
@@ -216,6 +217,13 @@ class Engine:
     def import_kmers(self, canon: np.ndarray) -> None:
         canon = np.ascontiguousarray(canon, dtype=np.uint64)
         self._check(self.L.g2s_import_kmers(self.h, canon.ctypes.data, canon.size))
+
+    def build_from_read_files(self, paths: list[str], solid: int = 2) -> int:
+        """Graph from FASTA / FASTQ files, parsed on the device; returns the number of records found."""
+        arr = (C.c_char_p * len(paths))(*[p.encode() for p in paths])
+        n = C.c_uint64(0)
+        self._check(self.L.g2s_build_from_read_files(self.h, arr, len(paths), solid, C.byref(n)))
+        return int(n.value)
 
     def build_graphs_from_reads(self, read_sets: list, solid: int = 2) -> None:
         """Per-gap filtered-reads mode: graph g is built from read_sets[g] (a [n, read_len] uint8 ASCII array, or a list

@@ -156,6 +156,11 @@ int g2s_num_devices(const g2s_engine *e);
  * solid canonical k-mers, e.g. the values of graph.iterator() (Graph.cpp:2243-2362). */
 int g2s_import_kmers(g2s_engine *e, const uint64_t *canon, size_t n);
 
+/* The same from the reads files themselves (FASTA with sequences over any number of lines, or four-line FASTQ; all files
+ * of one call in the same format): the raw bytes go to the device and are parsed there (line kinds by a scan, sequence
+ * characters compacted, read boundaries from the same prefix sums).  *n_reads_out (may be NULL) = records found. */
+int g2s_build_from_read_files(g2s_engine *e, const char *const *paths, size_t n_paths, int solid, uint64_t *n_reads_out);
+
 /* Graph import from a GATB graph file (<reads>.h5), the file Gap2Seq::execute loads instead of building the graph when
  * it is readable (src/Gap2Seq.cpp:171, 195-197): the partitions of group dsk/solid are read straight from the HDF5
  * container (gatb-core/src/gatb/debruijn/impl/Graph.cpp:171-184, 2243-2362 own the format) - no GATB, no libhdf5.
