@@ -79,6 +79,20 @@ def test_cfg3_full_size_matches_oracle(mode, full_workload):
         assert any(r.forward_count == 1073741822 for r in res), "no saturated count: the workload lost its repeats"
 
 
+@pytest.mark.parametrize("cluster", [1, 4, 8])
+def test_cfg3_every_wide_tier_shape_matches_oracle(cluster, full_workload, monkeypatch):
+    """The wide tier runs a gap on one CTA (`k_fill_cta`) or on a thread-block cluster of 2 / 4 / 8 CTAs (`k_fill_cluster`);
+    the engine picks the largest cluster that keeps the pass resident (2 for these 60 gaps, covered above).  The other
+    shapes are forced here (G2S_CLUSTER is read when a pass is planned); with 4 or 8 CTAs per gap the 58 gaps no longer
+    fit at once, so the work queue hands a cluster several gaps in a row."""
+    monkeypatch.setenv("G2S_CLUSTER", str(cluster))
+    w, e, og = full_workload("cfg3", 1.0)
+    specs = specs_of(w, **MODES["all_paths"])
+    st = parity.compare_with_oracle(e.fill_batch, og, specs, seed=404)
+    assert st["compared"] + len(st["order_dependent"]) == len(specs)
+    assert e.timing().wide_cluster == cluster
+
+
 def test_cfg4_30pct_matches_oracle(full_workload):
     """BASELINE configs[3] at 0.3 of its size: 30 Mbp genome, 3 000 gaps of 100 bp - 5 kbp (three times the CTAs that are
     resident at once: the device work queue is exercised)."""
